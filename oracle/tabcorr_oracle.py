@@ -1,0 +1,344 @@
+"""CPU oracle for the TabCorr prediction hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
+of ``bench.py`` may import this module.  The product (``tabcorr_b200``) never does: it fails
+loudly when its CUDA extension is missing.
+
+This is a plain-numpy restatement of what the reference (johannesulf/TabCorr v1.2.0) computes on
+the path ``TabCorr.predict`` / ``Interpolator.predict``.  Every function cites the reference
+lines it follows.  Parity status:
+
+* TabCorr-side arithmetic (quadrature, packed quadratic form, per-gal-type split, spline):
+  PINNED.  ``oracle/make_golden.py`` runs the reference's own, unmodified source
+  (``oracle/refstub.py`` imports it from /root/reference with stub modules for the missing
+  h5py/astropy/halotools) on the shipped fixtures and on synthetic tables, and
+  ``tests/test_oracle.py`` checks this module against those recorded outputs
+  (``tests/golden/*.npz``) to 1e-13.
+* halotools occupation arithmetic (zheng07 centrals/satellites, Heaviside assembly bias):
+  PARITY UNPINNED.  halotools is a third-party dependency that is not vendored in
+  /root/reference, is not installed in this image (``pyproject.toml:12`` lists a bare,
+  unpinned "halotools") and none of the reference's tests hold numeric values for it.  The
+  formulas below restate the published models (Zheng et al. 2007, eqs. 1/3/5; Hearin et al. 2016
+  "decorated HOD", eqs. 9-14) as implemented by halotools' ``Zheng07Cens.mean_occupation``,
+  ``Zheng07Sats.mean_occupation`` and ``HeavisideAssembias`` from memory of that code; they must
+  be re-checked against a real halotools install when one is available.  The call sites anchoring
+  them are ``tabcorr/tabcorr.py:556-563``.
+"""
+
+import itertools
+
+import numpy as np
+from scipy.special import erf
+
+__all__ = [
+    'OracleTable', 'Zheng07Oracle', 'symmetric_matrix_to_array', 'mean_occupation', 'predict',
+    'spline_interpolation_matrix', 'spline_interpolate', 'OracleInterpolator']
+
+
+# --------------------------------------------------------------------------------------------
+# occupation model (halotools restatement -- parity unpinned, see module docstring)
+# --------------------------------------------------------------------------------------------
+
+class Zheng07Oracle:
+    """zheng07 HOD with optional Heaviside assembly-bias decoration.
+
+    Mirrors the part of halotools' ``PrebuiltHodModelFactory('zheng07')`` /
+    ``('hearin15')``-style models that ``TabCorr.mean_occupation`` consumes
+    (``tabcorr/tabcorr.py:496-563``): ``param_dict``, ``gal_types``, ``redshift``,
+    ``mean_occupation_centrals`` and ``mean_occupation_satellites``.
+
+    Parameters in ``param_dict``: ``logMmin, sigma_logM, logM0, logM1, alpha`` and, when
+    ``decorated``, ``mean_occupation_centrals_assembias_param1`` and
+    ``mean_occupation_satellites_assembias_param1`` (strengths in [-1, 1]).
+    """
+
+    gal_types = ['centrals', 'satellites']
+
+    def __init__(self, param_dict=None, decorated=False, split=0.5, redshift=0.0,
+                 modulate_with_cenocc=False):
+        self.param_dict = dict(logMmin=12.02, sigma_logM=0.26, logM0=11.38, logM1=13.31,
+                               alpha=1.06)
+        if decorated:
+            self.param_dict['mean_occupation_centrals_assembias_param1'] = 0.5
+            self.param_dict['mean_occupation_satellites_assembias_param1'] = 0.5
+        if param_dict is not None:
+            self.param_dict.update(param_dict)
+        self.decorated = decorated
+        self.split = split
+        self.redshift = redshift
+        self.modulate_with_cenocc = modulate_with_cenocc
+
+    # -- baseline zheng07 ---------------------------------------------------------------
+    def _baseline_centrals(self, prim_haloprop):
+        # halotools Zheng07Cens.mean_occupation: logM = log10(mass);
+        # 0.5 * (1 + erf((logM - logMmin) / sigma_logM))
+        log_m = np.log10(prim_haloprop)
+        return 0.5 * (1.0 + erf((log_m - self.param_dict['logMmin']) /
+                                self.param_dict['sigma_logM']))
+
+    def _baseline_satellites(self, prim_haloprop):
+        # halotools Zheng07Sats.mean_occupation: M0 = 10**logM0, M1 = 10**logM1;
+        # ((M - M0) / M1)**alpha where M - M0 > 0, else 0; optionally times <N_cen>.
+        m0 = 10.0**self.param_dict['logM0']
+        m1 = 10.0**self.param_dict['logM1']
+        out = np.zeros_like(prim_haloprop, dtype=np.float64)
+        ok = prim_haloprop - m0 > 0
+        out[ok] = ((prim_haloprop[ok] - m0) / m1)**self.param_dict['alpha']
+        if self.modulate_with_cenocc:
+            out *= self._baseline_centrals(prim_haloprop)
+        return out
+
+    # -- Heaviside assembly bias ----------------------------------------------------------
+    def _decorate(self, baseline, percentile, strength, lower, upper):
+        # halotools HeavisideAssembias.assembias_decorator: haloes above the split percentile
+        # (type 1, fraction 1 - split) get +delta, the rest -delta * (1 - split) / split, which
+        # preserves the mean at fixed mass.  delta = strength * (largest perturbation keeping both
+        # sub-populations inside [lower, upper]); strength is clipped to [-1, 1].
+        split = self.split
+        strength = min(max(strength, -1.0), 1.0)
+        result = np.array(baseline, dtype=np.float64)
+        if not 0 < split < 1:
+            return result
+        ok = (result > lower) & (result < upper)
+        f = result[ok]
+        frac1 = 1.0 - split
+        frac2 = split
+        if strength > 0:
+            bound = np.minimum(upper - f, frac2 / frac1 * (f - lower))
+            delta = strength * bound
+        else:
+            bound = np.maximum(lower - f, frac2 / frac1 * (f - upper))
+            delta = -strength * bound
+        type1 = percentile[ok] > split
+        f = np.where(type1, f + delta, f - delta * frac1 / frac2)
+        result[ok] = f
+        return result
+
+    def mean_occupation_centrals(self, prim_haloprop=None, sec_haloprop_percentile=None, **kw):
+        f = self._baseline_centrals(np.asarray(prim_haloprop, dtype=np.float64))
+        if self.decorated:
+            f = self._decorate(
+                f, np.asarray(sec_haloprop_percentile),
+                self.param_dict['mean_occupation_centrals_assembias_param1'], 0.0, 1.0)
+        return f
+
+    def mean_occupation_satellites(self, prim_haloprop=None, sec_haloprop_percentile=None, **kw):
+        f = self._baseline_satellites(np.asarray(prim_haloprop, dtype=np.float64))
+        if self.decorated:
+            f = self._decorate(
+                f, np.asarray(sec_haloprop_percentile),
+                self.param_dict['mean_occupation_satellites_assembias_param1'], 0.0, np.inf)
+        return f
+
+
+# --------------------------------------------------------------------------------------------
+# table container
+# --------------------------------------------------------------------------------------------
+
+class OracleTable:
+    """The state of a reference ``TabCorr`` instance that ``predict`` reads.
+
+    ``gal_type`` is a numpy structured array with the columns written by
+    ``tabcorr/tabcorr.py:199-234`` (``n_h, log_prim_haloprop_min/max, sec_haloprop_percentile,
+    prim_haloprop_dist_index, gal_type`` ...); ``gal_type['gal_type']`` may be bytes or str.
+    """
+
+    def __init__(self, gal_type, tpcf_matrix, tpcf_shape, mode):
+        self.gal_type = gal_type
+        self.tpcf_matrix = np.asarray(tpcf_matrix, dtype=np.float64)  # tabcorr.py:399
+        self.tpcf_shape = tuple(int(s) for s in tpcf_shape)
+        self.mode = str(mode)
+        names = gal_type['gal_type']
+        if names.dtype.kind == 'S':
+            names = np.char.decode(names, 'utf-8')
+        self.gal_type_names = np.asarray(names, dtype=str)
+        self._pack_cache = None
+
+    def __len__(self):
+        return len(self.gal_type)
+
+
+# --------------------------------------------------------------------------------------------
+# TabCorr.predict
+# --------------------------------------------------------------------------------------------
+
+def symmetric_matrix_to_array(matrix):
+    """Row-major lower triangle including the diagonal (``tabcorr/tabcorr.py:770-806``)."""
+    n = matrix.shape[0]
+    sel = np.zeros((n * n + n) // 2, dtype=int)
+    for i in range(n):
+        sel[(i * (i + 1)) // 2:(i * (i + 1)) // 2 + (i + 1)] = np.arange(i * n, i * n + i + 1)
+    return matrix.ravel()[sel]
+
+
+def mean_occupation(table, model, n_gauss_prim=10, **occ_kwargs):
+    """Gauss-Legendre averaged occupation per table row (``tabcorr/tabcorr.py:537-578``)."""
+    gt = table.gal_type
+    log_min = gt['log_prim_haloprop_min']
+    d_log = gt['log_prim_haloprop_max'] - log_min
+    x_gauss, w_gauss = np.polynomial.legendre.leggauss(n_gauss_prim)  # :544
+    x_gauss = (x_gauss + 1) / 2  # :546
+    prim = 10**(log_min + d_log * x_gauss[:, np.newaxis]).T.ravel()  # :548-549
+    pct = np.repeat(gt['sec_haloprop_percentile'], n_gauss_prim)  # :550-551
+    names = np.repeat(table.gal_type_names, n_gauss_prim)  # :552
+    occ = np.zeros(len(prim))
+    cen = names == 'centrals'  # :555
+    occ[cen] = model.mean_occupation_centrals(
+        prim_haloprop=prim[cen], sec_haloprop_percentile=pct[cen], **occ_kwargs)  # :556-559
+    occ[~cen] = model.mean_occupation_satellites(
+        prim_haloprop=prim[~cen], sec_haloprop_percentile=pct[~cen], **occ_kwargs)  # :560-563
+    occ = occ.reshape(len(gt), n_gauss_prim)
+    prim = prim.reshape(occ.shape)
+    if 'prim_haloprop_dist_index' in gt.dtype.names:
+        n = gt['prim_haloprop_dist_index'][:, np.newaxis] + 1  # :570
+    else:
+        n = 0  # :574
+    return (np.sum(w_gauss * occ * prim**n, axis=-1) / np.sum(w_gauss * prim**n, axis=-1))  # :576-578
+
+
+def _pack_indices(table):
+    if table._pack_cache is None:
+        n = len(table)
+        i1 = symmetric_matrix_to_array(np.repeat(np.arange(n), n).reshape(n, n))  # :628-634
+        i2 = symmetric_matrix_to_array(np.tile(np.arange(n), n).reshape(n, n))  # :630-636
+        table._pack_cache = (i1, i2, np.where(i1 == i2, 1, 2))  # :638-639
+    return table._pack_cache
+
+
+def predict(table, occupation, separate_gal_type=False):
+    """``TabCorr.predict`` for a given occupation vector (``tabcorr/tabcorr.py:623-683``)."""
+    ngal = occupation * table.gal_type['n_h']  # :623
+    if table.mode == 'auto':
+        i1, i2, pref = _pack_indices(table)
+        ngal_sq = pref * ngal[i1] * ngal[i2]  # :641-642
+    if not separate_gal_type:
+        if table.mode == 'auto':
+            xi = np.einsum('ij, j', table.tpcf_matrix, ngal_sq) / np.sum(ngal_sq)  # :646-647
+        else:
+            xi = np.einsum('ij, j', table.tpcf_matrix, ngal) / np.sum(ngal)  # :649
+        return np.sum(ngal), xi.reshape(table.tpcf_shape)  # :650
+
+    if table.mode == 'auto':
+        xi = (table.tpcf_matrix * ngal_sq) / np.sum(ngal_sq)  # :653
+    else:
+        xi = (table.tpcf_matrix * ngal) / np.sum(ngal)  # :655
+    names = table.gal_type_names
+    ngal_dict, xi_dict = {}, {}
+    for name in np.unique(names):  # :660-662
+        ngal_dict[str(name)] = np.sum(ngal[names == name])
+    if table.mode == 'auto':
+        for n1, n2 in itertools.combinations_with_replacement(np.unique(names), 2):  # :665-675
+            mask = symmetric_matrix_to_array(
+                np.outer(n1 == names, n2 == names) | np.outer(n2 == names, n1 == names))
+            xi_dict['%s-%s' % (n1, n2)] = np.sum(xi * mask, axis=1).reshape(table.tpcf_shape)
+    else:
+        for name in np.unique(names):  # :678-681
+            xi_dict[str(name)] = np.sum(xi * (names == name), axis=1).reshape(table.tpcf_shape)
+    return ngal_dict, xi_dict
+
+
+# --------------------------------------------------------------------------------------------
+# Interpolator
+# --------------------------------------------------------------------------------------------
+
+def spline_interpolation_matrix(xp):
+    """Not-a-knot cubic spline as a matrix acting on the y-values
+    (``tabcorr/interpolator.py:219-272``)."""
+    xp = np.asarray(xp, dtype=np.float64)
+    if len(xp) < 4:
+        raise ValueError('Cannot perform spline interpolation with less than 4 values.')
+    n = len(xp) - 1
+    m = np.zeros((4 * n, 4 * n))
+    p4, p3, p2 = np.arange(4), np.arange(3), np.arange(2)
+    for i in range(n):  # :247-249 spline passes through the knots
+        m[i, i * 4:(i + 1) * 4] = xp[i]**p4
+        m[i + n, i * 4:(i + 1) * 4] = xp[i + 1]**p4
+    for i in range(n - 1):  # :252-259 continuity of first and second derivative
+        d1 = np.array([1, 2, 3]) * xp[i + 1]**p3
+        d2 = np.array([2, 6]) * xp[i + 1]**p2
+        m[i + 2 * n, i * 4 + 1:(i + 1) * 4] = d1
+        m[i + 2 * n, (i + 1) * 4 + 1:(i + 2) * 4] = -d1
+        m[i + 3 * n - 1, i * 4 + 2:(i + 1) * 4] = d2
+        m[i + 3 * n - 1, (i + 1) * 4 + 2:(i + 2) * 4] = -d2
+    m[-1, 3] = 6 * xp[1]  # :262-265 not-a-knot: third derivative continuous at xp[1], xp[-2]
+    m[-1, 7] = -6 * xp[1]
+    m[-2, -5] = 6 * xp[-2]
+    m[-2, -1] = -6 * xp[-2]
+    m = np.linalg.inv(m)  # :268
+    a = np.zeros((4 * n, len(xp)))
+    a[:, :-1] = m[:, :n]
+    a[:, 1:] += m[:, n:2 * n]
+    return a.reshape((n, 4, len(xp)))
+
+
+def spline_interpolate(x, xp, a, yp, extrapolate=False):
+    """Tensor-product evaluation, one axis at a time (``tabcorr/interpolator.py:312-331``)."""
+    if not isinstance(xp, list):
+        xp = [xp]
+    if not isinstance(a, list):
+        a = [a]
+    x = np.atleast_1d(x)
+    for xi, ai, xpi in zip(x, a, xp):
+        i_spline = np.digitize(xi, xpi) - 1  # :319
+        if xi == xpi[-1]:  # :320-321
+            i_spline = len(xpi) - 2
+        if i_spline < 0 or i_spline >= len(xpi) - 1:  # :322-328
+            if not extrapolate:
+                raise ValueError('The x-coordinates are outside of the interpolation range and '
+                                 'extrapolation is turned off.')
+            i_spline = min(max(i_spline, 0), len(xpi) - 2)
+        yp = np.einsum('ij,j...,i', ai[i_spline], yp, xi**np.arange(4))  # :329
+    return yp
+
+
+class OracleInterpolator:
+    """``Interpolator.__init__`` + ``predict`` (``tabcorr/interpolator.py:14-70,124-216``).
+
+    ``tables`` is a list of :class:`OracleTable`; ``param_table`` a dict ``{key: values[T]}`` whose
+    insertion order is the column order of the reference's ``param_dict_table``.
+    """
+
+    def __init__(self, tables, param_table):
+        keys = list(param_table.keys())
+        cols = [np.asarray(param_table[k], dtype=np.float64) for k in keys]
+        if any(len(c) != len(tables) for c in cols):  # :32-34
+            raise ValueError("The number of TabCorr instances does not match the number of "
+                             "entries in 'param_dict_table'.")
+        self.keys = keys
+        self.xp = [np.sort(np.unique(c)) for c in cols]  # :41
+        self.a = [spline_interpolation_matrix(xp) for xp in self.xp]  # :42
+        rows = np.stack(cols, axis=1)
+        if (np.prod([len(xp) for xp in self.xp]) != len(tables) or
+                len(np.unique(rows, axis=0)) != len(rows)):  # :45-57
+            raise ValueError("The 'param_dict_table' does not describe a grid.")
+        # :59-61 lexicographic sort by all columns, first column most significant
+        self.order = np.lexsort([c for c in cols[::-1]])
+        self.tables = tables
+
+    def predict(self, model, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
+                **occ_kwargs):
+        try:
+            x_model = np.array([model.param_dict[k] for k in self.keys])  # :168-177
+        except KeyError as err:
+            raise ValueError('The key {} is not present in the parameter dictionary of the '
+                             'model.'.format(err.args[0]))
+        results = []
+        for k in self.order:  # :188-194
+            occ = mean_occupation(self.tables[k], model, n_gauss_prim, **occ_kwargs)
+            results.append(predict(self.tables[k], occ, separate_gal_type))
+        shape = [len(xp) for xp in self.xp]
+        output = []
+        for i in range(2):  # :198-214
+            if separate_gal_type:
+                output.append({})
+                for key in results[0][i]:
+                    data = np.array([r[i][key] for r in results])
+                    data = data.reshape(shape + list(data.shape[1:]))
+                    output[-1][key] = spline_interpolate(x_model, self.xp, self.a, data,
+                                                         extrapolate=extrapolate)
+            else:
+                data = np.array([r[i] for r in results])
+                data = data.reshape(shape + list(data.shape[1:]))
+                output.append(spline_interpolate(x_model, self.xp, self.a, data,
+                                                 extrapolate=extrapolate))
+        return tuple(output)

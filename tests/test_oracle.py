@@ -1,0 +1,169 @@
+"""Pin the numpy oracle (oracle/tabcorr_oracle.py) against outputs of the reference's own source
+recorded in tests/golden/reference_outputs.npz (oracle/make_golden.py), and, where the reference
+checkout is present, against the reference itself run live."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tabcorr_oracle as orc
+from tabcorr_b200 import h5mini
+
+import cases
+
+RTOL = 1e-13
+
+
+def table_from_group(group):
+    return orc.OracleTable(group['gal_type'][()], group['tpcf_matrix'][()],
+                           group['tpcf_shape'][()], group.attrs['mode'])
+
+
+def table_from_dict(tab):
+    return orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                           tab['attrs']['mode'])
+
+
+def check(golden, name, result, rtol=RTOL):
+    ngal, xi = result
+    if isinstance(ngal, dict):
+        keys = [k.split('/')[-1] for k in golden if k.startswith(name + '/ngal/')]
+        assert sorted(keys) == sorted(ngal.keys())
+        for k in ngal:
+            np.testing.assert_allclose(ngal[k], golden['{}/ngal/{}'.format(name, k)], rtol=rtol)
+        keys = [k.split('/')[-1] for k in golden if k.startswith(name + '/xi/')]
+        assert sorted(keys) == sorted(xi.keys())
+        for k in xi:
+            ref = golden['{}/xi/{}'.format(name, k)]
+            np.testing.assert_allclose(xi[k], ref, rtol=rtol, atol=rtol * np.abs(ref).max())
+    else:
+        ref = golden[name + '/xi']
+        np.testing.assert_allclose(ngal, golden[name + '/ngal'], rtol=rtol)
+        np.testing.assert_allclose(xi, ref, rtol=rtol, atol=rtol * np.abs(ref).max())
+
+
+def test_known_answers_survey_appendix_b(golden):
+    # SURVEY.md Appendix B (KA1-KA3), produced independently during the survey
+    assert np.isclose(golden['bolplanck_wp/G10/ngal'], 0.02661553737533991, rtol=1e-14)
+    assert np.isclose(golden['bolplanck_wp/G10/xi'][0], 330.5673788146721, rtol=1e-14)
+    assert np.isclose(golden['bolplanck_wp/G10/xi'][-1], 10.40324779671382, rtol=1e-14)
+    assert np.isclose(golden['bolplanck_wp/G1/ngal'], 0.026704200819530274, rtol=1e-14)
+    assert np.isclose(golden['bolplanck_ds/G10/ngal'], 0.00111147736343942, rtol=1e-14)
+    assert np.isclose(golden['bolplanck_ds/G10/xi'][-1], 892573882737.356, rtol=1e-14)
+    assert np.isclose(golden['ds_efficient/a/ngal'], 0.0005687382151542917, rtol=1e-14)
+    assert np.isclose(golden['ds_efficient/a/xi'][-1], 306802620634.2734, rtol=1e-14)
+
+
+def test_bolplanck_wp(golden, golden_dir):
+    tab = table_from_group(h5mini.File(os.path.join(golden_dir, 'bolplanck_wp.hdf5')))
+    model = orc.Zheng07Oracle(cases.THETA_M18)
+    occ = orc.mean_occupation(tab, model)
+    np.testing.assert_allclose(occ, golden['bolplanck_wp/occ'], rtol=RTOL, atol=1e-300)
+    for g in (1, 10, 100):
+        check(golden, 'bolplanck_wp/G{}'.format(g),
+              orc.predict(tab, orc.mean_occupation(tab, model, g)))
+    check(golden, 'bolplanck_wp/sep', orc.predict(tab, occ, separate_gal_type=True))
+    check(golden, 'bolplanck_wp/m21',
+          orc.predict(tab, orc.mean_occupation(tab, orc.Zheng07Oracle(cases.THETA_M21))))
+
+
+def test_bolplanck_ds(golden, golden_dir):
+    tab = table_from_group(h5mini.File(os.path.join(golden_dir, 'bolplanck_ds.hdf5')))
+    occ = orc.mean_occupation(tab, orc.Zheng07Oracle(cases.THETA_M21))
+    check(golden, 'bolplanck_ds/G10', orc.predict(tab, occ))
+    check(golden, 'bolplanck_ds/sep', orc.predict(tab, occ, separate_gal_type=True))
+
+
+def test_ds_efficient_interpolator(golden, golden_dir):
+    f = h5mini.File(os.path.join(golden_dir, 'ds_efficient.hdf5'))
+    param = f['param_dict_table'][()]
+    order = np.argsort(param['tabcorr_index'])
+    tables = [table_from_group(f['tabcorr_{}'.format(i)]) for i in range(len(param))]
+    interp = orc.OracleInterpolator(tables, {'log_eta': param['log_eta'][order]})
+    for tag, log_eta in (('a', 0.1), ('b', -0.3), ('knot', float(param['log_eta'][order][1]))):
+        model = orc.Zheng07Oracle(dict(cases.THETA_AS, log_eta=log_eta))
+        check(golden, 'ds_efficient/' + tag, interp.predict(model))
+        check(golden, 'ds_efficient/{}_sep'.format(tag),
+              interp.predict(model, separate_gal_type=True))
+    model = orc.Zheng07Oracle(dict(cases.THETA_AS, log_eta=0.6))
+    with pytest.raises(ValueError):
+        interp.predict(model)
+    check(golden, 'ds_efficient/extrap', interp.predict(model, extrapolate=True))
+    model = orc.Zheng07Oracle(cases.THETA_AS)
+    with pytest.raises(ValueError):
+        interp.predict(model)  # log_eta missing from param_dict
+
+
+@pytest.mark.parametrize('name', sorted(cases.SYNTHETIC))
+def test_synthetic_tables(golden, name):
+    tab, draws, decorated = cases.synthetic_case(name, golden)
+    table = table_from_dict(tab)
+    for g in ((1, 10, 100) if name == 'syn240dec' else (10,)):
+        for i in range(cases.N_DRAWS):
+            model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=decorated)
+            occ = orc.mean_occupation(table, model, g)
+            np.testing.assert_allclose(occ, golden['{}/G{}/occ'.format(name, g)][i], rtol=RTOL,
+                                       atol=1e-300)
+            ngal, xi = orc.predict(table, occ)
+            ref = golden['{}/G{}/xi'.format(name, g)][i]
+            np.testing.assert_allclose(ngal, golden['{}/G{}/ngal'.format(name, g)][i], rtol=RTOL)
+            np.testing.assert_allclose(xi, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+    model = orc.Zheng07Oracle(cases.draws_row(draws, 0), decorated=decorated)
+    check(golden, name + '/sep0',
+          orc.predict(table, orc.mean_occupation(table, model), separate_gal_type=True))
+
+
+@pytest.mark.parametrize('name', sorted(cases.GRIDS))
+def test_synthetic_grids(golden, name):
+    tables, param_table, draws = cases.grid_case(name)
+    interp = orc.OracleInterpolator([table_from_dict(t) for t in tables], param_table)
+    for i in range(cases.N_DRAWS):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=True)
+        ngal, xi = interp.predict(model)
+        ref = golden[name + '/xi'][i]
+        np.testing.assert_allclose(ngal, golden[name + '/ngal'][i], rtol=1e-12)
+        np.testing.assert_allclose(xi, ref, rtol=1e-11, atol=1e-12 * np.abs(ref).max())
+    model = orc.Zheng07Oracle(cases.draws_row(draws, 0), decorated=True)
+    check(golden, name + '/sep0', interp.predict(model, separate_gal_type=True), rtol=1e-11)
+
+
+def test_spline(golden):
+    a = orc.spline_interpolation_matrix(golden['spline/xp'])
+    np.testing.assert_allclose(a, golden['spline/a'], rtol=1e-12, atol=1e-12)
+    y = np.array([orc.spline_interpolate(x, golden['spline/xp'], a, golden['spline/yp'])
+                  for x in golden['spline/x']])
+    np.testing.assert_allclose(y, golden['spline/y'], rtol=1e-12, atol=1e-13)
+    from scipy.interpolate import CubicSpline
+    cs = CubicSpline(golden['spline/xp'], golden['spline/yp'], bc_type='not-a-knot')
+    np.testing.assert_allclose(y, cs(golden['spline/x']), rtol=1e-11, atol=1e-12)
+    with pytest.raises(ValueError):
+        orc.spline_interpolation_matrix(np.arange(3.0))
+    with pytest.raises(ValueError):
+        orc.spline_interpolate(2.5, golden['spline/xp'], a, golden['spline/yp'])
+
+
+def test_packed_layout():
+    n = 7
+    m = np.arange(n * n).reshape(n, n)
+    m = np.tril(m) + np.tril(m, -1).T
+    packed = orc.symmetric_matrix_to_array(m)
+    rows, cols = np.tril_indices(n)
+    assert np.array_equal(packed, m[rows, cols])
+
+
+@pytest.mark.reference
+def test_against_live_reference():
+    from oracle import refstub
+    if not refstub.available():
+        pytest.skip('reference checkout not present')
+    tab, draws, decorated = cases.synthetic_case('syn36x3')
+    ref = refstub.make_tabcorr(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                               tab['attrs'])
+    table = table_from_dict(tab)
+    for i in range(4):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=decorated)
+        ngal_ref, xi_ref = ref.predict(model, check_consistency=False)
+        ngal, xi = orc.predict(table, orc.mean_occupation(table, model))
+        assert np.isclose(ngal, ngal_ref, rtol=1e-14)
+        np.testing.assert_allclose(xi, xi_ref, rtol=1e-13)
