@@ -1,0 +1,129 @@
+/* tabcorr_b200 -- C ABI of the B200 (sm_100a) implementation of TabCorr's prediction hot path.
+ *
+ * The reference (johannesulf/TabCorr v1.2.0) is pure Python and has no FFI layer; its boundary for
+ * this path is the Python API (tabcorr/tabcorr.py:374-416,465-683, tabcorr/interpolator.py:14-216).
+ * The entry points below are what a binding for that path needs: tabcorr_b200/_lib.py binds them
+ * with ctypes, and INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * TC_E* code (tc_last_error() then holds a message for the calling thread); nothing throws.
+ * Pointers named *_host are host memory, *_dev device memory of the table's device.  Launches are
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).  Device memory
+ * is allocated only inside tc_*_create / tc_table_plan; per-call scratch is supplied by the caller
+ * (tc_predict_workspace_bytes).
+ */
+#ifndef TABCORR_B200_H
+#define TABCORR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_VERSION 100
+
+#define TC_OK 0
+#define TC_EINVAL (-1)      /* bad argument */
+#define TC_ECUDA (-2)       /* CUDA runtime error, see tc_last_error() */
+#define TC_EUNSUPPORTED (-3) /* shape outside what the kernels support */
+#define TC_ENOMEM (-4)
+
+#define TC_MODE_AUTO 0  /* xi_r = w^T M_r w / (sum w)^2, tabcorr/tabcorr.py:641-647 */
+#define TC_MODE_CROSS 1 /* xi_r = M_r . w / sum w,        tabcorr/tabcorr.py:648-649 */
+
+/* Number of doubles per parameter draw consumed by tc_predict_batch / tc_occupation_batch:
+ * logMmin, sigma_logM, logM0, logM1, alpha, A_cen, A_sat  (the last two are the
+ * mean_occupation_{centrals,satellites}_assembias_param1 strengths, ignored unless decorated). */
+#define TC_N_THETA 7
+
+typedef struct tc_table tc_table;   /* device-resident table group (one gal_type, >=1 matrices) */
+typedef struct tc_interp tc_interp; /* tensor-product cubic spline over a table grid */
+
+/* Occupation model evaluated by the occupation kernel; replaces the halotools calls at
+ * tabcorr/tabcorr.py:556-563 (Zheng07Cens/Zheng07Sats, optionally HeavisideAssembias). */
+typedef struct tc_model {
+  int32_t family;               /* 0 = zheng07 */
+  int32_t decorated;            /* 1 = Heaviside assembly bias on centrals and satellites */
+  int32_t modulate_with_cenocc; /* 1 = <N_sat> is multiplied by the baseline <N_cen> */
+  int32_t reserved;
+  double split;                 /* percentile split of the decoration (halotools default 0.5) */
+} tc_model;
+
+const char* tc_last_error(void);
+int tc_version(void);
+
+/* TabCorr.read (tabcorr/tabcorr.py:374-416) for `n_tables` tables that share one gal_type table
+ * (n_tables > 1 is an Interpolator group, tabcorr/interpolator.py:63-70).  All inputs are host
+ * arrays in the reference's row order: the gal_type columns n_h, log_prim_haloprop_min/max,
+ * sec_haloprop_percentile, prim_haloprop_dist_index (NULL for legacy tables without that column,
+ * tabcorr.py:568-574), is_sat[i] = (gal_type[i] != 'centrals') (tabcorr.py:555), and per table
+ * the matrix exactly as stored: [n_r, n_rows (n_rows + 1) / 2] packed lower triangle
+ * (tabcorr.py:770-806) for TC_MODE_AUTO, [n_r, n_rows] for TC_MODE_CROSS. */
+int tc_table_create(tc_table** out, int mode, int n_rows, int n_r, int n_tables,
+                    const double* n_h_host, const double* log_min_host,
+                    const double* log_max_host, const double* sec_pct_host,
+                    const double* dist_index_host, const int32_t* is_sat_host,
+                    const double* const* tpcf_matrix_host, int device);
+int tc_table_destroy(tc_table* table);
+
+/* Shape queries. */
+int tc_table_n_rows(const tc_table* table);
+int tc_table_n_r(const tc_table* table);
+int tc_table_n_tables(const tc_table* table);
+
+/* Register the Gauss-Legendre rule used by mean_occupation (tabcorr.py:543-552,568-578):
+ * nodes x in [0, 1] and weights of numpy.polynomial.legendre.leggauss(n_gauss).  Builds (once per
+ * n_gauss, cached in the table) the node masses and normalised quadrature weights on the device. */
+int tc_table_plan(tc_table* table, int n_gauss, const double* x01_host, const double* w_host);
+
+/* TabCorr.mean_occupation (tabcorr.py:465-578) for B draws: occ_dev[B, n_rows] in reference row
+ * order.  theta_dev is [B, TC_N_THETA]. */
+int tc_occupation_batch(tc_table* table, const tc_model* model, int n_gauss,
+                        const double* theta_dev, int64_t n_draws, double* occ_dev, void* stream);
+
+/* Scratch bytes tc_predict_batch needs for n_draws (separate = separate_gal_type). */
+size_t tc_predict_workspace_bytes(const tc_table* table, int64_t n_draws, int separate);
+
+/* TabCorr.predict (tabcorr.py:580-683) for B draws, fused occupation + contraction.
+ * Exactly one of theta_dev ([B, TC_N_THETA], evaluated with `model` and the n_gauss plan) and
+ * occ_dev ([B, n_rows] precomputed occupations, the ndarray branch tabcorr.py:616-621) is non-NULL.
+ * Outputs, with T = n_tables, R = n_r:
+ *   separate == 0: ngal_dev[b * ngal_stride + t], xi_dev[b * xi_stride + t * R + r]
+ *   separate == 1: ngal_dev[b * ngal_stride + t * 2 + q], q = centrals, satellites;
+ *                  xi_dev[b * xi_stride + (t * R + r) * C + p] with C = 3, p = cen-cen, cen-sat,
+ *                  sat-sat (auto) or C = 2, p = centrals, satellites (cross); tabcorr.py:652-683.
+ * Strides are in doubles, so that several table groups can fill one [B, T_total, ...] buffer. */
+int tc_predict_batch(tc_table* table, const tc_model* model, int n_gauss, const double* theta_dev,
+                     const double* occ_dev, int64_t n_draws, int separate, double* ngal_dev,
+                     int64_t ngal_stride, double* xi_dev, int64_t xi_stride, void* workspace_dev,
+                     size_t workspace_bytes, void* stream);
+
+/* Interpolator.__init__ (tabcorr/interpolator.py:39-61): n_dims axes with n_knots[d] sorted knots
+ * (concatenated in knots_host) and the spline matrices a[d] of shape [n_knots[d]-1, 4, n_knots[d]]
+ * (spline_interpolation_matrix, interpolator.py:219-272; concatenated in a_host).
+ * grid_to_table_host[g] is the index, in the caller's table order, of the table at row-major grid
+ * position g (first axis slowest), i.e. the lexicographic sort of interpolator.py:59-61. */
+int tc_interp_create(tc_interp** out, int n_dims, const int32_t* n_knots_host,
+                     const double* knots_host, const double* a_host,
+                     const int32_t* grid_to_table_host, int device);
+int tc_interp_destroy(tc_interp* interp);
+
+/* spline_interpolate (interpolator.py:275-331) for B draws: out_dev[b, c] = sum over grid tables
+ * of w_t(x_b) data_dev[b, t, c], t in the caller's table order, n_cols values per table.
+ * x_dev is [B, n_dims].  Without extrapolate, draws outside the knot hull get NaN outputs and
+ * *flag_dev (int32, device) is set to 1 so that the host can raise the reference's ValueError
+ * (interpolator.py:322-326); with extrapolate the end segments are used (:327-328). */
+int tc_interp_apply_batch(tc_interp* interp, const double* x_dev, int64_t n_draws,
+                          const double* data_dev, int n_cols, double* out_dev, int extrapolate,
+                          int32_t* flag_dev, void* stream);
+
+/* Live FP64 tensor (DMMA) peak of the device in TFLOP/s, the roofline denominator bench.py
+ * reports (MEASURED_PEAKS.json carries no FP64 figure). */
+int tc_measure_dmma_peak(int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TABCORR_B200_H */

@@ -1,0 +1,1296 @@
+// tabcorr_b200 -- sm_100a kernels and C ABI for TabCorr's prediction hot path.
+//
+// What is computed (reference johannesulf/TabCorr v1.2.0, tabcorr/tabcorr.py:465-683): for each of
+// B parameter draws, the Gauss-Legendre averaged mean occupation of every tabulated halo bin
+// (:537-578), the tracer weights w = occ * n_h (:623), ngal = sum w and, per radial bin r, the
+// quadratic form xi_r = w^T M_r w / ngal^2 over the symmetric tracer-pair table (:641-647) or the
+// linear form M_r . w / ngal for cross-correlation tables (:648-649); optionally split by galaxy
+// type (:652-683).  Interpolator.predict (tabcorr/interpolator.py:124-216) runs this for every table
+// of a parameter grid and applies a tensor-product cubic spline (:275-331).
+//
+// How it is mapped to B200 (see DESIGN.md for the full account):
+//  * FP64 has no tcgen05/UMMA kind; the FP64 tensor path on sm_100a is the warp-level DMMA
+//    (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4).  Measured: 37.05 TFLOP/s per B200, and DFMA shares
+//    the same pipe (tools/fp64_peaks.cu), so the occupation arithmetic competes with the
+//    contraction for issue slots -- the kernel is built to minimise FP64 instructions outside DMMA.
+//  * The draws are the GEMM "n" dimension: one CTA owns a tile of 8*NT draws whose weights W live
+//    in shared memory in DMMA B-fragment order for the whole tile.  The table is the "A" operand:
+//    at load time M_r is rewritten as a lower-triangular matrix with doubled off-diagonal terms
+//    (exactly the reference's packed prefactor-2 sum) and re-tiled into a DMMA A-fragment stream,
+//    so that each warp streams its tiles from L2 with one coalesced 16-byte load per lane and
+//    k-step, with no shared-memory staging and no block-level synchronisation in the main loop.
+//    Only the lower triangle is multiplied: half the flops of the dense form.
+//  * Work inside a CTA is a list of chunks (radial bin, range of 16-row tiles) that the 12 warps
+//    take dynamically; each chunk ends in a register row-dot against W and a fixed-order shuffle
+//    reduction, and writes its partial sums to a scratch slot, so results are bitwise
+//    reproducible whatever the schedule or the number of GPUs.
+//
+// This file holds no CPU implementation of the path: without a CUDA device every entry point
+// that computes returns TC_ECUDA.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tabcorr_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define TC_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t err__ = (expr);                                                            \
+    if (err__ != cudaSuccess) {                                                            \
+      (void)cudaGetLastError();                                                            \
+      return fail(TC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));        \
+    }                                                                                      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// constants shared by host and device
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads = 384;        // 12 warps, 3 per SM sub-partition, <= 170 registers each
+constexpr int kWarps = kThreads / 32;
+constexpr int kGroupRows = 4;        // rows (secondary-percentile bins) sharing one mass bin
+constexpr int kSmemLimit = 227 * 1024;
+
+// One unit of contraction work.  Auto mode: radial bin `r`, 16-row tiles [mt0, mt1); for tile mt
+// the k-steps (4 table rows each) [k_begin, min(4 (mt + 1), k_cap)) are multiplied.  Cross mode:
+// 16-radial-bin tile `r`, k-steps [k_begin, k_cap).  `part_row` is where the result goes.
+struct Chunk {
+  int r, mt0, mt1, k_begin, k_cap, part_row, pad0, pad1;
+};
+
+struct OccPlan {       // device pointers, one per (layout, n_gauss)
+  int n_groups;
+  int n_gauss;
+  const double* node_logm;  // [n_groups, G]  log10 of the node masses
+  const double* node_m;     // [n_groups, G]  node masses
+  const int* grp_rows;      // [n_groups, kGroupRows] padded row index or -1
+  const int* grp_is_sat;    // [n_groups]
+  const double* row_c;      // [n_pad, G] normalised quadrature weights
+  const double* row_nh;     // [n_pad]
+  const double* row_pct;    // [n_pad] secondary-property percentile of the row
+};
+
+struct LayoutDev {
+  int n_rows;          // N of the table
+  int n_pad;           // padded rows, multiple of 16
+  int nc_pad;          // first satellite row in padded order
+  int n_parts;         // scratch rows per draw tile
+  int n_chunks;
+  int n_out;           // outputs per draw: Reff * n_comp
+  long long ks_per_r;  // k-steps per radial bin (auto) / per 16-bin tile (cross) in the A stream
+  const double2* afrag;
+  const Chunk* chunks;
+  const int* out_ptr;    // [n_out + 1] CSR: which scratch rows sum to output o
+  const int* out_parts;
+  const int* pad_to_row;  // [n_pad] reference row index or -1
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// index of (padded row i, draw b) in the shared W tile: DMMA B-fragment order, so that the lane
+// holding B[k = i % 4][n = b % 8] of k-step i / 4 and n-tile b / 8 reads consecutive doubles.
+template <int NT>
+__device__ __forceinline__ int widx(int i, int b) {
+  return (((i >> 2) * NT + (b >> 3)) << 5) + ((b & 7) << 2) + (i & 3);
+}
+
+struct DrawParams {
+  double logMmin, inv_sigma, m0, inv_m1, alpha, a_cen, a_sat;
+};
+
+__device__ __forceinline__ DrawParams load_draw(const double* __restrict__ theta) {
+  DrawParams p;
+  p.logMmin = theta[0];
+  p.inv_sigma = 1.0 / theta[1];
+  p.m0 = exp10(theta[2]);
+  p.inv_m1 = 1.0 / exp10(theta[3]);
+  p.alpha = theta[4];
+  p.a_cen = fmin(fmax(theta[5], -1.0), 1.0);
+  p.a_sat = fmin(fmax(theta[6], -1.0), 1.0);
+  return p;
+}
+
+// Heaviside assembly bias (halotools HeavisideAssembias, call site tabcorr.py:556-563): haloes above
+// the split percentile get +delta, the others -delta (1 - s) / s; delta is the strength times the
+// largest perturbation that keeps both sub-populations inside [lo, hi].
+__device__ __forceinline__ double decorate(double f, double strength, double split, double lo,
+                                           double hi, bool type1) {
+  if (!(split > 0.0 && split < 1.0) || !(f > lo && f < hi)) return f;
+  double ratio = split / (1.0 - split);
+  double delta;
+  if (strength > 0.0) {
+    delta = strength * fmin(hi - f, ratio * (f - lo));
+  } else {
+    delta = -strength * fmax(lo - f, ratio * (f - hi));
+  }
+  return type1 ? f + delta : f - delta * (1.0 - split) / split;
+}
+
+// Occupation phase for one tile of BM = 8 NT draws: thread (b = tid % BM, lane group tid / BM)
+// evaluates the baseline zheng07 occupations of its mass-bin groups at the G quadrature nodes once
+// and accumulates them into the (up to kGroupRows) rows sharing that mass bin.
+// store(padded_row, b, occ, n_h) receives the Gauss-Legendre averaged occupation.
+template <int BM, typename Store>
+__device__ __forceinline__ void occupation_tile(const OccPlan& plan, const tc_model& model,
+                                                const double* __restrict__ theta, long long b0,
+                                                long long n_draws, Store store) {
+  const int b = threadIdx.x % BM;
+  const int gl = threadIdx.x / BM;
+  constexpr int n_gl = kThreads / BM;
+  long long draw = b0 + b;
+  if (draw >= n_draws) draw = n_draws - 1;  // tail tile: recompute the last draw, never stored
+  const DrawParams p = load_draw(theta + draw * TC_N_THETA);
+  const int G = plan.n_gauss;
+  for (int grp = gl; grp < plan.n_groups; grp += n_gl) {
+    const int* rows = plan.grp_rows + grp * kGroupRows;
+    int row[kGroupRows];
+#pragma unroll
+    for (int s = 0; s < kGroupRows; s++) row[s] = rows[s];
+    const bool is_sat = plan.grp_is_sat[grp] != 0;
+    bool type1[kGroupRows];
+#pragma unroll
+    for (int s = 0; s < kGroupRows; s++)
+      type1[s] = row[s] >= 0 ? plan.row_pct[row[s]] > model.split : false;
+    double acc[kGroupRows] = {0.0, 0.0, 0.0, 0.0};
+    const double* logm = plan.node_logm + (size_t)grp * G;
+    const double* mass = plan.node_m + (size_t)grp * G;
+    for (int g = 0; g < G; g++) {
+      double f, lo = 0.0, hi, strength;
+      if (!is_sat) {
+        // Zheng07Cens: 0.5 (1 + erf((log10 M - logMmin) / sigma_logM))
+        f = 0.5 * (1.0 + erf((logm[g] - p.logMmin) * p.inv_sigma));
+        hi = 1.0;
+        strength = p.a_cen;
+      } else {
+        // Zheng07Sats: ((M - M0) / M1)^alpha for M > M0, else 0
+        double d = mass[g] - p.m0;
+        f = d > 0.0 ? exp(p.alpha * log(d * p.inv_m1)) : 0.0;
+        if (model.modulate_with_cenocc)
+          f *= 0.5 * (1.0 + erf((logm[g] - p.logMmin) * p.inv_sigma));
+        hi = CUDART_INF;
+        strength = p.a_sat;
+      }
+#pragma unroll
+      for (int s = 0; s < kGroupRows; s++) {
+        if (row[s] >= 0) {
+          double fs = model.decorated ? decorate(f, strength, model.split, lo, hi, type1[s]) : f;
+          acc[s] = fma(plan.row_c[(size_t)row[s] * G + g], fs, acc[s]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < kGroupRows; s++)
+      if (row[s] >= 0) store(row[s], b, acc[s], plan.row_nh[row[s]]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused occupation + contraction kernel
+// ------------------------------------------------------------------------------------------
+struct PredictArgs {
+  LayoutDev lay;
+  OccPlan plan;
+  tc_model model;
+  const double* theta;   // [B, TC_N_THETA] or nullptr
+  const double* occ;     // [B, n_rows] or nullptr
+  long long n_draws;
+  long long n_tiles;
+  double* parts;         // [n_tiles, n_parts, BM]
+  double* ngal_tile;     // [n_tiles, 2, BM]  centrals / satellites number density
+};
+
+template <int NT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs args) {
+  constexpr int BM = 8 * NT;
+  extern __shared__ __align__(16) double smem[];
+  double* Ws = smem;                                             // [n_pad / 4][NT][32]
+  int* counter = reinterpret_cast<int*>(smem + (size_t)args.lay.n_pad * BM);
+  const LayoutDev& lay = args.lay;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+
+  for (int i = tid; i < lay.n_pad * BM; i += kThreads) Ws[i] = 0.0;  // padding rows stay zero
+  __syncthreads();
+
+  for (long long tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+    const long long b0 = tile * BM;
+    // ---- phase 1: tracer weights W[row, draw] = occ * n_h into shared memory ---------------
+    if (args.theta != nullptr) {
+      occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws,
+                          [&](int row, int b, double occ, double nh) {
+                            Ws[widx<NT>(row, b)] = occ * nh;
+                          });
+    } else {
+      for (int i = tid; i < lay.n_pad * BM; i += kThreads) {
+        int row = i / BM, b = i % BM;
+        int src = lay.pad_to_row[row];
+        long long draw = b0 + b < args.n_draws ? b0 + b : args.n_draws - 1;
+        if (src >= 0)
+          Ws[widx<NT>(row, b)] = args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row];
+      }
+    }
+    if (tid == 0) *counter = 0;
+    __syncthreads();
+
+    // ---- number densities (one CTA per tile writes them) -----------------------------------
+    if (blockIdx.y == 0 && tid < BM) {
+      double nc = 0.0, ns = 0.0;
+      for (int i = 0; i < lay.nc_pad; i++) nc += Ws[widx<NT>(i, tid)];
+      for (int i = lay.nc_pad; i < lay.n_pad; i++) ns += Ws[widx<NT>(i, tid)];
+      args.ngal_tile[(tile * 2 + 0) * BM + tid] = nc;
+      args.ngal_tile[(tile * 2 + 1) * BM + tid] = ns;
+    }
+
+    // ---- phase 2: chunks of the triangular contraction, taken dynamically per warp ----------
+    double* parts = args.parts + (size_t)tile * lay.n_parts * BM;
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(counter, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      c = blockIdx.y + c * gridDim.y;
+      if (c >= lay.n_chunks) break;
+      const Chunk ch = lay.chunks[c];
+
+      if (MODE == TC_MODE_AUTO) {
+        double sums[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) sums[nt][0] = sums[nt][1] = 0.0;
+        for (int mt = ch.mt0; mt < ch.mt1; mt++) {
+          const int k_tile = 4 * (mt + 1);                 // k-steps of the full lower-triangular tile
+          const int k_end = min(k_tile, ch.k_cap);
+          // the upper 8 rows of the tile are zero in its last two k-steps: skip their DMMAs
+          const int k_both = min(k_end, k_tile - 2);
+          const double2* ap = lay.afrag +
+              ((size_t)ch.r * lay.ks_per_r + 2 * (size_t)mt * (mt + 1) + ch.k_begin) * 32 + lane;
+          const double* wk = Ws + (size_t)ch.k_begin * NT * 32 + lane;
+          double acc[2][NT][2];
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++)
+            acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
+          double2 a_next = ld_stream(ap);
+          int ks = ch.k_begin;
+          for (; ks < k_both; ks++) {
+            const double2 a = a_next;
+            ap += 32;
+            a_next = ld_stream(ap);  // the stream is padded by one k-step, always safe
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+              const double b = wk[nt * 32];
+              dmma884(acc[0][nt], a.x, b);
+              dmma884(acc[1][nt], a.y, b);
+            }
+            wk += NT * 32;
+          }
+          for (; ks < k_end; ks++) {
+            const double2 a = a_next;
+            ap += 32;
+            a_next = ld_stream(ap);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) dmma884(acc[1][nt], a.y, wk[nt * 32]);
+            wk += NT * 32;
+          }
+          // row-dot: acc[h][nt][e] = (M' W)[row = 16 mt + 8 h + g][draw = 8 nt + 2 tig + e]
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int row = 16 * mt + 8 * h + g;
+            const double* wr = Ws + (size_t)(row >> 2) * NT * 32 + (row & 3) + tig * 8;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+              sums[nt][0] = fma(acc[h][nt][0], wr[nt * 32], sums[nt][0]);
+              sums[nt][1] = fma(acc[h][nt][1], wr[nt * 32 + 4], sums[nt][1]);
+            }
+          }
+        }
+        // fixed-order reduction over the 8 row groups of the warp; recursive halving leaves the
+        // lane with row group g holding n-tile (g mod NT), i.e. draws 2 lane, 2 lane + 1 (mod BM)
+        double v[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) { v[nt][0] = sums[nt][0]; v[nt][1] = sums[nt][1]; }
+        int width = NT;  // number of live n-tiles per lane
+#pragma unroll
+        for (int bit = 4; bit >= 1; bit >>= 1) {  // g bit 2, 1, 0 <-> lane xor 16, 8, 4
+          const int xor_lanes = bit * 4;
+          if (width > bit) {
+            // halve: lanes with the g bit set keep the upper half
+            const bool upper = (g & bit) != 0;
+            const int half = width / 2;
+#pragma unroll
+            for (int i = 0; i < NT / 2; i++) {
+              if (i < half) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  double send = upper ? v[i][e] : v[i + half][e];
+                  double keep = upper ? v[i + half][e] : v[i][e];
+                  v[i][e] = keep + __shfl_xor_sync(0xffffffffu, send, xor_lanes);
+                }
+              }
+            }
+            width = half;
+          } else {
+#pragma unroll
+            for (int i = 0; i < NT; i++) {
+              if (i < width) {
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                  v[i][e] += __shfl_xor_sync(0xffffffffu, v[i][e], xor_lanes);
+              }
+            }
+          }
+        }
+        if (g < NT) {
+          double2 out = make_double2(v[0][0], v[0][1]);
+          *reinterpret_cast<double2*>(parts + (size_t)ch.part_row * BM + 8 * g + 2 * tig) = out;
+        }
+      } else {
+        // cross mode: a 16-radial-bin tile times a k-range of W; the product is the output
+        const double2* ap = lay.afrag + ((size_t)ch.r * lay.ks_per_r + ch.k_begin) * 32 + lane;
+        const double* wk = Ws + (size_t)ch.k_begin * NT * 32 + lane;
+        double acc[2][NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+          acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
+        double2 a_next = ld_stream(ap);
+        for (int ks = ch.k_begin; ks < ch.k_cap; ks++) {
+          const double2 a = a_next;
+          ap += 32;
+          a_next = ld_stream(ap);
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++) {
+            const double b = wk[nt * 32];
+            dmma884(acc[0][nt], a.x, b);
+            dmma884(acc[1][nt], a.y, b);
+          }
+          wk += NT * 32;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++)
+            *reinterpret_cast<double2*>(parts + (size_t)(ch.part_row + 8 * h + g) * BM + 8 * nt +
+                                        2 * tig) = make_double2(acc[h][nt][0], acc[h][nt][1]);
+      }
+    }
+    __syncthreads();  // W is overwritten by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: sum the scratch rows of every output in fixed order and normalise by ngal
+// ------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  LayoutDev lay;
+  const double* parts;
+  const double* ngal_tile;
+  long long n_draws;
+  int bm;
+  int mode;
+  int separate;
+  int n_tables;
+  double* ngal_out;
+  long long ngal_stride;
+  double* xi_out;
+  long long xi_stride;
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs args) {
+  const int bm = args.bm;
+  const long long tile = blockIdx.x;
+  const int b = threadIdx.x % bm;
+  const long long draw = tile * bm + b;
+  if (draw >= args.n_draws) return;
+  const double nc = args.ngal_tile[(tile * 2 + 0) * bm + b];
+  const double ns = args.ngal_tile[(tile * 2 + 1) * bm + b];
+  const double ngal = nc + ns;
+  const double norm = args.mode == TC_MODE_AUTO ? ngal * ngal : ngal;
+  const int o_step = (blockDim.x / bm) * gridDim.y;
+  const int o_first = threadIdx.x / bm + (blockDim.x / bm) * blockIdx.y;
+  if (o_first == 0) {
+    for (int t = 0; t < args.n_tables; t++) {
+      if (args.separate) {
+        args.ngal_out[draw * args.ngal_stride + 2 * t + 0] = nc;
+        args.ngal_out[draw * args.ngal_stride + 2 * t + 1] = ns;
+      } else {
+        args.ngal_out[draw * args.ngal_stride + t] = ngal;
+      }
+    }
+  }
+  const double* parts = args.parts + (size_t)tile * args.lay.n_parts * bm + b;
+  for (int o = o_first; o < args.lay.n_out; o += o_step) {
+    double s = 0.0;
+    for (int j = args.lay.out_ptr[o]; j < args.lay.out_ptr[o + 1]; j++)
+      s += parts[(size_t)args.lay.out_parts[j] * bm];
+    args.xi_out[draw * args.xi_stride + o] = s / norm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone occupation kernel (TabCorr.mean_occupation)
+// ------------------------------------------------------------------------------------------
+struct OccArgs {
+  OccPlan plan;
+  tc_model model;
+  const double* theta;
+  long long n_draws;
+  int n_rows;
+  const int* pad_to_row;
+  double* occ_out;
+};
+
+__global__ void __launch_bounds__(kThreads) occupation_kernel(const OccArgs args) {
+  constexpr int BM = 32;
+  const long long n_tiles = (args.n_draws + BM - 1) / BM;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long b0 = tile * BM;
+    occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws,
+                        [&](int row, int b, double occ, double) {
+                          int dst = args.pad_to_row[row];
+                          if (b0 + b < args.n_draws && dst >= 0)
+                            args.occ_out[(b0 + b) * args.n_rows + dst] = occ;
+                        });
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// interpolation kernel (spline_interpolate for B draws)
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxDims = 8;
+
+struct InterpDev {
+  int n_dims;
+  int n_tables;
+  int n_knots[kMaxDims];
+  int knot_off[kMaxDims];    // offset of axis d in knots
+  int a_off[kMaxDims];       // offset of axis d in a
+  const double* knots;
+  const double* a;
+  const int* grid_to_table;  // [n_tables]
+};
+
+struct InterpArgs {
+  InterpDev it;
+  const double* x;      // [B, n_dims]
+  long long n_draws;
+  const double* data;   // [B, T, n_cols]
+  int n_cols;
+  double* out;          // [B, n_cols]
+  int extrapolate;
+  int* flag;
+  int sum_knots;
+};
+
+__global__ void __launch_bounds__(128) interp_kernel(const InterpArgs args) {
+  extern __shared__ double ism[];
+  const InterpDev& it = args.it;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wd = ism + (size_t)warp * (args.sum_knots + it.n_tables);  // per-axis knot weights
+  double* wt = wd + args.sum_knots;                                    // per-table weights
+  const long long draw = (long long)blockIdx.x * 4 + warp;
+  if (draw >= args.n_draws) return;
+  bool outside = false;
+  for (int d = 0; d < it.n_dims; d++) {
+    const int nk = it.n_knots[d];
+    const double* xp = it.knots + it.knot_off[d];
+    const double x = args.x[draw * it.n_dims + d];
+    int seg = -1;
+    for (int k = 0; k < nk; k++) seg += xp[k] <= x ? 1 : 0;  // digitize(x, xp) - 1
+    if (x == xp[nk - 1]) seg = nk - 2;
+    if (seg < 0 || seg >= nk - 1 || !(x == x)) {
+      outside = true;
+      seg = min(max(seg, 0), nk - 2);
+    }
+    const double* a = it.a + it.a_off[d] + (size_t)seg * 4 * nk;
+    const double x2 = x * x, x3 = x2 * x;
+    for (int k = lane; k < nk; k += 32)
+      wd[it.knot_off[d] + k] = a[k] + a[nk + k] * x + a[2 * nk + k] * x2 + a[3 * nk + k] * x3;
+  }
+  __syncwarp();
+  for (int gpos = lane; gpos < it.n_tables; gpos += 32) {
+    int rem = gpos;
+    double w = 1.0;
+    for (int d = it.n_dims - 1; d >= 0; d--) {
+      const int k = rem % it.n_knots[d];
+      rem /= it.n_knots[d];
+      w *= wd[it.knot_off[d] + k];
+    }
+    wt[it.grid_to_table[gpos]] = w;
+  }
+  __syncwarp();
+  const bool bad = outside && !args.extrapolate;
+  if (bad && lane == 0) atomicOr(args.flag, 1);
+  const double* data = args.data + (size_t)draw * it.n_tables * args.n_cols;
+  for (int c = lane; c < args.n_cols; c += 32) {
+    double s = 0.0;
+    for (int t = 0; t < it.n_tables; t++) s = fma(wt[t], data[(size_t)t * args.n_cols + c], s);
+    args.out[draw * args.n_cols + c] = bad ? CUDART_NAN : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// DMMA peak microbenchmark (roofline denominator)
+// ------------------------------------------------------------------------------------------
+__global__ void dmma_peak_kernel(double* out, int iters) {
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - 1e-9 * threadIdx.x;
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884(c[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side table preparation
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int upload(const std::vector<T>& host, T** dev) {
+  *dev = nullptr;
+  size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+  TC_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), bytes));
+  if (!host.empty())
+    TC_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return TC_OK;
+}
+
+struct PlanHost {
+  OccPlan dev{};
+  std::vector<void*> allocations;
+};
+
+struct Layout {
+  bool built = false;
+  LayoutDev dev{};
+  std::vector<int> row_to_pad;
+  std::vector<void*> allocations;
+  std::map<int, PlanHost> plans;  // by n_gauss
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct tc_table {
+  int device = 0;
+  int mode = 0;
+  int n_rows = 0, n_r = 0, n_tables = 0, n_cen = 0;
+  std::vector<double> n_h, log_min, log_max, pct, dist;
+  bool has_dist = false;
+  std::vector<int> is_sat;
+  std::vector<std::vector<double>> matrices;  // host copies, kept to build the split layout lazily
+  std::map<int, std::pair<std::vector<double>, std::vector<double>>> rules;  // n_gauss -> (x, w)
+  Layout layouts[2];  // [separate]
+  std::mutex mutex;
+};
+
+struct tc_interp {
+  int device = 0;
+  InterpDev dev{};
+  int sum_knots = 0;
+  std::vector<void*> allocations;
+};
+
+namespace {
+
+// Build the padded row order and the A-fragment stream of one layout.
+int build_layout(tc_table* t, int separate) {
+  Layout& L = t->layouts[separate];
+  if (L.built) return TC_OK;
+  const int N = t->n_rows, R = t->n_r, T = t->n_tables;
+  const int Reff = R * T;
+  const int n_cen = t->n_cen, n_sat = N - n_cen;
+  // centrals first (stable); in the split layout the satellite block starts on a 16-row tile
+  const int nc_pad = separate ? round_up(n_cen, 16) : n_cen;
+  const int n_pad = std::max(16, round_up(nc_pad + n_sat, 16));
+  L.row_to_pad.assign(N, -1);
+  std::vector<int> pad_to_row(n_pad, -1);
+  {
+    int ic = 0, is = nc_pad;
+    for (int i = 0; i < N; i++) {
+      int p = t->is_sat[i] ? is++ : ic++;
+      L.row_to_pad[i] = p;
+      pad_to_row[p] = i;
+    }
+  }
+  const int T16 = n_pad / 16;
+  std::vector<Chunk> chunks;
+  std::vector<std::vector<int>> out_lists;
+  std::vector<double2> afrag;
+  long long ks_per_r = 0;
+  int n_parts = 0;
+
+  if (t->mode == TC_MODE_AUTO) {
+    ks_per_r = 2LL * T16 * (T16 + 1);
+    afrag.assign((size_t)Reff * ks_per_r * 32 + 32, make_double2(0.0, 0.0));
+    // M'[i][j] (j <= i) = M[i][j] (i == j) or 2 M[i][j]: the reference's packed prefactor sum
+    // (tabcorr.py:638-642) written as a lower-triangular matrix product.
+    for (int tb = 0; tb < T; tb++) {
+      const double* packed = t->matrices[tb].data();
+      const size_t P = (size_t)N * (N + 1) / 2;
+      for (int r = 0; r < R; r++) {
+        const double* m = packed + (size_t)r * P;
+        double2* dst = afrag.data() + (size_t)(tb * R + r) * ks_per_r * 32;
+        for (int i = 0; i < N; i++) {
+          const int pi = L.row_to_pad[i];
+          for (int j = 0; j <= i; j++) {
+            const int pj = L.row_to_pad[j];
+            double val = m[(size_t)i * (i + 1) / 2 + j];
+            if (i != j) val *= 2.0;
+            const int hi = std::max(pi, pj), lo = std::min(pi, pj);
+            const int mt = hi / 16, rr = hi % 16, ks = lo / 4, tg = lo % 4;
+            double2& d = dst[((size_t)2 * mt * (mt + 1) + ks) * 32 + (rr % 8) * 4 + tg];
+            if (rr < 8) d.x = val; else d.y = val;
+          }
+        }
+      }
+    }
+    // chunks: per radial bin, the tile range cut into pieces of similar cost
+    const int n_comp = separate ? 3 : 1;
+    out_lists.assign((size_t)Reff * n_comp, {});
+    const int c16 = nc_pad / 16;  // first satellite tile (split layout)
+    int pieces = std::max(1, std::min(T16, (6 * kWarps + Reff - 1) / Reff));
+    auto add_range = [&](int r, int mt_lo, int mt_hi, int k_begin, int k_cap, int comp, int np) {
+      // cost of tile mt ~ number of k-steps
+      auto cost = [&](int mt) { return std::max(0, std::min(4 * (mt + 1), k_cap) - k_begin); };
+      long long total = 0;
+      for (int mt = mt_lo; mt < mt_hi; mt++) total += cost(mt);
+      if (total == 0) return;
+      np = std::max(1, std::min(np, mt_hi - mt_lo));
+      long long acc = 0;
+      int start = mt_lo, piece = 0;
+      for (int mt = mt_lo; mt < mt_hi; mt++) {
+        acc += cost(mt);
+        bool last = mt == mt_hi - 1;
+        if (last || acc * np >= total * (piece + 1)) {
+          Chunk c{};
+          c.r = r; c.mt0 = start; c.mt1 = mt + 1; c.k_begin = k_begin; c.k_cap = k_cap;
+          c.part_row = n_parts++;
+          chunks.push_back(c);
+          out_lists[(size_t)r * n_comp + comp].push_back(c.part_row);
+          start = mt + 1;
+          piece++;
+        }
+      }
+    };
+    const int kinf = 1 << 28;
+    for (int r = 0; r < Reff; r++) {
+      if (!separate) {
+        add_range(r, 0, T16, 0, kinf, 0, pieces);
+      } else {
+        add_range(r, 0, c16, 0, kinf, 0, pieces);              // centrals-centrals
+        add_range(r, c16, T16, 0, nc_pad / 4, 1, pieces);       // centrals-satellites
+        add_range(r, c16, T16, nc_pad / 4, kinf, 2, pieces);    // satellites-satellites
+      }
+    }
+  } else {
+    const int n_rt = (Reff + 15) / 16;
+    ks_per_r = n_pad / 4;
+    afrag.assign((size_t)n_rt * ks_per_r * 32 + 32, make_double2(0.0, 0.0));
+    for (int tb = 0; tb < T; tb++) {
+      const double* m = t->matrices[tb].data();
+      for (int r = 0; r < R; r++) {
+        const int re = tb * R + r, rt = re / 16, rr = re % 16;
+        for (int i = 0; i < N; i++) {
+          const int pi = L.row_to_pad[i];
+          double2& d = afrag[((size_t)rt * ks_per_r + pi / 4) * 32 + (rr % 8) * 4 + pi % 4];
+          if (rr < 8) d.x = m[(size_t)r * N + i]; else d.y = m[(size_t)r * N + i];
+        }
+      }
+    }
+    const int n_comp = separate ? 2 : 1;
+    out_lists.assign((size_t)Reff * n_comp, {});
+    const int ks_total = n_pad / 4;
+    // k-ranges: split at the centrals/satellites boundary (split layout) and into pieces
+    std::vector<std::pair<int, int>> segs;
+    if (separate) {
+      segs.push_back({0, nc_pad / 4});
+      segs.push_back({nc_pad / 4, ks_total});
+    } else {
+      segs.push_back({0, ks_total});
+    }
+    const int want = std::max(1, (4 * kWarps + n_rt - 1) / n_rt / (int)segs.size());
+    for (int rt = 0; rt < n_rt; rt++) {
+      for (size_t sg = 0; sg < segs.size(); sg++) {
+        const int lo = segs[sg].first, hi = segs[sg].second;
+        if (hi <= lo) continue;
+        const int np = std::max(1, std::min(want, (hi - lo + 7) / 8));
+        for (int pc = 0; pc < np; pc++) {
+          Chunk c{};
+          c.r = rt;
+          c.k_begin = lo + (int)((long long)(hi - lo) * pc / np);
+          c.k_cap = lo + (int)((long long)(hi - lo) * (pc + 1) / np);
+          if (c.k_cap <= c.k_begin) continue;
+          c.part_row = n_parts;
+          n_parts += 16;
+          chunks.push_back(c);
+          for (int rr = 0; rr < 16; rr++) {
+            const int re = rt * 16 + rr;
+            if (re < Reff) out_lists[(size_t)re * n_comp + sg].push_back(c.part_row + rr);
+          }
+        }
+      }
+    }
+  }
+  // longest chunks first: the warps take them dynamically
+  auto chunk_cost = [&](const Chunk& c) {
+    if (t->mode != TC_MODE_AUTO) return (long long)(c.k_cap - c.k_begin);
+    long long s = 0;
+    for (int mt = c.mt0; mt < c.mt1; mt++)
+      s += std::max(0, std::min(4 * (mt + 1), c.k_cap) - c.k_begin);
+    return s;
+  };
+  std::stable_sort(chunks.begin(), chunks.end(),
+                   [&](const Chunk& a, const Chunk& b) { return chunk_cost(a) > chunk_cost(b); });
+
+  std::vector<int> out_ptr(out_lists.size() + 1, 0), out_parts;
+  for (size_t o = 0; o < out_lists.size(); o++) {
+    out_ptr[o + 1] = out_ptr[o] + (int)out_lists[o].size();
+    out_parts.insert(out_parts.end(), out_lists[o].begin(), out_lists[o].end());
+  }
+
+  double2* d_afrag; Chunk* d_chunks; int *d_out_ptr, *d_out_parts, *d_pad_to_row;
+  int rc;
+  if ((rc = upload(afrag, &d_afrag))) return rc;
+  L.allocations.push_back(d_afrag);
+  if ((rc = upload(chunks, &d_chunks))) return rc;
+  L.allocations.push_back(d_chunks);
+  if ((rc = upload(out_ptr, &d_out_ptr))) return rc;
+  L.allocations.push_back(d_out_ptr);
+  if ((rc = upload(out_parts, &d_out_parts))) return rc;
+  L.allocations.push_back(d_out_parts);
+  if ((rc = upload(pad_to_row, &d_pad_to_row))) return rc;
+  L.allocations.push_back(d_pad_to_row);
+
+  L.dev.n_rows = N;
+  L.dev.n_pad = n_pad;
+  L.dev.nc_pad = nc_pad;
+  L.dev.n_parts = std::max(n_parts, 1);
+  L.dev.n_chunks = (int)chunks.size();
+  L.dev.n_out = (int)out_lists.size();
+  L.dev.ks_per_r = ks_per_r;
+  L.dev.afrag = d_afrag;
+  L.dev.chunks = d_chunks;
+  L.dev.out_ptr = d_out_ptr;
+  L.dev.out_parts = d_out_parts;
+  L.dev.pad_to_row = d_pad_to_row;
+  L.built = true;
+  return TC_OK;
+}
+
+// Quadrature plan of a layout for one Gauss-Legendre rule (tabcorr.py:543-552,568-578).
+int build_plan(tc_table* t, int separate, int n_gauss) {
+  Layout& L = t->layouts[separate];
+  if (L.plans.count(n_gauss)) return TC_OK;
+  auto rule = t->rules.find(n_gauss);
+  if (rule == t->rules.end())
+    return fail(TC_EINVAL, "no quadrature rule registered for n_gauss=" + std::to_string(n_gauss) +
+                               " (call tc_table_plan first)");
+  const std::vector<double>& x01 = rule->second.first;
+  const std::vector<double>& wq = rule->second.second;
+  const int N = t->n_rows, G = n_gauss, n_pad = L.dev.n_pad;
+
+  struct Group { double lo, hi; int sat; std::vector<int> rows; };
+  std::vector<Group> groups;
+  for (int pass = 0; pass < 2; pass++) {  // centrals groups first
+    for (int i = 0; i < N; i++) {
+      if ((t->is_sat[i] != 0) != (pass == 1)) continue;
+      bool placed = false;
+      for (auto& gq : groups) {
+        if (gq.sat == pass && gq.lo == t->log_min[i] && gq.hi == t->log_max[i] &&
+            (int)gq.rows.size() < kGroupRows) {
+          gq.rows.push_back(i);
+          placed = true;
+          break;
+        }
+      }
+      if (!placed) groups.push_back(Group{t->log_min[i], t->log_max[i], pass, {i}});
+    }
+  }
+  const int n_groups = (int)groups.size();
+  std::vector<double> node_logm((size_t)n_groups * G), node_m((size_t)n_groups * G);
+  std::vector<int> grp_rows((size_t)n_groups * kGroupRows, -1), grp_is_sat(n_groups);
+  std::vector<double> row_c((size_t)n_pad * G, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
+  for (int q = 0; q < n_groups; q++) {
+    const Group& gq = groups[q];
+    grp_is_sat[q] = gq.sat;
+    for (int k = 0; k < G; k++) {
+      // prim_haloprop = 10**(log_min + d_log * x) and halotools' log10(prim_haloprop)
+      double m = std::pow(10.0, gq.lo + (gq.hi - gq.lo) * x01[k]);
+      node_m[(size_t)q * G + k] = m;
+      node_logm[(size_t)q * G + k] = std::log10(m);
+    }
+    for (size_t s = 0; s < gq.rows.size(); s++) {
+      const int i = gq.rows[s], p = L.row_to_pad[i];
+      grp_rows[(size_t)q * kGroupRows + s] = p;
+      row_nh[p] = t->n_h[i];
+      row_pct[p] = t->pct[i];
+      const double n = t->has_dist ? t->dist[i] + 1.0 : 0.0;  // tabcorr.py:568-574
+      double norm = 0.0;
+      for (int k = 0; k < G; k++) norm += wq[k] * std::pow(node_m[(size_t)q * G + k], n);
+      for (int k = 0; k < G; k++)
+        row_c[(size_t)p * G + k] = wq[k] * std::pow(node_m[(size_t)q * G + k], n) / norm;
+    }
+  }
+  PlanHost ph;
+  double *d_logm, *d_m, *d_c, *d_nh, *d_pct; int *d_rows, *d_sat;
+  int rc;
+  if ((rc = upload(node_logm, &d_logm))) return rc; ph.allocations.push_back(d_logm);
+  if ((rc = upload(node_m, &d_m))) return rc; ph.allocations.push_back(d_m);
+  if ((rc = upload(grp_rows, &d_rows))) return rc; ph.allocations.push_back(d_rows);
+  if ((rc = upload(grp_is_sat, &d_sat))) return rc; ph.allocations.push_back(d_sat);
+  if ((rc = upload(row_c, &d_c))) return rc; ph.allocations.push_back(d_c);
+  if ((rc = upload(row_nh, &d_nh))) return rc; ph.allocations.push_back(d_nh);
+  if ((rc = upload(row_pct, &d_pct))) return rc; ph.allocations.push_back(d_pct);
+  ph.dev.n_groups = n_groups;
+  ph.dev.n_gauss = G;
+  ph.dev.node_logm = d_logm;
+  ph.dev.node_m = d_m;
+  ph.dev.grp_rows = d_rows;
+  ph.dev.grp_is_sat = d_sat;
+  ph.dev.row_c = d_c;
+  ph.dev.row_nh = d_nh;
+  ph.dev.row_pct = d_pct;
+  L.plans[n_gauss] = ph;
+  return TC_OK;
+}
+
+int pick_nt(int n_pad, long long n_draws, int n_sm) {
+  int best = 0;
+  for (int nt : {8, 4, 2, 1}) {
+    size_t smem = (size_t)n_pad * 8 * nt * sizeof(double) + 16;
+    if (smem > (size_t)kSmemLimit) continue;
+    if (best == 0) best = nt;  // largest that fits
+    if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) return nt;
+    best = nt;  // keep shrinking while the grid would not fill the device
+  }
+  return best;
+}
+
+struct Workspace {
+  size_t parts_bytes, ngal_bytes, total;
+  long long n_tiles;
+  int nt;
+};
+
+Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
+  Workspace w{};
+  w.nt = pick_nt(L.dev.n_pad, n_draws, n_sm);
+  if (w.nt == 0) return w;
+  const int bm = 8 * w.nt;
+  w.n_tiles = (n_draws + bm - 1) / bm;
+  w.parts_bytes = (size_t)w.n_tiles * L.dev.n_parts * bm * sizeof(double);
+  w.ngal_bytes = (size_t)w.n_tiles * 2 * bm * sizeof(double);
+  w.total = w.parts_bytes + w.ngal_bytes;
+  return w;
+}
+
+int device_sms(int device, int* n_sm) {
+  static std::mutex m;
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lock(m);
+  auto it = cache.find(device);
+  if (it == cache.end()) {
+    int v = 0;
+    TC_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    it = cache.emplace(device, v).first;
+  }
+  *n_sm = it->second;
+  return TC_OK;
+}
+
+template <int NT, int MODE>
+int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
+  static std::mutex m;
+  static std::map<int, bool> configured;
+  int dev = 0;
+  TC_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(m);
+    if (!configured[dev]) {
+      TC_CUDA(cudaFuncSetAttribute(predict_kernel<NT, MODE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+      configured[dev] = true;
+    }
+  }
+  predict_kernel<NT, MODE><<<grid, kThreads, smem, stream>>>(args);
+  TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; (void)cudaGetLastError(); return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) { ok = false; (void)cudaGetLastError(); }
+  }
+  ~DeviceGuard() { if (prev >= 0) (void)cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* tc_last_error(void) { return g_last_error.c_str(); }
+
+int tc_version(void) { return TC_VERSION; }
+
+int tc_table_create(tc_table** out, int mode, int n_rows, int n_r, int n_tables,
+                    const double* n_h, const double* log_min, const double* log_max,
+                    const double* sec_pct, const double* dist_index, const int32_t* is_sat,
+                    const double* const* tpcf_matrix, int device) {
+  if (out == nullptr) return fail(TC_EINVAL, "tc_table_create: out is NULL");
+  *out = nullptr;
+  if (mode != TC_MODE_AUTO && mode != TC_MODE_CROSS)
+    return fail(TC_EINVAL, "tc_table_create: mode must be TC_MODE_AUTO or TC_MODE_CROSS");
+  if (n_rows <= 0 || n_r <= 0 || n_tables <= 0)
+    return fail(TC_EINVAL, "tc_table_create: n_rows, n_r and n_tables must be positive");
+  if (!n_h || !log_min || !log_max || !sec_pct || !is_sat || !tpcf_matrix)
+    return fail(TC_EINVAL, "tc_table_create: NULL input array");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_table_create: cannot select CUDA device " +
+                                           std::to_string(device) + " (no CUDA device available?)");
+  tc_table* t = new (std::nothrow) tc_table();
+  if (!t) return fail(TC_ENOMEM, "tc_table_create: out of host memory");
+  t->device = device;
+  t->mode = mode;
+  t->n_rows = n_rows;
+  t->n_r = n_r;
+  t->n_tables = n_tables;
+  t->n_h.assign(n_h, n_h + n_rows);
+  t->log_min.assign(log_min, log_min + n_rows);
+  t->log_max.assign(log_max, log_max + n_rows);
+  t->pct.assign(sec_pct, sec_pct + n_rows);
+  t->has_dist = dist_index != nullptr;
+  if (t->has_dist) t->dist.assign(dist_index, dist_index + n_rows);
+  t->is_sat.assign(is_sat, is_sat + n_rows);
+  t->n_cen = 0;
+  for (int i = 0; i < n_rows; i++) t->n_cen += t->is_sat[i] ? 0 : 1;
+  const size_t cols = mode == TC_MODE_AUTO ? (size_t)n_rows * (n_rows + 1) / 2 : (size_t)n_rows;
+  t->matrices.resize(n_tables);
+  for (int tb = 0; tb < n_tables; tb++) {
+    if (!tpcf_matrix[tb]) { delete t; return fail(TC_EINVAL, "tc_table_create: NULL matrix"); }
+    t->matrices[tb].assign(tpcf_matrix[tb], tpcf_matrix[tb] + (size_t)n_r * cols);
+  }
+  int rc = build_layout(t, 0);
+  if (rc != TC_OK) { tc_table_destroy(t); return rc; }
+  *out = t;
+  return TC_OK;
+}
+
+int tc_table_destroy(tc_table* t) {
+  if (!t) return TC_OK;
+  DeviceGuard guard(t->device);
+  for (Layout& L : t->layouts) {
+    for (void* p : L.allocations) (void)cudaFree(p);
+    for (auto& kv : L.plans)
+      for (void* p : kv.second.allocations) (void)cudaFree(p);
+  }
+  delete t;
+  return TC_OK;
+}
+
+int tc_table_n_rows(const tc_table* t) { return t ? t->n_rows : TC_EINVAL; }
+int tc_table_n_r(const tc_table* t) { return t ? t->n_r : TC_EINVAL; }
+int tc_table_n_tables(const tc_table* t) { return t ? t->n_tables : TC_EINVAL; }
+
+int tc_table_plan(tc_table* t, int n_gauss, const double* x01, const double* w) {
+  if (!t || !x01 || !w || n_gauss <= 0) return fail(TC_EINVAL, "tc_table_plan: bad argument");
+  std::lock_guard<std::mutex> lock(t->mutex);
+  DeviceGuard guard(t->device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_table_plan: cannot select the table's CUDA device");
+  if (!t->rules.count(n_gauss))
+    t->rules[n_gauss] = {std::vector<double>(x01, x01 + n_gauss), std::vector<double>(w, w + n_gauss)};
+  return build_plan(t, 0, n_gauss);
+}
+
+int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
+                        int64_t n_draws, double* occ, void* stream) {
+  if (!t || !model || !theta || !occ) return fail(TC_EINVAL, "tc_occupation_batch: NULL argument");
+  if (model->family != 0) return fail(TC_EUNSUPPORTED, "tc_occupation_batch: unknown model family");
+  if (n_draws <= 0) return TC_OK;
+  std::lock_guard<std::mutex> lock(t->mutex);
+  DeviceGuard guard(t->device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_occupation_batch: cannot select the table's CUDA device");
+  int rc = build_plan(t, 0, n_gauss);
+  if (rc != TC_OK) return rc;
+  int n_sm = 0;
+  if ((rc = device_sms(t->device, &n_sm))) return rc;
+  OccArgs args{};
+  args.plan = t->layouts[0].plans[n_gauss].dev;
+  args.model = *model;
+  args.theta = theta;
+  args.n_draws = n_draws;
+  args.n_rows = t->n_rows;
+  args.pad_to_row = t->layouts[0].dev.pad_to_row;
+  args.occ_out = occ;
+  long long n_tiles = (n_draws + 31) / 32;
+  int grid = (int)std::min<long long>(n_tiles, 4LL * n_sm);
+  occupation_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(args);
+  TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+size_t tc_predict_workspace_bytes(const tc_table* t, int64_t n_draws, int separate) {
+  if (!t || n_draws <= 0) return 0;
+  tc_table* tt = const_cast<tc_table*>(t);
+  std::lock_guard<std::mutex> lock(tt->mutex);
+  DeviceGuard guard(t->device);
+  if (!guard.ok) return 0;
+  if (build_layout(tt, separate ? 1 : 0) != TC_OK) return 0;
+  int n_sm = 0;
+  if (device_sms(t->device, &n_sm) != TC_OK) return 0;
+  return plan_workspace(t->layouts[separate ? 1 : 0], n_draws, n_sm).total;
+}
+
+int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
+                     const double* occ, int64_t n_draws, int separate, double* ngal,
+                     int64_t ngal_stride, double* xi, int64_t xi_stride, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
+  if (!t || !ngal || !xi) return fail(TC_EINVAL, "tc_predict_batch: NULL argument");
+  if ((theta == nullptr) == (occ == nullptr))
+    return fail(TC_EINVAL, "tc_predict_batch: exactly one of theta_dev and occ_dev must be given");
+  if (theta && !model) return fail(TC_EINVAL, "tc_predict_batch: model is NULL");
+  if (theta && model->family != 0)
+    return fail(TC_EUNSUPPORTED, "tc_predict_batch: unknown model family");
+  if (n_draws <= 0) return TC_OK;
+  separate = separate ? 1 : 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  std::lock_guard<std::mutex> lock(t->mutex);
+  DeviceGuard guard(t->device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_predict_batch: cannot select the table's CUDA device");
+  int rc = build_layout(t, separate);
+  if (rc != TC_OK) return rc;
+  Layout& L = t->layouts[separate];
+  if (!theta && t->rules.empty()) {
+    // the occupation branch needs n_h per padded row only; any plan carries it
+    const double x = 0.5, w = 2.0;
+    t->rules[1] = {std::vector<double>(1, x), std::vector<double>(1, w)};
+  }
+  const int plan_g = theta ? n_gauss : t->rules.begin()->first;
+  if ((rc = build_plan(t, separate, plan_g))) return rc;
+  int n_sm = 0;
+  if ((rc = device_sms(t->device, &n_sm))) return rc;
+  Workspace ws = plan_workspace(L, n_draws, n_sm);
+  if (ws.nt == 0)
+    return fail(TC_EUNSUPPORTED, "tc_predict_batch: table too large for the shared-memory tile (" +
+                                     std::to_string(L.dev.n_pad) + " padded rows)");
+  if (!workspace || workspace_bytes < ws.total)
+    return fail(TC_EINVAL, "tc_predict_batch: workspace too small, need " +
+                               std::to_string(ws.total) + " bytes");
+  const int n_comp_ngal = separate ? 2 : 1;
+  const int n_out = L.dev.n_out;
+  if (ngal_stride < (int64_t)t->n_tables * n_comp_ngal || xi_stride < n_out)
+    return fail(TC_EINVAL, "tc_predict_batch: output stride smaller than one draw's outputs");
+
+  PredictArgs args{};
+  args.lay = L.dev;
+  args.plan = L.plans[plan_g].dev;
+  if (model) args.model = *model;
+  args.theta = theta;
+  args.occ = occ;
+  args.n_draws = n_draws;
+  args.n_tiles = ws.n_tiles;
+  args.parts = static_cast<double*>(workspace);
+  args.ngal_tile = reinterpret_cast<double*>(static_cast<char*>(workspace) + ws.parts_bytes);
+
+  const int bm = 8 * ws.nt;
+  const size_t smem = (size_t)L.dev.n_pad * bm * sizeof(double) + 16;
+  int gx = (int)std::min<long long>(ws.n_tiles, n_sm);
+  int gy = 1;
+  if (ws.n_tiles < n_sm) gy = std::max(1, std::min(L.dev.n_chunks, n_sm / (int)ws.n_tiles));
+  dim3 grid(gx, gy);
+#define TC_LAUNCH(NT_)                                                                     \
+  rc = t->mode == TC_MODE_AUTO ? launch_predict<NT_, TC_MODE_AUTO>(args, grid, smem, stream) \
+                               : launch_predict<NT_, TC_MODE_CROSS>(args, grid, smem, stream)
+  switch (ws.nt) {
+    case 8: TC_LAUNCH(8); break;
+    case 4: TC_LAUNCH(4); break;
+    case 2: TC_LAUNCH(2); break;
+    default: TC_LAUNCH(1); break;
+  }
+#undef TC_LAUNCH
+  if (rc != TC_OK) return rc;
+
+  FinalizeArgs fa{};
+  fa.lay = L.dev;
+  fa.parts = args.parts;
+  fa.ngal_tile = args.ngal_tile;
+  fa.n_draws = n_draws;
+  fa.bm = bm;
+  fa.mode = t->mode;
+  fa.separate = separate;
+  fa.n_tables = t->n_tables;
+  fa.ngal_out = ngal;
+  fa.ngal_stride = ngal_stride;
+  fa.xi_out = xi;
+  fa.xi_stride = xi_stride;
+  const int outs_per_block = 256 / bm;
+  int fy = std::max(1, std::min(64, (n_out + outs_per_block - 1) / outs_per_block));
+  if (ws.n_tiles > 4LL * n_sm) fy = 1;
+  dim3 fgrid((unsigned)ws.n_tiles, fy);
+  finalize_kernel<<<fgrid, 256, 0, stream>>>(fa);
+  TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+int tc_interp_create(tc_interp** out, int n_dims, const int32_t* n_knots, const double* knots,
+                     const double* a, const int32_t* grid_to_table, int device) {
+  if (!out) return fail(TC_EINVAL, "tc_interp_create: out is NULL");
+  *out = nullptr;
+  if (n_dims <= 0 || n_dims > kMaxDims)
+    return fail(TC_EUNSUPPORTED, "tc_interp_create: between 1 and 8 interpolation axes supported");
+  if (!n_knots || !knots || !a || !grid_to_table)
+    return fail(TC_EINVAL, "tc_interp_create: NULL argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_interp_create: cannot select CUDA device " +
+                                           std::to_string(device));
+  tc_interp* it = new (std::nothrow) tc_interp();
+  if (!it) return fail(TC_ENOMEM, "tc_interp_create: out of host memory");
+  it->device = device;
+  it->dev.n_dims = n_dims;
+  long long n_tables = 1;
+  int knot_off = 0, a_off = 0;
+  for (int d = 0; d < n_dims; d++) {
+    if (n_knots[d] < 4) {
+      delete it;
+      return fail(TC_EINVAL, "tc_interp_create: at least 4 knots per axis are required");
+    }
+    it->dev.n_knots[d] = n_knots[d];
+    it->dev.knot_off[d] = knot_off;
+    it->dev.a_off[d] = a_off;
+    knot_off += n_knots[d];
+    a_off += (n_knots[d] - 1) * 4 * n_knots[d];
+    n_tables *= n_knots[d];
+  }
+  if (n_tables > 8192) {
+    delete it;
+    return fail(TC_EUNSUPPORTED, "tc_interp_create: more than 8192 grid tables");
+  }
+  it->dev.n_tables = (int)n_tables;
+  it->sum_knots = knot_off;
+  std::vector<double> hk(knots, knots + knot_off), ha(a, a + a_off);
+  std::vector<int> hg(grid_to_table, grid_to_table + n_tables);
+  double *dk, *da; int* dg;
+  int rc;
+  if ((rc = upload(hk, &dk))) { delete it; return rc; }
+  it->allocations.push_back(dk);
+  if ((rc = upload(ha, &da))) { tc_interp_destroy(it); return rc; }
+  it->allocations.push_back(da);
+  if ((rc = upload(hg, &dg))) { tc_interp_destroy(it); return rc; }
+  it->allocations.push_back(dg);
+  it->dev.knots = dk;
+  it->dev.a = da;
+  it->dev.grid_to_table = dg;
+  *out = it;
+  return TC_OK;
+}
+
+int tc_interp_destroy(tc_interp* it) {
+  if (!it) return TC_OK;
+  DeviceGuard guard(it->device);
+  for (void* p : it->allocations) (void)cudaFree(p);
+  delete it;
+  return TC_OK;
+}
+
+int tc_interp_apply_batch(tc_interp* it, const double* x, int64_t n_draws, const double* data,
+                          int n_cols, double* out, int extrapolate, int32_t* flag, void* stream) {
+  if (!it || !x || !data || !out || !flag || n_cols <= 0)
+    return fail(TC_EINVAL, "tc_interp_apply_batch: bad argument");
+  if (n_draws <= 0) return TC_OK;
+  DeviceGuard guard(it->device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_interp_apply_batch: cannot select the CUDA device");
+  InterpArgs args{};
+  args.it = it->dev;
+  args.x = x;
+  args.n_draws = n_draws;
+  args.data = data;
+  args.n_cols = n_cols;
+  args.out = out;
+  args.extrapolate = extrapolate;
+  args.flag = flag;
+  args.sum_knots = it->sum_knots;
+  size_t smem = (size_t)4 * (it->sum_knots + it->dev.n_tables) * sizeof(double);
+  if (smem > 48 * 1024) {
+    TC_CUDA(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  }
+  unsigned grid = (unsigned)((n_draws + 3) / 4);
+  interp_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(args);
+  TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+int tc_measure_dmma_peak(int device, double* tflops) {
+  if (!tflops) return fail(TC_EINVAL, "tc_measure_dmma_peak: NULL output");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_measure_dmma_peak: cannot select CUDA device");
+  int n_sm = 0;
+  int rc = device_sms(device, &n_sm);
+  if (rc) return rc;
+  double* scratch;
+  TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), (size_t)n_sm * 512 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  TC_CUDA(cudaEventCreate(&e0));
+  TC_CUDA(cudaEventCreate(&e1));
+  const int iters = 1 << 14;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    TC_CUDA(cudaEventRecord(e0));
+    dmma_peak_kernel<<<n_sm, 512>>>(scratch, iters);
+    TC_CUDA(cudaEventRecord(e1));
+    TC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    TC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = (double)n_sm * 16 * iters * 8 * 512.0 / (ms * 1e-3) * 1e-12;
+    if (rep > 0) best = std::max(best, tf);
+  }
+  (void)cudaEventDestroy(e0);
+  (void)cudaEventDestroy(e1);
+  (void)cudaFree(scratch);
+  *tflops = best;
+  return TC_OK;
+}
+
+}  // extern "C"

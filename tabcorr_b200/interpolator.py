@@ -1,0 +1,259 @@
+"""Drop-in ``Interpolator``: tensor-product cubic spline over a grid of device-resident tables.
+
+Mirrors ``tabcorr/interpolator.py``: ``__init__`` (:14-70) validates that ``param_dict_table``
+describes a full rectangular grid, sorts it and de-duplicates identical halo tables; ``predict``
+(:124-216) evaluates every grid table and applies ``spline_interpolate`` (:275-331).  Here all
+tables that share a halo table form one device table group, so a prediction is one fused
+occupation + contraction launch over ``T * R`` stacked radial bins followed by the spline kernel.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import h5mini
+from .models import ModelSpec, resolve_model, theta_from_params, ASSEMBIAS_KEYS
+from .tabcorr import (TabCorr, DeviceTableGroup, _to_device_f64, _torch, _h5py)
+from .table import Table
+
+
+def spline_interpolation_matrix(xp):
+    """Matrix form of the not-a-knot cubic spline through knots ``xp``
+    (``tabcorr/interpolator.py:219-272``).
+
+    Returns ``a`` with shape ``[len(xp) - 1, 4, len(xp)]`` such that the spline on segment ``i``
+    is ``sum_p sum_k a[i, p, k] y[k] x**p``.  The 4n polynomial coefficients (n segments) solve a
+    linear system whose rows are, in the reference's order: value at the left knot of each
+    segment, value at the right knot, continuity of the first and of the second derivative at the
+    interior knots, and continuity of the third derivative at the second and second-to-last knot.
+    """
+    xp = np.asarray(xp, dtype=np.float64)
+    if len(xp) < 4:
+        raise ValueError('Cannot perform spline interpolation with less than 4 values.')
+    n = len(xp) - 1
+    powers = np.arange(4)
+
+    def basis(x, derivative):
+        # d^derivative/dx^derivative of (1, x, x^2, x^3)
+        coeff = np.array([np.prod(np.arange(p, p - derivative, -1)) if p >= derivative else 0.0
+                          for p in powers], dtype=np.float64)
+        expo = np.clip(powers - derivative, 0, None)
+        return coeff * x**expo
+
+    system = np.zeros((4 * n, 4 * n))
+    for seg in range(n):
+        cols = slice(4 * seg, 4 * seg + 4)
+        system[seg, cols] = basis(xp[seg], 0)
+        system[n + seg, cols] = basis(xp[seg + 1], 0)
+    for seg in range(n - 1):
+        left, right = slice(4 * seg, 4 * seg + 4), slice(4 * seg + 4, 4 * seg + 8)
+        for derivative, row in ((1, 2 * n + seg), (2, 3 * n - 1 + seg)):
+            system[row, left] = basis(xp[seg + 1], derivative)
+            system[row, right] = -basis(xp[seg + 1], derivative)
+    # The reference scales these two rows by the knot position (interpolator.py:262-265), which
+    # leaves the solution unchanged; keep the scaling for bit-level agreement of the inverse, except
+    # where the knot is 0 and the reference's system would be singular.
+    scale_hi = xp[n - 1] if xp[n - 1] != 0 else 1.0
+    scale_lo = xp[1] if xp[1] != 0 else 1.0
+    system[4 * n - 2, 4 * (n - 2):4 * (n - 1)] = scale_hi * basis(xp[n - 1], 3)
+    system[4 * n - 2, 4 * (n - 1):4 * n] = -scale_hi * basis(xp[n - 1], 3)
+    system[4 * n - 1, 0:4] = scale_lo * basis(xp[1], 3)
+    system[4 * n - 1, 4:8] = -scale_lo * basis(xp[1], 3)
+
+    inverse = np.linalg.inv(system)
+    # right-hand side: rows [0, n) equal y[0..n-1], rows [n, 2n) equal y[1..n], the rest zero
+    a = np.zeros((4 * n, len(xp)))
+    a[:, :n] += inverse[:, :n]
+    a[:, 1:] += inverse[:, n:2 * n]
+    return a.reshape(n, 4, len(xp))
+
+
+class Interpolator:
+    """Interpolation of multiple TabCorr instances on a rectangular parameter grid."""
+
+    def __init__(self, tabcorr_list, param_dict_table, device=None):
+        if not isinstance(param_dict_table, Table):
+            param_dict_table = Table(param_dict_table)
+        if len(tabcorr_list) != len(param_dict_table):
+            raise ValueError("The number of TabCorr instances does not match the number of "
+                             "entries in 'param_dict_table'.")
+        self.tabcorr_list = tabcorr_list
+        self.param_dict_table = param_dict_table.copy()
+        self._keys = list(self.param_dict_table.colnames)
+
+        self.xp = []
+        self.a = []
+        for key in self._keys:
+            self.xp.append(np.sort(np.unique(param_dict_table[key].data)))
+            self.a.append(spline_interpolation_matrix(self.xp[-1]))
+
+        records = self.param_dict_table.as_array()
+        if (int(np.prod([len(xp) for xp in self.xp])) != len(self.param_dict_table) or
+                len(np.unique(records)) != len(records)):
+            raise ValueError("The 'param_dict_table' does not describe a grid.")
+
+        self.param_dict_table['tabcorr_index'] = np.arange(len(self.param_dict_table))
+        self.param_dict_table.sort(self.param_dict_table.colnames)
+
+        # identical halo tables share their occupations (interpolator.py:63-70)
+        all_gal_type = [np.array(tabcorr.gal_type.as_array().tolist()).ravel()
+                        for tabcorr in tabcorr_list]
+        unique = np.unique(all_gal_type, axis=0, return_index=True, return_inverse=True)
+        self.unique_gal_type_index = unique[1]
+        self.unique_gal_type_inverse = np.asarray(unique[2]).ravel()
+
+        first = tabcorr_list[0]
+        for tabcorr in tabcorr_list:
+            if (tabcorr.attrs['mode'] != first.attrs['mode'] or
+                    tuple(tabcorr.tpcf_shape) != tuple(first.tpcf_shape)):
+                raise ValueError('All TabCorr instances must share mode and tpcf_shape.')
+        self._device = device
+        self._groups = None
+        self._interp = None
+
+    # ------------------------------------------------------------------ I/O
+    @classmethod
+    def read(cls, fname, device=None):
+        """Read a TabCorr interpolator from the disk (``tabcorr/interpolator.py:72-96``)."""
+        import os
+        fname = os.fspath(fname)
+        fstream = _h5py.File(fname, 'r') if _h5py is not None else h5mini.File(fname)
+        try:
+            param_dict_table = Table(fstream['param_dict_table'][()])
+            param_dict_table.sort('tabcorr_index')
+            param_dict_table.remove_column('tabcorr_index')
+            # device groups are built by the Interpolator: keep the single tables host-side
+            tabcorr_list = [TabCorr.read(fstream['tabcorr_{}'.format(i)], device=device,
+                                         upload=False)
+                            for i in range(len(param_dict_table))]
+        finally:
+            fstream.close()
+        return cls(tabcorr_list, param_dict_table, device=device)
+
+    def write(self, fname, overwrite=False, max_args_size=1000000, matrix_dtype=np.float32):
+        """Write the interpolator in the reference's layout (``tabcorr/interpolator.py:98-122``)."""
+        from . import h5write
+        h5write.write_interpolator(self, fname, overwrite=overwrite, max_args_size=max_args_size,
+                                   matrix_dtype=matrix_dtype)
+
+    # ------------------------------------------------------------------ device state
+    def _ensure_device(self):
+        if self._groups is not None:
+            return
+        lib = _lib.load()
+        first = self.tabcorr_list[0]
+        n_r = int(np.prod(first.tpcf_shape))
+        groups = []
+        for u in range(len(self.unique_gal_type_index)):
+            members = [k for k in range(len(self.tabcorr_list))
+                       if self.unique_gal_type_inverse[k] == u]
+            group = DeviceTableGroup(
+                self.tabcorr_list[members[0]].gal_type,
+                [self.tabcorr_list[k].tpcf_matrix for k in members], first.attrs['mode'], n_r,
+                device=self._device)
+            groups.append((group, members))
+        # position of every table in the stacked [B, T, ...] buffers: groups back to back
+        slot_of_table = np.zeros(len(self.tabcorr_list), dtype=np.int64)
+        slot = 0
+        for group, members in groups:
+            for k in members:
+                slot_of_table[k] = slot
+                slot += 1
+        grid_to_slot = np.ascontiguousarray(
+            slot_of_table[np.asarray(self.param_dict_table['tabcorr_index'].data)], dtype=np.int32)
+        n_knots = np.ascontiguousarray([len(xp) for xp in self.xp], dtype=np.int32)
+        knots = np.ascontiguousarray(np.concatenate(self.xp), dtype=np.float64)
+        a = np.ascontiguousarray(np.concatenate([m.ravel() for m in self.a]), dtype=np.float64)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.tc_interp_create(
+            ctypes.byref(handle), len(self.xp), _lib.as_int32_p(n_knots), _lib.as_double_p(knots),
+            _lib.as_double_p(a), _lib.as_int32_p(grid_to_slot), groups[0][0].device))
+        self._lib = lib
+        self._interp = handle
+        self._groups = groups
+
+    def __del__(self):
+        handle = getattr(self, '_interp', None)
+        if handle:
+            try:
+                self._lib.tc_interp_destroy(handle)
+            except Exception:
+                pass
+            self._interp = None
+
+    # ------------------------------------------------------------------ prediction
+    def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
+                      model=None, as_numpy=True):
+        """Interpolated predictions for B parameter sets.
+
+        ``params`` is a dict of arrays ``[B]`` holding the occupation parameters and one entry per
+        interpolation axis (the column names of ``param_dict_table``).  Returns ``(ngal [B],
+        xi [B, *tpcf_shape])`` or per-gal-type dicts, like :meth:`predict`.
+        """
+        torch = _torch()
+        self._ensure_device()
+        for key in self._keys:
+            if key not in params:
+                raise ValueError('The key {} is not present in the parameter dictionary of the '
+                                 'model.'.format(key))
+        decorated = all(k in params for k in ASSEMBIAS_KEYS)
+        spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
+        theta_host = theta_from_params(params, None, spec)
+        n_draws = theta_host.shape[0]
+        x_host = np.empty((n_draws, len(self._keys)), dtype=np.float64)
+        for d, key in enumerate(self._keys):
+            x_host[:, d] = np.asarray(params[key], dtype=np.float64)
+        device = self._groups[0][0].device
+        theta = _to_device_f64(theta_host, device)
+        x = _to_device_f64(x_host, device)
+
+        separate = bool(separate_gal_type)
+        first_group = self._groups[0][0]
+        n_tables = len(self.tabcorr_list)
+        n_comp = first_group.n_comp(separate)
+        n_ng = 2 if separate else 1
+        n_r = first_group.n_r
+        ngal_t = torch.empty((n_draws, n_tables, n_ng), dtype=torch.float64, device=device)
+        xi_t = torch.empty((n_draws, n_tables, n_r * n_comp), dtype=torch.float64, device=device)
+        slot = 0
+        for group, members in self._groups:
+            group.predict_into(spec, int(n_gauss_prim), theta, None, separate, ngal_t,
+                               slot * n_ng, xi_t, slot * n_r * n_comp)
+            slot += len(members)
+
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        ngal = torch.empty((n_draws, n_ng), dtype=torch.float64, device=device)
+        xi = torch.empty((n_draws, n_r * n_comp), dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        for data, n_cols, out in ((ngal_t, n_ng, ngal), (xi_t, n_r * n_comp, xi)):
+            _lib.check(self._lib.tc_interp_apply_batch(
+                self._interp, x.data_ptr(), n_draws, data.data_ptr(), n_cols, out.data_ptr(),
+                int(bool(extrapolate)), flag.data_ptr(), stream))
+        if int(flag.item()) != 0:
+            raise ValueError('The x-coordinates are outside of the interpolation range and '
+                             'extrapolation is turned off.')
+        return self.tabcorr_list[0]._format_batch(ngal, xi.view(n_draws, n_r, n_comp), separate,
+                                                  as_numpy)
+
+    def predict(self, model, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
+                check_consistency=True, **occ_kwargs):
+        """Interpolate the predictions from multiple TabCorr instances
+        (``tabcorr/interpolator.py:124-216``).  The values of the parameters to interpolate must
+        be in ``model.param_dict``."""
+        TabCorr._no_occ_kwargs(occ_kwargs)
+        for key in self._keys:
+            if key not in model.param_dict:
+                raise ValueError('The key {} is not present in the parameter dictionary of the '
+                                 'model.'.format(key))
+        if check_consistency:
+            for i in self.unique_gal_type_index:
+                self.tabcorr_list[i]._check_consistency(model)
+        spec = resolve_model(model)
+        params = {k: np.atleast_1d(np.float64(v)) for k, v in model.param_dict.items()
+                  if np.isscalar(v)}
+        ngal, xi = self.predict_batch(params, separate_gal_type, n_gauss_prim, extrapolate,
+                                      model=spec)
+        if separate_gal_type:
+            return ({k: v[0] for k, v in ngal.items()}, {k: v[0] for k, v in xi.items()})
+        return ngal[0], xi[0]

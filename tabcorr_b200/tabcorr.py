@@ -1,0 +1,416 @@
+"""Drop-in ``TabCorr`` for the prediction path, backed by the sm_100a kernels.
+
+Mirrors the reference class for everything on the hot path (``tabcorr/tabcorr.py:374-416`` read,
+``:465-578`` mean_occupation, ``:580-683`` predict): same signatures, same return types (numpy
+scalars / arrays / dicts keyed by ``str``), same ``ValueError`` conditions.  The table itself is
+device resident from ``read`` on, and ``predict_batch`` evaluates B parameter sets in one fused
+launch.  Tabulation (``TabCorr.tabulate``) stays on the reference.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from . import _lib
+from . import h5mini
+from .models import (ModelSpec, THETA_KEYS, ASSEMBIAS_KEYS, resolve_model, theta_from_params)
+from .table import Table
+
+try:  # h5py is optional: used when present, otherwise the built-in reader
+    import h5py as _h5py
+except ImportError:  # pragma: no cover - h5py is absent in the benchmark image
+    _h5py = None
+
+_GROUP_TYPES = (h5mini.Group,) + ((_h5py.Group,) if _h5py is not None else ())
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            'tabcorr_b200 needs a CUDA device (B200, sm_100a): predictions are computed by the '
+            'CUDA extension only and there is no CPU fallback.')
+    if device is None:
+        return torch.cuda.current_device()
+    return torch.device(device).index if not isinstance(device, int) else device
+
+
+def leggauss01(n_gauss_prim):
+    """Gauss-Legendre nodes mapped to [0, 1] and weights (``tabcorr/tabcorr.py:543-546``)."""
+    x, w = np.polynomial.legendre.leggauss(int(n_gauss_prim))
+    return np.ascontiguousarray((x + 1) / 2), np.ascontiguousarray(w)
+
+
+class DeviceTableGroup:
+    """One gal_type table with one or more correlation matrices on the device (``tc_table``)."""
+
+    def __init__(self, gal_type, matrices, mode, n_r, device=None):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.mode = mode
+        self.n_rows = len(gal_type)
+        self.n_r = int(n_r)
+        self.n_tables = len(matrices)
+        names = np.asarray(gal_type['gal_type'].data)
+        is_sat = np.ascontiguousarray((names != 'centrals').astype(np.int32))  # tabcorr.py:555
+        self.is_sat = is_sat
+
+        def column(name):
+            return np.ascontiguousarray(gal_type[name].data, dtype=np.float64)
+
+        n_h, log_min, log_max = (column('n_h'), column('log_prim_haloprop_min'),
+                                 column('log_prim_haloprop_max'))
+        pct = column('sec_haloprop_percentile')
+        dist = (column('prim_haloprop_dist_index')
+                if 'prim_haloprop_dist_index' in gal_type.colnames else None)
+        mats = [np.ascontiguousarray(m, dtype=np.float64) for m in matrices]
+        n_cols = self.n_rows * (self.n_rows + 1) // 2 if mode == 'auto' else self.n_rows
+        for m in mats:
+            if m.shape != (self.n_r, n_cols):
+                raise ValueError('tpcf_matrix has shape {}, expected {}'.format(
+                    m.shape, (self.n_r, n_cols)))
+        c_double_p = ctypes.POINTER(ctypes.c_double)
+        mat_ptrs = (c_double_p * len(mats))(*[_lib.as_double_p(m) for m in mats])
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.tc_table_create(
+            ctypes.byref(handle), _lib.TC_MODE_AUTO if mode == 'auto' else _lib.TC_MODE_CROSS,
+            self.n_rows, self.n_r, self.n_tables, _lib.as_double_p(n_h),
+            _lib.as_double_p(log_min), _lib.as_double_p(log_max), _lib.as_double_p(pct),
+            _lib.as_double_p(dist) if dist is not None else None, _lib.as_int32_p(is_sat),
+            mat_ptrs, self.device))
+        self.handle = handle
+        self._planned = set()
+        self._workspace = None
+        self._lock = threading.Lock()
+
+    def __del__(self):
+        handle = getattr(self, 'handle', None)
+        if handle:
+            try:
+                self.lib.tc_table_destroy(handle)
+            except Exception:  # interpreter shutdown
+                pass
+            self.handle = None
+
+    def plan(self, n_gauss):
+        if n_gauss not in self._planned:
+            x01, w = leggauss01(n_gauss)
+            _lib.check(self.lib.tc_table_plan(self.handle, int(n_gauss), _lib.as_double_p(x01),
+                                              _lib.as_double_p(w)))
+            self._planned.add(n_gauss)
+
+    def n_comp(self, separate):
+        if not separate:
+            return 1
+        return 3 if self.mode == 'auto' else 2
+
+    def _workspace_for(self, n_draws, separate):
+        torch = _torch()
+        need = int(self.lib.tc_predict_workspace_bytes(self.handle, int(n_draws), int(separate)))
+        if need == 0:
+            _lib.check(-3 if n_draws > 0 else 0)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    @staticmethod
+    def _model_struct(spec):
+        return _lib.tc_model(spec.family, int(spec.decorated), int(spec.modulate_with_cenocc), 0,
+                             spec.split)
+
+    def occupation(self, spec, n_gauss, theta):
+        """theta: CUDA tensor [B, 7] -> CUDA tensor [B, n_rows] (mean_occupation)."""
+        torch = _torch()
+        self.plan(n_gauss)
+        n_draws = theta.shape[0]
+        occ = torch.zeros((n_draws, self.n_rows), dtype=torch.float64, device=self.device)
+        model = self._model_struct(spec)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.tc_occupation_batch(
+            self.handle, ctypes.byref(model), int(n_gauss), theta.data_ptr(), n_draws,
+            occ.data_ptr(), stream))
+        return occ
+
+    def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset):
+        """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
+        and ``xi`` starting at table offset ``*_offset`` (in doubles within a draw)."""
+        torch = _torch()
+        n_draws = (theta if theta is not None else occ).shape[0]
+        if theta is not None:
+            self.plan(n_gauss)
+        with self._lock:
+            workspace = self._workspace_for(n_draws, separate)
+            model = self._model_struct(spec if spec is not None else ModelSpec())
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            ngal_flat = ngal.view(n_draws, -1)
+            xi_flat = xi.view(n_draws, -1)
+            _lib.check(self.lib.tc_predict_batch(
+                self.handle, ctypes.byref(model), int(n_gauss),
+                theta.data_ptr() if theta is not None else None,
+                occ.data_ptr() if occ is not None else None, n_draws, int(separate),
+                ngal_flat.data_ptr() + 8 * ngal_offset, ngal_flat.stride(0),
+                xi_flat.data_ptr() + 8 * xi_offset, xi_flat.stride(0),
+                workspace.data_ptr(), workspace.numel(), stream))
+
+
+def _to_device_f64(array, device):
+    """Host array -> CUDA float64 tensor through pinned memory (asynchronous H2D copy)."""
+    torch = _torch()
+    if isinstance(array, torch.Tensor):
+        return array.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
+    host = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64))
+    return host.pin_memory().to(device=device, non_blocking=True)
+
+
+class TabCorr:
+    """Tabulated halo correlation functions with device-resident tables."""
+
+    def __init__(self):
+        self.init = False
+        self._device_group = None
+        self._device = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_arrays(cls, gal_type, tpcf_matrix, tpcf_shape, attrs, tpcf_args=(), tpcf_kwargs=None,
+                    device=None, upload=True):
+        """Build a table from plain arrays (what ``read`` does after parsing the file).
+
+        With ``upload`` (default) the table is copied to the device right away when one is
+        present; otherwise on its first prediction (an ``Interpolator`` uploads whole groups)."""
+        halotab = cls()
+        halotab.attrs = dict(attrs)
+        halotab.tpcf_matrix = np.asarray(tpcf_matrix).astype(np.float64)  # tabcorr.py:399
+        halotab.tpcf_args = tuple(tpcf_args)
+        halotab.tpcf_kwargs = dict(tpcf_kwargs or {})
+        halotab.tpcf_shape = tuple(int(s) for s in tpcf_shape)
+        halotab.gal_type = gal_type if isinstance(gal_type, Table) else Table(gal_type)
+        halotab._device = device
+        halotab.init = True
+        if upload and _torch().cuda.is_available():
+            halotab._ensure_device()
+        return halotab
+
+    @classmethod
+    def read(cls, fname, device=None, upload=True):
+        """Read tabulated correlation functions from the disk (``tabcorr/tabcorr.py:374-416``).
+
+        Parameters
+        ----------
+        fname : string, h5py.Group or tabcorr_b200.h5mini.Group
+            Name of the file or group containing the TabCorr object.
+        device : int or torch.device, optional
+            CUDA device that holds the table.  Default is the current device.
+        """
+        if isinstance(fname, _GROUP_TYPES):
+            fstream, close = fname, False
+        else:
+            fname = os.fspath(fname)
+            fstream = _h5py.File(fname, 'r') if _h5py is not None else h5mini.File(fname)
+            close = True
+        try:
+            attrs = {}
+            for key in fstream.attrs.keys():
+                attrs[key] = fstream.attrs[key]
+            tpcf_matrix = fstream['tpcf_matrix'][()]
+            tpcf_args = tuple(fstream['tpcf_args'][key][()] for key in fstream['tpcf_args'].keys())
+            tpcf_kwargs = {}
+            if 'tpcf_kwargs' in fstream:
+                for key in fstream['tpcf_kwargs'].keys():
+                    tpcf_kwargs[key] = fstream['tpcf_kwargs'][key][()]
+            tpcf_shape = tuple(fstream['tpcf_shape'][()])
+            gal_type = Table(fstream['gal_type'][()])
+        finally:
+            if close:
+                fstream.close()
+        return cls.from_arrays(gal_type, tpcf_matrix, tpcf_shape, attrs, tpcf_args, tpcf_kwargs,
+                               device=device, upload=upload)
+
+    @classmethod
+    def tabulate(cls, *args, **kwargs):
+        raise NotImplementedError(
+            'tabulation (halotools/Corrfunc pair counting, tabcorr/tabcorr.py:23-372) is outside '
+            'the accelerated path; tabulate with the reference package and TabCorr.read the file.')
+
+    def _ensure_device(self):
+        if self._device_group is None:
+            self._device_group = DeviceTableGroup(
+                self.gal_type, [self.tpcf_matrix], self.attrs['mode'],
+                int(np.prod(self.tpcf_shape)), device=self._device)
+        return self._device_group
+
+    # ------------------------------------------------------------------ model handling
+    def _check_consistency(self, model):
+        # same conditions and messages as tabcorr/tabcorr.py:496-535
+        if sorted(model.gal_types) != sorted(['centrals', 'satellites']):
+            raise ValueError(
+                'The model instance must only have centrals and satellites as galaxy types. '
+                'Check the `gal_types` attribute of the model instance.')
+        components = model._input_model_dictionary
+        for name in ('centrals_occupation', 'satellites_occupation'):
+            if components[name].prim_haloprop_key != self.attrs['prim_haloprop_key']:
+                raise ValueError('Mismatch in the primary halo properties of the model and the '
+                                 'TabCorr instance.')
+        for name in ('centrals_occupation', 'satellites_occupation'):
+            if (hasattr(components[name], 'sec_haloprop_key') and
+                    components[name].sec_haloprop_key != self.attrs['sec_haloprop_key']):
+                raise ValueError('Mismatch in the secondary halo properties of the model and the '
+                                 'TabCorr instance.')
+        if not np.abs(model.redshift - self.attrs['redshift']) < 0.05:
+            raise ValueError('Mismatch in the redshift of the model and the TabCorr instance.')
+
+    @staticmethod
+    def _no_occ_kwargs(occ_kwargs):
+        if occ_kwargs:
+            raise NotImplementedError(
+                'keyword arguments for the occupation functions ({}) are not supported by the '
+                'CUDA occupation kernel'.format(', '.join(occ_kwargs)))
+
+    # ------------------------------------------------------------------ reference API
+    def mean_occupation(self, model, n_gauss_prim=10, check_consistency=True, **occ_kwargs):
+        """Mean occupation of each halo/galaxy bin (``tabcorr/tabcorr.py:465-578``).
+
+        Returns a numpy array with the length of ``self.gal_type``.
+        """
+        self._no_occ_kwargs(occ_kwargs)
+        if check_consistency:
+            self._check_consistency(model)
+        spec = resolve_model(model)
+        group = self._ensure_device()
+        theta = _to_device_f64(theta_from_params(model.param_dict, 1, spec), group.device)
+        return group.occupation(spec, int(n_gauss_prim), theta)[0].cpu().numpy()
+
+    def mean_occupation_batch(self, params, n_gauss_prim=10, model=None):
+        """``mean_occupation`` for B parameter sets: CUDA tensor ``[B, N]``."""
+        spec, theta = self._spec_and_theta(params, model)
+        return self._ensure_device().occupation(spec, int(n_gauss_prim), theta)
+
+    def _spec_and_theta(self, params, model):
+        torch = _torch()
+        group = self._ensure_device()
+        if isinstance(params, dict):
+            decorated = all(k in params for k in ASSEMBIAS_KEYS)
+            spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
+            theta = _to_device_f64(theta_from_params(params, None, spec), group.device)
+        else:
+            spec = resolve_model(model) if model is not None else ModelSpec()
+            theta = _to_device_f64(params, group.device)
+            if theta.ndim != 2 or theta.shape[1] not in (5, len(THETA_KEYS)):
+                raise ValueError('params must be a dict of arrays or a [B, 5|7] array ordered as '
+                                 '{}'.format(', '.join(THETA_KEYS)))
+            if theta.shape[1] == 5:
+                theta = torch.cat([theta, torch.zeros((theta.shape[0], 2), dtype=torch.float64,
+                                                      device=theta.device)], dim=1)
+        return spec, theta
+
+    def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, model=None,
+                      occupation=None, as_numpy=True):
+        """Predict number density and correlation function for B parameter sets at once.
+
+        Parameters
+        ----------
+        params : dict of arrays ``[B]`` or array/tensor ``[B, 5|7]``
+            Occupation parameters keyed by their halotools names (``logMmin, sigma_logM, logM0,
+            logM1, alpha`` and, for decorated models, the two ``*_assembias_param1``), or the
+            same as columns in that order.  Ignored when ``occupation`` is given.
+        separate_gal_type : bool, optional
+            Split the result by galaxy type like ``predict`` does.
+        n_gauss_prim : int, optional
+            Gauss-Legendre points per mass bin.
+        model : model instance or ModelSpec, optional
+            Supplies the occupation family (decoration, split, ``modulate_with_cenocc``).  By
+            default the family is inferred from the keys of ``params``.
+        occupation : array ``[B, N]``, optional
+            Precomputed mean occupations (the ndarray branch of ``predict``).
+        as_numpy : bool, optional
+            Return host numpy arrays (default) or leave the results on the device.
+
+        Returns
+        -------
+        ngal : ``[B]`` (or dict of ``[B]``), xi : ``[B, *tpcf_shape]`` (or dict thereof)
+        """
+        torch = _torch()
+        group = self._ensure_device()
+        separate = bool(separate_gal_type)
+        if occupation is not None:
+            occ = _to_device_f64(occupation, group.device)
+            if occ.ndim != 2 or occ.shape[1] != group.n_rows:
+                raise ValueError('occupation must have shape [B, {}]'.format(group.n_rows))
+            spec, theta, n_draws = None, None, occ.shape[0]
+        else:
+            spec, theta = self._spec_and_theta(params, model)
+            occ, n_draws = None, theta.shape[0]
+        n_comp = group.n_comp(separate)
+        ngal = torch.empty((n_draws, 2 if separate else 1), dtype=torch.float64,
+                           device=group.device)
+        xi = torch.empty((n_draws, group.n_r, n_comp), dtype=torch.float64, device=group.device)
+        group.predict_into(spec, int(n_gauss_prim), theta, occ, separate, ngal, 0, xi, 0)
+        return self._format_batch(ngal, xi, separate, as_numpy)
+
+    def _format_batch(self, ngal, xi, separate, as_numpy):
+        """``ngal [B, 1|2]``, ``xi [B, R, C]`` device tensors -> reference-shaped outputs."""
+        shape = tuple(self.tpcf_shape)
+        if as_numpy:
+            ngal, xi = ngal.cpu().numpy(), xi.cpu().numpy()
+        if not separate:
+            return ngal[:, 0], xi[:, :, 0].reshape((xi.shape[0],) + shape)
+        ngal_keys, xi_keys = self._separate_keys()
+        ngal_dict = {key: ngal[:, j] for j, key in ngal_keys}
+        xi_dict = {key: xi[:, :, j].reshape((xi.shape[0],) + shape) for j, key in xi_keys}
+        return ngal_dict, xi_dict
+
+    def _separate_keys(self):
+        """Dictionary keys of ``separate_gal_type`` results in the reference's order
+        (``np.unique`` of the gal_type column, ``tabcorr/tabcorr.py:660-681``)."""
+        names = [str(n) for n in np.unique(self.gal_type['gal_type'].data)]
+        for name in names:
+            if name not in ('centrals', 'satellites'):
+                raise NotImplementedError(
+                    "galaxy type '{}': only 'centrals' and 'satellites' are supported".format(name))
+        index = {'centrals': 0, 'satellites': 1}
+        ngal_keys = [(index[n], n) for n in names]
+        if self.attrs['mode'] == 'auto':
+            xi_keys = []
+            for i, n1 in enumerate(names):
+                for n2 in names[i:]:
+                    xi_keys.append((index[n1] + index[n2], '%s-%s' % (n1, n2)))
+        else:
+            xi_keys = ngal_keys
+        return ngal_keys, xi_keys
+
+    def predict(self, model, separate_gal_type=False, n_gauss_prim=10, check_consistency=True,
+                **occ_kwargs):
+        """Predict the number density and correlation function for a model
+        (``tabcorr/tabcorr.py:580-683``).
+
+        ``model`` is a halotools-style model instance or a numpy array with the mean occupation
+        of each halo bin.  Returns ``(ngal, xi)`` as a numpy scalar and an array of shape
+        ``tpcf_shape``, or two dictionaries if ``separate_gal_type`` is True.
+        """
+        if isinstance(model, np.ndarray):
+            result = self.predict_batch(None, separate_gal_type, n_gauss_prim,
+                                        occupation=model[np.newaxis, :])
+        else:
+            self._no_occ_kwargs(occ_kwargs)
+            if check_consistency:
+                self._check_consistency(model)
+            spec = resolve_model(model)
+            theta = theta_from_params(model.param_dict, 1, spec)
+            result = self.predict_batch(theta, separate_gal_type, n_gauss_prim, model=spec)
+        ngal, xi = result
+        if separate_gal_type:
+            return ({k: v[0] for k, v in ngal.items()}, {k: v[0] for k, v in xi.items()})
+        return ngal[0], xi[0]
+
+    def write(self, fname, overwrite=False, max_args_size=1000000, matrix_dtype=np.float32):
+        """Write the table in the reference's HDF5 layout (``tabcorr/tabcorr.py:418-463``)."""
+        from . import h5write
+        h5write.write_tabcorr(self, fname, overwrite=overwrite, max_args_size=max_args_size,
+                              matrix_dtype=matrix_dtype)

@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path, called through the reference-shaped Python API (which goes
+through the C ABI), against the golden vectors recorded from the reference's own source and
+against the numpy oracle on the same seeded inputs.
+
+Tolerance: north_star asks for rtol 1e-10 in FP64.  xi can cross zero for sign-mixed multipole
+tables, so the comparison is |delta| <= RTOL * max(|xi_ref|, scale) with scale = max |xi_ref| over
+the radial bins of that draw ("cancellation").
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def tb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import tabcorr_b200
+    return tabcorr_b200
+
+
+def close(actual, ref, rtol=RTOL):
+    actual, ref = np.asarray(actual), np.asarray(ref)
+    scale = np.abs(ref).max(axis=-1, keepdims=True) if ref.ndim else np.abs(ref)
+    np.testing.assert_allclose(actual, ref, rtol=rtol, atol=float(rtol) * 1e-3 * np.max(scale))
+
+
+def make_model(tb, theta, decorated=False, **kw):
+    model = tb.models.Zheng07Model(decorated=decorated, **kw)
+    model.param_dict.update(theta)
+    return model
+
+
+def table_from_dict(tb, tab):
+    return tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                  tab['attrs'])
+
+
+def check_golden(golden, name, result):
+    ngal, xi = result
+    if isinstance(ngal, dict):
+        assert sorted(ngal) == sorted(k.split('/')[-1] for k in golden
+                                      if k.startswith(name + '/ngal/'))
+        assert sorted(xi) == sorted(k.split('/')[-1] for k in golden
+                                    if k.startswith(name + '/xi/'))
+        for k in ngal:
+            assert isinstance(k, str)
+            close(ngal[k], golden['{}/ngal/{}'.format(name, k)])
+        total = np.sum([np.abs(golden['{}/xi/{}'.format(name, k)]) for k in xi], axis=0)
+        for k in xi:
+            ref = golden['{}/xi/{}'.format(name, k)]
+            assert xi[k].shape == ref.shape
+            np.testing.assert_allclose(xi[k], ref, rtol=RTOL, atol=RTOL * 1e-3 * total.max())
+    else:
+        close(ngal, golden[name + '/ngal'])
+        assert np.shape(xi) == golden[name + '/xi'].shape
+        close(xi, golden[name + '/xi'])
+
+
+def test_bolplanck_wp(tb, golden, golden_dir):
+    halotab = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_wp.hdf5'))
+    model = tb.PrebuiltHodModelFactory('zheng07', threshold=-18, redshift=0.0)
+    assert model.param_dict == cases.THETA_M18
+    occ = halotab.mean_occupation(model)
+    np.testing.assert_allclose(occ, golden['bolplanck_wp/occ'], rtol=1e-11, atol=1e-15)
+    for g in (1, 10, 100):
+        ngal, xi = halotab.predict(model, n_gauss_prim=g)
+        assert isinstance(ngal, np.floating) and xi.shape == (19,)
+        check_golden(golden, 'bolplanck_wp/G{}'.format(g), (ngal, xi))
+    check_golden(golden, 'bolplanck_wp/sep', halotab.predict(model, separate_gal_type=True))
+    check_golden(golden, 'bolplanck_wp/m21', halotab.predict(
+        tb.PrebuiltHodModelFactory('zheng07', threshold=-21)))
+    # the ndarray branch of predict (tabcorr.py:616-621)
+    check_golden(golden, 'bolplanck_wp/G10', halotab.predict(golden['bolplanck_wp/occ']))
+
+
+def test_bolplanck_ds(tb, golden, golden_dir):
+    halotab = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_ds.hdf5'))
+    model = tb.PrebuiltHodModelFactory('zheng07', threshold=-21)
+    check_golden(golden, 'bolplanck_ds/G10', halotab.predict(model))
+    check_golden(golden, 'bolplanck_ds/sep', halotab.predict(model, separate_gal_type=True))
+
+
+def test_consistency_errors(tb, golden_dir):
+    halotab = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_wp.hdf5'))
+    with pytest.raises(ValueError, match='redshift'):
+        halotab.predict(tb.PrebuiltHodModelFactory('zheng07', threshold=-18, redshift=0.5))
+    with pytest.raises(ValueError, match='primary halo'):
+        halotab.predict(tb.PrebuiltHodModelFactory('zheng07', threshold=-18,
+                                                   prim_haloprop_key='halo_m200b'))
+    with pytest.raises(ValueError, match='secondary halo'):
+        halotab.predict(tb.PrebuiltHodModelFactory('decorated-zheng07', threshold=-18,
+                                                   sec_haloprop_key='halo_spin'))
+    model = tb.PrebuiltHodModelFactory('zheng07', threshold=-18)
+    model.gal_types = ['centrals']
+    with pytest.raises(ValueError, match='galaxy types'):
+        halotab.predict(model)
+    halotab.predict(tb.PrebuiltHodModelFactory('zheng07', threshold=-18, redshift=0.5),
+                    check_consistency=False)
+
+
+def test_ds_efficient_interpolator(tb, golden, golden_dir):
+    interp = tb.Interpolator.read(os.path.join(golden_dir, 'ds_efficient.hdf5'))
+    assert len(interp.tabcorr_list) == 4 and list(interp.unique_gal_type_index) == [0]
+    knot = float(interp.xp[0][1])
+    for tag, log_eta in (('a', 0.1), ('b', -0.3), ('knot', knot)):
+        model = make_model(tb, dict(cases.THETA_AS, log_eta=log_eta), redshift=0.5,
+                           prim_haloprop_key='halo_m258m')
+        check_golden(golden, 'ds_efficient/' + tag, interp.predict(model))
+        check_golden(golden, 'ds_efficient/{}_sep'.format(tag),
+                     interp.predict(model, separate_gal_type=True))
+    model = make_model(tb, dict(cases.THETA_AS, log_eta=0.6), redshift=0.5,
+                       prim_haloprop_key='halo_m258m')
+    with pytest.raises(ValueError, match='outside of the interpolation'):
+        interp.predict(model)
+    check_golden(golden, 'ds_efficient/extrap', interp.predict(model, extrapolate=True))
+    model = make_model(tb, cases.THETA_AS, redshift=0.5, prim_haloprop_key='halo_m258m')
+    with pytest.raises(ValueError, match='log_eta'):
+        interp.predict(model)
+    check_golden(golden, 'ds_efficient/table0', interp.tabcorr_list[0].predict(model))
+
+
+@pytest.mark.parametrize('name', sorted(cases.SYNTHETIC))
+def test_synthetic_tables(tb, golden, name):
+    tab, draws, decorated = cases.synthetic_case(name, golden)
+    halotab = table_from_dict(tb, tab)
+    for g in ((1, 10, 100) if name == 'syn240dec' else (10,)):
+        ngal, xi = halotab.predict_batch(draws, n_gauss_prim=g)
+        assert xi.shape == (cases.N_DRAWS,) + tuple(tab['tpcf_shape'])
+        close(ngal, golden['{}/G{}/ngal'.format(name, g)])
+        ref = golden['{}/G{}/xi'.format(name, g)]
+        close(xi.reshape(cases.N_DRAWS, -1), ref.reshape(cases.N_DRAWS, -1))
+        occ = halotab.mean_occupation_batch(draws, n_gauss_prim=g).cpu().numpy()
+        np.testing.assert_allclose(occ, golden['{}/G{}/occ'.format(name, g)], rtol=1e-11,
+                                   atol=1e-15)
+    model = make_model(tb, cases.draws_row(draws, 0), decorated=decorated)
+    check_golden(golden, name + '/sep0', halotab.predict(model, separate_gal_type=True))
+    # single-model API == row 0 of the batch, bitwise
+    ngal0, xi0 = halotab.predict(model)
+    ngal, xi = halotab.predict_batch(draws)
+    assert ngal0 == ngal[0] and np.array_equal(xi0, xi[0])
+
+
+@pytest.mark.parametrize('name', sorted(cases.GRIDS))
+def test_synthetic_grids(tb, golden, name):
+    tables, param_table, draws = cases.grid_case(name)
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    ngal, xi = interp.predict_batch(draws)
+    close(ngal, golden[name + '/ngal'])
+    close(xi.reshape(cases.N_DRAWS, -1), golden[name + '/xi'].reshape(cases.N_DRAWS, -1),
+          rtol=1e-9)
+    model = make_model(tb, cases.draws_row(draws, 0), decorated=True)
+    check_golden(golden, name + '/sep0', interp.predict(model, separate_gal_type=True))
+
+
+def test_interpolator_mixed_halo_tables(tb):
+    """Grid tables with different gal_type tables form several device groups."""
+    from oracle import tabcorr_oracle as orc
+    axes = {'log_eta': np.linspace(-0.5, 0.5, 4)}
+    tables, param_table = cases.synthetic.make_grid_tables(axes, n_mass=8, n_sec=2, n_r=5)
+    tables[2]['gal_type'] = tables[2]['gal_type'].copy()
+    tables[2]['gal_type']['n_h'] *= 1.25
+    draws = cases.synthetic.make_draws(5, seed=3, decorated=True, extra={'log_eta': (-0.5, 0.5)})
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    assert len(interp.unique_gal_type_index) == 2
+    ngal, xi = interp.predict_batch(draws)
+    ref = orc.OracleInterpolator(
+        [orc.OracleTable(t['gal_type'], t['tpcf_matrix'], t['tpcf_shape'], 'auto')
+         for t in tables], param_table)
+    for i in range(5):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=True)
+        ngal_ref, xi_ref = ref.predict(model)
+        close(ngal[i], ngal_ref)
+        close(xi[i], xi_ref, rtol=1e-9)
+
+
+@pytest.mark.parametrize('n_draws', [1, 7, 200, 3000])
+def test_batch_sizes_against_oracle(tb, n_draws):
+    """Every draw-tile width (8, 16, 32, 64 draws per CTA) and ragged tails."""
+    from oracle import tabcorr_oracle as orc
+    tab = cases.synthetic.make_table(n_mass=20, n_sec=2, n_r=7, seed=5)
+    draws = cases.synthetic.make_draws(n_draws, seed=n_draws, decorated=True)
+    halotab = table_from_dict(tb, tab)
+    ngal, xi = halotab.predict_batch(draws)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    for i in np.unique(np.linspace(0, n_draws - 1, 25).astype(int)):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=True)
+        ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model))
+        close(ngal[i], ngal_ref)
+        close(xi[i], xi_ref)
+
+
+def test_batch_invariance_bitwise(tb):
+    """A draw's result does not depend on the batch it is in (tile width, position, schedule)."""
+    tab = cases.synthetic.make_table(n_mass=60, n_sec=2, n_r=20)
+    halotab = table_from_dict(tb, tab)
+    draws = cases.synthetic.make_draws(20000, seed=2)
+    ngal, xi = halotab.predict_batch(draws)
+    for sl in (slice(0, 1), slice(5, 14), slice(100, 500), slice(19000, 20000)):
+        sub = {k: v[sl] for k, v in draws.items()}
+        ngal_s, xi_s = halotab.predict_batch(sub)
+        assert np.array_equal(ngal_s, ngal[sl]) and np.array_equal(xi_s, xi[sl])
+
+
+def test_full_size_properties(tb):
+    """BASELINE configs[1] at full size (N=240, R=20, B=1e5): size-independent properties plus a
+    sample of draws against the oracle."""
+    from oracle import tabcorr_oracle as orc
+    tab = cases.synthetic.make_table(n_mass=60, n_sec=2, n_r=20)
+    halotab = table_from_dict(tb, tab)
+    n_draws = 100000
+    draws = cases.synthetic.make_draws(n_draws, seed=1)
+    ngal, xi = halotab.predict_batch(draws)
+    assert np.all(np.isfinite(ngal)) and np.all(np.isfinite(xi))
+    # sum of the per-type parts equals the total (tests/test_general.py:8-28, rtol 1e-6 there)
+    ngal_sep, xi_sep = halotab.predict_batch(draws, separate_gal_type=True)
+    assert sorted(ngal_sep) == ['centrals', 'satellites']
+    assert sorted(xi_sep) == ['centrals-centrals', 'centrals-satellites', 'satellites-satellites']
+    np.testing.assert_allclose(ngal_sep['centrals'] + ngal_sep['satellites'], ngal, rtol=1e-13)
+    total = sum(xi_sep.values())
+    scale = sum(np.abs(v) for v in xi_sep.values()).max(axis=1, keepdims=True)
+    assert np.all(np.abs(total - xi) <= 1e-12 * scale)
+    # xi is invariant under a common rescaling of the tracer weights: scale the occupations
+    occ = halotab.mean_occupation_batch(draws)
+    ngal2, xi2 = halotab.predict_batch(None, occupation=occ * 3.0)
+    np.testing.assert_allclose(ngal2, 3.0 * ngal, rtol=1e-13)
+    np.testing.assert_allclose(xi2, xi, rtol=1e-12)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    for i in np.random.default_rng(0).integers(0, n_draws, 40):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i))
+        ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model))
+        close(ngal[i], ngal_ref)
+        close(xi[i], xi_ref)
+
+
+def test_n_gauss_prim_convergence(tb, golden_dir):
+    # tests/test_general.py:31-43
+    halotab = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_wp.hdf5'))
+    model = tb.PrebuiltHodModelFactory('zheng07', threshold=-20)
+    ngal_1, xi_1 = halotab.predict(model, n_gauss_prim=1)
+    ngal_2, xi_2 = halotab.predict(model, n_gauss_prim=10)
+    ngal_3, xi_3 = halotab.predict(model, n_gauss_prim=100)
+    assert not np.isclose(ngal_1, ngal_2, atol=0, rtol=1e-6)
+    assert not np.allclose(xi_1, xi_2, atol=0, rtol=1e-6)
+    assert np.isclose(ngal_2, ngal_3, atol=0, rtol=1e-6)
+    assert np.allclose(xi_2, xi_3, atol=0, rtol=1e-6)
+
+
+def test_interpolator_matches_scipy_cubic(tb):
+    # tests/test_general.py:46-69
+    from scipy.interpolate import interp1d
+    name = 'grid2d'
+    tables, param_table, draws = cases.grid_case(name)
+    axes = cases.GRIDS[name][0]
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    base = cases.draws_row(draws, 0)
+    for key in axes:
+        bins = axes[key]
+        model = make_model(tb, dict(base, alpha_s=1.1, log_eta=0.1), decorated=True)
+        xi_bins = []
+        for x in bins:
+            model.param_dict[key] = x
+            xi_bins.append(interp.predict(model)[1])
+        xi_bins = np.array(xi_bins)
+        for x in np.linspace(np.amin(bins), np.amax(bins), 10):
+            model.param_dict[key] = x
+            xi_tabcorr = interp.predict(model)[1]
+            xi_scipy = [interp1d(bins, xi_bins[:, i], kind='cubic')(x)
+                        for i in range(len(xi_tabcorr))]
+            assert np.allclose(xi_tabcorr, xi_scipy)
+
+
+def test_modulate_with_cenocc_and_split(tb):
+    from oracle import tabcorr_oracle as orc
+    tab = cases.synthetic.make_table(n_mass=15, n_sec=2, n_r=4, seed=9)
+    halotab = table_from_dict(tb, tab)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    draws = cases.synthetic.make_draws(6, seed=4, decorated=True)
+    for kw in (dict(modulate_with_cenocc=True), dict(split=0.3),
+               dict(split=0.7, modulate_with_cenocc=True)):
+        spec = tb.models.ModelSpec(decorated=True, **kw)
+        ngal, xi = halotab.predict_batch(draws, model=spec)
+        for i in range(6):
+            model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=True, **kw)
+            ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model))
+            close(ngal[i], ngal_ref)
+            close(xi[i], xi_ref)
+
+
+def test_legacy_table_without_dist_index(tb):
+    from oracle import tabcorr_oracle as orc
+    tab = cases.synthetic.make_table(n_mass=10, n_sec=1, n_r=3, seed=2)
+    names = [n for n in tab['gal_type'].dtype.names if n != 'prim_haloprop_dist_index']
+    legacy = np.zeros(len(tab['gal_type']), dtype=[(n, tab['gal_type'].dtype[n]) for n in names])
+    for n in names:
+        legacy[n] = tab['gal_type'][n]
+    tab['gal_type'] = legacy
+    halotab = table_from_dict(tb, tab)
+    table = orc.OracleTable(legacy, tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    model = orc.Zheng07Oracle(cases.THETA_M21)
+    ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model))
+    ngal, xi = halotab.predict(make_model(tb, cases.THETA_M21))
+    close(ngal, ngal_ref)
+    close(xi, xi_ref)
+
+
+def test_unsupported_model_fails_loudly(tb, golden_dir):
+    halotab = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_wp.hdf5'))
+
+    class Other:
+        param_dict = {'a': 1.0}
+
+    with pytest.raises(NotImplementedError):
+        halotab.predict(Other(), check_consistency=False)
+    with pytest.raises(NotImplementedError):
+        halotab.predict(tb.PrebuiltHodModelFactory('zheng07', threshold=-18), foo=1)
