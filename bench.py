@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the TabCorr prediction hot path on B200 (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): a synthetic
+bolplanck-shaped w_p table with N = 240 tracer rows (60 mass bins x 2 secondary-percentile bins x
+centrals/satellites), R = 20 radial bins, n_gauss_prim = 10, and a batch of 1e5 zheng07 draws per
+GPU.  One step = one prediction (ngal + w_p) of every draw of the batch.  Under torchrun every rank
+holds a replica of the table and its own 1e5 draws (weak scaling); the results are collected on
+rank 0 with one NCCL gather per step, inside the timed region.
+
+Prints ONE JSON line.  `value` is device-timed throughput with the parameters already in HBM;
+`e2e` is the same metric through the public API ``TabCorr.predict_batch`` with host numpy inputs
+and outputs (pinned H2D + D2H inside the timed region, wall clock).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_MASS, N_SEC, N_R, N_GAUSS = 60, 2, 20, 10
+DRAWS_PER_GPU = 100000
+METRIC = 'HOD predictions/sec (ngal+wp)'
+UNIT = 'predictions/s'
+
+
+def workload_config(n_draws):
+    n = 2 * N_SEC * N_MASS
+    return {
+        'workload': 'BASELINE configs[1]: synthetic bolplanck-shaped wp table, N={} tracer rows '
+                    '({} mass x {} sec x cen/sat), R={} r_p bins, n_gauss_prim={}, {} zheng07 '
+                    'draws per GPU'.format(n, N_MASS, N_SEC, N_R, N_GAUSS, n_draws),
+        'n_tracers': n, 'n_r': N_R, 'n_gauss_prim': N_GAUSS, 'draws_per_gpu': n_draws,
+        'l2': 'flushed between timed steps (256 MiB device write)',
+    }
+
+
+def algorithmic_flops(n, r):
+    """dense W.M_r plus row-dot, per prediction."""
+    return 2.0 * r * n * n + 2.0 * r * n
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms: the oracle port of the reference loop (README.md:72-74 idiom)
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Time the reference algorithm (numpy port) on draws[lo:hi]; returns (n, seconds)."""
+    lo, hi, repeats = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from oracle import tabcorr_oracle as orc
+    from tabcorr_b200 import synthetic
+    tab = synthetic.make_table(n_mass=N_MASS, n_sec=N_SEC, n_r=N_R)
+    draws = synthetic.make_draws(DRAWS_PER_GPU, seed=1)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    model = orc.Zheng07Oracle()
+    orc.predict(table, orc.mean_occupation(table, model, N_GAUSS))  # warm caches
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        for i in range(lo, hi):
+            for key, values in draws.items():
+                model.param_dict[key] = values[i]
+            orc.predict(table, orc.mean_occupation(table, model, N_GAUSS))
+    return (hi - lo) * repeats, time.perf_counter() - t0
+
+
+def cpu_baseline_single(n_sample):
+    n, seconds = _cpu_worker((0, n_sample, 1))
+    return {'value': n / seconds, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': 'first {} of the {} draws, oracle/tabcorr_oracle.py (numpy port of '
+                      'TabCorr.predict incl. mean_occupation), 1 process, 1 thread'.format(
+                          n_sample, DRAWS_PER_GPU)}
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's algorithm on all host cores (multiprocessing fan-out,
+    one table copy per worker), same workload/metric; each step is a bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 150
+    ctx = mp.get_context('fork')
+    jobs = [(w * per_worker, (w + 1) * per_worker, 1) for w in range(cores)]
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, [(0, 20, 1)] * cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker, jobs)
+        seconds = time.perf_counter() - t0
+    n_total = per_worker * cores * args.steps
+    value = n_total / seconds
+    sample = ('{} draws per step ({} per worker x {} workers) of the same table and draw set, '
+              'numpy port of the reference loop (the reference itself needs h5py/astropy/'
+              'halotools, absent here)'.format(per_worker * cores, per_worker, cores))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * seconds / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': workload_config(DRAWS_PER_GPU),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '50'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.06)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, sm_max, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        with open(self.path) as f:
+            for row in f:
+                cells = [c.strip() for c in row.split(',')]
+                if len(cells) < 7:
+                    continue
+                try:
+                    sm.append(float(cells[0]))
+                    sm_max.append(float(cells[1]))
+                except ValueError:
+                    continue
+                for name, cell in zip(names, cells[3:7]):
+                    if cell.lower().startswith('active'):
+                        reasons.add(name)
+        os.unlink(self.path)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(np.max(sm_max)) if sm_max else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import tabcorr_b200
+    from tabcorr_b200 import _lib, synthetic
+    from tabcorr_b200.models import ModelSpec, theta_from_params
+    from tabcorr_b200.distributed import gather_rows, predict_batch_sharded
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; the hot path has no CPU fallback '
+                         '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    n_draws = args.draws
+    tab = synthetic.make_table(n_mass=N_MASS, n_sec=N_SEC, n_r=N_R)
+    n_rows = len(tab['gal_type'])
+    halotab = tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'],
+                                               tab['tpcf_shape'], tab['attrs'], device=local_rank)
+    all_draws = synthetic.make_draws(n_draws * world, seed=1)
+    draws = {k: np.ascontiguousarray(v[rank * n_draws:(rank + 1) * n_draws])
+             for k, v in all_draws.items()}
+    group = halotab._ensure_device()
+    spec = ModelSpec()
+    theta = torch.from_numpy(theta_from_params(draws, None, spec)).to(device)
+    ngal = torch.empty((n_draws, 1), dtype=torch.float64, device=device)
+    xi = torch.empty((n_draws, N_R, 1), dtype=torch.float64, device=device)
+    result = torch.empty((n_draws, 1 + N_R), dtype=torch.float64, device=device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    lib = _lib.load()
+
+    def step():
+        group.predict_into(spec, N_GAUSS, theta, None, False, ngal, 0, xi, 0)
+        if world > 1:  # the one collective of the path: results to rank 0
+            result[:, :1].copy_(ngal)
+            result[:, 1:].copy_(xi.view(n_draws, N_R))
+            gather_rows(result, n_draws * world, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed throughput -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    _lib.check(lib.tc_profile_enable(1))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kernel_ms, finalize_ms = [], []
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # evict the table and the draws from L2 between timed steps
+        starts[i].record()
+        step()
+        stops[i].record()
+        stops[i].synchronize()
+        a, b = ctypes.c_float(), ctypes.c_float()
+        _lib.check(lib.tc_profile_read(ctypes.byref(a), ctypes.byref(b)))
+        kernel_ms.append(a.value)
+        finalize_ms.append(b.value)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    _lib.check(lib.tc_profile_enable(0))
+    total_ms = float(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = n_draws * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API (host numpy in, host numpy out) --------------------
+    def e2e_step():
+        if world == 1:
+            return halotab.predict_batch(draws, n_gauss_prim=N_GAUSS)
+        return predict_batch_sharded(halotab, all_draws, n_gauss_prim=N_GAUSS, dst=0)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_result = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n_draws * world * args.steps / e2e_s
+    h2d = n_draws * 7 * 8
+    d2h = n_draws * (1 + N_R) * 8
+
+    # numerics sanity inside the bench: the e2e results equal the device-timed ones
+    same = True
+    if rank == 0:
+        ngal_host, xi_host = host_result
+        same = (np.array_equal(ngal_host[:n_draws], ngal[:, 0].cpu().numpy()) and
+                np.array_equal(xi_host[:n_draws], xi[:, :, 0].cpu().numpy()))
+
+    if rank == 0:
+        peak = ctypes.c_double()
+        _lib.check(lib.tc_measure_dmma_peak(local_rank, ctypes.byref(peak)))
+        flops = algorithmic_flops(n_rows, N_R) * n_draws
+        k_ms = float(np.mean(kernel_ms))
+        achieved = flops / (k_ms * 1e-3) * 1e-12
+        n_pad = (n_rows + 15) // 16 * 16
+        executed = 2.0 * N_R * 64.0 * (n_pad // 8) * (n_pad // 8 + 1) / 2 * n_draws
+        roofline = {
+            'bound': 'tensor', 'kernel': 'predict_kernel<8, auto> (fused occupation + DMMA '
+                                         'quadratic form)',
+            'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
+            'frac': achieved / peak.value, 'traffic': None,
+            'peak_source': 'FP64 DMMA (mma.sync m8n8k4 f64) peak measured live by '
+                           'tc_measure_dmma_peak; MEASURED_PEAKS.json has no FP64 figure',
+            'flops_per_prediction': algorithmic_flops(n_rows, N_R),
+            'note': 'achieved counts the dense algorithmic flops 2RN^2+2RN (SURVEY 8d); the '
+                    'kernel multiplies only the lower triangle, executed_* count those flops',
+            'executed_tflops': executed / (k_ms * 1e-3) * 1e-12,
+            'executed_frac': executed / (k_ms * 1e-3) * 1e-12 / peak.value,
+            'kernel_ms': k_ms, 'finalize_ms': float(np.mean(finalize_ms)),
+            'kernel_share_of_step': float(np.sum(kernel_ms) / total_ms) if world == 1 else None,
+        }
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(n_draws),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'timing': 'wall clock around predict_batch calls'},
+            'gpu_launches': 2 * args.steps, 'roofline': roofline, 'clocks': clocks,
+            'results_consistent': bool(same),
+        }
+        if world == 1 and not args.no_cpu:
+            line['cpu_baseline'] = cpu_baseline_single(args.cpu_sample)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=20)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    parser.add_argument('--draws', type=int, default=DRAWS_PER_GPU, help='draws per GPU')
+    parser.add_argument('--cpu-sample', type=int, default=8000,
+                        help='draws of the workload timed for cpu_baseline')
+    parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = parser.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -123,6 +123,17 @@ int tc_interp_apply_batch(tc_interp* interp, const double* x_dev, int64_t n_draw
  * reports (MEASURED_PEAKS.json carries no FP64 figure). */
 int tc_measure_dmma_peak(int device, double* tflops_out);
 
+/* Element-wise evaluation of the occupation kernel's table-driven math on the current device, for
+ * accuracy tests: kind 0: out = 0.5 (1 + erf(x)); kind 1: out = x^y for x > 0. */
+int tc_debug_math(int kind, const double* x_dev, const double* y_dev, double* out_dev, int64_t n,
+                  void* stream);
+
+/* Per-kernel device timing of the most recent tc_predict_batch (CUDA events recorded on its
+ * stream around the fused kernel and around the finalize kernel); used by bench.py for the
+ * roofline of the dominant kernel.  Not thread safe; off by default. */
+int tc_profile_enable(int on);
+int tc_profile_read(float* predict_ms_out, float* finalize_ms_out);
+
 #ifdef __cplusplus
 }
 #endif

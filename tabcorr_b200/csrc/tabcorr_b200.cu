@@ -82,6 +82,7 @@ struct Chunk {
 struct OccPlan {       // device pointers, one per (layout, n_gauss)
   int n_groups;
   int n_gauss;
+  int n_gauss_pad;          // n_gauss rounded up to even; the padding node has zero weight
   const double* node_logm;  // [n_groups, G]  log10 of the node masses
   const double* node_m;     // [n_groups, G]  node masses
   const int* grp_rows;      // [n_groups, kGroupRows] padded row index or -1
@@ -101,6 +102,7 @@ struct LayoutDev {
   long long ks_per_r;  // k-steps per radial bin (auto) / per 16-bin tile (cross) in the A stream
   const double2* afrag;
   const Chunk* chunks;
+  const long long* chunk_cost_prefix;  // [n_chunks + 1] cumulative cost of the sorted chunks
   const int* out_ptr;    // [n_out + 1] CSR: which scratch rows sum to output o
   const int* out_parts;
   const int* pad_to_row;  // [n_pad] reference row index or -1
@@ -126,6 +128,82 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
 template <int NT>
 __device__ __forceinline__ int widx(int i, int b) {
   return (((i >> 2) * NT + (b >> 3)) << 5) + ((b & 7) << 2) + (i & 3);
+}
+
+// ------------------------------------------------------------------------------------------
+// table-driven double-precision math for the occupation phase
+//
+// The FP64 pipe is shared with DMMA, and the CUDA math library's erf/log/exp spend most of their
+// issue slots on constant loads and range branches (ncu: 211 warp instructions per evaluation).
+// The occupation functions only need ~1e-14 accuracy (parity bar: rtol 1e-10 on ngal, xi), so the
+// kernel uses branch-free piecewise polynomials with coefficients in shared memory:
+//   cen:  0.5 (1 + erf(x))  degree-13 polynomial on 25 intervals of width 0.5 covering [-6.25, 6.25]
+//         (absolute error < 2e-15; exactly the 1e-16-level noise 1 + erf(x) has in the reference);
+//   sat:  t^alpha = exp(alpha log t) with a 128-entry log table (degree-7 log1p) and a 32-entry
+//         2^(j/32) table (degree-6 exp); relative error < 3e-14 over the reachable range.
+// The tables are computed on the host in long double when the library first touches a device.
+// ------------------------------------------------------------------------------------------
+constexpr int kErfDeg = 13;
+constexpr int kErfIntervals = 25;
+constexpr int kErfStride = 32;                                  // doubles per coefficient row
+constexpr int kErfDoubles = (kErfDeg + 1) * kErfStride;         // 448
+constexpr int kLogEntries = 128;                                // (1 / c_i, ln c_i) pairs
+constexpr int kExpEntries = 32;
+constexpr int kTabLog = kErfDoubles;
+constexpr int kTabExp = kTabLog + 2 * kLogEntries;
+constexpr int kTabDoubles = kTabExp + kExpEntries;              // 736 doubles = 5888 bytes
+constexpr double kRoundMagic = 6755399441055744.0;              // 2^52 + 2^51: round-to-nearest int
+
+__device__ double g_math_tables[kTabDoubles];
+
+__device__ __forceinline__ void load_math_tables(double* tab) {
+  for (int i = threadIdx.x; i < kTabDoubles; i += blockDim.x) tab[i] = g_math_tables[i];
+}
+
+// 0.5 (1 + erf(x)), clamped to [0, 1]
+__device__ __forceinline__ double half_erfc_neg(double x, const double* __restrict__ tab) {
+  double u = fma(x, 2.0, 12.0);              // interval index: centres at x = -6 + i / 2
+  u = fmin(fmax(u, 0.0), (double)(kErfIntervals - 1));
+  const double v = u + kRoundMagic;
+  const int i = __double2loint(v);
+  const double t = u - (v - kRoundMagic);    // in [-0.5, 0.5]
+  const double* c = tab + i;
+  double p = c[kErfDeg * kErfStride];
+#pragma unroll
+  for (int k = kErfDeg - 1; k >= 0; k--) p = fma(p, t, c[k * kErfStride]);
+  return fmin(fmax(p, 0.0), 1.0);
+}
+
+// t^alpha for t > 0 (normal double)
+__device__ __forceinline__ double pow_pos(double t, double alpha, const double* __restrict__ tab) {
+  const long long bits = __double_as_longlong(t);
+  const int e = (int)(bits >> 52) - 1023;
+  const int i = (int)(bits >> 45) & (kLogEntries - 1);
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double2 lc = *reinterpret_cast<const double2*>(tab + kTabLog + 2 * i);
+  const double r = fma(m, lc.x, -1.0);       // |r| < 2^-8
+  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(p, r, 1.0 / 5.0);
+  p = fma(p, r, -1.0 / 4.0);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  p = fma(p, r, 1.0);
+  const double lg = fma((double)e, 0.6931471805599453094, fma(p, r, lc.y));
+  double y = alpha * lg;
+  y = fmin(fmax(y, -700.0), 700.0);
+  const double v = fma(y, 46.16624130844682903551 /* 32 / ln 2 */, kRoundMagic);
+  const int k = __double2loint(v);
+  const double kf = v - kRoundMagic;
+  double q = fma(-kf, 0.0216608493924982895 /* hi(ln2 / 32) */, y);
+  q = fma(-kf, 1.4168872360403518e-18 /* lo */, q);
+  double w = fma(q, 1.0 / 720.0, 1.0 / 120.0);
+  w = fma(w, q, 1.0 / 24.0);
+  w = fma(w, q, 1.0 / 6.0);
+  w = fma(w, q, 0.5);
+  w = fma(w, q, 1.0);
+  w = fma(w, q, 1.0);
+  const double res = tab[kTabExp + (k & (kExpEntries - 1))] * w;
+  return __longlong_as_double(__double_as_longlong(res) + ((long long)(k >> 5) << 52));
 }
 
 struct DrawParams {
@@ -160,21 +238,40 @@ __device__ __forceinline__ double decorate(double f, double strength, double spl
   return type1 ? f + delta : f - delta * (1.0 - split) / split;
 }
 
+// Baseline occupation of one quadrature node.
+__device__ __forceinline__ double baseline_occupation(bool is_sat, double logm, double mass,
+                                                      const DrawParams& p, int modulate,
+                                                      const double* __restrict__ tab) {
+  if (!is_sat) {
+    // Zheng07Cens: 0.5 (1 + erf((log10 M - logMmin) / sigma_logM))
+    return half_erfc_neg((logm - p.logMmin) * p.inv_sigma, tab);
+  }
+  // Zheng07Sats: ((M - M0) / M1)^alpha for M > M0, else 0
+  const double d = mass - p.m0;
+  const bool pos = d > 0.0;
+  double f = pow_pos(pos ? d * p.inv_m1 : 1.0, p.alpha, tab);
+  f = pos ? f : 0.0;
+  if (modulate) f *= half_erfc_neg((logm - p.logMmin) * p.inv_sigma, tab);
+  return f;
+}
+
 // Occupation phase for one tile of BM = 8 NT draws: thread (b = tid % BM, lane group tid / BM)
-// evaluates the baseline zheng07 occupations of its mass-bin groups at the G quadrature nodes once
-// and accumulates them into the (up to kGroupRows) rows sharing that mass bin.
-// store(padded_row, b, occ, n_h) receives the Gauss-Legendre averaged occupation.
+// evaluates the baseline zheng07 occupations of its mass-bin groups at the quadrature nodes once
+// (two nodes per iteration for instruction-level parallelism; the plan pads G to an even count
+// with zero-weight nodes) and accumulates them into the (up to kGroupRows) rows sharing that mass
+// bin.  store(padded_row, b, occ, n_h) receives the Gauss-Legendre averaged occupation.
 template <int BM, typename Store>
 __device__ __forceinline__ void occupation_tile(const OccPlan& plan, const tc_model& model,
                                                 const double* __restrict__ theta, long long b0,
-                                                long long n_draws, Store store) {
+                                                long long n_draws, const double* __restrict__ tab,
+                                                Store store) {
   const int b = threadIdx.x % BM;
   const int gl = threadIdx.x / BM;
   constexpr int n_gl = kThreads / BM;
   long long draw = b0 + b;
   if (draw >= n_draws) draw = n_draws - 1;  // tail tile: recompute the last draw, never stored
   const DrawParams p = load_draw(theta + draw * TC_N_THETA);
-  const int G = plan.n_gauss;
+  const int G = plan.n_gauss_pad;
   for (int grp = gl; grp < plan.n_groups; grp += n_gl) {
     const int* rows = plan.grp_rows + grp * kGroupRows;
     int row[kGroupRows];
@@ -188,27 +285,21 @@ __device__ __forceinline__ void occupation_tile(const OccPlan& plan, const tc_mo
     double acc[kGroupRows] = {0.0, 0.0, 0.0, 0.0};
     const double* logm = plan.node_logm + (size_t)grp * G;
     const double* mass = plan.node_m + (size_t)grp * G;
-    for (int g = 0; g < G; g++) {
-      double f, lo = 0.0, hi, strength;
-      if (!is_sat) {
-        // Zheng07Cens: 0.5 (1 + erf((log10 M - logMmin) / sigma_logM))
-        f = 0.5 * (1.0 + erf((logm[g] - p.logMmin) * p.inv_sigma));
-        hi = 1.0;
-        strength = p.a_cen;
-      } else {
-        // Zheng07Sats: ((M - M0) / M1)^alpha for M > M0, else 0
-        double d = mass[g] - p.m0;
-        f = d > 0.0 ? exp(p.alpha * log(d * p.inv_m1)) : 0.0;
-        if (model.modulate_with_cenocc)
-          f *= 0.5 * (1.0 + erf((logm[g] - p.logMmin) * p.inv_sigma));
-        hi = CUDART_INF;
-        strength = p.a_sat;
-      }
+    const double hi = is_sat ? CUDART_INF : 1.0;
+    const double strength = is_sat ? p.a_sat : p.a_cen;
+    for (int g = 0; g < G; g += 2) {
+      const double f0 = baseline_occupation(is_sat, logm[g], mass[g], p,
+                                            model.modulate_with_cenocc, tab);
+      const double f1 = baseline_occupation(is_sat, logm[g + 1], mass[g + 1], p,
+                                            model.modulate_with_cenocc, tab);
 #pragma unroll
       for (int s = 0; s < kGroupRows; s++) {
         if (row[s] >= 0) {
-          double fs = model.decorated ? decorate(f, strength, model.split, lo, hi, type1[s]) : f;
-          acc[s] = fma(plan.row_c[(size_t)row[s] * G + g], fs, acc[s]);
+          const double* c = plan.row_c + (size_t)row[s] * G + g;
+          const double fs0 = model.decorated ? decorate(f0, strength, model.split, 0.0, hi, type1[s]) : f0;
+          const double fs1 = model.decorated ? decorate(f1, strength, model.split, 0.0, hi, type1[s]) : f1;
+          acc[s] = fma(c[0], fs0, acc[s]);
+          acc[s] = fma(c[1], fs1, acc[s]);
         }
       }
     }
@@ -238,19 +329,58 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
   constexpr int BM = 8 * NT;
   extern __shared__ __align__(16) double smem[];
   double* Ws = smem;                                             // [n_pad / 4][NT][32]
-  int* counter = reinterpret_cast<int*>(smem + (size_t)args.lay.n_pad * BM);
+  double* tab = smem + (size_t)args.lay.n_pad * BM;              // math tables
+  int* sync = reinterpret_cast<int*>(tab + kTabDoubles);         // [0] chunk counter, [1..2] range
   const LayoutDev& lay = args.lay;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
 
   for (int i = tid; i < lay.n_pad * BM; i += kThreads) Ws[i] = 0.0;  // padding rows stay zero
+  load_math_tables(tab);
+
+  // Work = n_tiles x n_chunks chunks, each tile's chunk list in the same (longest first) order.
+  // The grid cuts the total COST into equal contiguous ranges, so that every CTA gets the same
+  // amount of DMMA work whatever the number of draws; a CTA recomputes the weights of the (at
+  // most two) tiles it shares with its neighbours.
+  const long long tile_cost = lay.chunk_cost_prefix[lay.n_chunks];
+  const long long total_cost = tile_cost * args.n_tiles;
+  const long long cost_lo = total_cost / gridDim.x * blockIdx.x +
+                            total_cost % gridDim.x * blockIdx.x / gridDim.x;
+  const long long cost_hi = total_cost / gridDim.x * (blockIdx.x + 1) +
+                            total_cost % gridDim.x * (blockIdx.x + 1) / gridDim.x;
+  const long long tile_first = cost_lo / tile_cost;
+  const long long tile_last = (cost_hi + tile_cost - 1) / tile_cost;  // exclusive
   __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+  for (long long tile = tile_first; tile < tile_last && tile < args.n_tiles; tile++) {
     const long long b0 = tile * BM;
+    // chunk range [c_lo, c_hi) of this tile owned by this CTA: first chunk whose start cost is
+    // >= the range boundary (binary search in the prefix sums; boundaries of neighbouring CTAs
+    // agree because they search the same value)
+    if (tid < 2) {
+      const long long bound = (tid == 0 ? cost_lo : cost_hi) - tile * tile_cost;
+      int lo = 0, hi = lay.n_chunks;
+      if (bound <= 0) {
+        hi = 0;
+      } else if (bound >= tile_cost) {
+        lo = lay.n_chunks;
+      } else {
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (lay.chunk_cost_prefix[mid] < bound) lo = mid + 1; else hi = mid;
+        }
+      }
+      sync[1 + tid] = lo < hi ? lo : hi;
+    }
+    __syncthreads();
+    const int c_lo = sync[1], c_hi = sync[2];
+    if (c_lo >= c_hi) {   // the range boundary fell inside this tile's last chunk: nothing here
+      __syncthreads();
+      continue;
+    }
     // ---- phase 1: tracer weights W[row, draw] = occ * n_h into shared memory ---------------
     if (args.theta != nullptr) {
-      occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws,
+      occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws, tab,
                           [&](int row, int b, double occ, double nh) {
                             Ws[widx<NT>(row, b)] = occ * nh;
                           });
@@ -263,11 +393,11 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
           Ws[widx<NT>(row, b)] = args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row];
       }
     }
-    if (tid == 0) *counter = 0;
+    if (tid == 0) sync[0] = c_lo;
     __syncthreads();
 
-    // ---- number densities (one CTA per tile writes them) -----------------------------------
-    if (blockIdx.y == 0 && tid < BM) {
+    // ---- number densities (written by the CTA that owns the tile's first chunk) -------------
+    if (c_lo == 0 && tid < BM) {
       double nc = 0.0, ns = 0.0;
       for (int i = 0; i < lay.nc_pad; i++) nc += Ws[widx<NT>(i, tid)];
       for (int i = lay.nc_pad; i < lay.n_pad; i++) ns += Ws[widx<NT>(i, tid)];
@@ -279,10 +409,9 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
     double* parts = args.parts + (size_t)tile * lay.n_parts * BM;
     for (;;) {
       int c = 0;
-      if (lane == 0) c = atomicAdd(counter, 1);
+      if (lane == 0) c = atomicAdd(&sync[0], 1);
       c = __shfl_sync(0xffffffffu, c, 0);
-      c = blockIdx.y + c * gridDim.y;
-      if (c >= lay.n_chunks) break;
+      if (c >= c_hi) break;
       const Chunk ch = lay.chunks[c];
 
       if (MODE == TC_MODE_AUTO) {
@@ -470,18 +599,32 @@ struct OccArgs {
   double* occ_out;
 };
 
-__global__ void __launch_bounds__(kThreads) occupation_kernel(const OccArgs args) {
+__global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs args) {
   constexpr int BM = 32;
+  __shared__ double tab[kTabDoubles];
+  load_math_tables(tab);
+  __syncthreads();
   const long long n_tiles = (args.n_draws + BM - 1) / BM;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long b0 = tile * BM;
-    occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws,
+    occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws, tab,
                         [&](int row, int b, double occ, double) {
                           int dst = args.pad_to_row[row];
                           if (b0 + b < args.n_draws && dst >= 0)
                             args.occ_out[(b0 + b) * args.n_rows + dst] = occ;
                         });
   }
+}
+
+// element-wise evaluation of the table-driven math, for the accuracy tests (tc_debug_math)
+__global__ void debug_math_kernel(int kind, const double* x, const double* y, double* out,
+                                  long long n) {
+  __shared__ double tab[kTabDoubles];
+  load_math_tables(tab);
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = kind == 0 ? half_erfc_neg(x[i], tab) : pow_pos(x[i], y[i], tab);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -779,6 +922,10 @@ int build_layout(tc_table* t, int separate) {
   std::stable_sort(chunks.begin(), chunks.end(),
                    [&](const Chunk& a, const Chunk& b) { return chunk_cost(a) > chunk_cost(b); });
 
+  std::vector<long long> cost_prefix(chunks.size() + 1, 0);
+  for (size_t c = 0; c < chunks.size(); c++)
+    cost_prefix[c + 1] = cost_prefix[c] + std::max<long long>(1, chunk_cost(chunks[c]));
+
   std::vector<int> out_ptr(out_lists.size() + 1, 0), out_parts;
   for (size_t o = 0; o < out_lists.size(); o++) {
     out_ptr[o + 1] = out_ptr[o] + (int)out_lists[o].size();
@@ -786,7 +933,10 @@ int build_layout(tc_table* t, int separate) {
   }
 
   double2* d_afrag; Chunk* d_chunks; int *d_out_ptr, *d_out_parts, *d_pad_to_row;
+  long long* d_cost_prefix;
   int rc;
+  if ((rc = upload(cost_prefix, &d_cost_prefix))) return rc;
+  L.allocations.push_back(d_cost_prefix);
   if ((rc = upload(afrag, &d_afrag))) return rc;
   L.allocations.push_back(d_afrag);
   if ((rc = upload(chunks, &d_chunks))) return rc;
@@ -807,6 +957,7 @@ int build_layout(tc_table* t, int separate) {
   L.dev.ks_per_r = ks_per_r;
   L.dev.afrag = d_afrag;
   L.dev.chunks = d_chunks;
+  L.dev.chunk_cost_prefix = d_cost_prefix;
   L.dev.out_ptr = d_out_ptr;
   L.dev.out_parts = d_out_parts;
   L.dev.pad_to_row = d_pad_to_row;
@@ -844,17 +995,22 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
     }
   }
   const int n_groups = (int)groups.size();
-  std::vector<double> node_logm((size_t)n_groups * G), node_m((size_t)n_groups * G);
+  const int GP = (G + 1) / 2 * 2;  // the kernel evaluates two nodes per iteration
+  std::vector<double> node_logm((size_t)n_groups * GP), node_m((size_t)n_groups * GP);
   std::vector<int> grp_rows((size_t)n_groups * kGroupRows, -1), grp_is_sat(n_groups);
-  std::vector<double> row_c((size_t)n_pad * G, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
+  std::vector<double> row_c((size_t)n_pad * GP, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
   for (int q = 0; q < n_groups; q++) {
     const Group& gq = groups[q];
     grp_is_sat[q] = gq.sat;
     for (int k = 0; k < G; k++) {
       // prim_haloprop = 10**(log_min + d_log * x) and halotools' log10(prim_haloprop)
       double m = std::pow(10.0, gq.lo + (gq.hi - gq.lo) * x01[k]);
-      node_m[(size_t)q * G + k] = m;
-      node_logm[(size_t)q * G + k] = std::log10(m);
+      node_m[(size_t)q * GP + k] = m;
+      node_logm[(size_t)q * GP + k] = std::log10(m);
+    }
+    for (int k = G; k < GP; k++) {  // zero-weight padding node
+      node_m[(size_t)q * GP + k] = node_m[(size_t)q * GP];
+      node_logm[(size_t)q * GP + k] = node_logm[(size_t)q * GP];
     }
     for (size_t s = 0; s < gq.rows.size(); s++) {
       const int i = gq.rows[s], p = L.row_to_pad[i];
@@ -863,9 +1019,9 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
       row_pct[p] = t->pct[i];
       const double n = t->has_dist ? t->dist[i] + 1.0 : 0.0;  // tabcorr.py:568-574
       double norm = 0.0;
-      for (int k = 0; k < G; k++) norm += wq[k] * std::pow(node_m[(size_t)q * G + k], n);
+      for (int k = 0; k < G; k++) norm += wq[k] * std::pow(node_m[(size_t)q * GP + k], n);
       for (int k = 0; k < G; k++)
-        row_c[(size_t)p * G + k] = wq[k] * std::pow(node_m[(size_t)q * G + k], n) / norm;
+        row_c[(size_t)p * GP + k] = wq[k] * std::pow(node_m[(size_t)q * GP + k], n) / norm;
     }
   }
   PlanHost ph;
@@ -880,6 +1036,7 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   if ((rc = upload(row_pct, &d_pct))) return rc; ph.allocations.push_back(d_pct);
   ph.dev.n_groups = n_groups;
   ph.dev.n_gauss = G;
+  ph.dev.n_gauss_pad = GP;
   ph.dev.node_logm = d_logm;
   ph.dev.node_m = d_m;
   ph.dev.grp_rows = d_rows;
@@ -891,10 +1048,14 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   return TC_OK;
 }
 
+size_t predict_smem_bytes(int n_pad, int nt) {
+  return ((size_t)n_pad * 8 * nt + kTabDoubles) * sizeof(double) + 16;
+}
+
 int pick_nt(int n_pad, long long n_draws, int n_sm) {
   int best = 0;
   for (int nt : {8, 4, 2, 1}) {
-    size_t smem = (size_t)n_pad * 8 * nt * sizeof(double) + 16;
+    size_t smem = predict_smem_bytes(n_pad, nt);
     if (smem > (size_t)kSmemLimit) continue;
     if (best == 0) best = nt;  // largest that fits
     if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) return nt;
@@ -919,6 +1080,56 @@ Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
   w.ngal_bytes = (size_t)w.n_tiles * 2 * bm * sizeof(double);
   w.total = w.parts_bytes + w.ngal_bytes;
   return w;
+}
+
+// Coefficient tables of the occupation math (see half_erfc_neg / pow_pos), computed in long double.
+int ensure_math_tables(int device) {
+  static std::mutex m;
+  static std::map<int, bool> done;
+  std::lock_guard<std::mutex> lock(m);
+  if (done[device]) return TC_OK;
+  std::vector<double> tab(kTabDoubles, 0.0);
+  const int n = kErfDeg + 1;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int i = 0; i < kErfIntervals; i++) {
+    const long double xc = -6.0L + 0.5L * i;  // x = xc + s / 4 with s in [-1, 1]; t = s / 2
+    std::vector<long double> fs(n), sn(n);
+    for (int j = 0; j < n; j++) {
+      sn[j] = cosl(pi * (j + 0.5L) / n);
+      fs[j] = 0.5L * erfcl(-(xc + 0.25L * sn[j]));
+    }
+    // Chebyshev coefficients of the interpolant, then Chebyshev -> monomial in s
+    std::vector<long double> a(n, 0.0L);
+    for (int k = 0; k < n; k++) {
+      long double sum = 0.0L;
+      for (int j = 0; j < n; j++) sum += fs[j] * cosl(k * pi * (j + 0.5L) / n);
+      a[k] = (k == 0 ? 1.0L : 2.0L) * sum / n;
+    }
+    std::vector<long double> mono(n, 0.0L), t0(n, 0.0L), t1(n, 0.0L), t2(n, 0.0L);
+    t0[0] = 1.0L;                 // T_0
+    t1[1] = 1.0L;                 // T_1
+    for (int d = 0; d < n; d++) mono[d] += a[0] * t0[d] + (n > 1 ? a[1] * t1[d] : 0.0L);
+    for (int k = 2; k < n; k++) {  // T_k = 2 s T_{k-1} - T_{k-2}
+      for (int d = 0; d < n; d++) t2[d] = (d > 0 ? 2.0L * t1[d - 1] : 0.0L) - t0[d];
+      for (int d = 0; d < n; d++) mono[d] += a[k] * t2[d];
+      t0 = t1;
+      t1 = t2;
+    }
+    long double scale = 1.0L;    // s = 2 t
+    for (int d = 0; d < n; d++) {
+      tab[(size_t)d * kErfStride + i] = (double)(mono[d] * scale);
+      scale *= 2.0L;
+    }
+  }
+  for (int i = 0; i < kLogEntries; i++) {
+    const double inv_c = (double)(1.0L / (1.0L + (i + 0.5L) / kLogEntries));
+    tab[kTabLog + 2 * i] = inv_c;
+    tab[kTabLog + 2 * i + 1] = (double)(-logl((long double)inv_c));
+  }
+  for (int j = 0; j < kExpEntries; j++) tab[kTabExp + j] = (double)exp2l((long double)j / kExpEntries);
+  TC_CUDA(cudaMemcpyToSymbol(g_math_tables, tab.data(), sizeof(double) * kTabDoubles));
+  done[device] = true;
+  return TC_OK;
 }
 
 int device_sms(int device, int* n_sm) {
@@ -953,6 +1164,14 @@ int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t
   TC_CUDA(cudaGetLastError());
   return TC_OK;
 }
+
+// optional per-kernel timing for bench.py (tc_profile_enable / tc_profile_read)
+struct Profile {
+  bool enabled = false;
+  bool recorded = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+Profile g_profile;
 
 struct DeviceGuard {
   int prev = -1;
@@ -1012,7 +1231,8 @@ int tc_table_create(tc_table** out, int mode, int n_rows, int n_r, int n_tables,
     if (!tpcf_matrix[tb]) { delete t; return fail(TC_EINVAL, "tc_table_create: NULL matrix"); }
     t->matrices[tb].assign(tpcf_matrix[tb], tpcf_matrix[tb] + (size_t)n_r * cols);
   }
-  int rc = build_layout(t, 0);
+  int rc = ensure_math_tables(device);
+  if (rc == TC_OK) rc = build_layout(t, 0);
   if (rc != TC_OK) { tc_table_destroy(t); return rc; }
   *out = t;
   return TC_OK;
@@ -1135,14 +1355,13 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   args.ngal_tile = reinterpret_cast<double*>(static_cast<char*>(workspace) + ws.parts_bytes);
 
   const int bm = 8 * ws.nt;
-  const size_t smem = (size_t)L.dev.n_pad * bm * sizeof(double) + 16;
-  int gx = (int)std::min<long long>(ws.n_tiles, n_sm);
-  int gy = 1;
-  if (ws.n_tiles < n_sm) gy = std::max(1, std::min(L.dev.n_chunks, n_sm / (int)ws.n_tiles));
-  dim3 grid(gx, gy);
+  const size_t smem = predict_smem_bytes(L.dev.n_pad, ws.nt);
+  const int gx = (int)std::min<long long>(ws.n_tiles * L.dev.n_chunks, n_sm);
+  dim3 grid(gx, 1);
 #define TC_LAUNCH(NT_)                                                                     \
   rc = t->mode == TC_MODE_AUTO ? launch_predict<NT_, TC_MODE_AUTO>(args, grid, smem, stream) \
                                : launch_predict<NT_, TC_MODE_CROSS>(args, grid, smem, stream)
+  if (g_profile.enabled) TC_CUDA(cudaEventRecord(g_profile.ev[0], stream));
   switch (ws.nt) {
     case 8: TC_LAUNCH(8); break;
     case 4: TC_LAUNCH(4); break;
@@ -1151,6 +1370,7 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   }
 #undef TC_LAUNCH
   if (rc != TC_OK) return rc;
+  if (g_profile.enabled) TC_CUDA(cudaEventRecord(g_profile.ev[1], stream));
 
   FinalizeArgs fa{};
   fa.lay = L.dev;
@@ -1171,6 +1391,28 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   dim3 fgrid((unsigned)ws.n_tiles, fy);
   finalize_kernel<<<fgrid, 256, 0, stream>>>(fa);
   TC_CUDA(cudaGetLastError());
+  if (g_profile.enabled) {
+    TC_CUDA(cudaEventRecord(g_profile.ev[2], stream));
+    g_profile.recorded = true;
+  }
+  return TC_OK;
+}
+
+int tc_profile_enable(int on) {
+  if (on && !g_profile.ev[0]) {
+    for (auto& e : g_profile.ev) TC_CUDA(cudaEventCreate(&e));
+  }
+  g_profile.enabled = on != 0;
+  g_profile.recorded = false;
+  return TC_OK;
+}
+
+int tc_profile_read(float* predict_ms, float* finalize_ms) {
+  if (!predict_ms || !finalize_ms) return fail(TC_EINVAL, "tc_profile_read: NULL output");
+  if (!g_profile.recorded) return fail(TC_EINVAL, "tc_profile_read: nothing recorded");
+  TC_CUDA(cudaEventSynchronize(g_profile.ev[2]));
+  TC_CUDA(cudaEventElapsedTime(predict_ms, g_profile.ev[0], g_profile.ev[1]));
+  TC_CUDA(cudaEventElapsedTime(finalize_ms, g_profile.ev[1], g_profile.ev[2]));
   return TC_OK;
 }
 
@@ -1258,6 +1500,19 @@ int tc_interp_apply_batch(tc_interp* it, const double* x, int64_t n_draws, const
   }
   unsigned grid = (unsigned)((n_draws + 3) / 4);
   interp_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(args);
+  TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+int tc_debug_math(int kind, const double* x, const double* y, double* out, int64_t n,
+                  void* stream) {
+  if (!x || !out || (kind != 0 && !y) || n < 0) return fail(TC_EINVAL, "tc_debug_math: bad argument");
+  if (n == 0) return TC_OK;
+  int device = 0;
+  TC_CUDA(cudaGetDevice(&device));
+  int rc = ensure_math_tables(device);
+  if (rc) return rc;
+  debug_math_kernel<<<256, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, x, y, out, n);
   TC_CUDA(cudaGetLastError());
   return TC_OK;
 }

@@ -146,9 +146,10 @@ def resolve_model(model):
         'cannot map {!r} to a kernel occupation family (zheng07, decorated zheng07)'.format(model))
 
 
-def theta_from_params(params, n_draws=None, spec=None):
+def theta_from_params(params, n_draws=None, spec=None, alloc=None):
     """``[B, 7]`` float64 array in kernel order from a dict of scalars/arrays keyed by halotools
-    parameter names.  Missing assembly-bias strengths default to 0."""
+    parameter names.  Missing assembly-bias strengths default to 0.  ``alloc(shape)`` may supply
+    the output buffer (e.g. pinned host memory)."""
     missing = [k for k in ZHENG07_KEYS if k not in params]
     if missing:
         raise ValueError('missing occupation parameters: {}'.format(', '.join(missing)))
@@ -159,7 +160,8 @@ def theta_from_params(params, n_draws=None, spec=None):
     columns = [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in THETA_KEYS]
     if n_draws is None:
         n_draws = max([c.shape[0] for c in columns if c.ndim > 0] + [1])
-    theta = np.empty((n_draws, len(THETA_KEYS)), dtype=np.float64)
+    shape = (n_draws, len(THETA_KEYS))
+    theta = np.empty(shape, dtype=np.float64) if alloc is None else alloc(shape)
     for j, column in enumerate(columns):
         theta[:, j] = column
     return theta

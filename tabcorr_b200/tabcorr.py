@@ -160,13 +160,39 @@ class DeviceTableGroup:
                 workspace.data_ptr(), workspace.numel(), stream))
 
 
+class _PinnedStage:
+    """Pinned host staging buffer whose numpy view is filled in place, then copied H2D."""
+
+    def __init__(self):
+        self.tensor = None
+
+    def __call__(self, shape):
+        torch = _torch()
+        self.tensor = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+        return self.tensor.numpy()
+
+    def to(self, device):
+        return self.tensor.to(device=device, non_blocking=True)
+
+
 def _to_device_f64(array, device):
     """Host array -> CUDA float64 tensor through pinned memory (asynchronous H2D copy)."""
     torch = _torch()
     if isinstance(array, torch.Tensor):
         return array.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
-    host = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64))
-    return host.pin_memory().to(device=device, non_blocking=True)
+    array = np.asarray(array, dtype=np.float64)
+    stage = _PinnedStage()
+    stage(array.shape)[...] = array
+    return stage.to(device)
+
+
+def _to_host(tensor):
+    """CUDA tensor -> numpy array through pinned memory (one asynchronous D2H copy + sync)."""
+    torch = _torch()
+    host = torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+    host.copy_(tensor, non_blocking=True)
+    torch.cuda.current_stream(tensor.device).synchronize()
+    return host.numpy()
 
 
 class TabCorr:
@@ -298,7 +324,9 @@ class TabCorr:
         if isinstance(params, dict):
             decorated = all(k in params for k in ASSEMBIAS_KEYS)
             spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
-            theta = _to_device_f64(theta_from_params(params, None, spec), group.device)
+            stage = _PinnedStage()
+            theta_from_params(params, None, spec, alloc=stage)
+            theta = stage.to(group.device)
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             theta = _to_device_f64(params, group.device)
@@ -358,7 +386,7 @@ class TabCorr:
         """``ngal [B, 1|2]``, ``xi [B, R, C]`` device tensors -> reference-shaped outputs."""
         shape = tuple(self.tpcf_shape)
         if as_numpy:
-            ngal, xi = ngal.cpu().numpy(), xi.cpu().numpy()
+            ngal, xi = _to_host(ngal), _to_host(xi)
         if not separate:
             return ngal[:, 0], xi[:, :, 0].reshape((xi.shape[0],) + shape)
         ngal_keys, xi_keys = self._separate_keys()

@@ -323,3 +323,28 @@ def test_unsupported_model_fails_loudly(tb, golden_dir):
         halotab.predict(Other(), check_consistency=False)
     with pytest.raises(NotImplementedError):
         halotab.predict(tb.PrebuiltHodModelFactory('zheng07', threshold=-18), foo=1)
+
+
+def test_device_math_accuracy(tb):
+    """The table-driven erf / pow of the occupation kernel against mpmath-free references:
+    scipy.special.erf (absolute error bar 3e-15) and numpy power (relative 1e-13)."""
+    import torch
+    from scipy.special import erf
+    from tabcorr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-7, 7, 200000), np.linspace(-6.3, 6.3, 100001),
+                        [-100.0, 100.0, 0.0, -6.0, 6.0, 5.999999, -5.75, -1e-300]])
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xd)
+    _lib.check(lib.tc_debug_math(0, xd.data_ptr(), None, out.data_ptr(), len(x), None))
+    got = out.cpu().numpy()
+    assert np.all((got >= 0) & (got <= 1))
+    assert np.max(np.abs(got - 0.5 * (1 + erf(x)))) < 3e-15
+    t = 10**rng.uniform(-25, 8, 300000)
+    alpha = rng.uniform(0.3, 2.5, len(t))
+    td, ad = torch.from_numpy(t).cuda(), torch.from_numpy(alpha).cuda()
+    out = torch.empty_like(td)
+    _lib.check(lib.tc_debug_math(1, td.data_ptr(), ad.data_ptr(), out.data_ptr(), len(t), None))
+    got = out.cpu().numpy()
+    assert np.max(np.abs(got / t**alpha - 1)) < 1e-13
