@@ -69,7 +69,7 @@ int fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------
 constexpr int kThreads = 384;        // 12 warps, 3 per SM sub-partition, <= 170 registers each
 constexpr int kWarps = kThreads / 32;
-constexpr int kGroupRows = 4;        // rows (secondary-percentile bins) sharing one mass bin
+constexpr int kGroupRows = 2;        // rows (secondary-percentile bins) sharing one mass bin
 constexpr int kSmemLimit = 227 * 1024;
 
 // One unit of contraction work.  Auto mode: radial bin `r`, 16-row tiles [mt0, mt1); for tile mt
@@ -83,6 +83,7 @@ struct OccPlan {       // device pointers, one per (layout, n_gauss)
   int n_groups;
   int n_gauss;
   int n_gauss_pad;          // n_gauss rounded up to even; the padding node has zero weight
+  int zero_row;             // index of an all-zero row of row_c (second row of 1-row groups)
   const double* node_logm;  // [n_groups, G]  log10 of the node masses
   const double* node_m;     // [n_groups, G]  node masses
   const int* grp_rows;      // [n_groups, kGroupRows] padded row index or -1
@@ -144,7 +145,7 @@ __device__ __forceinline__ int widx(int i, int b) {
 // The tables are computed on the host in long double when the library first touches a device.
 // ------------------------------------------------------------------------------------------
 constexpr int kErfDeg = 13;
-constexpr int kErfIntervals = 25;
+constexpr int kErfIntervals = 27;                               // 25 polynomial + 2 saturated
 constexpr int kErfStride = 32;                                  // doubles per coefficient row
 constexpr int kErfDoubles = (kErfDeg + 1) * kErfStride;         // 448
 constexpr int kLogEntries = 128;                                // (1 / c_i, ln c_i) pairs
@@ -160,26 +161,25 @@ __device__ __forceinline__ void load_math_tables(double* tab) {
   for (int i = threadIdx.x; i < kTabDoubles; i += blockDim.x) tab[i] = g_math_tables[i];
 }
 
-// 0.5 (1 + erf(x)), clamped to [0, 1]
+// 0.5 (1 + erf(x)) for |x| < 2^49.  Interval i = rint(2 x + 12) is centred at x = -6 + i / 2;
+// intervals below 0 / above 24 map to two extra table columns holding the constants 0 and 1, so
+// the range clamp is two integer min/max instead of double-precision ones (7 instructions each).
 __device__ __forceinline__ double half_erfc_neg(double x, const double* __restrict__ tab) {
-  double u = fma(x, 2.0, 12.0);              // interval index: centres at x = -6 + i / 2
-  u = fmin(fmax(u, 0.0), (double)(kErfIntervals - 1));
-  const double v = u + kRoundMagic;
+  const double v = fma(x, 2.0, 12.0 + kRoundMagic);
   const int i = __double2loint(v);
-  const double t = u - (v - kRoundMagic);    // in [-0.5, 0.5]
-  const double* c = tab + i;
+  const double t = fma(x, 2.0, 12.0 - (v - kRoundMagic));   // in [-0.5, 0.5]
+  const double* c = tab + (min(max(i, -1), kErfIntervals - 2) + 1);
   double p = c[kErfDeg * kErfStride];
 #pragma unroll
   for (int k = kErfDeg - 1; k >= 0; k--) p = fma(p, t, c[k * kErfStride]);
-  return fmin(fmax(p, 0.0), 1.0);
+  return p;
 }
 
-// t^alpha for t > 0 (normal double)
+// t^alpha for t > 0 (normal double); |alpha ln t| beyond ~690 saturates instead of overflowing
 __device__ __forceinline__ double pow_pos(double t, double alpha, const double* __restrict__ tab) {
-  const long long bits = __double_as_longlong(t);
-  const int e = (int)(bits >> 52) - 1023;
-  const int i = (int)(bits >> 45) & (kLogEntries - 1);
-  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const int hi = __double2hiint(t);
+  const int i = (hi >> 13) & (kLogEntries - 1);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(t));
   const double2 lc = *reinterpret_cast<const double2*>(tab + kTabLog + 2 * i);
   const double r = fma(m, lc.x, -1.0);       // |r| < 2^-8
   double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
@@ -188,11 +188,10 @@ __device__ __forceinline__ double pow_pos(double t, double alpha, const double* 
   p = fma(p, r, 1.0 / 3.0);
   p = fma(p, r, -0.5);
   p = fma(p, r, 1.0);
-  const double lg = fma((double)e, 0.6931471805599453094, fma(p, r, lc.y));
-  double y = alpha * lg;
-  y = fmin(fmax(y, -700.0), 700.0);
+  const double e = (double)((hi >> 20) - 1023);
+  const double lg = fma(e, 0.6931471805599453094, fma(p, r, lc.y));
+  const double y = alpha * lg;
   const double v = fma(y, 46.16624130844682903551 /* 32 / ln 2 */, kRoundMagic);
-  const int k = __double2loint(v);
   const double kf = v - kRoundMagic;
   double q = fma(-kf, 0.0216608493924982895 /* hi(ln2 / 32) */, y);
   q = fma(-kf, 1.4168872360403518e-18 /* lo */, q);
@@ -202,8 +201,10 @@ __device__ __forceinline__ double pow_pos(double t, double alpha, const double* 
   w = fma(w, q, 0.5);
   w = fma(w, q, 1.0);
   w = fma(w, q, 1.0);
-  const double res = tab[kTabExp + (k & (kExpEntries - 1))] * w;
-  return __longlong_as_double(__double_as_longlong(res) + ((long long)(k >> 5) << 52));
+  const int k = __double2loint(v);
+  const double res = tab[kTabExp + (k & (kExpEntries - 1))] * w;   // in [1, 2) * (1 +- 0.011)
+  const int scale = min(max(k >> 5, -1000), 1000);
+  return __hiloint2double(__double2hiint(res) + (scale << 20), __double2loint(res));
 }
 
 struct DrawParams {
@@ -223,26 +224,28 @@ __device__ __forceinline__ DrawParams load_draw(const double* __restrict__ theta
 }
 
 // Heaviside assembly bias (halotools HeavisideAssembias, call site tabcorr.py:556-563): haloes above
-// the split percentile get +delta, the others -delta (1 - s) / s; delta is the strength times the
-// largest perturbation that keeps both sub-populations inside [lo, hi].
-__device__ __forceinline__ double decorate(double f, double strength, double split, double lo,
-                                           double hi, bool type1) {
-  if (!(split > 0.0 && split < 1.0) || !(f > lo && f < hi)) return f;
-  double ratio = split / (1.0 - split);
-  double delta;
-  if (strength > 0.0) {
-    delta = strength * fmin(hi - f, ratio * (f - lo));
-  } else {
-    delta = -strength * fmax(lo - f, ratio * (f - hi));
-  }
-  return type1 ? f + delta : f - delta * (1.0 - split) / split;
+// the split percentile get +delta, the others -delta (1 - s) / s; delta is the strength A times the
+// largest perturbation that keeps both sub-populations inside [lo, hi]:
+//   A > 0:  delta = A min(hi - f, s / (1 - s) (f - lo))
+//   A <= 0: delta = -A max(lo - f, s / (1 - s) (f - hi)) = A min(f - lo, s / (1 - s) (hi - f))
+// Returns delta (0 where the baseline is on a bound or the split is degenerate); lo = 0.
+__device__ __forceinline__ double assembias_delta(double f, double strength, double ratio,
+                                                  double hi, bool split_ok) {
+  const double up = hi - f, down = f;
+  const bool positive = strength > 0.0;
+  const double p = positive ? up : down;
+  const double q = ratio * (positive ? down : up);
+  const double m = p < q ? p : q;
+  const bool inside = split_ok && f > 0.0 && f < hi;
+  return inside ? strength * m : 0.0;
 }
 
 // Baseline occupation of one quadrature node.
-__device__ __forceinline__ double baseline_occupation(bool is_sat, double logm, double mass,
-                                                      const DrawParams& p, int modulate,
+template <bool SAT, bool MODULATE>
+__device__ __forceinline__ double baseline_occupation(double logm, double mass,
+                                                      const DrawParams& p,
                                                       const double* __restrict__ tab) {
-  if (!is_sat) {
+  if (!SAT) {
     // Zheng07Cens: 0.5 (1 + erf((log10 M - logMmin) / sigma_logM))
     return half_erfc_neg((logm - p.logMmin) * p.inv_sigma, tab);
   }
@@ -251,61 +254,102 @@ __device__ __forceinline__ double baseline_occupation(bool is_sat, double logm, 
   const bool pos = d > 0.0;
   double f = pow_pos(pos ? d * p.inv_m1 : 1.0, p.alpha, tab);
   f = pos ? f : 0.0;
-  if (modulate) f *= half_erfc_neg((logm - p.logMmin) * p.inv_sigma, tab);
+  if (MODULATE) f *= half_erfc_neg((logm - p.logMmin) * p.inv_sigma, tab);
   return f;
 }
 
+// One mass-bin group: the baseline occupation at each quadrature node is evaluated once (two nodes
+// per iteration for instruction-level parallelism; the plan pads G to an even count with
+// zero-weight nodes) and accumulated into the two rows (secondary-percentile bins) of the group.
+// A group with a single row points its second row at an all-zero weight row.
+template <bool SAT, bool DECORATED, bool MODULATE>
+__device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, const DrawParams& p,
+                                                 double split, const double* __restrict__ tab,
+                                                 double& occ0, double& occ1) {
+  const int G = plan.n_gauss_pad;
+  const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
+  const double* c0 = plan.row_c + (size_t)row0 * G;
+  const double* c1 = plan.row_c + (size_t)(row1 >= 0 ? row1 : plan.zero_row) * G;
+  const double* node = (SAT && !MODULATE ? plan.node_m : plan.node_logm) + (size_t)grp * G;
+  const double* node2 = plan.node_m + (size_t)grp * G;
+  double k0 = 0.0, k1 = 0.0, ratio = 0.0;
+  bool split_ok = false;
+  if (DECORATED) {
+    split_ok = split > 0.0 && split < 1.0;
+    ratio = split / (1.0 - split);
+    const double down = -(1.0 - split) / split;
+    k0 = plan.row_pct[row0] > split ? 1.0 : down;
+    k1 = (row1 >= 0 && plan.row_pct[row1] > split) ? 1.0 : down;
+  }
+  const double hi = SAT ? CUDART_INF : 1.0;
+  const double strength = SAT ? p.a_sat : p.a_cen;
+  double a0 = 0.0, a1 = 0.0;
+  for (int g = 0; g < G; g += 2) {
+    double fa, fb;
+    if (SAT && MODULATE) {
+      fa = baseline_occupation<SAT, MODULATE>(node[g], node2[g], p, tab);
+      fb = baseline_occupation<SAT, MODULATE>(node[g + 1], node2[g + 1], p, tab);
+    } else {
+      fa = baseline_occupation<SAT, MODULATE>(node[g], node[g], p, tab);
+      fb = baseline_occupation<SAT, MODULATE>(node[g + 1], node[g + 1], p, tab);
+    }
+    if (DECORATED) {
+      const double da = assembias_delta(fa, strength, ratio, hi, split_ok);
+      const double db = assembias_delta(fb, strength, ratio, hi, split_ok);
+      a0 = fma(c0[g], fma(k0, da, fa), a0);
+      a1 = fma(c1[g], fma(k1, da, fa), a1);
+      a0 = fma(c0[g + 1], fma(k0, db, fb), a0);
+      a1 = fma(c1[g + 1], fma(k1, db, fb), a1);
+    } else {
+      a0 = fma(c0[g], fa, a0);
+      a1 = fma(c1[g], fa, a1);
+      a0 = fma(c0[g + 1], fb, a0);
+      a1 = fma(c1[g + 1], fb, a1);
+    }
+  }
+  occ0 = a0;
+  occ1 = a1;
+}
+
 // Occupation phase for one tile of BM = 8 NT draws: thread (b = tid % BM, lane group tid / BM)
-// evaluates the baseline zheng07 occupations of its mass-bin groups at the quadrature nodes once
-// (two nodes per iteration for instruction-level parallelism; the plan pads G to an even count
-// with zero-weight nodes) and accumulates them into the (up to kGroupRows) rows sharing that mass
-// bin.  store(padded_row, b, occ, n_h) receives the Gauss-Legendre averaged occupation.
-template <int BM, typename Store>
-__device__ __forceinline__ void occupation_tile(const OccPlan& plan, const tc_model& model,
-                                                const double* __restrict__ theta, long long b0,
-                                                long long n_draws, const double* __restrict__ tab,
-                                                Store store) {
+// handles draw b and every (kThreads / BM)-th mass-bin group.  Groups are ordered centrals first,
+// so the galaxy type is uniform over a warp.  store(padded_row, b, occ, n_h) receives the
+// Gauss-Legendre averaged occupation of each row.
+template <int BM, bool DECORATED, bool MODULATE, typename Store>
+__device__ __forceinline__ void occupation_tile_impl(const OccPlan& plan, const tc_model& model,
+                                                     const double* __restrict__ theta,
+                                                     long long b0, long long n_draws,
+                                                     const double* __restrict__ tab, Store store) {
   const int b = threadIdx.x % BM;
   const int gl = threadIdx.x / BM;
   constexpr int n_gl = kThreads / BM;
   long long draw = b0 + b;
   if (draw >= n_draws) draw = n_draws - 1;  // tail tile: recompute the last draw, never stored
-  const DrawParams p = load_draw(theta + draw * TC_N_THETA);
-  const int G = plan.n_gauss_pad;
+  DrawParams p = load_draw(theta + draw * TC_N_THETA);
+  if (!model.decorated) p.a_cen = p.a_sat = 0.0;  // strengths are ignored unless decorated
   for (int grp = gl; grp < plan.n_groups; grp += n_gl) {
-    const int* rows = plan.grp_rows + grp * kGroupRows;
-    int row[kGroupRows];
-#pragma unroll
-    for (int s = 0; s < kGroupRows; s++) row[s] = rows[s];
-    const bool is_sat = plan.grp_is_sat[grp] != 0;
-    bool type1[kGroupRows];
-#pragma unroll
-    for (int s = 0; s < kGroupRows; s++)
-      type1[s] = row[s] >= 0 ? plan.row_pct[row[s]] > model.split : false;
-    double acc[kGroupRows] = {0.0, 0.0, 0.0, 0.0};
-    const double* logm = plan.node_logm + (size_t)grp * G;
-    const double* mass = plan.node_m + (size_t)grp * G;
-    const double hi = is_sat ? CUDART_INF : 1.0;
-    const double strength = is_sat ? p.a_sat : p.a_cen;
-    for (int g = 0; g < G; g += 2) {
-      const double f0 = baseline_occupation(is_sat, logm[g], mass[g], p,
-                                            model.modulate_with_cenocc, tab);
-      const double f1 = baseline_occupation(is_sat, logm[g + 1], mass[g + 1], p,
-                                            model.modulate_with_cenocc, tab);
-#pragma unroll
-      for (int s = 0; s < kGroupRows; s++) {
-        if (row[s] >= 0) {
-          const double* c = plan.row_c + (size_t)row[s] * G + g;
-          const double fs0 = model.decorated ? decorate(f0, strength, model.split, 0.0, hi, type1[s]) : f0;
-          const double fs1 = model.decorated ? decorate(f1, strength, model.split, 0.0, hi, type1[s]) : f1;
-          acc[s] = fma(c[0], fs0, acc[s]);
-          acc[s] = fma(c[1], fs1, acc[s]);
-        }
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < kGroupRows; s++)
-      if (row[s] >= 0) store(row[s], b, acc[s], plan.row_nh[row[s]]);
+    double occ0, occ1;
+    if (plan.grp_is_sat[grp])
+      occupation_group<true, DECORATED, MODULATE>(plan, grp, p, model.split, tab, occ0, occ1);
+    else
+      occupation_group<false, DECORATED, false>(plan, grp, p, model.split, tab, occ0, occ1);
+    const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
+    store(row0, b, occ0, plan.row_nh[row0]);
+    if (row1 >= 0) store(row1, b, occ1, plan.row_nh[row1]);
+  }
+}
+
+template <int BM, typename Store>
+__device__ __forceinline__ void occupation_tile(const OccPlan& plan, const tc_model& model,
+                                                const double* __restrict__ theta, long long b0,
+                                                long long n_draws, const double* __restrict__ tab,
+                                                Store store) {
+  if (model.modulate_with_cenocc) {   // rare: keep one generic instantiation
+    occupation_tile_impl<BM, true, true>(plan, model, theta, b0, n_draws, tab, store);
+  } else if (model.decorated) {
+    occupation_tile_impl<BM, true, false>(plan, model, theta, b0, n_draws, tab, store);
+  } else {
+    occupation_tile_impl<BM, false, false>(plan, model, theta, b0, n_draws, tab, store);
   }
 }
 
@@ -998,7 +1042,7 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   const int GP = (G + 1) / 2 * 2;  // the kernel evaluates two nodes per iteration
   std::vector<double> node_logm((size_t)n_groups * GP), node_m((size_t)n_groups * GP);
   std::vector<int> grp_rows((size_t)n_groups * kGroupRows, -1), grp_is_sat(n_groups);
-  std::vector<double> row_c((size_t)n_pad * GP, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
+  std::vector<double> row_c((size_t)(n_pad + 1) * GP, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
   for (int q = 0; q < n_groups; q++) {
     const Group& gq = groups[q];
     grp_is_sat[q] = gq.sat;
@@ -1037,6 +1081,7 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   ph.dev.n_groups = n_groups;
   ph.dev.n_gauss = G;
   ph.dev.n_gauss_pad = GP;
+  ph.dev.zero_row = n_pad;
   ph.dev.node_logm = d_logm;
   ph.dev.node_m = d_m;
   ph.dev.grp_rows = d_rows;
@@ -1091,7 +1136,8 @@ int ensure_math_tables(int device) {
   std::vector<double> tab(kTabDoubles, 0.0);
   const int n = kErfDeg + 1;
   const long double pi = 3.14159265358979323846264338327950288L;
-  for (int i = 0; i < kErfIntervals; i++) {
+  tab[kErfIntervals - 1] = 1.0;  // saturated columns: 0 below the first, 1 above the last interval
+  for (int i = 0; i < kErfIntervals - 2; i++) {
     const long double xc = -6.0L + 0.5L * i;  // x = xc + s / 4 with s in [-1, 1]; t = s / 2
     std::vector<long double> fs(n), sn(n);
     for (int j = 0; j < n; j++) {
@@ -1117,7 +1163,7 @@ int ensure_math_tables(int device) {
     }
     long double scale = 1.0L;    // s = 2 t
     for (int d = 0; d < n; d++) {
-      tab[(size_t)d * kErfStride + i] = (double)(mono[d] * scale);
+      tab[(size_t)d * kErfStride + i + 1] = (double)(mono[d] * scale);
       scale *= 2.0L;
     }
   }
