@@ -189,6 +189,8 @@ def _to_device_f64(array, device):
 def _to_host(tensor):
     """CUDA tensor -> numpy array through pinned memory (one asynchronous D2H copy + sync)."""
     torch = _torch()
+    if not tensor.is_cuda:  # already on the host (gloo tests of the gather plumbing)
+        return tensor.numpy()
     host = torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
     host.copy_(tensor, non_blocking=True)
     torch.cuda.current_stream(tensor.device).synchronize()

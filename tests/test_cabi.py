@@ -1,0 +1,94 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol the header declares.
+No compute call is made here: without a CUDA device every computing entry point must fail loudly
+(TC_ECUDA), never fall back to the host."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tabcorr_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'tabcorr_b200.h')
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tc_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    if not os.path.isfile(_lib.LIB_PATH):
+        from tabcorr_b200 import build
+        build.build()
+    return _lib.load()
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(raw, name), name
+
+
+def test_version_and_constants(lib):
+    text = open(HEADER).read()
+    assert lib.tc_version() == int(re.search(r'#define TC_VERSION (\d+)', text).group(1))
+    assert int(re.search(r'#define TC_N_THETA (\d+)', text).group(1)) == _lib.TC_N_THETA
+    assert ctypes.sizeof(_lib.tc_model) == 24  # 4 x int32 + double, as declared in the header
+
+
+def test_argument_errors_do_not_need_a_device(lib):
+    handle = ctypes.c_void_p()
+    # bad mode / NULL arrays are rejected before any CUDA call
+    assert lib.tc_table_create(ctypes.byref(handle), 7, 4, 1, 1, None, None, None, None, None,
+                               None, None, 0) == -1
+    assert b'mode' in lib.tc_last_error()
+    assert lib.tc_table_create(ctypes.byref(handle), 0, 4, 1, 1, None, None, None, None, None,
+                               None, None, 0) == -1
+    assert lib.tc_table_destroy(None) == 0
+    assert lib.tc_interp_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    n = 4
+    ones = np.ones(n)
+    is_sat = np.array([0, 0, 1, 1], dtype=np.int32)
+    matrix = np.ones((1, n * (n + 1) // 2))
+    c_double_p = ctypes.POINTER(ctypes.c_double)
+    mats = (c_double_p * 1)(_lib.as_double_p(matrix))
+    handle = ctypes.c_void_p()
+    status = lib.tc_table_create(
+        ctypes.byref(handle), 0, n, 1, 1, _lib.as_double_p(ones), _lib.as_double_p(ones),
+        _lib.as_double_p(ones * 2), _lib.as_double_p(ones * 0.5), None, _lib.as_int32_p(is_sat),
+        mats, 0)
+    assert status == -2  # TC_ECUDA
+    assert not handle.value
+    with pytest.raises(_lib.TabCorrB200Error):
+        _lib.check(status)
+    peak = ctypes.c_double()
+    assert lib.tc_measure_dmma_peak(0, ctypes.byref(peak)) == -2
+
+
+def test_python_api_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    import tabcorr_b200
+    from tabcorr_b200 import synthetic
+    tab = synthetic.make_table(n_mass=4, n_sec=1, n_r=3)
+    halotab = tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'],
+                                               tab['tpcf_shape'], tab['attrs'])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        halotab.predict_batch(synthetic.make_draws(3))

@@ -1,0 +1,120 @@
+"""World-size-2 tests of the multi-GPU plumbing on CPU (gloo): draw sharding, the one gather of the
+path, and ``predict_batch_sharded`` end to end.  The per-rank "device" here is a stand-in whose
+``predict_batch`` evaluates the numpy oracle (allowed in tests only), so that what is tested is
+exactly the host logic that runs around the CUDA path on the GPU box: shard bounds, padding of
+ragged slabs, row order after the gather, and that only ``dst`` receives the result."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tabcorr_b200 import distributed as tcd  # noqa: E402
+from tabcorr_b200 import synthetic  # noqa: E402
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 8, 100003):
+        for world in (1, 2, 3, 8):
+            bounds = [tcd.shard_bounds(n, r, world) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == n
+            for (lo, hi), (lo2, hi2) in zip(bounds[:-1], bounds[1:]):
+                assert hi == lo2 and lo <= hi
+            sizes = [hi - lo for lo, hi in bounds]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        tcd.shard_bounds(10, 2, 2)
+
+
+def test_shard_params_dict_and_array():
+    draws = synthetic.make_draws(11, seed=3)
+    draws['scalar'] = 0.5
+    part = tcd.shard_params(draws, 1, 2)
+    assert len(part['logMmin']) == 6 and part['scalar'] == 0.5
+    assert np.array_equal(part['alpha'], draws['alpha'][5:])
+    arr = np.arange(22.0).reshape(11, 2)
+    assert np.array_equal(tcd.shard_params(arr, 0, 2), arr[:5])
+
+
+class OracleBackedTable:
+    """Stand-in for a device table in the gloo tests: same ``predict_batch`` contract (torch
+    tensors when ``as_numpy=False``), arithmetic by the oracle."""
+
+    def __init__(self):
+        from oracle import tabcorr_oracle as orc
+        self.orc = orc
+        tab = synthetic.make_table(n_mass=5, n_sec=2, n_r=4, seed=5)
+        self.table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+
+    def predict_batch(self, params, n_gauss_prim=10, model=None, as_numpy=True):
+        n = len(params['logMmin'])
+        ngal, xi = np.empty(n), np.empty((n, 4))
+        for i in range(n):
+            m = self.orc.Zheng07Oracle({k: float(v[i]) for k, v in params.items()})
+            ngal[i], xi[i] = self.orc.predict(
+                self.table, self.orc.mean_occupation(self.table, m, n_gauss_prim))
+        if as_numpy:
+            return ngal, xi
+        return torch.from_numpy(ngal), torch.from_numpy(xi)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_draws, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # 1. raw gather of ragged slabs
+        lo, hi = tcd.shard_bounds(n_draws, rank, world)
+        local = torch.arange(lo, hi, dtype=torch.float64)[:, None] * torch.tensor([[1.0, -2.0]])
+        full = tcd.gather_rows(local, n_draws, dst=0)
+        if rank == 0:
+            assert full.shape == (n_draws, 2)
+            assert torch.equal(full[:, 0], torch.arange(n_draws, dtype=torch.float64))
+            assert torch.equal(full[:, 1], -2.0 * torch.arange(n_draws, dtype=torch.float64))
+        else:
+            assert full is None
+        # 2. the sharded prediction: every rank holds all draws, evaluates its slice
+        halotab = OracleBackedTable()
+        draws = synthetic.make_draws(n_draws, seed=21)
+        result = tcd.predict_batch_sharded(halotab, draws, n_gauss_prim=4, dst=0)
+        if rank == 0:
+            np.save(os.path.join(out_dir, 'ngal.npy'), result[0])
+            np.save(os.path.join(out_dir, 'xi.npy'), result[1])
+        else:
+            assert result is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_draws', [9, 16])
+def test_world_size_2_gather_equals_single_process(tmp_path, n_draws):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_draws, str(tmp_path)), nprocs=2, join=True)
+    ngal = np.load(tmp_path / 'ngal.npy')
+    xi = np.load(tmp_path / 'xi.npy')
+    single = OracleBackedTable().predict_batch(synthetic.make_draws(n_draws, seed=21),
+                                               n_gauss_prim=4)
+    # same per-draw arithmetic whatever the partition: bitwise equality
+    assert np.array_equal(ngal, single[0])
+    assert np.array_equal(xi, single[1])
+
+
+def test_single_process_passthrough():
+    local = torch.ones((3, 2), dtype=torch.float64)
+    assert tcd.gather_rows(local, 3) is local
