@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -69,6 +70,7 @@ int fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------
 constexpr int kThreads = 384;        // 12 warps, 3 per SM sub-partition, <= 170 registers each
 constexpr int kWarps = kThreads / 32;
+constexpr int kOccUnroll = 5;        // quadrature nodes in flight per lane (n_gauss_prim = 10 default)
 constexpr int kGroupRows = 2;        // rows (secondary-percentile bins) sharing one mass bin
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -81,8 +83,10 @@ struct Chunk {
 
 struct OccPlan {       // device pointers, one per (layout, n_gauss)
   int n_groups;
+  int n_cen_groups;         // groups are ordered centrals first
   int n_gauss;
-  int n_gauss_pad;          // n_gauss rounded up to even; the padding node has zero weight
+  int n_gauss_pad;          // n_gauss rounded up to a multiple of `unroll`; padding nodes have zero weight
+  int unroll;               // nodes evaluated per iteration: kOccUnroll when it divides n_gauss, else 2
   int zero_row;             // index of an all-zero row of row_c (second row of 1-row groups)
   const double* node_logm;  // [n_groups, G]  log10 of the node masses
   const double* node_m;     // [n_groups, G]  node masses
@@ -258,11 +262,12 @@ __device__ __forceinline__ double baseline_occupation(double logm, double mass,
   return f;
 }
 
-// One mass-bin group: the baseline occupation at each quadrature node is evaluated once (two nodes
-// per iteration for instruction-level parallelism; the plan pads G to an even count with
+// One mass-bin group: the baseline occupation at each quadrature node is evaluated once (U nodes
+// per iteration as independent dependency chains -- beside DMMA warps a dependent DFMA gets an
+// issue turn only every ~24-32 cycles, tools/fp64_mix.cu; the plan pads G to a multiple of U with
 // zero-weight nodes) and accumulated into the two rows (secondary-percentile bins) of the group.
 // A group with a single row points its second row at an all-zero weight row.
-template <bool SAT, bool DECORATED, bool MODULATE>
+template <bool SAT, bool DECORATED, bool MODULATE, int U>
 __device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, const DrawParams& p,
                                                  double split, const double* __restrict__ tab,
                                                  double& occ0, double& occ1) {
@@ -284,72 +289,103 @@ __device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, c
   const double hi = SAT ? CUDART_INF : 1.0;
   const double strength = SAT ? p.a_sat : p.a_cen;
   double a0 = 0.0, a1 = 0.0;
-  for (int g = 0; g < G; g += 2) {
-    double fa, fb;
-    if (SAT && MODULATE) {
-      fa = baseline_occupation<SAT, MODULATE>(node[g], node2[g], p, tab);
-      fb = baseline_occupation<SAT, MODULATE>(node[g + 1], node2[g + 1], p, tab);
-    } else {
-      fa = baseline_occupation<SAT, MODULATE>(node[g], node[g], p, tab);
-      fb = baseline_occupation<SAT, MODULATE>(node[g + 1], node[g + 1], p, tab);
-    }
-    if (DECORATED) {
-      const double da = assembias_delta(fa, strength, ratio, hi, split_ok);
-      const double db = assembias_delta(fb, strength, ratio, hi, split_ok);
-      a0 = fma(c0[g], fma(k0, da, fa), a0);
-      a1 = fma(c1[g], fma(k1, da, fa), a1);
-      a0 = fma(c0[g + 1], fma(k0, db, fb), a0);
-      a1 = fma(c1[g + 1], fma(k1, db, fb), a1);
-    } else {
-      a0 = fma(c0[g], fa, a0);
-      a1 = fma(c1[g], fa, a1);
-      a0 = fma(c0[g + 1], fb, a0);
-      a1 = fma(c1[g + 1], fb, a1);
+  for (int g = 0; g < G; g += U) {
+    double f[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      f[u] = baseline_occupation<SAT, MODULATE>(node[g + u], SAT && MODULATE ? node2[g + u]
+                                                                             : node[g + u], p, tab);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (DECORATED) {
+        const double d = assembias_delta(f[u], strength, ratio, hi, split_ok);
+        a0 = fma(c0[g + u], fma(k0, d, f[u]), a0);
+        a1 = fma(c1[g + u], fma(k1, d, f[u]), a1);
+      } else {
+        a0 = fma(c0[g + u], f[u], a0);
+        a1 = fma(c1[g + u], f[u], a1);
+      }
     }
   }
   occ0 = a0;
   occ1 = a1;
 }
 
-// Occupation phase for one tile of BM = 8 NT draws: thread (b = tid % BM, lane group tid / BM)
-// handles draw b and every (kThreads / BM)-th mass-bin group.  Groups are ordered centrals first,
-// so the galaxy type is uniform over a warp.  store(padded_row, b, occ, n_h) receives the
-// Gauss-Legendre averaged occupation of each row.
-template <int BM, bool DECORATED, bool MODULATE, typename Store>
-__device__ __forceinline__ void occupation_tile_impl(const OccPlan& plan, const tc_model& model,
-                                                     const double* __restrict__ theta,
-                                                     long long b0, long long n_draws,
+// Occupation work item of one warp: the 8 draws of one n-tile (lane & 7) times the mass-bin groups
+// [g_begin, g_end), four groups in flight per warp (lane >> 3).  A range never mixes centrals and
+// satellites (groups are ordered centrals first), so the galaxy type is warp-uniform.
+// store(padded_row, occ, n_h) receives the Gauss-Legendre averaged occupation of each row.
+template <bool DECORATED, bool MODULATE, int U, typename Store>
+__device__ __forceinline__ void occupation_item_impl(const OccPlan& plan, const tc_model& model,
+                                                     const double* __restrict__ theta_row,
+                                                     int g_begin, int g_end,
                                                      const double* __restrict__ tab, Store store) {
-  const int b = threadIdx.x % BM;
-  const int gl = threadIdx.x / BM;
-  constexpr int n_gl = kThreads / BM;
-  long long draw = b0 + b;
-  if (draw >= n_draws) draw = n_draws - 1;  // tail tile: recompute the last draw, never stored
-  DrawParams p = load_draw(theta + draw * TC_N_THETA);
+  DrawParams p = load_draw(theta_row);
   if (!model.decorated) p.a_cen = p.a_sat = 0.0;  // strengths are ignored unless decorated
-  for (int grp = gl; grp < plan.n_groups; grp += n_gl) {
+  const bool sat = g_begin >= plan.n_cen_groups;
+  for (int grp = g_begin + (threadIdx.x >> 3 & 3); grp < g_end; grp += 4) {
     double occ0, occ1;
-    if (plan.grp_is_sat[grp])
-      occupation_group<true, DECORATED, MODULATE>(plan, grp, p, model.split, tab, occ0, occ1);
+    if (sat)
+      occupation_group<true, DECORATED, MODULATE, U>(plan, grp, p, model.split, tab, occ0, occ1);
     else
-      occupation_group<false, DECORATED, false>(plan, grp, p, model.split, tab, occ0, occ1);
+      occupation_group<false, DECORATED, false, U>(plan, grp, p, model.split, tab, occ0, occ1);
     const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
-    store(row0, b, occ0, plan.row_nh[row0]);
-    if (row1 >= 0) store(row1, b, occ1, plan.row_nh[row1]);
+    store(row0, occ0, plan.row_nh[row0]);
+    if (row1 >= 0) store(row1, occ1, plan.row_nh[row1]);
   }
 }
 
-template <int BM, typename Store>
-__device__ __forceinline__ void occupation_tile(const OccPlan& plan, const tc_model& model,
-                                                const double* __restrict__ theta, long long b0,
-                                                long long n_draws, const double* __restrict__ tab,
+template <typename Store>
+__device__ __forceinline__ void occupation_item(const OccPlan& plan, const tc_model& model,
+                                                const double* __restrict__ theta_row, int g_begin,
+                                                int g_end, const double* __restrict__ tab,
                                                 Store store) {
   if (model.modulate_with_cenocc) {   // rare: keep one generic instantiation
-    occupation_tile_impl<BM, true, true>(plan, model, theta, b0, n_draws, tab, store);
+    occupation_item_impl<true, true, 2>(plan, model, theta_row, g_begin, g_end, tab, store);
+  } else if (plan.unroll == kOccUnroll) {
+    if (model.decorated)
+      occupation_item_impl<true, false, kOccUnroll>(plan, model, theta_row, g_begin, g_end, tab, store);
+    else
+      occupation_item_impl<false, false, kOccUnroll>(plan, model, theta_row, g_begin, g_end, tab, store);
   } else if (model.decorated) {
-    occupation_tile_impl<BM, true, false>(plan, model, theta, b0, n_draws, tab, store);
+    occupation_item_impl<true, false, 2>(plan, model, theta_row, g_begin, g_end, tab, store);
   } else {
-    occupation_tile_impl<BM, false, false>(plan, model, theta, b0, n_draws, tab, store);
+    occupation_item_impl<false, false, 2>(plan, model, theta_row, g_begin, g_end, tab, store);
+  }
+}
+
+// Group range q of n_ranges = n_ranges_cen + n_ranges_sat: each galaxy type's groups are cut into
+// pieces whose length is a multiple of 4 (the groups a warp evaluates at a time).
+__device__ __forceinline__ void occupation_range(const OccPlan& plan, int n_ranges_cen,
+                                                 int n_ranges_sat, int q, int& g_begin,
+                                                 int& g_end) {
+  const bool sat = q >= n_ranges_cen;
+  const int first = sat ? plan.n_cen_groups : 0;
+  const int count = sat ? plan.n_groups - plan.n_cen_groups : plan.n_cen_groups;
+  const int pieces = sat ? n_ranges_sat : n_ranges_cen;
+  const int piece = sat ? q - n_ranges_cen : q;
+  const int units = (count + 3) >> 2;
+  g_begin = first + min(count, 4 * (int)((long long)units * piece / pieces));
+  g_end = first + min(count, 4 * (int)((long long)units * (piece + 1) / pieces));
+}
+
+// ------------------------------------------------------------------------------------------
+// pipeline flags in shared memory: monotonically increasing counters, so a waiter can never be
+// lapped (a parity-based mbarrier can: a warp that only ran occupation items of a tile may meet
+// that tile's barrier one or two phases later)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flag_wait(const int* counter, int target) {
+  const volatile int* c = counter;
+  while (*c < target) __nanosleep(40);
+  __threadfence_block();   // acquire: order the W reads / writes that follow after the flag read
+}
+// all lanes call it after their last shared-memory access of the item
+__device__ __forceinline__ void flag_signal(int* counter, int lane) {
+  __threadfence_block();   // release: this lane's W accesses before the flag update
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicAdd(counter, 1);
   }
 }
 
@@ -366,218 +402,273 @@ struct PredictArgs {
   long long n_tiles;
   double* parts;         // [n_tiles, n_parts, BM]
   double* ngal_tile;     // [n_tiles, 2, BM]  centrals / satellites number density
+  int n_buf;             // W tiles in shared memory: 2 = occupation of tile t + 1 overlaps tile t
+  int n_ranges_cen;      // occupation items per n-tile: group ranges of centrals ...
+  int n_ranges_sat;      // ... and of satellites
+  int occ_stride;        // every occ_stride-th slot of a tile's work list is an occupation item
 };
 
+struct PredictCtrl {
+  int full[2];                  // occupation items finished, per W buffer (n_occ per tile)
+  int empty[2];                 // warps that left a tile's work list, per W buffer (kWarps per tile)
+  int next;                     // work-list cursor
+  int first_lo, last_hi;        // chunk range of the CTA's first / last tile
+  int n_local;                  // tiles this CTA works on
+  long long tile_first;
+};
+
+// One contraction chunk by one warp.  W is the draw tile in B-fragment order.
+template <int NT, int MODE>
+__device__ __forceinline__ void run_chunk(const LayoutDev& lay, const Chunk& ch,
+                                          const double* __restrict__ Ws,
+                                          double* __restrict__ parts, int lane) {
+  constexpr int BM = 8 * NT;
+  const int g = lane >> 2, tig = lane & 3;
+  if (MODE == TC_MODE_AUTO) {
+    double sums[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) sums[nt][0] = sums[nt][1] = 0.0;
+    for (int mt = ch.mt0; mt < ch.mt1; mt++) {
+      const int k_tile = 4 * (mt + 1);                 // k-steps of the full lower-triangular tile
+      const int k_end = min(k_tile, ch.k_cap);
+      // the upper 8 rows of the tile are zero in its last two k-steps: skip their DMMAs
+      const int k_both = min(k_end, k_tile - 2);
+      const double2* ap = lay.afrag +
+          ((size_t)ch.r * lay.ks_per_r + 2 * (size_t)mt * (mt + 1) + ch.k_begin) * 32 + lane;
+      const double* wk = Ws + (size_t)ch.k_begin * NT * 32 + lane;
+      double acc[2][NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+        acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
+      double2 a_next = ld_stream(ap);
+      int ks = ch.k_begin;
+      for (; ks < k_both; ks++) {
+        const double2 a = a_next;
+        ap += 32;
+        a_next = ld_stream(ap);  // the stream is padded by one k-step, always safe
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          const double b = wk[nt * 32];
+          dmma884(acc[0][nt], a.x, b);
+          dmma884(acc[1][nt], a.y, b);
+        }
+        wk += NT * 32;
+      }
+      for (; ks < k_end; ks++) {
+        const double2 a = a_next;
+        ap += 32;
+        a_next = ld_stream(ap);
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[1][nt], a.y, wk[nt * 32]);
+        wk += NT * 32;
+      }
+      // row-dot: acc[h][nt][e] = (M' W)[row = 16 mt + 8 h + g][draw = 8 nt + 2 tig + e]
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int row = 16 * mt + 8 * h + g;
+        const double* wr = Ws + (size_t)(row >> 2) * NT * 32 + (row & 3) + tig * 8;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          sums[nt][0] = fma(acc[h][nt][0], wr[nt * 32], sums[nt][0]);
+          sums[nt][1] = fma(acc[h][nt][1], wr[nt * 32 + 4], sums[nt][1]);
+        }
+      }
+    }
+    // fixed-order butterfly over the 8 row groups of the warp (lane xor 16, 8, 4): every lane ends
+    // with the full sums; the lanes of row group 0 store them
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double v = sums[nt][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        sums[nt][e] = v;
+      }
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+        *reinterpret_cast<double2*>(parts + (size_t)ch.part_row * BM + 8 * nt + 2 * tig) =
+            make_double2(sums[nt][0], sums[nt][1]);
+    }
+  } else {
+    // cross mode: a 16-radial-bin tile times a k-range of W; the product is the output
+    const double2* ap = lay.afrag + ((size_t)ch.r * lay.ks_per_r + ch.k_begin) * 32 + lane;
+    const double* wk = Ws + (size_t)ch.k_begin * NT * 32 + lane;
+    double acc[2][NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+      acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
+    double2 a_next = ld_stream(ap);
+    for (int ks = ch.k_begin; ks < ch.k_cap; ks++) {
+      const double2 a = a_next;
+      ap += 32;
+      a_next = ld_stream(ap);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        const double b = wk[nt * 32];
+        dmma884(acc[0][nt], a.x, b);
+        dmma884(acc[1][nt], a.y, b);
+      }
+      wk += NT * 32;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+        *reinterpret_cast<double2*>(parts + (size_t)(ch.part_row + 8 * h + g) * BM + 8 * nt +
+                                    2 * tig) = make_double2(acc[h][nt][0], acc[h][nt][1]);
+  }
+}
+
+// The kernel is a barrier-free software pipeline over the CTA's draw tiles.  Work is a sequence of
+// per-tile lists of S slots that the 12 warps take from one shared cursor:
+//   slot 0                          number densities of tile j (one warp, sequential row order)
+//   every occ_stride-th next slot   occupation item (n-tile, group range) of tile j + n_buf - 1,
+//                                   written into the other W buffer
+//   the remaining slots             contraction chunks of tile j, longest first
+// Dependencies always point backwards in that sequence, so taking slots in order cannot deadlock:
+// a chunk waits until full[buf] counts all occupation items of its tile, an occupation item until
+// empty[buf] counts every warp having left the list of the tile that used its buffer before.
 template <int NT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs args) {
   constexpr int BM = 8 * NT;
   extern __shared__ __align__(16) double smem[];
-  double* Ws = smem;                                             // [n_pad / 4][NT][32]
-  double* tab = smem + (size_t)args.lay.n_pad * BM;              // math tables
-  int* sync = reinterpret_cast<int*>(tab + kTabDoubles);         // [0] chunk counter, [1..2] range
   const LayoutDev& lay = args.lay;
+  const int n_buf = args.n_buf;
+  const size_t tile_doubles = (size_t)lay.n_pad * BM;
+  double* tab = smem + n_buf * tile_doubles;                               // math tables
+  PredictCtrl* ctrl = reinterpret_cast<PredictCtrl*>(tab + kTabDoubles);
   const int tid = threadIdx.x, lane = tid & 31;
-  const int g = lane >> 2, tig = lane & 3;
 
-  for (int i = tid; i < lay.n_pad * BM; i += kThreads) Ws[i] = 0.0;  // padding rows stay zero
+  for (size_t i = tid; i < n_buf * tile_doubles; i += kThreads) smem[i] = 0.0;  // padding rows stay 0
   load_math_tables(tab);
 
-  // Work = n_tiles x n_chunks chunks, each tile's chunk list in the same (longest first) order.
-  // The grid cuts the total COST into equal contiguous ranges, so that every CTA gets the same
-  // amount of DMMA work whatever the number of draws; a CTA recomputes the weights of the (at
-  // most two) tiles it shares with its neighbours.
-  const long long tile_cost = lay.chunk_cost_prefix[lay.n_chunks];
-  const long long total_cost = tile_cost * args.n_tiles;
-  const long long cost_lo = total_cost / gridDim.x * blockIdx.x +
-                            total_cost % gridDim.x * blockIdx.x / gridDim.x;
-  const long long cost_hi = total_cost / gridDim.x * (blockIdx.x + 1) +
-                            total_cost % gridDim.x * (blockIdx.x + 1) / gridDim.x;
-  const long long tile_first = cost_lo / tile_cost;
-  const long long tile_last = (cost_hi + tile_cost - 1) / tile_cost;  // exclusive
-  __syncthreads();
-
-  for (long long tile = tile_first; tile < tile_last && tile < args.n_tiles; tile++) {
-    const long long b0 = tile * BM;
-    // chunk range [c_lo, c_hi) of this tile owned by this CTA: first chunk whose start cost is
-    // >= the range boundary (binary search in the prefix sums; boundaries of neighbouring CTAs
-    // agree because they search the same value)
-    if (tid < 2) {
-      const long long bound = (tid == 0 ? cost_lo : cost_hi) - tile * tile_cost;
+  const int n_occ = NT * (args.n_ranges_cen + args.n_ranges_sat);
+  if (tid == 0) {
+    // The grid cuts the total COST (n_tiles x per-tile chunk cost) into equal contiguous ranges, so
+    // that every CTA gets the same amount of DMMA work whatever the number of draws; a CTA
+    // recomputes the weights of the (at most two) tiles it shares with its neighbours.
+    const long long tile_cost = lay.chunk_cost_prefix[lay.n_chunks];
+    const long long total_cost = tile_cost * args.n_tiles;
+    const long long cost_lo = total_cost / gridDim.x * blockIdx.x +
+                              total_cost % gridDim.x * blockIdx.x / gridDim.x;
+    const long long cost_hi = total_cost / gridDim.x * (blockIdx.x + 1) +
+                              total_cost % gridDim.x * (blockIdx.x + 1) / gridDim.x;
+    long long tile_first = cost_lo / tile_cost;
+    long long tile_last = min((cost_hi + tile_cost - 1) / tile_cost, args.n_tiles);  // exclusive
+    // first chunk whose start cost is >= the range boundary (neighbouring CTAs search the same
+    // value, so their chunk ranges meet exactly)
+    auto first_chunk_at = [&](long long bound) {
+      if (bound <= 0) return 0;
+      if (bound >= tile_cost) return lay.n_chunks;
       int lo = 0, hi = lay.n_chunks;
-      if (bound <= 0) {
-        hi = 0;
-      } else if (bound >= tile_cost) {
-        lo = lay.n_chunks;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lay.chunk_cost_prefix[mid] < bound) lo = mid + 1; else hi = mid;
+      }
+      return lo;
+    };
+    int first_lo = first_chunk_at(cost_lo - tile_first * tile_cost);
+    if (first_lo >= lay.n_chunks) { tile_first++; first_lo = 0; }
+    int last_hi = lay.n_chunks;
+    if (tile_last > tile_first) {
+      last_hi = first_chunk_at(cost_hi - (tile_last - 1) * tile_cost);
+      if (last_hi <= (tile_last - 1 == tile_first ? first_lo : 0)) { tile_last--; last_hi = lay.n_chunks; }
+    }
+    ctrl->tile_first = tile_first;
+    ctrl->n_local = (int)max(tile_last - tile_first, 0LL);
+    ctrl->first_lo = first_lo;
+    ctrl->last_hi = last_hi;
+    ctrl->next = 0;
+    ctrl->full[0] = ctrl->full[1] = ctrl->empty[0] = ctrl->empty[1] = 0;
+  }
+  __syncthreads();
+  const int n_local = ctrl->n_local;
+  const long long tile_first = ctrl->tile_first;
+  const int first_lo = ctrl->first_lo, last_hi = ctrl->last_hi;
+  const int occ_ahead = n_buf - 1;
+  const int S = 1 + lay.n_chunks + n_occ;
+  const int stride = args.occ_stride;
+
+  int left = -occ_ahead;   // lists [.., left) have been left behind by this warp
+  int full_seen = -1;      // newest tile whose W this warp has seen complete
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&ctrl->next, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    const int list = i / S - occ_ahead;          // tile (local index) whose list the slot is in
+    const int s = i - (list + occ_ahead) * S;
+    // this warp has finished everything it took from earlier lists: release those tiles
+    const int upto = min(list, n_local);
+    for (int t = max(left, 0); t < upto; t++) flag_signal(&ctrl->empty[t % n_buf], lane);
+    left = max(left, upto);
+    if (list >= n_local) break;
+
+    int kind = 0, idx = 0;                       // 0 ngal, 1 occupation, 2 chunk
+    if (s > 0) {
+      const int u = s - 1, q = u / stride;
+      if (u - q * stride == stride - 1 && q < n_occ) { kind = 1; idx = q; }
+      else { kind = 2; idx = u - min(n_occ, q); }
+    }
+
+    if (kind == 1) {
+      // ---- occupation item idx of tile list + occ_ahead -> W[(list + occ_ahead) % n_buf] ------
+      const int j = list + occ_ahead;
+      if (j >= n_local) continue;
+      const int buf = j % n_buf;
+      if (j >= n_buf) flag_wait(&ctrl->empty[buf], (j / n_buf) * kWarps);
+      double* Ws = smem + buf * tile_doubles;
+      const int nt = idx % NT, q = idx / NT;
+      const int b = 8 * nt + (lane & 7);
+      long long draw = (tile_first + j) * BM + b;
+      if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: recompute the last draw
+      if (args.theta != nullptr) {
+        int g_begin, g_end;
+        occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
+        occupation_item(args.plan, args.model, args.theta + draw * TC_N_THETA, g_begin, g_end, tab,
+                        [&](int row, double occ, double nh) { Ws[widx<NT>(row, b)] = occ * nh; });
       } else {
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (lay.chunk_cost_prefix[mid] < bound) lo = mid + 1; else hi = mid;
+        const int n_q = args.n_ranges_cen + args.n_ranges_sat;
+        const int r_begin = (int)((long long)lay.n_pad * q / n_q);
+        const int r_end = (int)((long long)lay.n_pad * (q + 1) / n_q);
+        for (int row = r_begin + (lane >> 3); row < r_end; row += 4) {
+          const int src = lay.pad_to_row[row];
+          if (src >= 0)
+            Ws[widx<NT>(row, b)] = args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row];
         }
       }
-      sync[1 + tid] = lo < hi ? lo : hi;
-    }
-    __syncthreads();
-    const int c_lo = sync[1], c_hi = sync[2];
-    if (c_lo >= c_hi) {   // the range boundary fell inside this tile's last chunk: nothing here
-      __syncthreads();
+      flag_signal(&ctrl->full[buf], lane);
       continue;
     }
-    // ---- phase 1: tracer weights W[row, draw] = occ * n_h into shared memory ---------------
-    if (args.theta != nullptr) {
-      occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws, tab,
-                          [&](int row, int b, double occ, double nh) {
-                            Ws[widx<NT>(row, b)] = occ * nh;
-                          });
+
+    if (list < 0) continue;                      // prologue lists hold occupation items only
+    const int c_lo = list == 0 ? first_lo : 0;
+    const int c_hi = list == n_local - 1 ? last_hi : lay.n_chunks;
+    if (kind == 0 ? c_lo != 0 : (idx < c_lo || idx >= c_hi)) continue;
+    const int buf = list % n_buf;
+    if (full_seen < list) {
+      flag_wait(&ctrl->full[buf], (list / n_buf + 1) * n_occ);
+      full_seen = list;
+    }
+    const double* Ws = smem + buf * tile_doubles;
+    const long long tile = tile_first + list;
+
+    if (kind == 0) {
+      // ---- number densities (by the CTA that owns the tile's first chunk) ---------------------
+      for (int b = lane; b < BM; b += 32) {
+        double nc = 0.0, ns = 0.0;
+        for (int r = 0; r < lay.nc_pad; r++) nc += Ws[widx<NT>(r, b)];
+        for (int r = lay.nc_pad; r < lay.n_pad; r++) ns += Ws[widx<NT>(r, b)];
+        args.ngal_tile[(tile * 2 + 0) * BM + b] = nc;
+        args.ngal_tile[(tile * 2 + 1) * BM + b] = ns;
+      }
     } else {
-      for (int i = tid; i < lay.n_pad * BM; i += kThreads) {
-        int row = i / BM, b = i % BM;
-        int src = lay.pad_to_row[row];
-        long long draw = b0 + b < args.n_draws ? b0 + b : args.n_draws - 1;
-        if (src >= 0)
-          Ws[widx<NT>(row, b)] = args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row];
-      }
+      const Chunk ch = lay.chunks[idx];
+      run_chunk<NT, MODE>(lay, ch, Ws, args.parts + (size_t)tile * lay.n_parts * BM, lane);
     }
-    if (tid == 0) sync[0] = c_lo;
-    __syncthreads();
-
-    // ---- number densities (written by the CTA that owns the tile's first chunk) -------------
-    if (c_lo == 0 && tid < BM) {
-      double nc = 0.0, ns = 0.0;
-      for (int i = 0; i < lay.nc_pad; i++) nc += Ws[widx<NT>(i, tid)];
-      for (int i = lay.nc_pad; i < lay.n_pad; i++) ns += Ws[widx<NT>(i, tid)];
-      args.ngal_tile[(tile * 2 + 0) * BM + tid] = nc;
-      args.ngal_tile[(tile * 2 + 1) * BM + tid] = ns;
-    }
-
-    // ---- phase 2: chunks of the triangular contraction, taken dynamically per warp ----------
-    double* parts = args.parts + (size_t)tile * lay.n_parts * BM;
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&sync[0], 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= c_hi) break;
-      const Chunk ch = lay.chunks[c];
-
-      if (MODE == TC_MODE_AUTO) {
-        double sums[NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++) sums[nt][0] = sums[nt][1] = 0.0;
-        for (int mt = ch.mt0; mt < ch.mt1; mt++) {
-          const int k_tile = 4 * (mt + 1);                 // k-steps of the full lower-triangular tile
-          const int k_end = min(k_tile, ch.k_cap);
-          // the upper 8 rows of the tile are zero in its last two k-steps: skip their DMMAs
-          const int k_both = min(k_end, k_tile - 2);
-          const double2* ap = lay.afrag +
-              ((size_t)ch.r * lay.ks_per_r + 2 * (size_t)mt * (mt + 1) + ch.k_begin) * 32 + lane;
-          const double* wk = Ws + (size_t)ch.k_begin * NT * 32 + lane;
-          double acc[2][NT][2];
-#pragma unroll
-          for (int nt = 0; nt < NT; nt++)
-            acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
-          double2 a_next = ld_stream(ap);
-          int ks = ch.k_begin;
-          for (; ks < k_both; ks++) {
-            const double2 a = a_next;
-            ap += 32;
-            a_next = ld_stream(ap);  // the stream is padded by one k-step, always safe
-#pragma unroll
-            for (int nt = 0; nt < NT; nt++) {
-              const double b = wk[nt * 32];
-              dmma884(acc[0][nt], a.x, b);
-              dmma884(acc[1][nt], a.y, b);
-            }
-            wk += NT * 32;
-          }
-          for (; ks < k_end; ks++) {
-            const double2 a = a_next;
-            ap += 32;
-            a_next = ld_stream(ap);
-#pragma unroll
-            for (int nt = 0; nt < NT; nt++) dmma884(acc[1][nt], a.y, wk[nt * 32]);
-            wk += NT * 32;
-          }
-          // row-dot: acc[h][nt][e] = (M' W)[row = 16 mt + 8 h + g][draw = 8 nt + 2 tig + e]
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int row = 16 * mt + 8 * h + g;
-            const double* wr = Ws + (size_t)(row >> 2) * NT * 32 + (row & 3) + tig * 8;
-#pragma unroll
-            for (int nt = 0; nt < NT; nt++) {
-              sums[nt][0] = fma(acc[h][nt][0], wr[nt * 32], sums[nt][0]);
-              sums[nt][1] = fma(acc[h][nt][1], wr[nt * 32 + 4], sums[nt][1]);
-            }
-          }
-        }
-        // fixed-order reduction over the 8 row groups of the warp; recursive halving leaves the
-        // lane with row group g holding n-tile (g mod NT), i.e. draws 2 lane, 2 lane + 1 (mod BM)
-        double v[NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++) { v[nt][0] = sums[nt][0]; v[nt][1] = sums[nt][1]; }
-        int width = NT;  // number of live n-tiles per lane
-#pragma unroll
-        for (int bit = 4; bit >= 1; bit >>= 1) {  // g bit 2, 1, 0 <-> lane xor 16, 8, 4
-          const int xor_lanes = bit * 4;
-          if (width > bit) {
-            // halve: lanes with the g bit set keep the upper half
-            const bool upper = (g & bit) != 0;
-            const int half = width / 2;
-#pragma unroll
-            for (int i = 0; i < NT / 2; i++) {
-              if (i < half) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                  double send = upper ? v[i][e] : v[i + half][e];
-                  double keep = upper ? v[i + half][e] : v[i][e];
-                  v[i][e] = keep + __shfl_xor_sync(0xffffffffu, send, xor_lanes);
-                }
-              }
-            }
-            width = half;
-          } else {
-#pragma unroll
-            for (int i = 0; i < NT; i++) {
-              if (i < width) {
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-                  v[i][e] += __shfl_xor_sync(0xffffffffu, v[i][e], xor_lanes);
-              }
-            }
-          }
-        }
-        if (g < NT) {
-          double2 out = make_double2(v[0][0], v[0][1]);
-          *reinterpret_cast<double2*>(parts + (size_t)ch.part_row * BM + 8 * g + 2 * tig) = out;
-        }
-      } else {
-        // cross mode: a 16-radial-bin tile times a k-range of W; the product is the output
-        const double2* ap = lay.afrag + ((size_t)ch.r * lay.ks_per_r + ch.k_begin) * 32 + lane;
-        const double* wk = Ws + (size_t)ch.k_begin * NT * 32 + lane;
-        double acc[2][NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++)
-          acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
-        double2 a_next = ld_stream(ap);
-        for (int ks = ch.k_begin; ks < ch.k_cap; ks++) {
-          const double2 a = a_next;
-          ap += 32;
-          a_next = ld_stream(ap);
-#pragma unroll
-          for (int nt = 0; nt < NT; nt++) {
-            const double b = wk[nt * 32];
-            dmma884(acc[0][nt], a.x, b);
-            dmma884(acc[1][nt], a.y, b);
-          }
-          wk += NT * 32;
-        }
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-#pragma unroll
-          for (int nt = 0; nt < NT; nt++)
-            *reinterpret_cast<double2*>(parts + (size_t)(ch.part_row + 8 * h + g) * BM + 8 * nt +
-                                        2 * tig) = make_double2(acc[h][nt][0], acc[h][nt][1]);
-      }
-    }
-    __syncthreads();  // W is overwritten by the next tile
   }
 }
 
@@ -639,24 +730,34 @@ struct OccArgs {
   const double* theta;
   long long n_draws;
   int n_rows;
+  int n_ranges_cen, n_ranges_sat;
   const int* pad_to_row;
   double* occ_out;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs args) {
-  constexpr int BM = 32;
   __shared__ double tab[kTabDoubles];
   load_math_tables(tab);
   __syncthreads();
-  const long long n_tiles = (args.n_draws + BM - 1) / BM;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long b0 = tile * BM;
-    occupation_tile<BM>(args.plan, args.model, args.theta, b0, args.n_draws, tab,
-                        [&](int row, int b, double occ, double) {
-                          int dst = args.pad_to_row[row];
-                          if (b0 + b < args.n_draws && dst >= 0)
-                            args.occ_out[(b0 + b) * args.n_rows + dst] = occ;
-                        });
+  // one warp per item = 8 draws x one group range; four groups in flight per warp
+  const int lane = threadIdx.x & 31;
+  const int n_ranges = args.n_ranges_cen + args.n_ranges_sat;
+  const long long n_blocks = (args.n_draws + 7) / 8;
+  const long long n_items = n_blocks * n_ranges;
+  const long long warp0 = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  for (long long item = warp0; item < n_items; item += (long long)gridDim.x * kWarps) {
+    const long long block = item / n_ranges;
+    const int q = (int)(item - block * n_ranges);
+    const long long draw = block * 8 + (lane & 7);
+    const bool live = draw < args.n_draws;
+    int g_begin, g_end;
+    occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
+    occupation_item(args.plan, args.model,
+                    args.theta + (live ? draw : args.n_draws - 1) * TC_N_THETA, g_begin, g_end, tab,
+                    [&](int row, double occ, double) {
+                      const int dst = args.pad_to_row[row];
+                      if (live && dst >= 0) args.occ_out[draw * args.n_rows + dst] = occ;
+                    });
   }
 }
 
@@ -792,6 +893,12 @@ struct Layout {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Tuning knobs for experiments (tools/bench_variants.py): TC_TUNE_<NAME>=<int> in the environment.
+int tune(const char* name, int fallback) {
+  const char* v = std::getenv((std::string("TC_TUNE_") + name).c_str());
+  return v && *v ? std::atoi(v) : fallback;
+}
+
 }  // namespace
 
 struct tc_table {
@@ -872,7 +979,7 @@ int build_layout(tc_table* t, int separate) {
     const int n_comp = separate ? 3 : 1;
     out_lists.assign((size_t)Reff * n_comp, {});
     const int c16 = nc_pad / 16;  // first satellite tile (split layout)
-    int pieces = std::max(1, std::min(T16, (6 * kWarps + Reff - 1) / Reff));
+    int pieces = std::max(1, std::min(T16, (tune("CHUNKS", 6 * kWarps) + Reff - 1) / Reff));
     auto add_range = [&](int r, int mt_lo, int mt_hi, int k_begin, int k_cap, int comp, int np) {
       // cost of tile mt ~ number of k-steps
       auto cost = [&](int mt) { return std::max(0, std::min(4 * (mt + 1), k_cap) - k_begin); };
@@ -955,7 +1062,6 @@ int build_layout(tc_table* t, int separate) {
       }
     }
   }
-  // longest chunks first: the warps take them dynamically
   auto chunk_cost = [&](const Chunk& c) {
     if (t->mode != TC_MODE_AUTO) return (long long)(c.k_cap - c.k_begin);
     long long s = 0;
@@ -963,6 +1069,7 @@ int build_layout(tc_table* t, int separate) {
       s += std::max(0, std::min(4 * (mt + 1), c.k_cap) - c.k_begin);
     return s;
   };
+  // longest chunks first (only the end of a CTA's last tile is sensitive to the order)
   std::stable_sort(chunks.begin(), chunks.end(),
                    [&](const Chunk& a, const Chunk& b) { return chunk_cost(a) > chunk_cost(b); });
 
@@ -1039,7 +1146,9 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
     }
   }
   const int n_groups = (int)groups.size();
-  const int GP = (G + 1) / 2 * 2;  // the kernel evaluates two nodes per iteration
+  // the kernel evaluates `unroll` nodes per iteration
+  const int unroll = tune("OCC_UNROLL", kOccUnroll) == kOccUnroll && G % kOccUnroll == 0 ? kOccUnroll : 2;
+  const int GP = round_up(G, unroll);
   std::vector<double> node_logm((size_t)n_groups * GP), node_m((size_t)n_groups * GP);
   std::vector<int> grp_rows((size_t)n_groups * kGroupRows, -1), grp_is_sat(n_groups);
   std::vector<double> row_c((size_t)(n_pad + 1) * GP, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
@@ -1079,8 +1188,11 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   if ((rc = upload(row_nh, &d_nh))) return rc; ph.allocations.push_back(d_nh);
   if ((rc = upload(row_pct, &d_pct))) return rc; ph.allocations.push_back(d_pct);
   ph.dev.n_groups = n_groups;
+  ph.dev.n_cen_groups = 0;
+  for (int q = 0; q < n_groups; q++) ph.dev.n_cen_groups += grp_is_sat[q] ? 0 : 1;
   ph.dev.n_gauss = G;
   ph.dev.n_gauss_pad = GP;
+  ph.dev.unroll = unroll;
   ph.dev.zero_row = n_pad;
   ph.dev.node_logm = d_logm;
   ph.dev.node_m = d_m;
@@ -1093,31 +1205,40 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   return TC_OK;
 }
 
-size_t predict_smem_bytes(int n_pad, int nt) {
-  return ((size_t)n_pad * 8 * nt + kTabDoubles) * sizeof(double) + 16;
+size_t predict_smem_bytes(int n_pad, int nt, int n_buf) {
+  return ((size_t)n_buf * n_pad * 8 * nt + kTabDoubles) * sizeof(double) + sizeof(PredictCtrl);
 }
 
-int pick_nt(int n_pad, long long n_draws, int n_sm) {
-  int best = 0;
-  for (int nt : {8, 4, 2, 1}) {
-    size_t smem = predict_smem_bytes(n_pad, nt);
-    if (smem > (size_t)kSmemLimit) continue;
-    if (best == 0) best = nt;  // largest that fits
-    if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) return nt;
-    best = nt;  // keep shrinking while the grid would not fill the device
+// Draw-tile width (8 nt draws) and number of W buffers: two buffers (occupation of the next tile
+// overlaps the contraction of the current one) whenever they fit, the widest tile that fits, and
+// narrower tiles only while the batch is too small to give every SM a tile.
+void pick_tile(int n_pad, long long n_draws, int n_sm, int* nt_out, int* n_buf_out) {
+  *nt_out = 0;
+  *n_buf_out = 0;
+  for (int n_buf : {2, 1}) {
+    int best = 0;
+    for (int nt = 8; nt >= 1; nt--) {
+      if (predict_smem_bytes(n_pad, nt, n_buf) > (size_t)kSmemLimit) continue;
+      best = nt;  // the largest that fits, shrinking while the grid would not fill the device
+      if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) break;
+    }
+    if (best) {
+      *nt_out = best;
+      *n_buf_out = n_buf;
+      return;
+    }
   }
-  return best;
 }
 
 struct Workspace {
   size_t parts_bytes, ngal_bytes, total;
   long long n_tiles;
-  int nt;
+  int nt, n_buf;
 };
 
 Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
   Workspace w{};
-  w.nt = pick_nt(L.dev.n_pad, n_draws, n_sm);
+  pick_tile(L.dev.n_pad, n_draws, n_sm, &w.nt, &w.n_buf);
   if (w.nt == 0) return w;
   const int bm = 8 * w.nt;
   w.n_tiles = (n_draws + bm - 1) / bm;
@@ -1125,6 +1246,23 @@ Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
   w.ngal_bytes = (size_t)w.n_tiles * 2 * bm * sizeof(double);
   w.total = w.parts_bytes + w.ngal_bytes;
   return w;
+}
+
+// Occupation items per n-tile: about kOccItemsPerTile / nt group ranges, split between centrals and
+// satellites in proportion to their groups (at least one each where the type exists).
+constexpr int kOccItemsPerTile = 14;
+
+void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat) {
+  const int cen = plan.n_cen_groups, sat = plan.n_groups - plan.n_cen_groups;
+  const int want = std::max(2, (tune("OCC_ITEMS", kOccItemsPerTile) + nt - 1) / nt);
+  auto share = [&](int count) {
+    if (count == 0) return 0;
+    const int units = (count + 3) / 4;
+    return std::max(1, std::min(units, (int)std::lround((double)want * count / (cen + sat))));
+  };
+  *n_cen = share(cen);
+  *n_sat = share(sat);
+  if (*n_cen + *n_sat == 0) *n_cen = 1;  // table without rows cannot happen; keep n_occ > 0
 }
 
 // Coefficient tables of the occupation math (see half_erfc_neg / pow_pos), computed in long double.
@@ -1330,8 +1468,10 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   args.n_rows = t->n_rows;
   args.pad_to_row = t->layouts[0].dev.pad_to_row;
   args.occ_out = occ;
-  long long n_tiles = (n_draws + 31) / 32;
-  int grid = (int)std::min<long long>(n_tiles, 4LL * n_sm);
+  pick_ranges(args.plan, 1, &args.n_ranges_cen, &args.n_ranges_sat);
+  const long long n_items = (n_draws + 7) / 8 * (args.n_ranges_cen + args.n_ranges_sat);
+  int grid = (int)std::max<long long>(1, std::min<long long>((n_items + kWarps - 1) / kWarps,
+                                                             (long long)n_sm));
   occupation_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(args);
   TC_CUDA(cudaGetLastError());
   return TC_OK;
@@ -1400,8 +1540,19 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   args.parts = static_cast<double*>(workspace);
   args.ngal_tile = reinterpret_cast<double*>(static_cast<char*>(workspace) + ws.parts_bytes);
 
+  args.n_buf = ws.n_buf;
+  pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat);
+  {
+    // occupation items take every occ_stride-th slot of the first ~70 % of a tile's work list;
+    // with a single W buffer they must all come before the chunks that wait for them
+    const int n_occ = ws.nt * (args.n_ranges_cen + args.n_ranges_sat);
+    const int slots = L.dev.n_chunks + n_occ;
+    // (every occupation slot must exist: stride * n_occ <= slots)
+    const int spread = std::min(100, std::max(1, tune("OCC_SPREAD", 90)));
+    args.occ_stride = ws.n_buf == 1 ? 1 : std::max(1, (int)((long long)spread * slots / (100LL * n_occ)));
+  }
   const int bm = 8 * ws.nt;
-  const size_t smem = predict_smem_bytes(L.dev.n_pad, ws.nt);
+  const size_t smem = predict_smem_bytes(L.dev.n_pad, ws.nt, ws.n_buf);
   const int gx = (int)std::min<long long>(ws.n_tiles * L.dev.n_chunks, n_sm);
   dim3 grid(gx, 1);
 #define TC_LAUNCH(NT_)                                                                     \
@@ -1410,7 +1561,11 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   if (g_profile.enabled) TC_CUDA(cudaEventRecord(g_profile.ev[0], stream));
   switch (ws.nt) {
     case 8: TC_LAUNCH(8); break;
+    case 7: TC_LAUNCH(7); break;
+    case 6: TC_LAUNCH(6); break;
+    case 5: TC_LAUNCH(5); break;
     case 4: TC_LAUNCH(4); break;
+    case 3: TC_LAUNCH(3); break;
     case 2: TC_LAUNCH(2); break;
     default: TC_LAUNCH(1); break;
   }

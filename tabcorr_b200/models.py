@@ -146,10 +146,9 @@ def resolve_model(model):
         'cannot map {!r} to a kernel occupation family (zheng07, decorated zheng07)'.format(model))
 
 
-def theta_from_params(params, n_draws=None, spec=None, alloc=None):
-    """``[B, 7]`` float64 array in kernel order from a dict of scalars/arrays keyed by halotools
-    parameter names.  Missing assembly-bias strengths default to 0.  ``alloc(shape)`` may supply
-    the output buffer (e.g. pinned host memory)."""
+def theta_columns(params, spec=None):
+    """The ``TC_N_THETA`` columns (arrays ``[B]`` or scalars) of a parameter dict in kernel order;
+    raises ``ValueError`` for missing parameters like :func:`theta_from_params`."""
     missing = [k for k in ZHENG07_KEYS if k not in params]
     if missing:
         raise ValueError('missing occupation parameters: {}'.format(', '.join(missing)))
@@ -157,7 +156,14 @@ def theta_from_params(params, n_draws=None, spec=None, alloc=None):
         missing = [k for k in ASSEMBIAS_KEYS if k not in params]
         if missing:
             raise ValueError('missing assembly-bias parameters: {}'.format(', '.join(missing)))
-    columns = [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in THETA_KEYS]
+    return [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in THETA_KEYS]
+
+
+def theta_from_params(params, n_draws=None, spec=None, alloc=None):
+    """``[B, 7]`` float64 array in kernel order from a dict of scalars/arrays keyed by halotools
+    parameter names.  Missing assembly-bias strengths default to 0.  ``alloc(shape)`` may supply
+    the output buffer (e.g. pinned host memory)."""
+    columns = theta_columns(params, spec)
     if n_draws is None:
         n_draws = max([c.shape[0] for c in columns if c.ndim > 0] + [1])
     shape = (n_draws, len(THETA_KEYS))

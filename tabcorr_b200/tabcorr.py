@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _lib
 from . import h5mini
-from .models import (ModelSpec, THETA_KEYS, ASSEMBIAS_KEYS, resolve_model, theta_from_params)
+from .models import (ModelSpec, THETA_KEYS, ASSEMBIAS_KEYS, resolve_model, theta_columns,
+                     theta_from_params)
 from .table import Table
 
 try:  # h5py is optional: used when present, otherwise the built-in reader
@@ -88,6 +89,7 @@ class DeviceTableGroup:
         self.handle = handle
         self._planned = set()
         self._workspace = None
+        self._copy_streams = None
         self._lock = threading.Lock()
 
     def __del__(self):
@@ -98,6 +100,13 @@ class DeviceTableGroup:
             except Exception:  # interpreter shutdown
                 pass
             self.handle = None
+
+    def copy_streams(self):
+        """Two side streams (host-to-device, device-to-host) for the pipelined batch path."""
+        if self._copy_streams is None:
+            torch = _torch()
+            self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._copy_streams
 
     def plan(self, n_gauss):
         if n_gauss not in self._planned:
@@ -341,7 +350,7 @@ class TabCorr:
         return spec, theta
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, model=None,
-                      occupation=None, as_numpy=True):
+                      occupation=None, as_numpy=True, pipeline_chunk=25000):
         """Predict number density and correlation function for B parameter sets at once.
 
         Parameters
@@ -361,6 +370,10 @@ class TabCorr:
             Precomputed mean occupations (the ndarray branch of ``predict``).
         as_numpy : bool, optional
             Return host numpy arrays (default) or leave the results on the device.
+        pipeline_chunk : int, optional
+            With host inputs and host outputs, batches larger than this many draws are cut into
+            chunks whose host-to-device copy, kernels and device-to-host copy overlap on three
+            CUDA streams.  Results do not depend on it.
 
         Returns
         -------
@@ -369,6 +382,10 @@ class TabCorr:
         torch = _torch()
         group = self._ensure_device()
         separate = bool(separate_gal_type)
+        if (occupation is None and as_numpy and not isinstance(params, torch.Tensor) and
+                pipeline_chunk and pipeline_chunk > 0):
+            return self._predict_batch_pipelined(params, model, separate, int(n_gauss_prim),
+                                                 int(pipeline_chunk))
         if occupation is not None:
             occ = _to_device_f64(occupation, group.device)
             if occ.ndim != 2 or occ.shape[1] != group.n_rows:
@@ -383,6 +400,60 @@ class TabCorr:
         xi = torch.empty((n_draws, group.n_r, n_comp), dtype=torch.float64, device=group.device)
         group.predict_into(spec, int(n_gauss_prim), theta, occ, separate, ngal, 0, xi, 0)
         return self._format_batch(ngal, xi, separate, as_numpy)
+
+    def _predict_batch_pipelined(self, params, model, separate, n_gauss, chunk):
+        """Host parameters in, host results out: the draws are cut into chunks; chunk i + 1 is
+        staged in pinned memory and copied to the device while chunk i is evaluated and chunk
+        i - 1 is copied back (copy streams + events; the kernels stay on the current stream)."""
+        torch = _torch()
+        group = self._ensure_device()
+        device = group.device
+        if isinstance(params, dict):
+            decorated = all(k in params for k in ASSEMBIAS_KEYS)
+            spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
+            columns = theta_columns(params, spec)
+        else:
+            spec = resolve_model(model) if model is not None else ModelSpec()
+            array = np.asarray(params, dtype=np.float64)
+            if array.ndim != 2 or array.shape[1] not in (5, len(THETA_KEYS)):
+                raise ValueError('params must be a dict of arrays or a [B, 5|7] array ordered as '
+                                 '{}'.format(', '.join(THETA_KEYS)))
+            columns = [array[:, j] for j in range(array.shape[1])]
+            columns += [np.float64(0.0)] * (len(THETA_KEYS) - len(columns))
+        n_draws = max([c.shape[0] for c in columns if np.ndim(c) > 0] + [1])
+        n_ng, n_comp = (2 if separate else 1), group.n_comp(separate)
+        f64 = torch.float64
+        theta_pin = torch.empty((n_draws, len(THETA_KEYS)), dtype=f64, pin_memory=True)
+        ngal_pin = torch.empty((n_draws, n_ng), dtype=f64, pin_memory=True)
+        xi_pin = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, pin_memory=True)
+        theta_np = theta_pin.numpy()
+        theta = torch.empty((n_draws, len(THETA_KEYS)), dtype=f64, device=device)
+        ngal = torch.empty((n_draws, n_ng), dtype=f64, device=device)
+        xi = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, device=device)
+        compute = torch.cuda.current_stream(device)
+        h2d, d2h = group.copy_streams()
+        # the fresh device buffers may be recycled memory with work pending on the compute stream
+        h2d.wait_stream(compute)
+        d2h.wait_stream(compute)
+        for lo in range(0, n_draws, chunk):
+            hi = min(lo + chunk, n_draws)
+            for j, column in enumerate(columns):
+                theta_np[lo:hi, j] = column[lo:hi] if np.ndim(column) > 0 else column
+            with torch.cuda.stream(h2d):
+                theta[lo:hi].copy_(theta_pin[lo:hi], non_blocking=True)
+                staged = torch.cuda.Event()
+                staged.record(h2d)
+            compute.wait_event(staged)
+            group.predict_into(spec, n_gauss, theta[lo:hi], None, separate, ngal[lo:hi], 0,
+                               xi[lo:hi], 0)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                ngal_pin[lo:hi].copy_(ngal[lo:hi], non_blocking=True)
+                xi_pin[lo:hi].copy_(xi[lo:hi], non_blocking=True)
+        d2h.synchronize()
+        return self._format_batch(ngal_pin.numpy(), xi_pin.numpy(), separate, False)
 
     def _format_batch(self, ngal, xi, separate, as_numpy):
         """``ngal [B, 1|2]``, ``xi [B, R, C]`` device tensors -> reference-shaped outputs."""

@@ -199,6 +199,40 @@ def test_batch_sizes_against_oracle(tb, n_draws):
         close(xi[i], xi_ref)
 
 
+@pytest.mark.parametrize('n_mass,n_sec,mode', [
+    (60, 2, 'auto'),     # n_pad 240: 56-draw tiles, two W buffers (the headline shape)
+    (72, 2, 'auto'),     # n_pad 288: 48-draw tiles
+    (80, 2, 'auto'),     # n_pad 320: 40-draw tiles
+    (100, 2, 'auto'),    # n_pad 400: 32-draw tiles
+    (125, 2, 'auto'),    # n_pad 512: 24-draw tiles (BASELINE configs[4] table shape)
+    (150, 2, 'auto'),    # n_pad 608: 16-draw tiles
+    (250, 2, 'auto'),    # n_pad 1008: 8-draw tiles
+    (450, 2, 'auto'),    # n_pad 1808: 8-draw tiles, single W buffer (no overlap)
+    (276, 2, 'cross'),   # n_pad 1104, the ds_efficient shape
+    (500, 2, 'cross'),   # n_pad 2000: single W buffer
+])
+def test_every_tile_width_against_oracle(tb, n_mass, n_sec, mode):
+    """Each draw-tile width / W-buffer count the launcher can pick, with several tiles per CTA
+    (10^4 draws), against the oracle on a sample of draws; total and per-gal-type results."""
+    from oracle import tabcorr_oracle as orc
+    n_r = 3
+    tab = cases.synthetic.make_table(n_mass=n_mass, n_sec=n_sec, n_r=n_r, seed=17, mode=mode)
+    n_draws = 10000
+    draws = cases.synthetic.make_draws(n_draws, seed=n_mass, decorated=True)
+    halotab = table_from_dict(tb, tab)
+    ngal, xi = halotab.predict_batch(draws)
+    ngal_sep, xi_sep = halotab.predict_batch(draws, separate_gal_type=True)
+    np.testing.assert_allclose(ngal_sep['centrals'] + ngal_sep['satellites'], ngal, rtol=1e-13)
+    scale = sum(np.abs(v) for v in xi_sep.values()).max(axis=1, keepdims=True)
+    assert np.all(np.abs(sum(xi_sep.values()) - xi) <= 1e-12 * scale)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], mode)
+    for i in [0, 1, 55, 56, 4999, n_draws - 57, n_draws - 1]:
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=True)
+        ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model))
+        close(ngal[i], ngal_ref)
+        close(xi[i], xi_ref)
+
+
 def test_batch_invariance_bitwise(tb):
     """A draw's result does not depend on the batch it is in (tile width, position, schedule)."""
     tab = cases.synthetic.make_table(n_mass=60, n_sec=2, n_r=20)
