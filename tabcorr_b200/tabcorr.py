@@ -257,7 +257,9 @@ class TabCorr:
             for key in fstream.attrs.keys():
                 attrs[key] = fstream.attrs[key]
             tpcf_matrix = fstream['tpcf_matrix'][()]
-            tpcf_args = tuple(fstream['tpcf_args'][key][()] for key in fstream['tpcf_args'].keys())
+            # (a table whose arguments were all dropped by max_args_size has no such group)
+            tpcf_args = (tuple(fstream['tpcf_args'][key][()] for key in fstream['tpcf_args'].keys())
+                         if 'tpcf_args' in fstream else ())
             tpcf_kwargs = {}
             if 'tpcf_kwargs' in fstream:
                 for key in fstream['tpcf_kwargs'].keys():
