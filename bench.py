@@ -33,6 +33,9 @@ if ROOT not in sys.path:
 
 N_MASS, N_SEC, N_R, N_GAUSS = 60, 2, 20, 10
 DRAWS_PER_GPU = 100000
+# dram__bytes_read.sum + dram__bytes_write.sum of predict_kernel for this workload (one launch =
+# 1e5 draws), from the committed ncu capture; only reported for the default batch size
+NCU_DRAM_BYTES_PER_LAUNCH = 23334144 + 15222272
 METRIC = 'HOD predictions/sec (ngal+wp)'
 UNIT = 'predictions/s'
 
@@ -263,8 +266,8 @@ def run_gpu_arm(args):
             return halotab.predict_batch(draws, n_gauss_prim=N_GAUSS)
         return predict_batch_sharded(halotab, all_draws, n_gauss_prim=N_GAUSS, dst=0)
 
-    for _ in range(2):
-        e2e_step()
+    for _ in range(4):  # also warms torch's pinned-memory cache (results of two calls stay alive)
+        host_result = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -298,7 +301,10 @@ def run_gpu_arm(args):
             'bound': 'tensor', 'kernel': 'predict_kernel<8, auto> (fused occupation + DMMA '
                                          'quadratic form)',
             'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
-            'frac': achieved / peak.value, 'traffic': None,
+            'frac': achieved / peak.value, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
+            'traffic_unit': 'bytes of DRAM read + write per launch',
+            'traffic_source': 'ncu --set full capture of this command, '
+                              'profiles/r01_predict_kernel_N240_R20.md',
             'peak_source': 'FP64 DMMA (mma.sync m8n8k4 f64) peak measured live by '
                            'tc_measure_dmma_peak; MEASURED_PEAKS.json has no FP64 figure',
             'flops_per_prediction': algorithmic_flops(n_rows, N_R),
@@ -309,6 +315,8 @@ def run_gpu_arm(args):
             'kernel_ms': k_ms, 'finalize_ms': float(np.mean(finalize_ms)),
             'kernel_share_of_step': float(np.sum(kernel_ms) / total_ms) if world == 1 else None,
         }
+        if n_draws != DRAWS_PER_GPU:
+            roofline['traffic'] = None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps,
@@ -316,7 +324,8 @@ def run_gpu_arm(args):
             'data': 'synthetic', 'config': workload_config(n_draws),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'timing': 'wall clock around predict_batch calls'},
-            'gpu_launches': 2 * args.steps, 'roofline': roofline, 'clocks': clocks,
+            'gpu_launches': 2 * args.steps,  # predict_kernel + finalize_kernel per timed step
+             'roofline': roofline, 'clocks': clocks,
             'results_consistent': bool(same),
         }
         if world == 1 and not args.no_cpu:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 100
+#define TC_VERSION 101
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -78,16 +78,23 @@ int tc_table_n_tables(const tc_table* table);
  * n_gauss, cached in the table) the node masses and normalised quadrature weights on the device. */
 int tc_table_plan(tc_table* table, int n_gauss, const double* x01_host, const double* w_host);
 
+/* Layout of the parameter draws theta_dev, selected by theta_ld:
+ *   theta_ld == 0:        [B, TC_N_THETA], one row per draw;
+ *   theta_ld >= n_draws:  [TC_N_THETA, theta_ld], one contiguous column per parameter (what a
+ *                         sampler that keeps one array per parameter -- model.param_dict keys --
+ *                         hands over without a transpose). */
+
 /* TabCorr.mean_occupation (tabcorr.py:465-578) for B draws: occ_dev[B, n_rows] in reference row
- * order.  theta_dev is [B, TC_N_THETA]. */
+ * order. */
 int tc_occupation_batch(tc_table* table, const tc_model* model, int n_gauss,
-                        const double* theta_dev, int64_t n_draws, double* occ_dev, void* stream);
+                        const double* theta_dev, int64_t theta_ld, int64_t n_draws,
+                        double* occ_dev, void* stream);
 
 /* Scratch bytes tc_predict_batch needs for n_draws (separate = separate_gal_type). */
 size_t tc_predict_workspace_bytes(const tc_table* table, int64_t n_draws, int separate);
 
 /* TabCorr.predict (tabcorr.py:580-683) for B draws, fused occupation + contraction.
- * Exactly one of theta_dev ([B, TC_N_THETA], evaluated with `model` and the n_gauss plan) and
+ * Exactly one of theta_dev (layout above; evaluated with `model` and the n_gauss plan) and
  * occ_dev ([B, n_rows] precomputed occupations, the ndarray branch tabcorr.py:616-621) is non-NULL.
  * Outputs, with T = n_tables, R = n_r:
  *   separate == 0: ngal_dev[b * ngal_stride + t], xi_dev[b * xi_stride + t * R + r]
@@ -96,7 +103,8 @@ size_t tc_predict_workspace_bytes(const tc_table* table, int64_t n_draws, int se
  *                  sat-sat (auto) or C = 2, p = centrals, satellites (cross); tabcorr.py:652-683.
  * Strides are in doubles, so that several table groups can fill one [B, T_total, ...] buffer. */
 int tc_predict_batch(tc_table* table, const tc_model* model, int n_gauss, const double* theta_dev,
-                     const double* occ_dev, int64_t n_draws, int separate, double* ngal_dev,
+                     int64_t theta_ld, const double* occ_dev, int64_t n_draws, int separate,
+                     double* ngal_dev,
                      int64_t ngal_stride, double* xi_dev, int64_t xi_stride, void* workspace_dev,
                      size_t workspace_bytes, void* stream);
 

@@ -69,13 +69,13 @@ def load():
     lib.tc_table_plan.argtypes = [vp, ctypes.c_int, c_double_p, c_double_p]
     lib.tc_occupation_batch.restype = ctypes.c_int
     lib.tc_occupation_batch.argtypes = [vp, ctypes.POINTER(tc_model), ctypes.c_int, vp,
-                                        ctypes.c_int64, vp, vp]
+                                        ctypes.c_int64, ctypes.c_int64, vp, vp]
     lib.tc_predict_workspace_bytes.restype = ctypes.c_size_t
     lib.tc_predict_workspace_bytes.argtypes = [vp, ctypes.c_int64, ctypes.c_int]
     lib.tc_predict_batch.restype = ctypes.c_int
     lib.tc_predict_batch.argtypes = [
-        vp, ctypes.POINTER(tc_model), ctypes.c_int, vp, vp, ctypes.c_int64, ctypes.c_int, vp,
-        ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_size_t, vp]
+        vp, ctypes.POINTER(tc_model), ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64,
+        ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_size_t, vp]
     lib.tc_interp_create.restype = ctypes.c_int
     lib.tc_interp_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, c_int32_p, c_double_p,
                                      c_double_p, c_int32_p, ctypes.c_int]

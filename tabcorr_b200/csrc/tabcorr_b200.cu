@@ -215,15 +215,17 @@ struct DrawParams {
   double logMmin, inv_sigma, m0, inv_m1, alpha, a_cen, a_sat;
 };
 
-__device__ __forceinline__ DrawParams load_draw(const double* __restrict__ theta) {
+// theta points at the draw's first parameter; consecutive parameters are `ps` doubles apart
+// (1 for the [B, TC_N_THETA] layout, the leading dimension for the [TC_N_THETA, ld] layout)
+__device__ __forceinline__ DrawParams load_draw(const double* __restrict__ theta, long long ps) {
   DrawParams p;
   p.logMmin = theta[0];
-  p.inv_sigma = 1.0 / theta[1];
-  p.m0 = exp10(theta[2]);
-  p.inv_m1 = 1.0 / exp10(theta[3]);
-  p.alpha = theta[4];
-  p.a_cen = fmin(fmax(theta[5], -1.0), 1.0);
-  p.a_sat = fmin(fmax(theta[6], -1.0), 1.0);
+  p.inv_sigma = 1.0 / theta[ps];
+  p.m0 = exp10(theta[2 * ps]);
+  p.inv_m1 = 1.0 / exp10(theta[3 * ps]);
+  p.alpha = theta[4 * ps];
+  p.a_cen = fmin(fmax(theta[5 * ps], -1.0), 1.0);
+  p.a_sat = fmin(fmax(theta[6 * ps], -1.0), 1.0);
   return p;
 }
 
@@ -318,9 +320,9 @@ __device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, c
 template <bool DECORATED, bool MODULATE, int U, typename Store>
 __device__ __forceinline__ void occupation_item_impl(const OccPlan& plan, const tc_model& model,
                                                      const double* __restrict__ theta_row,
-                                                     int g_begin, int g_end,
+                                                     long long theta_ps, int g_begin, int g_end,
                                                      const double* __restrict__ tab, Store store) {
-  DrawParams p = load_draw(theta_row);
+  DrawParams p = load_draw(theta_row, theta_ps);
   if (!model.decorated) p.a_cen = p.a_sat = 0.0;  // strengths are ignored unless decorated
   const bool sat = g_begin >= plan.n_cen_groups;
   for (int grp = g_begin + (threadIdx.x >> 3 & 3); grp < g_end; grp += 4) {
@@ -337,20 +339,20 @@ __device__ __forceinline__ void occupation_item_impl(const OccPlan& plan, const 
 
 template <typename Store>
 __device__ __forceinline__ void occupation_item(const OccPlan& plan, const tc_model& model,
-                                                const double* __restrict__ theta_row, int g_begin,
-                                                int g_end, const double* __restrict__ tab,
-                                                Store store) {
+                                                const double* __restrict__ theta_row,
+                                                long long theta_ps, int g_begin, int g_end,
+                                                const double* __restrict__ tab, Store store) {
   if (model.modulate_with_cenocc) {   // rare: keep one generic instantiation
-    occupation_item_impl<true, true, 2>(plan, model, theta_row, g_begin, g_end, tab, store);
+    occupation_item_impl<true, true, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
   } else if (plan.unroll == kOccUnroll) {
     if (model.decorated)
-      occupation_item_impl<true, false, kOccUnroll>(plan, model, theta_row, g_begin, g_end, tab, store);
+      occupation_item_impl<true, false, kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
     else
-      occupation_item_impl<false, false, kOccUnroll>(plan, model, theta_row, g_begin, g_end, tab, store);
+      occupation_item_impl<false, false, kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
   } else if (model.decorated) {
-    occupation_item_impl<true, false, 2>(plan, model, theta_row, g_begin, g_end, tab, store);
+    occupation_item_impl<true, false, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
   } else {
-    occupation_item_impl<false, false, 2>(plan, model, theta_row, g_begin, g_end, tab, store);
+    occupation_item_impl<false, false, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
   }
 }
 
@@ -396,7 +398,8 @@ struct PredictArgs {
   LayoutDev lay;
   OccPlan plan;
   tc_model model;
-  const double* theta;   // [B, TC_N_THETA] or nullptr
+  const double* theta;   // parameter draws or nullptr: theta[draw * theta_ds + k * theta_ps]
+  long long theta_ds, theta_ps;
   const double* occ;     // [B, n_rows] or nullptr
   long long n_draws;
   long long n_tiles;
@@ -628,7 +631,8 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       if (args.theta != nullptr) {
         int g_begin, g_end;
         occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
-        occupation_item(args.plan, args.model, args.theta + draw * TC_N_THETA, g_begin, g_end, tab,
+        occupation_item(args.plan, args.model, args.theta + draw * args.theta_ds, args.theta_ps,
+                        g_begin, g_end, tab,
                         [&](int row, double occ, double nh) { Ws[widx<NT>(row, b)] = occ * nh; });
       } else {
         const int n_q = args.n_ranges_cen + args.n_ranges_sat;
@@ -728,6 +732,7 @@ struct OccArgs {
   OccPlan plan;
   tc_model model;
   const double* theta;
+  long long theta_ds, theta_ps;
   long long n_draws;
   int n_rows;
   int n_ranges_cen, n_ranges_sat;
@@ -753,7 +758,8 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
     int g_begin, g_end;
     occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
     occupation_item(args.plan, args.model,
-                    args.theta + (live ? draw : args.n_draws - 1) * TC_N_THETA, g_begin, g_end, tab,
+                    args.theta + (live ? draw : args.n_draws - 1) * args.theta_ds, args.theta_ps,
+                    g_begin, g_end, tab,
                     [&](int row, double occ, double) {
                       const int dst = args.pad_to_row[row];
                       if (live && dst >= 0) args.occ_out[draw * args.n_rows + dst] = occ;
@@ -1449,8 +1455,10 @@ int tc_table_plan(tc_table* t, int n_gauss, const double* x01, const double* w) 
 }
 
 int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
-                        int64_t n_draws, double* occ, void* stream) {
+                        int64_t theta_ld, int64_t n_draws, double* occ, void* stream) {
   if (!t || !model || !theta || !occ) return fail(TC_EINVAL, "tc_occupation_batch: NULL argument");
+  if (theta_ld != 0 && theta_ld < n_draws)
+    return fail(TC_EINVAL, "tc_occupation_batch: theta_ld must be 0 or >= n_draws");
   if (model->family != 0) return fail(TC_EUNSUPPORTED, "tc_occupation_batch: unknown model family");
   if (n_draws <= 0) return TC_OK;
   std::lock_guard<std::mutex> lock(t->mutex);
@@ -1464,6 +1472,8 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   args.plan = t->layouts[0].plans[n_gauss].dev;
   args.model = *model;
   args.theta = theta;
+  args.theta_ds = theta_ld ? 1 : TC_N_THETA;
+  args.theta_ps = theta_ld ? theta_ld : 1;
   args.n_draws = n_draws;
   args.n_rows = t->n_rows;
   args.pad_to_row = t->layouts[0].dev.pad_to_row;
@@ -1490,13 +1500,16 @@ size_t tc_predict_workspace_bytes(const tc_table* t, int64_t n_draws, int separa
 }
 
 int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
-                     const double* occ, int64_t n_draws, int separate, double* ngal,
+                     int64_t theta_ld, const double* occ, int64_t n_draws, int separate,
+                     double* ngal,
                      int64_t ngal_stride, double* xi, int64_t xi_stride, void* workspace,
                      size_t workspace_bytes, void* stream_) {
   if (!t || !ngal || !xi) return fail(TC_EINVAL, "tc_predict_batch: NULL argument");
   if ((theta == nullptr) == (occ == nullptr))
     return fail(TC_EINVAL, "tc_predict_batch: exactly one of theta_dev and occ_dev must be given");
   if (theta && !model) return fail(TC_EINVAL, "tc_predict_batch: model is NULL");
+  if (theta && theta_ld != 0 && theta_ld < n_draws)
+    return fail(TC_EINVAL, "tc_predict_batch: theta_ld must be 0 or >= n_draws");
   if (theta && model->family != 0)
     return fail(TC_EUNSUPPORTED, "tc_predict_batch: unknown model family");
   if (n_draws <= 0) return TC_OK;
@@ -1534,6 +1547,8 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   args.plan = L.plans[plan_g].dev;
   if (model) args.model = *model;
   args.theta = theta;
+  args.theta_ds = theta_ld ? 1 : TC_N_THETA;
+  args.theta_ps = theta_ld ? theta_ld : 1;
   args.occ = occ;
   args.n_draws = n_draws;
   args.n_tiles = ws.n_tiles;

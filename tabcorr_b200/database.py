@@ -94,5 +94,17 @@ def read(suite, redshift, tpcf, i_cosmo=0, i_phase=0, sim_config=None, tab_confi
     return Interpolator.read(path / '{}_{}.hdf5'.format(tpcf, tab_config), device=device)
 
 
+def read_set(suite, redshift, tpcf, i_cosmo=(0,), i_phase=0, sim_config=None,
+             tab_config='default', device=None):
+    """One ``Interpolator`` per cosmology as a :class:`~tabcorr_b200.tableset.TableSet`, for
+    batches whose draws each name a cosmology (``table_index`` = position in ``i_cosmo``).  Not in
+    the reference, where a sampler would call ``read`` once per cosmology
+    (``tabcorr/database.py:253-286``)."""
+    from .tableset import TableSet
+    return TableSet([read(suite, redshift, tpcf, i_cosmo=int(c), i_phase=i_phase,
+                          sim_config=sim_config, tab_config=tab_config, device=device)
+                     for c in i_cosmo])
+
+
 # alias kept for backwards compatibility, as in the reference (tabcorr/database.py:290)
 tabcorr = read

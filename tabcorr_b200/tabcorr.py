@@ -49,6 +49,39 @@ def leggauss01(n_gauss_prim):
     return np.ascontiguousarray((x + 1) / 2), np.ascontiguousarray(w)
 
 
+def chunk_schedule(n_draws, chunk='auto', edge=None, largest=1 << 20):
+    """Chunk boundaries ``[(lo, hi), ...]`` of the pipelined host-to-host batch path.
+
+    ``chunk``: int (fixed size), sequence of sizes (the last repeats) or 'auto': one chunk up to
+    30 000 draws; otherwise a head and a tail of ``edge`` draws (default: a tenth of the batch,
+    at most 65 536) around equal chunks of at most ``largest`` draws."""
+    n_draws = int(n_draws)
+    if edge is None:
+        edge = min(max(n_draws // 10, 1), 65536)
+    if isinstance(chunk, str):
+        if chunk != 'auto':
+            raise ValueError("pipeline_chunk must be 'auto', an int or a sequence of ints")
+        if n_draws <= 30000:
+            sizes = [max(n_draws, 1)]
+        else:
+            middle = n_draws - 2 * edge
+            pieces = -(-middle // largest)
+            sizes = [edge] + [middle // pieces + (1 if i < middle % pieces else 0)
+                              for i in range(pieces)] + [edge]
+    elif isinstance(chunk, (list, tuple)):
+        sizes = [int(c) for c in chunk]
+        if not sizes or min(sizes) <= 0:
+            raise ValueError('chunk sizes must be positive')
+    else:
+        sizes = [int(chunk)] if int(chunk) > 0 else [max(n_draws, 1)]
+    bounds, lo, i = [], 0, 0
+    while lo < n_draws:
+        hi = min(n_draws, lo + sizes[min(i, len(sizes) - 1)])
+        bounds.append((lo, hi))
+        lo, i = hi, i + 1
+    return bounds
+
+
 class DeviceTableGroup:
     """One gal_type table with one or more correlation matrices on the device (``tc_table``)."""
 
@@ -143,15 +176,19 @@ class DeviceTableGroup:
         model = self._model_struct(spec)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.tc_occupation_batch(
-            self.handle, ctypes.byref(model), int(n_gauss), theta.data_ptr(), n_draws,
+            self.handle, ctypes.byref(model), int(n_gauss), theta.data_ptr(), 0, n_draws,
             occ.data_ptr(), stream))
         return occ
 
-    def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset):
+    def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset,
+                     theta_columns=False):
         """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
-        and ``xi`` starting at table offset ``*_offset`` (in doubles within a draw)."""
+        and ``xi`` starting at table offset ``*_offset`` (in doubles within a draw).  ``theta`` is
+        ``[B, 7]``, or ``[7, B]`` (one contiguous column per parameter) with ``theta_columns``."""
         torch = _torch()
-        n_draws = (theta if theta is not None else occ).shape[0]
+        n_draws = (theta.shape[1] if theta_columns else theta.shape[0]) if theta is not None \
+            else occ.shape[0]
+        theta_ld = theta.stride(0) if (theta is not None and theta_columns) else 0
         if theta is not None:
             self.plan(n_gauss)
         with self._lock:
@@ -162,7 +199,7 @@ class DeviceTableGroup:
             xi_flat = xi.view(n_draws, -1)
             _lib.check(self.lib.tc_predict_batch(
                 self.handle, ctypes.byref(model), int(n_gauss),
-                theta.data_ptr() if theta is not None else None,
+                theta.data_ptr() if theta is not None else None, theta_ld,
                 occ.data_ptr() if occ is not None else None, n_draws, int(separate),
                 ngal_flat.data_ptr() + 8 * ngal_offset, ngal_flat.stride(0),
                 xi_flat.data_ptr() + 8 * xi_offset, xi_flat.stride(0),
@@ -352,7 +389,7 @@ class TabCorr:
         return spec, theta
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, model=None,
-                      occupation=None, as_numpy=True, pipeline_chunk=25000):
+                      occupation=None, as_numpy=True, pipeline_chunk='auto'):
         """Predict number density and correlation function for B parameter sets at once.
 
         Parameters
@@ -372,10 +409,14 @@ class TabCorr:
             Precomputed mean occupations (the ndarray branch of ``predict``).
         as_numpy : bool, optional
             Return host numpy arrays (default) or leave the results on the device.
-        pipeline_chunk : int, optional
-            With host inputs and host outputs, batches larger than this many draws are cut into
-            chunks whose host-to-device copy, kernels and device-to-host copy overlap on three
-            CUDA streams.  Results do not depend on it.
+        pipeline_chunk : 'auto', int or sequence of int, optional
+            With host inputs and host outputs the draws are cut into chunks whose host-to-device
+            copy, kernels and device-to-host copy overlap on three CUDA streams.  An int is a
+            fixed chunk size, a sequence gives the chunk sizes explicitly (the last one repeats),
+            0 disables chunking.  'auto' (default) uses a short first and last chunk -- only the
+            first chunk's upload and the last chunk's download are not hidden behind a kernel --
+            and few large chunks in between, because every launch pays an un-overlapped
+            occupation phase for its first tile.  Results do not depend on it.
 
         Returns
         -------
@@ -385,9 +426,10 @@ class TabCorr:
         group = self._ensure_device()
         separate = bool(separate_gal_type)
         if (occupation is None and as_numpy and not isinstance(params, torch.Tensor) and
-                pipeline_chunk and pipeline_chunk > 0):
+                (isinstance(pipeline_chunk, (str, list, tuple)) or
+                 (pipeline_chunk and pipeline_chunk > 0))):
             return self._predict_batch_pipelined(params, model, separate, int(n_gauss_prim),
-                                                 int(pipeline_chunk))
+                                                 pipeline_chunk)
         if occupation is not None:
             occ = _to_device_f64(occupation, group.device)
             if occ.ndim != 2 or occ.shape[1] != group.n_rows:
@@ -425,11 +467,15 @@ class TabCorr:
         n_draws = max([c.shape[0] for c in columns if np.ndim(c) > 0] + [1])
         n_ng, n_comp = (2 if separate else 1), group.n_comp(separate)
         f64 = torch.float64
-        theta_pin = torch.empty((n_draws, len(THETA_KEYS)), dtype=f64, pin_memory=True)
+        # parameters are staged one contiguous column per parameter (a strided fill of [B, 7] rows
+        # costs 4x more host time); chunk [lo, hi) owns the block [7 lo, 7 hi) viewed as
+        # [7, hi - lo], so that every chunk is one contiguous host-to-device copy
+        n_theta = len(THETA_KEYS)
+        theta_pin = torch.empty(n_draws * n_theta, dtype=f64, pin_memory=True)
         ngal_pin = torch.empty((n_draws, n_ng), dtype=f64, pin_memory=True)
         xi_pin = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, pin_memory=True)
         theta_np = theta_pin.numpy()
-        theta = torch.empty((n_draws, len(THETA_KEYS)), dtype=f64, device=device)
+        theta = torch.empty(n_draws * n_theta, dtype=f64, device=device)
         ngal = torch.empty((n_draws, n_ng), dtype=f64, device=device)
         xi = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, device=device)
         compute = torch.cuda.current_stream(device)
@@ -437,17 +483,18 @@ class TabCorr:
         # the fresh device buffers may be recycled memory with work pending on the compute stream
         h2d.wait_stream(compute)
         d2h.wait_stream(compute)
-        for lo in range(0, n_draws, chunk):
-            hi = min(lo + chunk, n_draws)
+        for lo, hi in chunk_schedule(n_draws, chunk):
+            block = theta_np[n_theta * lo:n_theta * hi].reshape(n_theta, hi - lo)
             for j, column in enumerate(columns):
-                theta_np[lo:hi, j] = column[lo:hi] if np.ndim(column) > 0 else column
+                block[j] = column[lo:hi] if np.ndim(column) > 0 else column
+            theta_chunk = theta[n_theta * lo:n_theta * hi]
             with torch.cuda.stream(h2d):
-                theta[lo:hi].copy_(theta_pin[lo:hi], non_blocking=True)
+                theta_chunk.copy_(theta_pin[n_theta * lo:n_theta * hi], non_blocking=True)
                 staged = torch.cuda.Event()
                 staged.record(h2d)
             compute.wait_event(staged)
-            group.predict_into(spec, n_gauss, theta[lo:hi], None, separate, ngal[lo:hi], 0,
-                               xi[lo:hi], 0)
+            group.predict_into(spec, n_gauss, theta_chunk.view(n_theta, hi - lo), None, separate,
+                               ngal[lo:hi], 0, xi[lo:hi], 0, theta_columns=True)
             done = torch.cuda.Event()
             done.record(compute)
             with torch.cuda.stream(d2h):

@@ -11,7 +11,7 @@ tab = synthetic.make_table(n_mass=60, n_sec=2, n_r=20)
 halotab = tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], tab['attrs'])
 draws = synthetic.make_draws(n_draws, seed=1)
 ref = None
-for chunk in (0, 100000, 50000, 34000, 25000, 20000, 12500, 8000):
+for chunk in (0, 'auto', 100000, 50000, 25000, [10000, 80000, 10000], [5000, 90000, 5000], [10000, 40000, 40000, 10000], [20000, 60000, 20000], [6000, 44000, 44000, 6000]):
     for _ in range(3):
         out = halotab.predict_batch(draws, pipeline_chunk=chunk)
     torch.cuda.synchronize()
