@@ -1215,24 +1215,34 @@ size_t predict_smem_bytes(int n_pad, int nt, int n_buf) {
   return ((size_t)n_buf * n_pad * 8 * nt + kTabDoubles) * sizeof(double) + sizeof(PredictCtrl);
 }
 
-// Draw-tile width (8 nt draws) and number of W buffers: two buffers (occupation of the next tile
-// overlaps the contraction of the current one) whenever they fit, the widest tile that fits, and
-// narrower tiles only while the batch is too small to give every SM a tile.
+// Draw-tile width (8 nt draws) and number of W buffers.  Two buffers let the occupation of the
+// next tile overlap the contraction of the current one, but halve the tile width that fits in
+// shared memory, and the width is what the table stream from L2 is amortised over: measured on
+// B200, N = 240: 2 x 56 draws = 1 x 64 draws (4.03 ms per 1e5 draws), N = 500: 1 x 48 draws beats
+// 2 x 24 draws (16.9 vs 18.1 ms).  So two buffers are used while they leave at least 40 draws;
+// within a buffer count the widest tile that fits, narrower only while the batch is too small to
+// give every SM a tile.
 void pick_tile(int n_pad, long long n_draws, int n_sm, int* nt_out, int* n_buf_out) {
   *nt_out = 0;
   *n_buf_out = 0;
-  for (int n_buf : {2, 1}) {
-    int best = 0;
-    for (int nt = 8; nt >= 1; nt--) {
-      if (predict_smem_bytes(n_pad, nt, n_buf) > (size_t)kSmemLimit) continue;
-      best = nt;  // the largest that fits, shrinking while the grid would not fill the device
-      if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) break;
-    }
-    if (best) {
-      *nt_out = best;
-      *n_buf_out = n_buf;
-      return;
-    }
+  const int forced = tune("NBUF", 0);
+  auto widest = [&](int n_buf) {
+    for (int nt = 8; nt >= 1; nt--)
+      if (predict_smem_bytes(n_pad, nt, n_buf) <= (size_t)kSmemLimit) return nt;
+    return 0;
+  };
+  int n_buf = widest(2) >= 5 ? 2 : 1;
+  if (forced == 1 || forced == 2) n_buf = forced;
+  if (widest(n_buf) == 0) n_buf = 1;
+  int best = 0;
+  for (int nt = 8; nt >= 1; nt--) {
+    if (predict_smem_bytes(n_pad, nt, n_buf) > (size_t)kSmemLimit) continue;
+    best = nt;  // the largest that fits, shrinking while the grid would not fill the device
+    if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) break;
+  }
+  if (best) {
+    *nt_out = best;
+    *n_buf_out = n_buf;
   }
 }
 

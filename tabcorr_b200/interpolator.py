@@ -13,8 +13,9 @@ import numpy as np
 
 from . import _lib
 from . import h5mini
-from .models import ModelSpec, resolve_model, theta_from_params, ASSEMBIAS_KEYS
-from .tabcorr import (TabCorr, DeviceTableGroup, _to_device_f64, _torch, _h5py)
+from .models import ModelSpec, resolve_model, ASSEMBIAS_KEYS
+from .tabcorr import (TabCorr, DeviceTableGroup, _to_device_f64, _torch, _h5py,
+                      theta_to_device)
 from .table import Table
 
 
@@ -199,14 +200,14 @@ class Interpolator:
                                  'model.'.format(key))
         decorated = all(k in params for k in ASSEMBIAS_KEYS)
         spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
-        theta_host = theta_from_params(params, None, spec)
-        n_draws = theta_host.shape[0]
-        x_host = np.empty((n_draws, len(self._keys)), dtype=np.float64)
-        for d, key in enumerate(self._keys):
-            x_host[:, d] = np.asarray(params[key], dtype=np.float64)
         device = self._groups[0][0].device
-        theta = _to_device_f64(theta_host, device)
-        x = _to_device_f64(x_host, device)
+        theta = theta_to_device(params, spec, device)
+        n_draws = theta.shape[0]
+        coordinates = [np.asarray(params[key], dtype=np.float64) for key in self._keys]
+        if any(c.ndim > 0 and c.shape[0] != n_draws for c in coordinates):
+            raise ValueError('interpolation coordinates and occupation parameters differ in length')
+        x = _to_device_f64(np.stack([np.broadcast_to(c, (n_draws,)) for c in coordinates]),
+                           device).t().contiguous()
 
         separate = bool(separate_gal_type)
         first_group = self._groups[0][0]

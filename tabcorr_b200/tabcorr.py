@@ -123,6 +123,7 @@ class DeviceTableGroup:
         self._planned = set()
         self._workspace = None
         self._copy_streams = None
+        self._single = None
         self._lock = threading.Lock()
 
     def __del__(self):
@@ -180,6 +181,30 @@ class DeviceTableGroup:
             occ.data_ptr(), stream))
         return occ
 
+    def predict_one(self, spec, n_gauss, values, separate):
+        """One parameter set (``values``: the 7 kernel parameters) -> host arrays
+        ``ngal [T, 1|2]``, ``xi [T, R, C]`` (copies).  Latency path, see ``_SingleDrawBuffers``."""
+        torch = _torch()
+        self.plan(n_gauss)
+        with self._lock:
+            if self._single is None:
+                self._single = _SingleDrawBuffers(self)
+            buf = self._single
+            buf.theta_np[:] = values
+            n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
+            model = self._model_struct(spec)
+            stream = torch.cuda.current_stream(self.device)
+            _lib.check(self.lib.tc_predict_batch(
+                self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(), 0, None, 1,
+                int(separate), buf.ngal.data_ptr(), self.n_tables * n_ng, buf.xi.data_ptr(),
+                self.n_tables * self.n_r * n_comp, buf.workspace.data_ptr(),
+                buf.workspace.numel(), stream.cuda_stream))
+            stream.synchronize()
+            ngal = buf.ngal_np[:self.n_tables * n_ng].reshape(self.n_tables, n_ng).copy()
+            xi = buf.xi_np[:self.n_tables * self.n_r * n_comp].reshape(
+                self.n_tables, self.n_r, n_comp).copy()
+        return ngal, xi
+
     def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset,
                      theta_columns=False):
         """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
@@ -206,6 +231,25 @@ class DeviceTableGroup:
                 workspace.data_ptr(), workspace.numel(), stream))
 
 
+class _SingleDrawBuffers:
+    """Persistent buffers of the one-draw fast path (``TabCorr.predict(model)``): the parameters
+    and the results live in pinned host memory that the kernels access directly (unified
+    addressing), so a call is one ctypes call (two launches) and one stream synchronisation -- no
+    copies, no allocations."""
+
+    def __init__(self, group):
+        torch = _torch()
+        f64 = torch.float64
+        self.theta = torch.zeros(len(THETA_KEYS), dtype=f64, pin_memory=True)
+        self.ngal = torch.zeros(2 * group.n_tables, dtype=f64, pin_memory=True)
+        self.xi = torch.zeros(group.n_tables * group.n_r * 3, dtype=f64, pin_memory=True)
+        self.theta_np, self.ngal_np, self.xi_np = (self.theta.numpy(), self.ngal.numpy(),
+                                                   self.xi.numpy())
+        need = max(int(group.lib.tc_predict_workspace_bytes(group.handle, 1, sep))
+                   for sep in (0, 1))
+        self.workspace = torch.empty(max(need, 8), dtype=torch.uint8, device=group.device)
+
+
 class _PinnedStage:
     """Pinned host staging buffer whose numpy view is filled in place, then copied H2D."""
 
@@ -230,6 +274,20 @@ def _to_device_f64(array, device):
     stage = _PinnedStage()
     stage(array.shape)[...] = array
     return stage.to(device)
+
+
+def theta_to_device(params, spec, device):
+    """Parameter dict -> CUDA ``[B, 7]`` tensor.  The columns are staged contiguously in pinned
+    memory (filling ``[B, 7]`` rows column by column costs 4x more host time), copied
+    asynchronously and transposed on the device."""
+    torch = _torch()
+    columns = theta_columns(params, spec)
+    n_draws = max([c.shape[0] for c in columns if c.ndim > 0] + [1])
+    stage = torch.empty((len(columns), n_draws), dtype=torch.float64, pin_memory=True)
+    stage_np = stage.numpy()
+    for j, column in enumerate(columns):
+        stage_np[j] = column
+    return stage.to(device=device, non_blocking=True).t().contiguous()
 
 
 def _to_host(tensor):
@@ -374,9 +432,7 @@ class TabCorr:
         if isinstance(params, dict):
             decorated = all(k in params for k in ASSEMBIAS_KEYS)
             spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
-            stage = _PinnedStage()
-            theta_from_params(params, None, spec, alloc=stage)
-            theta = stage.to(group.device)
+            theta = theta_to_device(params, spec, group.device)
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             theta = _to_device_f64(params, group.device)
@@ -552,8 +608,10 @@ class TabCorr:
             if check_consistency:
                 self._check_consistency(model)
             spec = resolve_model(model)
-            theta = theta_from_params(model.param_dict, 1, spec)
-            result = self.predict_batch(theta, separate_gal_type, n_gauss_prim, model=spec)
+            values = theta_from_params(model.param_dict, 1, spec)[0]
+            ngal, xi = self._ensure_device().predict_one(spec, int(n_gauss_prim), values,
+                                                         bool(separate_gal_type))
+            result = self._format_batch(ngal, xi, bool(separate_gal_type), False)
         ngal, xi = result
         if separate_gal_type:
             return ({k: v[0] for k, v in ngal.items()}, {k: v[0] for k, v in xi.items()})
