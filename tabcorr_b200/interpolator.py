@@ -8,6 +8,7 @@ occupation + contraction launch over ``T * R`` stacked radial bins followed by t
 """
 
 import ctypes
+import threading
 
 import numpy as np
 
@@ -112,6 +113,8 @@ class Interpolator:
         self._device = device
         self._groups = None
         self._interp = None
+        self._one = None
+        self._one_lock = threading.Lock()
 
     # ------------------------------------------------------------------ I/O
     @classmethod
@@ -184,6 +187,61 @@ class Interpolator:
             self._interp = None
 
     # ------------------------------------------------------------------ prediction
+    def _predict_one(self, spec, n_gauss, values, x_values, separate, extrapolate):
+        """Latency path of :meth:`predict`: one parameter set, persistent buffers, parameters,
+        coordinates, results and the out-of-range flag in pinned host memory that the kernels
+        access directly; one stream synchronisation, no copies, no allocations."""
+        torch = _torch()
+        self._ensure_device()
+        first_group = self._groups[0][0]
+        device = first_group.device
+        n_tables = len(self.tabcorr_list)
+        n_r = first_group.n_r
+        with self._one_lock:
+            if self._one is None:
+                f64 = torch.float64
+                self._one = {
+                    'theta': torch.zeros(7, dtype=f64, pin_memory=True),
+                    'x': torch.zeros(len(self._keys), dtype=f64, pin_memory=True),
+                    'flag': torch.zeros(1, dtype=torch.int32, pin_memory=True),
+                    'ngal': torch.zeros(2, dtype=f64, pin_memory=True),
+                    'xi': torch.zeros(n_r * 3, dtype=f64, pin_memory=True),
+                    'ngal_t': torch.zeros(n_tables * 2, dtype=f64, device=device),
+                    'xi_t': torch.zeros(n_tables * n_r * 3, dtype=f64, device=device),
+                    'workspace': [torch.empty(max(8, max(
+                        int(self._lib.tc_predict_workspace_bytes(group.handle, 1, sep))
+                        for sep in (0, 1))), dtype=torch.uint8, device=device)
+                        for group, _ in self._groups],
+                }
+            buf = self._one
+            buf['theta'].numpy()[:] = values
+            buf['x'].numpy()[:] = x_values
+            buf['flag'].numpy()[0] = 0
+            n_ng, n_comp = (2 if separate else 1), first_group.n_comp(separate)
+            n_cols = n_r * n_comp
+            stream = torch.cuda.current_stream(device)
+            model = DeviceTableGroup._model_struct(spec)
+            slot = 0
+            for (group, members), workspace in zip(self._groups, buf['workspace']):
+                group.plan(n_gauss)
+                _lib.check(self._lib.tc_predict_batch(
+                    group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(), 0,
+                    None, 1, int(separate), buf['ngal_t'].data_ptr() + 8 * slot * n_ng,
+                    n_tables * n_ng, buf['xi_t'].data_ptr() + 8 * slot * n_cols, n_tables * n_cols,
+                    workspace.data_ptr(), workspace.numel(), stream.cuda_stream))
+                slot += len(members)
+            for data, cols, out in ((buf['ngal_t'], n_ng, buf['ngal']), (buf['xi_t'], n_cols, buf['xi'])):
+                _lib.check(self._lib.tc_interp_apply_batch(
+                    self._interp, buf['x'].data_ptr(), 1, data.data_ptr(), cols, out.data_ptr(),
+                    int(bool(extrapolate)), buf['flag'].data_ptr(), stream.cuda_stream))
+            stream.synchronize()
+            if int(buf['flag'].numpy()[0]) != 0:
+                raise ValueError('The x-coordinates are outside of the interpolation range and '
+                                 'extrapolation is turned off.')
+            ngal = buf['ngal'].numpy()[:n_ng].reshape(1, n_ng).copy()
+            xi = buf['xi'].numpy()[:n_cols].reshape(1, n_r, n_comp).copy()
+        return self.tabcorr_list[0]._format_batch(ngal, xi, separate, False)
+
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
                       model=None, as_numpy=True):
         """Interpolated predictions for B parameter sets.
@@ -251,10 +309,11 @@ class Interpolator:
             for i in self.unique_gal_type_index:
                 self.tabcorr_list[i]._check_consistency(model)
         spec = resolve_model(model)
-        params = {k: np.atleast_1d(np.float64(v)) for k, v in model.param_dict.items()
-                  if np.isscalar(v)}
-        ngal, xi = self.predict_batch(params, separate_gal_type, n_gauss_prim, extrapolate,
-                                      model=spec)
+        from .models import theta_from_params
+        values = theta_from_params(model.param_dict, 1, spec)[0]
+        x_values = [np.float64(model.param_dict[key]) for key in self._keys]
+        ngal, xi = self._predict_one(spec, int(n_gauss_prim), values, x_values,
+                                     bool(separate_gal_type), extrapolate)
         if separate_gal_type:
             return ({k: v[0] for k, v in ngal.items()}, {k: v[0] for k, v in xi.items()})
         return ngal[0], xi[0]

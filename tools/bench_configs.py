@@ -76,7 +76,7 @@ def main():
         return 2.0 * n_r * n * n + 2.0 * n_r * n if mode == 'auto' else 2.0 * n_r * n
 
     def want(name):
-        return args.only is None or args.only in name
+        return args.only is None or args.only in name or name in args.only
 
     def table_of(tab):
         return tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'],
@@ -139,7 +139,7 @@ def main():
              executed_frac=executed_flops(n, n_r, 'auto') * n_draws / (ms * 1e-3) / (peak.value * 1e12))
 
     # ---- cfg4: database-style Interpolators, per-draw cosmology -------------------------------------
-    if want('cfg4') and world == 1:
+    if want('cfg4') and world == 1 and 'real' not in (args.only or ''):
         axes_wp = {'alpha_s': np.linspace(0.8, 1.2, 4), 'log_eta': np.log10(np.geomspace(1 / 3, 3, 4))}
         axes_xi = {'alpha_c': np.linspace(0.0, 0.4, 4), 'alpha_s': np.linspace(0.8, 1.2, 4),
                    'log_eta': np.log10(np.geomspace(1 / 3, 3, 4))}
@@ -170,6 +170,7 @@ def main():
                  single_interpolator_preds_per_s=n_one / ms_one * 1e3,
                  executed_frac_single=executed_flops(120, 14 * t_tables, 'auto') * n_one /
                  (ms_one * 1e-3) / (peak.value * 1e12))
+    if want('cfg4') and world == 1:
         interp = tabcorr_b200.Interpolator.read(os.path.join(golden, 'ds_efficient.hdf5'))
         model = Zheng07Model(threshold=-21, redshift=0.5, prim_haloprop_key='halo_m258m')
         model.param_dict['log_eta'] = 0.1
