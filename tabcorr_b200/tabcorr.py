@@ -157,8 +157,11 @@ class DeviceTableGroup:
     def _workspace_for(self, n_draws, separate):
         torch = _torch()
         need = int(self.lib.tc_predict_workspace_bytes(self.handle, int(n_draws), int(separate)))
-        if need == 0:
-            _lib.check(-3 if n_draws > 0 else 0)
+        if need == 0 and n_draws > 0:
+            raise _lib.TabCorrB200Error(
+                'table too large for the CUDA kernel: the weights of 8 draws x {} halo bins do not '
+                'fit the 227 KB shared-memory tile (at most ~3500 bins are supported)'.format(
+                    self.n_rows))
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._workspace

@@ -160,3 +160,79 @@ def test_cfg3_decorated_multipoles_against_oracle(tb):
         ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model, 100))
         close(ngal_100[i], ngal_ref)
         np.testing.assert_allclose(xi_100[i], xi_ref, rtol=RTOL, atol=RTOL * np.abs(xi_ref).max())
+
+
+def _oracle_check(tb, tab, draws, decorated, mode='auto', rows=(0, 1, -1), n_gauss=10):
+    from oracle import tabcorr_oracle as orc
+    halotab = table_from_dict(tb, tab)
+    ngal, xi = halotab.predict_batch(draws, n_gauss_prim=n_gauss)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], mode)
+    n_draws = len(ngal)
+    for i in rows:
+        i = i % n_draws
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=decorated)
+        ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model, n_gauss))
+        close(ngal[i], ngal_ref)
+        close(xi[i].ravel(), np.ravel(xi_ref))
+    return halotab, ngal, xi
+
+
+@pytest.mark.parametrize('n_mass,n_sec,n_r,mode', [
+    (2, 1, 1, 'auto'), (2, 2, 3, 'auto'), (2, 1, 1, 'cross'), (3, 3, 2, 'auto'), (7, 2, 17, 'cross'),
+    (8, 1, 16, 'auto'), (9, 2, 33, 'auto'), (31, 2, 5, 'cross'), (64, 2, 2, 'auto'),
+])
+def test_edge_shapes_against_oracle(tb, n_mass, n_sec, n_r, mode):
+    """Smallest tables, R = 1, row counts around the 16-row tile and 4-row k-step boundaries."""
+    tab = cases.synthetic.make_table(n_mass=n_mass, n_sec=n_sec, n_r=n_r, seed=n_mass + n_r,
+                                     mode=mode)
+    draws = cases.synthetic.make_draws(70, seed=n_r, decorated=True)
+    _oracle_check(tb, tab, draws, True, mode, rows=(0, 7, 8, 63, 64, -1))
+
+
+def test_single_galaxy_type_tables(tb):
+    """Tables holding only centrals or only satellites (the reference accepts any gal_type set)."""
+    full = cases.synthetic.make_table(n_mass=12, n_sec=2, n_r=4, seed=2)
+    draws = cases.synthetic.make_draws(40, seed=5, decorated=True)
+    n = len(full['gal_type'])
+    rows_i, cols_i = np.tril_indices(n)
+    for name in ('centrals', 'satellites'):
+        keep = np.flatnonzero(full['gal_type']['gal_type'] == name.encode())
+        dense = np.zeros((4, n, n))
+        dense[:, rows_i, cols_i] = full['tpcf_matrix']
+        dense = dense + np.transpose(np.tril(dense, -1), (0, 2, 1))
+        sub = dense[:, keep][:, :, keep]
+        r2, c2 = np.tril_indices(len(keep))
+        tab = dict(full, gal_type=full['gal_type'][keep], tpcf_matrix=sub[:, r2, c2])
+        halotab, ngal, xi = _oracle_check(tb, tab, draws, True)
+        ngal_sep, xi_sep = halotab.predict_batch(draws, separate_gal_type=True)
+        assert list(ngal_sep) == [name] and list(xi_sep) == ['{0}-{0}'.format(name)]
+        np.testing.assert_allclose(ngal_sep[name], ngal, rtol=1e-13)
+        np.testing.assert_allclose(xi_sep['{0}-{0}'.format(name)], xi, rtol=1e-12)
+
+
+def test_table_too_large_for_the_tile_fails_loudly(tb):
+    """A table whose padded rows do not fit one 8-draw W tile in shared memory is refused with an
+    error naming the limit -- not computed some other way."""
+    n_mass = 950   # N = 3800 rows -> 3808 padded rows x 8 draws x 8 B > 227 KB
+    gal_type = cases.synthetic.make_gal_type(n_mass, 2)
+    matrix = np.ones((1, len(gal_type)))
+    attrs = dict(cases.synthetic.make_table(n_mass=2, n_sec=1, n_r=1, mode='cross')['attrs'])
+    halotab = tb.TabCorr.from_arrays(gal_type, matrix, (1,), attrs)
+    with pytest.raises(Exception, match='too large|workspace|unsupported'):
+        halotab.predict_batch(cases.synthetic.make_draws(10, seed=1))
+
+
+def test_non_finite_parameters_do_not_poison_neighbours(tb):
+    """A NaN / inf parameter set yields a non-finite result for that draw only."""
+    tab = cases.synthetic.make_table(n_mass=20, n_sec=2, n_r=6, seed=3)
+    halotab = table_from_dict(tb, tab)
+    draws = cases.synthetic.make_draws(200, seed=9)
+    ref = halotab.predict_batch(draws)
+    bad = {k: v.copy() for k, v in draws.items()}
+    bad['logMmin'][17] = np.nan
+    bad['alpha'][101] = np.inf
+    out = halotab.predict_batch(bad)
+    good = np.ones(200, dtype=bool)
+    good[[17, 101]] = False
+    assert np.array_equal(out[0][good], ref[0][good]) and np.array_equal(out[1][good], ref[1][good])
+    assert not np.isfinite(out[0][17])
