@@ -147,6 +147,11 @@ __device__ __forceinline__ int widx(int i, int b) {
 //   sat:  t^alpha = exp(alpha log t) with a 128-entry log table (degree-7 log1p) and a 32-entry
 //         2^(j/32) table (degree-6 exp); relative error < 3e-14 over the reachable range.
 // The tables are computed on the host in long double when the library first touches a device.
+// (Tried: degree 7 on 193 intervals of width 1/16 -- same accuracy, 8 instead of 14 coefficient
+// loads per evaluation.  Not faster: with finer intervals the lanes of a warp hit more distinct
+// table columns, so every load costs more shared-memory wavefronts; standalone occupation kernel
+// 0.536 vs 0.503 ms per 1e5 draws, fused kernel unchanged.  The small table also leaves room for
+// wider draw tiles.)
 // ------------------------------------------------------------------------------------------
 constexpr int kErfDeg = 13;
 constexpr int kErfIntervals = 27;                               // 25 polynomial + 2 saturated
@@ -1568,12 +1573,14 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   args.n_buf = ws.n_buf;
   pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat);
   {
-    // occupation items take every occ_stride-th slot of the first ~70 % of a tile's work list;
+    // occupation items take every occ_stride-th slot of the first 70 % of a tile's work list (an
+    // item runs for tens of microseconds beside DMMA warps that starve its scalar FP64, so the
+    // last one must be taken well before the list ends: 70 % measured 2 % faster than 90 %);
     // with a single W buffer they must all come before the chunks that wait for them
     const int n_occ = ws.nt * (args.n_ranges_cen + args.n_ranges_sat);
     const int slots = L.dev.n_chunks + n_occ;
     // (every occupation slot must exist: stride * n_occ <= slots)
-    const int spread = std::min(100, std::max(1, tune("OCC_SPREAD", 90)));
+    const int spread = std::min(100, std::max(1, tune("OCC_SPREAD", 70)));
     args.occ_stride = ws.n_buf == 1 ? 1 : std::max(1, (int)((long long)spread * slots / (100LL * n_occ)));
   }
   const int bm = 8 * ws.nt;

@@ -60,12 +60,17 @@ def gather_rows(local, n_total, dst=0, group=None):
 
 
 def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, group=None,
-                          **predict_kwargs):
+                          n_chunks=3, **predict_kwargs):
     """``halotab.predict_batch`` over all ranks of the process group.
 
     ``params`` holds ALL draws on every rank (dict of ``[B]`` arrays or ``[B, k]`` array); each
     rank evaluates its slice and rank ``dst`` receives ``(ngal [B], xi [B, *tpcf_shape])`` as numpy
     arrays (other ranks get ``None``).  Works for ``TabCorr`` and ``Interpolator`` instances.
+
+    The slice is evaluated in ``n_chunks`` pieces: the gather of piece c (asynchronous, NCCL) and,
+    on ``dst``, the device-to-host copy of the gathered piece c - 1 overlap the kernels of the
+    next piece, so that rank ``dst``'s PCIe link -- which carries every rank's results -- is busy
+    during the computation instead of after it.  Results do not depend on ``n_chunks``.
     """
     import torch
     import torch.distributed as dist
@@ -76,13 +81,82 @@ def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, g
     else:
         n_total = len(params)
     local = shard_params(params, rank, world)
-    ngal, xi = halotab.predict_batch(local, n_gauss_prim=n_gauss_prim, model=model,
-                                     as_numpy=False, **predict_kwargs)
-    shape = tuple(xi.shape[1:])
-    slab = torch.cat([ngal.reshape(-1, 1), xi.reshape(xi.shape[0], -1)], dim=1)
-    full = gather_rows(slab, n_total, dst=dst, group=group)
-    if full is None:
+    lo_rank, hi_rank = shard_bounds(n_total, rank, world)
+    n_local = hi_rank - lo_rank
+    rows_max = max(shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0]
+                   for r in range(world))
+    n_chunks = max(1, min(int(n_chunks), rows_max)) if world > 1 else 1
+    # piece c of every rank covers the same local row range [c0, c1) (clipped to the rank's rows)
+    cuts = [rows_max * c // n_chunks for c in range(n_chunks + 1)]
+
+    def piece(c):
+        c0, c1 = min(cuts[c], n_local), min(cuts[c + 1], n_local)
+        if isinstance(local, dict):
+            return {k: (v[c0:c1] if np.ndim(v) > 0 else v) for k, v in local.items()}, c1 - c0
+        return local[c0:c1], c1 - c0
+
+    host, shape, pending = None, None, None
+    use_cuda = torch.cuda.is_available()
+    copy_stream = torch.cuda.Stream() if (use_cuda and rank == dst and world > 1) else None
+
+    def drain(entry):
+        """On dst: wait for gather c, then copy every rank's rows into the pinned host array."""
+        work, slabs, c = entry
+        if rank != dst or copy_stream is None:
+            work.wait()
+            if rank != dst:
+                return
+        else:
+            # only the copy stream waits for the gather: the compute stream keeps launching
+            with torch.cuda.stream(copy_stream):
+                work.wait()
+        for r in range(world):
+            lo_r, hi_r = shard_bounds(n_total, r, world)
+            c0, c1 = min(cuts[c], hi_r - lo_r), min(cuts[c + 1], hi_r - lo_r)
+            if c1 <= c0:
+                continue
+            if copy_stream is not None:
+                with torch.cuda.stream(copy_stream):
+                    host[lo_r + c0:lo_r + c1].copy_(slabs[r][:c1 - c0], non_blocking=True)
+                slabs[r].record_stream(copy_stream)
+            else:
+                host[lo_r + c0:lo_r + c1].copy_(slabs[r][:c1 - c0])
+
+    for c in range(n_chunks):
+        sub, n_sub = piece(c)
+        if n_sub > 0:
+            ngal, xi = halotab.predict_batch(sub, n_gauss_prim=n_gauss_prim, model=model,
+                                             as_numpy=False, **predict_kwargs)
+            shape = tuple(xi.shape[1:])
+            slab = torch.cat([ngal.reshape(-1, 1), xi.reshape(xi.shape[0], -1)], dim=1)
+        else:
+            slab = None
+        if world == 1:
+            from .tabcorr import _to_host
+            full = _to_host(slab)
+            return full[:, 0], full[:, 1:].reshape((n_total,) + shape)
+        if shape is None:   # a rank without rows still takes part in the gathers
+            shape = tuple(halotab.tpcf_shape)
+        width = 1 + int(np.prod(shape))
+        rows = cuts[c + 1] - cuts[c]
+        device = slab.device if slab is not None else (
+            torch.device('cuda', torch.cuda.current_device()) if use_cuda else torch.device('cpu'))
+        if slab is None or slab.shape[0] != rows:
+            padded = torch.zeros((rows, width), dtype=torch.float64, device=device)
+            if slab is not None:
+                padded[:slab.shape[0]] = slab
+            slab = padded
+        if rank == dst and host is None:
+            host = torch.empty((n_total, width), dtype=torch.float64, pin_memory=use_cuda)
+        slabs = [torch.empty_like(slab) for _ in range(world)] if rank == dst else None
+        work = dist.gather(slab.contiguous(), slabs, dst=dst, group=group, async_op=True)
+        if pending is not None:
+            drain(pending)
+        pending = (work, slabs, c)
+    drain(pending)
+    if rank != dst:
         return None
-    from .tabcorr import _to_host
-    full = _to_host(full)
+    if copy_stream is not None:
+        copy_stream.synchronize()
+    full = host.numpy()
     return full[:, 0], full[:, 1:].reshape((n_total,) + shape)
