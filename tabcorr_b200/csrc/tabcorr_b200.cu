@@ -151,7 +151,10 @@ __device__ __forceinline__ int widx(int i, int b) {
 // loads per evaluation.  Not faster: with finer intervals the lanes of a warp hit more distinct
 // table columns, so every load costs more shared-memory wavefronts; standalone occupation kernel
 // 0.536 vs 0.503 ms per 1e5 draws, fused kernel unchanged.  The small table also leaves room for
-// wider draw tiles.)
+// wider draw tiles.  Also tried: high and low words of the coefficients in separate 32-word rows,
+// two conflict-free LDS.32 instead of one conflicting LDS.64 -- bank conflicts 4x lower, time
+// unchanged (0.490 ms): ncu shows the occupation code at 56 % issue, 54 % LSU, 35 % FP64 pipe
+// utilisation with 77 warp instructions per 32 evaluations, bound by no single unit.)
 // ------------------------------------------------------------------------------------------
 constexpr int kErfDeg = 13;
 constexpr int kErfIntervals = 27;                               // 25 polynomial + 2 saturated

@@ -71,6 +71,8 @@ def main():
         print('| {} | {} | {:.1f}% | {:.1f}% |'.format(op, count, 100.0 * count / total_e,
                                                         100.0 * mix_s[op] / total_s))
     # regions: SASS address ranges between the first and last DMMA = contraction loops
+    if not any('DMMA' in r[i_src] for r in data):
+        return
     first = next(i for i, r in enumerate(data) if 'DMMA' in r[i_src])
     last = max(i for i, r in enumerate(data) if 'DMMA' in r[i_src])
     bar = [i for i, r in enumerate(data) if 'BAR.SYNC' in r[i_src]]
