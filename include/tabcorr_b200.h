@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 101
+#define TC_VERSION 102
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -32,6 +32,14 @@ extern "C" {
 
 #define TC_MODE_AUTO 0  /* xi_r = w^T M_r w / (sum w)^2, tabcorr/tabcorr.py:641-647 */
 #define TC_MODE_CROSS 1 /* xi_r = M_r . w / sum w,        tabcorr/tabcorr.py:648-649 */
+
+/* Arithmetic of the auto-mode contraction.  FP64: DMMA tensor cores, parity with the reference
+ * to rtol 1e-10.  3XTF32 (optional, auto tables only): table entries and tracer weights split into
+ * TF32 high + low parts, hi*hi + lo*hi + hi*lo accumulated in FP32 on the TF32 tensor cores,
+ * row-dot and normalisation in FP64; relative error ~1e-7 of the term magnitudes (tested 1e-6).
+ * The occupation arithmetic is FP64 in both. */
+#define TC_PRECISION_FP64 0
+#define TC_PRECISION_3XTF32 1
 
 /* Number of doubles per parameter draw consumed by tc_predict_batch / tc_occupation_batch:
  * logMmin, sigma_logM, logM0, logM1, alpha, A_cen, A_sat  (the last two are the
@@ -104,7 +112,7 @@ size_t tc_predict_workspace_bytes(const tc_table* table, int64_t n_draws, int se
  * Strides are in doubles, so that several table groups can fill one [B, T_total, ...] buffer. */
 int tc_predict_batch(tc_table* table, const tc_model* model, int n_gauss, const double* theta_dev,
                      int64_t theta_ld, const double* occ_dev, int64_t n_draws, int separate,
-                     double* ngal_dev,
+                     int precision, double* ngal_dev,
                      int64_t ngal_stride, double* xi_dev, int64_t xi_stride, void* workspace_dev,
                      size_t workspace_bytes, void* stream);
 

@@ -14,6 +14,18 @@ LIB_PATH = os.path.join(HERE, 'libtabcorr_b200.so')
 
 TC_MODE_AUTO = 0
 TC_MODE_CROSS = 1
+TC_PRECISION_FP64 = 0
+TC_PRECISION_3XTF32 = 1
+
+
+def precision_code(precision):
+    """'fp64' | '3xtf32' (or the integer codes) -> TC_PRECISION_*."""
+    table = {'fp64': TC_PRECISION_FP64, 'f64': TC_PRECISION_FP64, '3xtf32': TC_PRECISION_3XTF32,
+             TC_PRECISION_FP64: TC_PRECISION_FP64, TC_PRECISION_3XTF32: TC_PRECISION_3XTF32}
+    key = precision.lower() if isinstance(precision, str) else precision
+    if key not in table:
+        raise ValueError("precision must be 'fp64' or '3xtf32'")
+    return table[key]
 TC_N_THETA = 7
 
 # every symbol include/tabcorr_b200.h declares
@@ -75,7 +87,8 @@ def load():
     lib.tc_predict_batch.restype = ctypes.c_int
     lib.tc_predict_batch.argtypes = [
         vp, ctypes.POINTER(tc_model), ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64,
-        ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_size_t, vp]
+        ctypes.c_int, ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_size_t,
+        vp]
     lib.tc_interp_create.restype = ctypes.c_int
     lib.tc_interp_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, c_int32_p, c_double_p,
                                      c_double_p, c_int32_p, ctypes.c_int]

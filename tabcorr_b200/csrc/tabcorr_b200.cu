@@ -106,6 +106,8 @@ struct LayoutDev {
   int n_out;           // outputs per draw: Reff * n_comp
   long long ks_per_r;  // k-steps per radial bin (auto) / per 16-bin tile (cross) in the A stream
   const double2* afrag;
+  const float4* afrag32;   // 3xTF32 mode: per k8-step a 32-lane block of high parts, then of low parts
+  long long ks8_per_r;     // k8-steps per radial bin in afrag32
   const Chunk* chunks;
   const long long* chunk_cost_prefix;  // [n_chunks + 1] cumulative cost of the sorted chunks
   const int* out_ptr;    // [n_out + 1] CSR: which scratch rows sum to output o
@@ -128,12 +130,78 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
   return v;
 }
 
+// internal kernel mode: auto-correlation table contracted in 3xTF32 (tc_predict_batch precision 1)
+constexpr int kModeAutoTf32 = 2;
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const float4& a, float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+        "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// d = a * b with a fresh (zero) accumulator
+__device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const float4& a, float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+        "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.0f));
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// 3xTF32 mode: index (in floats) of the HIGH part of (padded row i, draw b) in the shared W tile;
+// the low part is two floats further.  m16n8k8 B-fragment order: per k8-step and n-tile the lane
+// holding B[k = i % 4 (+ 4)][n = b % 8] reads one float4 {hi(k), hi(k + 4), lo(k), lo(k + 4)}.
+// The tile has the same size as the FP64 one (8 bytes per weight).
+template <int NT>
+__device__ __forceinline__ int widx32(int i, int b) {
+  return (((((i >> 3) * NT + (b >> 3)) << 5) + ((b & 7) << 2) + (i & 3)) << 2) + ((i >> 2) & 1);
+}
+
 // index of (padded row i, draw b) in the shared W tile: DMMA B-fragment order, so that the lane
 // holding B[k = i % 4][n = b % 8] of k-step i / 4 and n-tile b / 8 reads consecutive doubles.
 template <int NT>
 __device__ __forceinline__ int widx(int i, int b) {
   return (((i >> 2) * NT + (b >> 3)) << 5) + ((b & 7) << 2) + (i & 3);
 }
+
+// store / load one tracer weight of the shared W tile in the representation of the mode
+template <int NT, int MODE>
+__device__ __forceinline__ void store_weight(double* Ws, int row, int b, double w) {
+  if (MODE == kModeAutoTf32) {
+    float* wf = reinterpret_cast<float*>(Ws) + widx32<NT>(row, b);
+    const float hi = to_tf32((float)w);
+    wf[0] = hi;
+    wf[2] = to_tf32((float)(w - (double)hi));
+  } else {
+    Ws[widx<NT>(row, b)] = w;
+  }
+}
+template <int NT, int MODE>
+__device__ __forceinline__ double load_weight(const double* Ws, int row, int b) {
+  if (MODE == kModeAutoTf32) {
+    const float* wf = reinterpret_cast<const float*>(Ws) + widx32<NT>(row, b);
+    return (double)wf[0] + (double)wf[2];
+  }
+  return Ws[widx<NT>(row, b)];
+}
+
 
 // ------------------------------------------------------------------------------------------
 // table-driven double-precision math for the occupation phase
@@ -417,6 +485,7 @@ struct PredictArgs {
   int n_ranges_cen;      // occupation items per n-tile: group ranges of centrals ...
   int n_ranges_sat;      // ... and of satellites
   int occ_stride;        // every occ_stride-th slot of a tile's work list is an occupation item
+  int tf32_segment;      // 3xTF32 mode: k8-steps per FP32 accumulation chain
 };
 
 struct PredictCtrl {
@@ -534,6 +603,95 @@ __device__ __forceinline__ void run_chunk(const LayoutDev& lay, const Chunk& ch,
   }
 }
 
+// One contraction chunk in 3xTF32: every table entry and every weight is split into a TF32 high
+// part and a TF32 low part (22 significant bits together); hi*hi + lo*hi + hi*lo are accumulated in
+// FP32 by the warp-level m16n8k8 MMA (k8-steps of 8 table columns, 16-row tiles as in the FP64
+// path), the row-dot and everything after it stay in FP64.  Relative error ~1e-7 of the sum of the
+// term magnitudes (tests: 1e-6).
+constexpr int kTf32Segment = 1 << 20;   // k8-steps per FP32 running sum (default: the whole tile)
+
+template <int NT>
+__device__ __forceinline__ void run_chunk_tf32(const LayoutDev& lay, const Chunk& ch,
+                                               const double* __restrict__ Ws,
+                                               double* __restrict__ parts, int lane,
+                                               int segment) {
+  constexpr int BM = 8 * NT;
+  const int g = lane >> 2, tig = lane & 3;
+  const float* Wf = reinterpret_cast<const float*>(Ws);
+  const int k_begin = ch.k_begin >> 1, k_cap = ch.k_cap >> 1;   // k4-steps -> k8-steps
+  double sums[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) sums[nt][0] = sums[nt][1] = 0.0;
+  for (int mt = ch.mt0; mt < ch.mt1; mt++) {
+    const int k_end = min(2 * (mt + 1), k_cap);
+    const float4* ap = lay.afrag32 +
+        (((size_t)ch.r * lay.ks8_per_r + (size_t)mt * (mt + 1) + k_begin) * 2) * 32 + lane;
+    const float4* wk = reinterpret_cast<const float4*>(Wf) + (size_t)k_begin * NT * 32 + lane;
+    float4 hi_next = ld_stream4(ap), lo_next = ld_stream4(ap + 32);
+    int ks = k_begin;
+    while (ks < k_end) {
+      // optional: cut the FP32 running sum every `segment` k8-steps (row-dot into the FP64 sums)
+      const int seg_end = min(ks + segment, k_end);
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+      for (; ks < seg_end; ks++) {
+        const float4 a_hi = hi_next, a_lo = lo_next;
+        ap += 64;
+        hi_next = ld_stream4(ap);        // the stream is padded by one k8-step, always safe
+        lo_next = ld_stream4(ap + 32);
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          const float4 w = wk[nt * 32];  // {hi(k), hi(k + 4), lo(k), lo(k + 4)}
+          // The tensor core truncates its FP32 accumulator after every MMA -- up to one ulp of the
+          // RUNNING sum, always towards zero: chained over a 16-row tile's 30 k8-steps that is a
+          // bias of 1e-6 (measured, tools/tf32_error.py).  So each k8-step starts from a zero
+          // accumulator (its truncations are relative to the small increment) and is added to the
+          // running sum with round-to-nearest FADDs, which are unbiased and nearly free.
+          float d[4];
+          mma_tf32_zero(d, a_lo, w.x, w.y);   // small terms first
+          mma_tf32(d, a_hi, w.z, w.w);
+          mma_tf32(d, a_hi, w.x, w.y);
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[nt][j] += d[j];
+        }
+        wk += NT * 32;
+      }
+      // row-dot: acc[nt][2 h + e] = (M' W)[row = 16 mt + 8 h + g][draw = 8 nt + 2 tig + e]
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int row = 16 * mt + 8 * h + g;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const float* wf = Wf + widx32<NT>(row, 8 * nt + 2 * tig + e);
+            const float a = acc[nt][2 * h + e];
+            sums[nt][e] += (double)fmaf(a, wf[2], a * wf[0]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      double v = sums[nt][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      sums[nt][e] = v;
+    }
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+      *reinterpret_cast<double2*>(parts + (size_t)ch.part_row * BM + 8 * nt + 2 * tig) =
+          make_double2(sums[nt][0], sums[nt][1]);
+  }
+}
+
 // The kernel is a barrier-free software pipeline over the CTA's draw tiles.  Work is a sequence of
 // per-tile lists of S slots that the 12 warps take from one shared cursor:
 //   slot 0                          number densities of tile j (one warp, sequential row order)
@@ -641,7 +799,9 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
         occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
         occupation_item(args.plan, args.model, args.theta + draw * args.theta_ds, args.theta_ps,
                         g_begin, g_end, tab,
-                        [&](int row, double occ, double nh) { Ws[widx<NT>(row, b)] = occ * nh; });
+                        [&](int row, double occ, double nh) {
+                          store_weight<NT, MODE>(Ws, row, b, occ * nh);
+                        });
       } else {
         const int n_q = args.n_ranges_cen + args.n_ranges_sat;
         const int r_begin = (int)((long long)lay.n_pad * q / n_q);
@@ -649,7 +809,8 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
         for (int row = r_begin + (lane >> 3); row < r_end; row += 4) {
           const int src = lay.pad_to_row[row];
           if (src >= 0)
-            Ws[widx<NT>(row, b)] = args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row];
+            store_weight<NT, MODE>(Ws, row, b,
+                                   args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row]);
         }
       }
       flag_signal(&ctrl->full[buf], lane);
@@ -672,14 +833,18 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       // ---- number densities (by the CTA that owns the tile's first chunk) ---------------------
       for (int b = lane; b < BM; b += 32) {
         double nc = 0.0, ns = 0.0;
-        for (int r = 0; r < lay.nc_pad; r++) nc += Ws[widx<NT>(r, b)];
-        for (int r = lay.nc_pad; r < lay.n_pad; r++) ns += Ws[widx<NT>(r, b)];
+        for (int r = 0; r < lay.nc_pad; r++) nc += load_weight<NT, MODE>(Ws, r, b);
+        for (int r = lay.nc_pad; r < lay.n_pad; r++) ns += load_weight<NT, MODE>(Ws, r, b);
         args.ngal_tile[(tile * 2 + 0) * BM + b] = nc;
         args.ngal_tile[(tile * 2 + 1) * BM + b] = ns;
       }
     } else {
       const Chunk ch = lay.chunks[idx];
-      run_chunk<NT, MODE>(lay, ch, Ws, args.parts + (size_t)tile * lay.n_parts * BM, lane);
+      if constexpr (MODE == kModeAutoTf32)
+        run_chunk_tf32<NT>(lay, ch, Ws, args.parts + (size_t)tile * lay.n_parts * BM, lane,
+                           args.tf32_segment);
+      else
+        run_chunk<NT, MODE>(lay, ch, Ws, args.parts + (size_t)tile * lay.n_parts * BM, lane);
     }
   }
 }
@@ -899,6 +1064,7 @@ struct PlanHost {
 
 struct Layout {
   bool built = false;
+  bool built32 = false;   // afrag32 (3xTF32 mode) is built on first use
   LayoutDev dev{};
   std::vector<int> row_to_pad;
   std::vector<void*> allocations;
@@ -1127,6 +1293,61 @@ int build_layout(tc_table* t, int separate) {
   L.dev.out_parts = d_out_parts;
   L.dev.pad_to_row = d_pad_to_row;
   L.built = true;
+  return TC_OK;
+}
+
+// round an FP32 value to TF32 (10 explicit mantissa bits), ties to even
+float tf32_round_host(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, sizeof(u));
+  u += 0xfffu + ((u >> 13) & 1u);
+  u &= 0xffffe000u;
+  std::memcpy(&x, &u, sizeof(u));
+  return x;
+}
+
+// A-fragment stream of the 3xTF32 mode: the same lower-triangular M' as build_layout, in m16n8k8
+// fragments (16-row tiles x k8-steps of 8 columns), every entry split into TF32 high and low part.
+int build_afrag32(tc_table* t, int separate) {
+  Layout& L = t->layouts[separate];
+  if (L.built32) return TC_OK;
+  if (t->mode != TC_MODE_AUTO)
+    return fail(TC_EUNSUPPORTED, "the 3xTF32 mode exists for auto-correlation tables only");
+  const int N = t->n_rows, R = t->n_r, T = t->n_tables, Reff = R * T;
+  const int T16 = L.dev.n_pad / 16;
+  const long long ks8_per_r = (long long)T16 * (T16 + 1);
+  std::vector<float4> frag((size_t)Reff * ks8_per_r * 64 + 64, make_float4(0.f, 0.f, 0.f, 0.f));
+  const size_t P = (size_t)N * (N + 1) / 2;
+  for (int tb = 0; tb < T; tb++) {
+    const double* packed = t->matrices[tb].data();
+    for (int r = 0; r < R; r++) {
+      const double* m = packed + (size_t)r * P;
+      float4* dst = frag.data() + (size_t)(tb * R + r) * ks8_per_r * 64;
+      for (int i = 0; i < N; i++) {
+        const int pi = L.row_to_pad[i];
+        for (int j = 0; j <= i; j++) {
+          const int pj = L.row_to_pad[j];
+          double val = m[(size_t)i * (i + 1) / 2 + j];
+          if (i != j) val *= 2.0;
+          const int hi_r = std::max(pi, pj), lo_c = std::min(pi, pj);
+          const int mt = hi_r / 16, rr = hi_r % 16, ks = lo_c / 8, kk = lo_c % 8;
+          const int lane = (rr % 8) * 4 + (kk % 4), reg = (rr / 8) + 2 * (kk / 4);
+          const float hi = tf32_round_host((float)val);
+          const float lo = tf32_round_host((float)(val - (double)hi));
+          float4* block = dst + ((size_t)mt * (mt + 1) + ks) * 64;
+          reinterpret_cast<float*>(&block[lane])[reg] = hi;
+          reinterpret_cast<float*>(&block[32 + lane])[reg] = lo;
+        }
+      }
+    }
+  }
+  float4* d_frag;
+  int rc;
+  if ((rc = upload(frag, &d_frag))) return rc;
+  L.allocations.push_back(d_frag);
+  L.dev.afrag32 = d_frag;
+  L.dev.ks8_per_r = ks8_per_r;
+  L.built32 = true;
   return TC_OK;
 }
 
@@ -1519,7 +1740,7 @@ size_t tc_predict_workspace_bytes(const tc_table* t, int64_t n_draws, int separa
 
 int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
                      int64_t theta_ld, const double* occ, int64_t n_draws, int separate,
-                     double* ngal,
+                     int precision, double* ngal,
                      int64_t ngal_stride, double* xi, int64_t xi_stride, void* workspace,
                      size_t workspace_bytes, void* stream_) {
   if (!t || !ngal || !xi) return fail(TC_EINVAL, "tc_predict_batch: NULL argument");
@@ -1530,6 +1751,11 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
     return fail(TC_EINVAL, "tc_predict_batch: theta_ld must be 0 or >= n_draws");
   if (theta && model->family != 0)
     return fail(TC_EUNSUPPORTED, "tc_predict_batch: unknown model family");
+  if (precision != TC_PRECISION_FP64 && precision != TC_PRECISION_3XTF32)
+    return fail(TC_EINVAL, "tc_predict_batch: precision must be TC_PRECISION_FP64 or _3XTF32");
+  if (precision == TC_PRECISION_3XTF32 && t->mode != TC_MODE_AUTO)
+    return fail(TC_EUNSUPPORTED, "tc_predict_batch: the 3xTF32 mode exists for auto-correlation "
+                                 "tables only (cross tables are bound by the occupation phase)");
   if (n_draws <= 0) return TC_OK;
   separate = separate ? 1 : 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1538,6 +1764,7 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   if (!guard.ok) return fail(TC_ECUDA, "tc_predict_batch: cannot select the table's CUDA device");
   int rc = build_layout(t, separate);
   if (rc != TC_OK) return rc;
+  if (precision == TC_PRECISION_3XTF32 && (rc = build_afrag32(t, separate))) return rc;
   Layout& L = t->layouts[separate];
   if (!theta && t->rules.empty()) {
     // the occupation branch needs n_h per padded row only; any plan carries it
@@ -1586,13 +1813,16 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
     const int spread = std::min(100, std::max(1, tune("OCC_SPREAD", 70)));
     args.occ_stride = ws.n_buf == 1 ? 1 : std::max(1, (int)((long long)spread * slots / (100LL * n_occ)));
   }
+  args.tf32_segment = std::max(1, tune("TF32_SEG", kTf32Segment));
   const int bm = 8 * ws.nt;
   const size_t smem = predict_smem_bytes(L.dev.n_pad, ws.nt, ws.n_buf);
   const int gx = (int)std::min<long long>(ws.n_tiles * L.dev.n_chunks, n_sm);
   dim3 grid(gx, 1);
-#define TC_LAUNCH(NT_)                                                                     \
-  rc = t->mode == TC_MODE_AUTO ? launch_predict<NT_, TC_MODE_AUTO>(args, grid, smem, stream) \
-                               : launch_predict<NT_, TC_MODE_CROSS>(args, grid, smem, stream)
+#define TC_LAUNCH(NT_)                                                                        \
+  rc = precision == TC_PRECISION_3XTF32                                                       \
+           ? launch_predict<NT_, kModeAutoTf32>(args, grid, smem, stream)                     \
+           : t->mode == TC_MODE_AUTO ? launch_predict<NT_, TC_MODE_AUTO>(args, grid, smem, stream) \
+                                     : launch_predict<NT_, TC_MODE_CROSS>(args, grid, smem, stream)
   if (g_profile.enabled) TC_CUDA(cudaEventRecord(g_profile.ev[0], stream));
   switch (ws.nt) {
     case 8: TC_LAUNCH(8); break;

@@ -226,7 +226,8 @@ class Interpolator:
                 group.plan(n_gauss)
                 _lib.check(self._lib.tc_predict_batch(
                     group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(), 0,
-                    None, 1, int(separate), buf['ngal_t'].data_ptr() + 8 * slot * n_ng,
+                    None, 1, int(separate), _lib.TC_PRECISION_FP64,
+                    buf['ngal_t'].data_ptr() + 8 * slot * n_ng,
                     n_tables * n_ng, buf['xi_t'].data_ptr() + 8 * slot * n_cols, n_tables * n_cols,
                     workspace.data_ptr(), workspace.numel(), stream.cuda_stream))
                 slot += len(members)
@@ -243,7 +244,7 @@ class Interpolator:
         return self.tabcorr_list[0]._format_batch(ngal, xi, separate, False)
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
-                      model=None, as_numpy=True):
+                      model=None, as_numpy=True, precision='fp64'):
         """Interpolated predictions for B parameter sets.
 
         ``params`` is a dict of arrays ``[B]`` holding the occupation parameters and one entry per
@@ -269,6 +270,9 @@ class Interpolator:
 
         separate = bool(separate_gal_type)
         first_group = self._groups[0][0]
+        precision = _lib.precision_code(precision)
+        if first_group.mode != 'auto':
+            precision = _lib.TC_PRECISION_FP64
         n_tables = len(self.tabcorr_list)
         n_comp = first_group.n_comp(separate)
         n_ng = 2 if separate else 1
@@ -278,7 +282,7 @@ class Interpolator:
         slot = 0
         for group, members in self._groups:
             group.predict_into(spec, int(n_gauss_prim), theta, None, separate, ngal_t,
-                               slot * n_ng, xi_t, slot * n_r * n_comp)
+                               slot * n_ng, xi_t, slot * n_r * n_comp, precision=precision)
             slot += len(members)
 
         flag = torch.zeros(1, dtype=torch.int32, device=device)

@@ -199,7 +199,7 @@ class DeviceTableGroup:
             stream = torch.cuda.current_stream(self.device)
             _lib.check(self.lib.tc_predict_batch(
                 self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(), 0, None, 1,
-                int(separate), buf.ngal.data_ptr(), self.n_tables * n_ng, buf.xi.data_ptr(),
+                int(separate), _lib.TC_PRECISION_FP64, buf.ngal.data_ptr(), self.n_tables * n_ng, buf.xi.data_ptr(),
                 self.n_tables * self.n_r * n_comp, buf.workspace.data_ptr(),
                 buf.workspace.numel(), stream.cuda_stream))
             stream.synchronize()
@@ -209,7 +209,7 @@ class DeviceTableGroup:
         return ngal, xi
 
     def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset,
-                     theta_columns=False):
+                     theta_columns=False, precision=_lib.TC_PRECISION_FP64):
         """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
         and ``xi`` starting at table offset ``*_offset`` (in doubles within a draw).  ``theta`` is
         ``[B, 7]``, or ``[7, B]`` (one contiguous column per parameter) with ``theta_columns``."""
@@ -229,7 +229,7 @@ class DeviceTableGroup:
                 self.handle, ctypes.byref(model), int(n_gauss),
                 theta.data_ptr() if theta is not None else None, theta_ld,
                 occ.data_ptr() if occ is not None else None, n_draws, int(separate),
-                ngal_flat.data_ptr() + 8 * ngal_offset, ngal_flat.stride(0),
+                int(precision), ngal_flat.data_ptr() + 8 * ngal_offset, ngal_flat.stride(0),
                 xi_flat.data_ptr() + 8 * xi_offset, xi_flat.stride(0),
                 workspace.data_ptr(), workspace.numel(), stream))
 
@@ -448,7 +448,7 @@ class TabCorr:
         return spec, theta
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, model=None,
-                      occupation=None, as_numpy=True, pipeline_chunk='auto'):
+                      occupation=None, as_numpy=True, pipeline_chunk='auto', precision='fp64'):
         """Predict number density and correlation function for B parameter sets at once.
 
         Parameters
@@ -468,6 +468,11 @@ class TabCorr:
             Precomputed mean occupations (the ndarray branch of ``predict``).
         as_numpy : bool, optional
             Return host numpy arrays (default) or leave the results on the device.
+        precision : 'fp64' or '3xtf32', optional
+            'fp64' (default) matches the reference to rtol 1e-10.  '3xtf32' contracts
+            auto-correlation tables on the TF32 tensor cores with split operands (relative error
+            ~1e-7, about twice the throughput); occupations stay FP64.  Cross-correlation tables
+            always use FP64 (they are bound by the occupation arithmetic).
         pipeline_chunk : 'auto', int or sequence of int, optional
             With host inputs and host outputs the draws are cut into chunks whose host-to-device
             copy, kernels and device-to-host copy overlap on three CUDA streams.  An int is a
@@ -484,11 +489,14 @@ class TabCorr:
         torch = _torch()
         group = self._ensure_device()
         separate = bool(separate_gal_type)
+        precision = _lib.precision_code(precision)
+        if group.mode != 'auto':
+            precision = _lib.TC_PRECISION_FP64
         if (occupation is None and as_numpy and not isinstance(params, torch.Tensor) and
                 (isinstance(pipeline_chunk, (str, list, tuple)) or
                  (pipeline_chunk and pipeline_chunk > 0))):
             return self._predict_batch_pipelined(params, model, separate, int(n_gauss_prim),
-                                                 pipeline_chunk)
+                                                 pipeline_chunk, precision)
         if occupation is not None:
             occ = _to_device_f64(occupation, group.device)
             if occ.ndim != 2 or occ.shape[1] != group.n_rows:
@@ -501,10 +509,12 @@ class TabCorr:
         ngal = torch.empty((n_draws, 2 if separate else 1), dtype=torch.float64,
                            device=group.device)
         xi = torch.empty((n_draws, group.n_r, n_comp), dtype=torch.float64, device=group.device)
-        group.predict_into(spec, int(n_gauss_prim), theta, occ, separate, ngal, 0, xi, 0)
+        group.predict_into(spec, int(n_gauss_prim), theta, occ, separate, ngal, 0, xi, 0,
+                           precision=precision)
         return self._format_batch(ngal, xi, separate, as_numpy)
 
-    def _predict_batch_pipelined(self, params, model, separate, n_gauss, chunk):
+    def _predict_batch_pipelined(self, params, model, separate, n_gauss, chunk,
+                                 precision=_lib.TC_PRECISION_FP64):
         """Host parameters in, host results out: the draws are cut into chunks; chunk i + 1 is
         staged in pinned memory and copied to the device while chunk i is evaluated and chunk
         i - 1 is copied back (copy streams + events; the kernels stay on the current stream)."""
@@ -553,7 +563,8 @@ class TabCorr:
                 staged.record(h2d)
             compute.wait_event(staged)
             group.predict_into(spec, n_gauss, theta_chunk.view(n_theta, hi - lo), None, separate,
-                               ngal[lo:hi], 0, xi[lo:hi], 0, theta_columns=True)
+                               ngal[lo:hi], 0, xi[lo:hi], 0, theta_columns=True,
+                               precision=precision)
             done = torch.cuda.Event()
             done.record(compute)
             with torch.cuda.stream(d2h):

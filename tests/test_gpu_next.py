@@ -236,3 +236,67 @@ def test_non_finite_parameters_do_not_poison_neighbours(tb):
     good[[17, 101]] = False
     assert np.array_equal(out[0][good], ref[0][good]) and np.array_equal(out[1][good], ref[1][good])
     assert not np.isfinite(out[0][17])
+
+
+# ---------------------------------------------------------------------------------------------
+# optional 3xTF32 mode (north_star: "an optional 3xTF32 mode at rtol 1e-6")
+# ---------------------------------------------------------------------------------------------
+TF32_RTOL = 1e-6
+
+
+def _abs_table(tb, tab):
+    """Same table with |M|: its prediction is the sum of the term magnitudes of xi, the scale a
+    relative error bound of a sign-mixed sum has to refer to."""
+    return table_from_dict(tb, dict(tab, tpcf_matrix=np.abs(tab['tpcf_matrix'])))
+
+
+@pytest.mark.parametrize('kw,decorated', [
+    (dict(n_mass=60, n_sec=2, n_r=20), False),
+    (dict(n_mass=60, n_sec=2, n_r=42, kind='multipole', tpcf_shape=(3, 14)), True),
+    (dict(n_mass=13, n_sec=1, n_r=3), True),
+    (dict(n_mass=125, n_sec=2, n_r=4), False),
+])
+def test_3xtf32_mode_within_1e6_of_fp64(tb, kw, decorated):
+    tab = cases.synthetic.make_table(**kw)
+    halotab = table_from_dict(tb, tab)
+    draws = cases.synthetic.make_draws(3000, seed=41, decorated=decorated)
+    ngal, xi = halotab.predict_batch(draws)
+    ngal_t, xi_t = halotab.predict_batch(draws, precision='3xtf32')
+    assert xi_t.shape == xi.shape
+    np.testing.assert_allclose(ngal_t, ngal, rtol=TF32_RTOL)
+    _, scale = _abs_table(tb, tab).predict_batch(draws)
+    err = np.abs(xi_t - xi) / scale
+    assert err.max() < TF32_RTOL, err.max()
+    assert not np.array_equal(xi_t, xi)          # it really is the other arithmetic
+    # per-gal-type split, device-resident and chunked host paths agree with each other bitwise
+    ngal_s, xi_s = halotab.predict_batch(draws, separate_gal_type=True, precision='3xtf32')
+    total = sum(xi_s.values())
+    assert (np.abs(total - xi) / scale).max() < 3 * TF32_RTOL
+    again = halotab.predict_batch(draws, precision='3xtf32', pipeline_chunk=[700, 1500, 800])
+    assert np.array_equal(again[1], xi_t) and np.array_equal(again[0], ngal_t)
+
+
+def test_3xtf32_mode_scope(tb, golden_dir):
+    import os
+    # cross tables: the request is accepted and served in FP64 (occupation-bound path)
+    ds = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_ds.hdf5'))
+    draws = cases.synthetic.make_draws(100, seed=2)
+    a, b = ds.predict_batch(draws), ds.predict_batch(draws, precision='3xtf32')
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # the real auto table (float32 on disk: the TF32 split of the table is exact)
+    wp = tb.TabCorr.read(os.path.join(golden_dir, 'bolplanck_wp.hdf5'))
+    a, b = wp.predict_batch(draws), wp.predict_batch(draws, precision='3xtf32')
+    np.testing.assert_allclose(b[0], a[0], rtol=TF32_RTOL)
+    scale = table_from_dict(tb, dict(gal_type=wp.gal_type.as_array(), attrs=wp.attrs,
+                                     tpcf_matrix=np.abs(wp.tpcf_matrix),
+                                     tpcf_shape=wp.tpcf_shape)).predict_batch(draws)[1]
+    assert (np.abs(b[1] - a[1]) / scale).max() < TF32_RTOL
+    with pytest.raises(ValueError):
+        wp.predict_batch(draws, precision='fp16')
+    # Interpolator
+    tables, param_table, grid_draws = cases.grid_case('grid2d')
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    a = interp.predict_batch(grid_draws)
+    b = interp.predict_batch(grid_draws, precision='3xtf32')
+    np.testing.assert_allclose(b[0], a[0], rtol=TF32_RTOL)
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6 * np.abs(a[1]).max())

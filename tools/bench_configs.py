@@ -132,9 +132,11 @@ def main():
         halotab = table_of(tab)
         draws = synthetic.make_draws(n_draws, seed=1, decorated=decorated)
         ms = device_run(halotab, draws, decorated, n_gauss_prim=n_gauss)
+        ms_tf32 = device_run(halotab, draws, decorated, n_gauss_prim=n_gauss, precision='3xtf32')
         n, n_r = len(tab['gal_type']), kw['n_r']
         emit(config=name, n_tracers=n, n_r=n_r, mode='auto', n_gauss_prim=n_gauss, n_draws=n_draws,
              batch_ms=ms, preds_per_s=n_draws / ms * 1e3,
+             batch_ms_3xtf32=ms_tf32, preds_per_s_3xtf32=n_draws / ms_tf32 * 1e3,
              algorithmic_tflops=algorithmic_flops(n, n_r, 'auto') * n_draws / (ms * 1e-3) * 1e-12,
              executed_frac=executed_flops(n, n_r, 'auto') * n_draws / (ms * 1e-3) / (peak.value * 1e12))
 

@@ -88,6 +88,8 @@ def main():
         t_theta = timed(lambda: group.predict_into(spec, args.n_gauss, theta, None, False, ngal, 0, xi, 0))
         t_occ = timed(lambda: group.predict_into(None, args.n_gauss, None, occ, False, ngal, 0, xi, 0))
         t_only = timed(lambda: group.occupation(spec, args.n_gauss, theta))
+        t_tf32 = (timed(lambda: group.predict_into(spec, args.n_gauss, theta, None, False, ngal, 0,
+                                                   xi, 0, precision=1)) if mode == 'auto' else None)
         n_pad = (n + 15) // 16 * 16
         if mode == 'auto':
             executed = 2.0 * n_r * 64.0 * (n_pad // 8) * (n_pad // 8 + 1) / 2
@@ -99,7 +101,8 @@ def main():
             'shape': name, 'tune': tune, 'n_gauss': args.n_gauss, 'n_draws': args.draws,
             'theta_ms': t_theta, 'theta_preds_per_s': args.draws / t_theta * 1e3,
             'occ_input_ms': t_occ, 'occ_input_preds_per_s': args.draws / t_occ * 1e3,
-            'occupation_kernel_ms': t_only,
+            'occupation_kernel_ms': t_only, 'tf32_theta_ms': t_tf32,
+            'tf32_preds_per_s': args.draws / t_tf32 * 1e3 if t_tf32 else None,
             'occupation_evals_per_s': args.draws * n * args.n_gauss / t_only * 1e3,
             'executed_frac_theta': executed * args.draws / (t_theta * 1e-3) / (peak.value * 1e12),
             'executed_frac_occ_input': executed * args.draws / (t_occ * 1e-3) / (peak.value * 1e12),
