@@ -35,7 +35,7 @@ N_MASS, N_SEC, N_R, N_GAUSS = 60, 2, 20, 10
 DRAWS_PER_GPU = 100000
 # dram__bytes_read.sum + dram__bytes_write.sum of predict_kernel for this workload (one launch =
 # 1e5 draws), from the committed ncu capture; only reported for the default batch size
-NCU_DRAM_BYTES_PER_LAUNCH = 23334144 + 15222272
+NCU_DRAM_BYTES_PER_LAUNCH = 22611712 + 14923520
 METRIC = 'HOD predictions/sec (ngal+wp)'
 UNIT = 'predictions/s'
 
@@ -127,7 +127,9 @@ def run_reference_arm(args):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: NVML in a background
+    thread (a sample every 5 ms; the main thread releases the GIL while it waits on CUDA events),
+    `nvidia-smi -lms` as a fallback when pynvml is missing."""
 
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
@@ -137,19 +139,61 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def _nvml_loop(self, nvml, handle):
+        names = {'hw_slowdown': nvml.nvmlClocksEventReasonHwSlowdown,
+                 'hw_thermal_slowdown': nvml.nvmlClocksEventReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nvml.nvmlClocksEventReasonSwThermalSlowdown,
+                 'sw_power_cap': nvml.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)))
+                mask = nvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
 
     def start(self):
+        try:
+            import pynvml as nvml
+            nvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            index = self.index
+            if visible:
+                entries = [v.strip() for v in visible.split(',') if v.strip()]
+                if self.index < len(entries) and entries[self.index].isdigit():
+                    index = int(entries[self.index])
+            handle = nvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '50'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join()
+            return {'sm_mhz': float(np.median(self.sm)) if self.sm else None,
+                    'sm_max_mhz': self.sm_max, 'samples': len(self.sm),
+                    'reasons': sorted(self.reasons), 'source': 'nvml'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.06)
@@ -173,7 +217,7 @@ class ClockSampler:
         os.unlink(self.path)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(np.max(sm_max)) if sm_max else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi'}
 
 
 # ---------------------------------------------------------------------------------------------
