@@ -92,3 +92,21 @@ def test_python_api_fails_loudly_without_a_device():
                                                tab['tpcf_shape'], tab['attrs'])
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         halotab.predict_batch(synthetic.make_draws(3))
+
+
+def test_header_prototypes_match_the_binding(lib):
+    """Every prototype in the header has as many parameters as the ctypes binding declares
+    (a mismatch would corrupt the call without any error on x86-64)."""
+    text = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    protos = re.findall(r'\b(tc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    assert len(protos) == len(declared_symbols())
+    for name, params in protos:
+        params = params.strip()
+        n_params = 0 if params in ('', 'void') else len(params.split(','))
+        assert len(getattr(lib, name).argtypes or []) == n_params, name
+    assert _lib.TC_PRECISION_FP64 == int(re.search(r'#define TC_PRECISION_FP64 (\d+)', text).group(1))
+    assert _lib.TC_PRECISION_3XTF32 == int(
+        re.search(r'#define TC_PRECISION_3XTF32 (\d+)', text).group(1))
+    assert _lib.precision_code('3xTF32') == 1 and _lib.precision_code('fp64') == 0
+    with pytest.raises(ValueError):
+        _lib.precision_code('bf16')

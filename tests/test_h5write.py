@@ -137,3 +137,22 @@ def test_structures_mirror_h5py_fixture(tmp_path, golden_dir):
     for key in (b'tpcf', b'mode', b'prim_haloprop_key', b'sec_haloprop_key'):
         assert len(ref_attrs[key]) == len(new_attrs[key])
         assert ref_attrs[key][:-12] == new_attrs[key][:-12]   # up to the heap address + index
+
+
+def test_reader_rejects_damaged_files_cleanly(tmp_path, golden_dir):
+    """Truncated or corrupted files raise (H5FormatError / a plain exception), they never hang or
+    return silently wrong tables."""
+    raw = open(os.path.join(golden_dir, 'bolplanck_ds.hdf5'), 'rb').read()
+    bad = tmp_path / 'bad.hdf5'
+    for cut in (0, 7, 95, 500, 2000):
+        bad.write_bytes(raw[:cut])
+        with pytest.raises(Exception):
+            tabcorr_b200.TabCorr.read(bad, upload=False)
+    bad.write_bytes(b'\x89HDF\r\n\x1a\n' + b'\x02' + raw[9:])      # superblock version 2
+    with pytest.raises(h5mini.H5FormatError, match='superblock version'):
+        tabcorr_b200.TabCorr.read(bad, upload=False)
+    bad.write_bytes(b'not an hdf5 file at all' * 10)
+    with pytest.raises(h5mini.H5FormatError, match='signature'):
+        tabcorr_b200.TabCorr.read(bad, upload=False)
+    with pytest.raises(OSError):
+        tabcorr_b200.TabCorr.read(tmp_path / 'missing.hdf5', upload=False)
