@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 102
+#define TC_VERSION 103
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -41,26 +41,41 @@ extern "C" {
 #define TC_PRECISION_FP64 0
 #define TC_PRECISION_3XTF32 1
 
-/* Number of doubles per parameter draw consumed by tc_predict_batch / tc_occupation_batch:
- * logMmin, sigma_logM, logM0, logM1, alpha, A_cen, A_sat  (the last two are the
- * mean_occupation_{centrals,satellites}_assembias_param1 strengths, ignored unless decorated). */
-#define TC_N_THETA 7
+/* Occupation families of the occupation kernel (tc_model.family) and the number of doubles per
+ * parameter draw each consumes (tc_model_n_theta):
+ *   TC_FAMILY_ZHENG07 (7):  logMmin, sigma_logM, logM0, logM1, alpha, A_cen, A_sat
+ *   TC_FAMILY_LEAUTHAUD11 (18): smhm_m0_0, smhm_m0_a, smhm_m1_0, smhm_m1_a, smhm_beta_0,
+ *       smhm_beta_a, smhm_delta_0, smhm_delta_a, smhm_gamma_0, smhm_gamma_a, scatter_model_param1,
+ *       alphasat, bsat, bcut, betacut, betasat, A_cen, A_sat
+ * (halotools param_dict names; A_cen / A_sat are the mean_occupation_{centrals,satellites}_
+ * assembias_param1 strengths, ignored unless decorated). */
+#define TC_FAMILY_ZHENG07 0
+#define TC_FAMILY_LEAUTHAUD11 1
+#define TC_N_THETA 7              /* zheng07 */
+#define TC_N_THETA_LEAUTHAUD11 18
+#define TC_N_THETA_MAX 18
 
 typedef struct tc_table tc_table;   /* device-resident table group (one gal_type, >=1 matrices) */
 typedef struct tc_interp tc_interp; /* tensor-product cubic spline over a table grid */
 
 /* Occupation model evaluated by the occupation kernel; replaces the halotools calls at
- * tabcorr/tabcorr.py:556-563 (Zheng07Cens/Zheng07Sats, optionally HeavisideAssembias). */
+ * tabcorr/tabcorr.py:556-563 (Zheng07Cens/Zheng07Sats or Leauthaud11Cens/Leauthaud11Sats,
+ * optionally decorated with HeavisideAssembias). */
 typedef struct tc_model {
-  int32_t family;               /* 0 = zheng07 */
+  int32_t family;               /* TC_FAMILY_* */
   int32_t decorated;            /* 1 = Heaviside assembly bias on centrals and satellites */
   int32_t modulate_with_cenocc; /* 1 = <N_sat> is multiplied by the baseline <N_cen> */
   int32_t reserved;
   double split;                 /* percentile split of the decoration (halotools default 0.5) */
+  double threshold;             /* leauthaud11: log10 of the stellar-mass threshold */
+  double redshift;              /* leauthaud11: redshift of the stellar-to-halo-mass relation */
 } tc_model;
 
 const char* tc_last_error(void);
 int tc_version(void);
+
+/* Doubles per parameter draw of the model's family, or TC_EUNSUPPORTED. */
+int tc_model_n_theta(const tc_model* model);
 
 /* TabCorr.read (tabcorr/tabcorr.py:374-416) for `n_tables` tables that share one gal_type table
  * (n_tables > 1 is an Interpolator group, tabcorr/interpolator.py:63-70).  All inputs are host
@@ -86,14 +101,14 @@ int tc_table_n_tables(const tc_table* table);
  * n_gauss, cached in the table) the node masses and normalised quadrature weights on the device. */
 int tc_table_plan(tc_table* table, int n_gauss, const double* x01_host, const double* w_host);
 
-/* Layout of the parameter draws theta_dev, selected by theta_ld:
- *   theta_ld == 0:        [B, TC_N_THETA], one row per draw;
- *   theta_ld >= n_draws:  [TC_N_THETA, theta_ld], one contiguous column per parameter (what a
+/* Layout of the parameter draws theta_dev (n_theta = tc_model_n_theta), selected by theta_ld:
+ *   theta_ld == 0:        [B, n_theta], one row per draw;
+ *   theta_ld >= n_draws:  [n_theta, theta_ld], one contiguous column per parameter (what a
  *                         sampler that keeps one array per parameter -- model.param_dict keys --
  *                         hands over without a transpose). */
 
 /* TabCorr.mean_occupation (tabcorr.py:465-578) for B draws: occ_dev[B, n_rows] in reference row
- * order. */
+ * order.  All families. */
 int tc_occupation_batch(tc_table* table, const tc_model* model, int n_gauss,
                         const double* theta_dev, int64_t theta_ld, int64_t n_draws,
                         double* occ_dev, void* stream);
@@ -104,6 +119,9 @@ size_t tc_predict_workspace_bytes(const tc_table* table, int64_t n_draws, int se
 /* TabCorr.predict (tabcorr.py:580-683) for B draws, fused occupation + contraction.
  * Exactly one of theta_dev (layout above; evaluated with `model` and the n_gauss plan) and
  * occ_dev ([B, n_rows] precomputed occupations, the ndarray branch tabcorr.py:616-621) is non-NULL.
+ * The fused occupation phase implements TC_FAMILY_ZHENG07; for the other families the call
+ * returns TC_EUNSUPPORTED and the caller chains tc_occupation_batch -> occ_dev (what
+ * tabcorr_b200.DeviceTableGroup.predict_into does).
  * Outputs, with T = n_tables, R = n_r:
  *   separate == 0: ngal_dev[b * ngal_stride + t], xi_dev[b * xi_stride + t * R + r]
  *   separate == 1: ngal_dev[b * ngal_stride + t * 2 + q], q = centrals, satellites;

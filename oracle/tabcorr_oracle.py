@@ -22,7 +22,10 @@ lines it follows.  Parity status:
   "decorated HOD", eqs. 9-14) as implemented by halotools' ``Zheng07Cens.mean_occupation``,
   ``Zheng07Sats.mean_occupation`` and ``HeavisideAssembias`` from memory of that code; they must
   be re-checked against a real halotools install when one is available.  The call sites anchoring
-  them are ``tabcorr/tabcorr.py:556-563``.
+  them are ``tabcorr/tabcorr.py:556-563``.  The same holds for ``Leauthaud11Oracle``
+  (``Leauthaud11Cens`` / ``Leauthaud11Sats`` over ``Behroozi10SmHm``: Leauthaud et al. 2011
+  eqs. 8-14, Behroozi et al. 2010 eq. 21, with halotools' h = 0.7 conversions and its numerical
+  inversion of the stellar-to-halo-mass relation by a 100-knot interpolating cubic spline).
 """
 
 import itertools
@@ -31,7 +34,7 @@ import numpy as np
 from scipy.special import erf
 
 __all__ = [
-    'OracleTable', 'Zheng07Oracle', 'symmetric_matrix_to_array', 'mean_occupation', 'predict',
+    'OracleTable', 'Zheng07Oracle', 'Leauthaud11Oracle', 'symmetric_matrix_to_array', 'mean_occupation', 'predict',
     'spline_interpolation_matrix', 'spline_interpolate', 'OracleInterpolator']
 
 
@@ -129,6 +132,82 @@ class Zheng07Oracle:
                 f, np.asarray(sec_haloprop_percentile),
                 self.param_dict['mean_occupation_satellites_assembias_param1'], 0.0, np.inf)
         return f
+
+
+class Leauthaud11Oracle(Zheng07Oracle):
+    """leauthaud11 HOD (halotools ``PrebuiltHodModelFactory('leauthaud11')``) with optional
+    Heaviside assembly-bias decoration (``'hearin15'``).  PARITY UNPINNED (module docstring).
+
+    ``param_dict``: the ten ``smhm_*`` parameters of ``Behroozi10SmHm``, ``scatter_model_param1``
+    (constant log-normal scatter), ``alphasat, bsat, bcut, betacut, betasat`` and, when decorated,
+    the two ``*_assembias_param1`` strengths.  ``threshold`` is log10 of the stellar-mass
+    threshold, ``redshift`` the redshift at which the SMHM parameters are evaluated.
+    """
+
+    littleh = 0.7
+    DEFAULTS = dict(smhm_m0_0=10.72, smhm_m0_a=0.59, smhm_m1_0=12.35, smhm_m1_a=0.3,
+                    smhm_beta_0=0.43, smhm_beta_a=0.18, smhm_delta_0=0.56, smhm_delta_a=0.18,
+                    smhm_gamma_0=1.54, smhm_gamma_a=2.52, scatter_model_param1=0.2,
+                    alphasat=1.0, bsat=10.62, bcut=1.47, betacut=-0.13, betasat=0.859)
+
+    def __init__(self, param_dict=None, threshold=10.5, redshift=0.0, decorated=False, split=0.5,
+                 modulate_with_cenocc=True):
+        self.param_dict = dict(self.DEFAULTS)
+        if decorated:
+            self.param_dict['mean_occupation_centrals_assembias_param1'] = 0.5
+            self.param_dict['mean_occupation_satellites_assembias_param1'] = 0.5
+        if param_dict is not None:
+            self.param_dict.update(param_dict)
+        self.threshold = threshold
+        self.redshift = redshift
+        self.decorated = decorated
+        self.split = split
+        self.modulate_with_cenocc = modulate_with_cenocc
+
+    def mean_log_halo_mass(self, log_stellar_mass):
+        # Behroozi10SmHm.mean_log_halo_mass: parameters were fit with h = 0.7, inputs/outputs are
+        # in h = 1 units: M* -> M* / h^2 on the way in, M_h -> M_h h on the way out.
+        p, a1 = self.param_dict, 1.0 / (1.0 + self.redshift) - 1.0
+        stellar_mass = 10.0**np.asarray(log_stellar_mass, dtype=np.float64) / self.littleh**2
+        logm0 = p['smhm_m0_0'] + p['smhm_m0_a'] * a1
+        logm1 = p['smhm_m1_0'] + p['smhm_m1_a'] * a1
+        beta = p['smhm_beta_0'] + p['smhm_beta_a'] * a1
+        delta = p['smhm_delta_0'] + p['smhm_delta_a'] * a1
+        gamma = p['smhm_gamma_0'] + p['smhm_gamma_a'] * a1
+        ratio = stellar_mass / 10.0**logm0
+        log_halo_mass = (logm1 + beta * np.log10(ratio) + ratio**delta / (1.0 + ratio**(-gamma))
+                         - 0.5)
+        return np.log10(10.0**log_halo_mass * self.littleh)
+
+    def mean_log_stellar_mass(self, prim_haloprop):
+        # Behroozi10SmHm.mean_stellar_mass: tabulate on 100 knots, interpolate the inverse with
+        # model_helpers.custom_spline = scipy InterpolatedUnivariateSpline(k=3)
+        from scipy.interpolate import InterpolatedUnivariateSpline
+        log_stellar_mass_table = np.linspace(8.5, 12.5, 100)
+        log_halo_mass_table = self.mean_log_halo_mass(log_stellar_mass_table)
+        if not np.all(np.diff(log_halo_mass_table) > 0):
+            raise ValueError('the stellar-to-halo-mass relation is not monotonic')
+        spline = InterpolatedUnivariateSpline(log_halo_mass_table, log_stellar_mass_table, k=3)
+        return spline(np.log10(prim_haloprop))
+
+    def _baseline_centrals(self, prim_haloprop):
+        # Leauthaud11Cens.mean_occupation
+        logmstar = self.mean_log_stellar_mass(prim_haloprop)
+        logscatter = np.sqrt(2.0) * self.param_dict['scatter_model_param1']
+        return 0.5 * (1.0 - erf((self.threshold - logmstar) / logscatter))
+
+    def _baseline_satellites(self, prim_haloprop):
+        # Leauthaud11Sats.mean_occupation with _update_satellite_params
+        p = self.param_dict
+        knee_threshold = 10.0**self.mean_log_halo_mass(self.threshold) * self.littleh
+        knee_mass = 1.0e12
+        msat = knee_mass * p['bsat'] * (knee_threshold / knee_mass)**p['betasat']
+        mcut = knee_mass * p['bcut'] * (knee_threshold / knee_mass)**p['betacut']
+        mass = np.asarray(prim_haloprop, dtype=np.float64)
+        out = np.exp(-mcut / (mass * self.littleh)) * (mass * self.littleh / msat)**p['alphasat']
+        if self.modulate_with_cenocc:
+            out = out * self._baseline_centrals(mass)
+        return out
 
 
 # --------------------------------------------------------------------------------------------

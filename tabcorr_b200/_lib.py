@@ -27,10 +27,13 @@ def precision_code(precision):
         raise ValueError("precision must be 'fp64' or '3xtf32'")
     return table[key]
 TC_N_THETA = 7
+TC_N_THETA_LEAUTHAUD11 = 18
+TC_FAMILY_ZHENG07 = 0
+TC_FAMILY_LEAUTHAUD11 = 1
 
 # every symbol include/tabcorr_b200.h declares
 SYMBOLS = (
-    'tc_last_error', 'tc_version', 'tc_table_create', 'tc_table_destroy', 'tc_table_n_rows',
+    'tc_last_error', 'tc_version', 'tc_model_n_theta', 'tc_table_create', 'tc_table_destroy', 'tc_table_n_rows',
     'tc_table_n_r', 'tc_table_n_tables', 'tc_table_plan', 'tc_occupation_batch',
     'tc_predict_workspace_bytes', 'tc_predict_batch', 'tc_interp_create', 'tc_interp_destroy',
     'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math')
@@ -43,7 +46,8 @@ class TabCorrB200Error(RuntimeError):
 class tc_model(ctypes.Structure):
     _fields_ = [('family', ctypes.c_int32), ('decorated', ctypes.c_int32),
                 ('modulate_with_cenocc', ctypes.c_int32), ('reserved', ctypes.c_int32),
-                ('split', ctypes.c_double)]
+                ('split', ctypes.c_double), ('threshold', ctypes.c_double),
+                ('redshift', ctypes.c_double)]
 
 
 _lib = None
@@ -67,6 +71,8 @@ def load():
     lib.tc_last_error.argtypes = []
     lib.tc_version.restype = ctypes.c_int
     lib.tc_version.argtypes = []
+    lib.tc_model_n_theta.restype = ctypes.c_int
+    lib.tc_model_n_theta.argtypes = [ctypes.POINTER(tc_model)]
     lib.tc_table_create.restype = ctypes.c_int
     lib.tc_table_create.argtypes = [
         ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,

@@ -255,8 +255,8 @@ __device__ __forceinline__ double half_erfc_neg(double x, const double* __restri
   return p;
 }
 
-// t^alpha for t > 0 (normal double); |alpha ln t| beyond ~690 saturates instead of overflowing
-__device__ __forceinline__ double pow_pos(double t, double alpha, const double* __restrict__ tab) {
+// ln t for t > 0 (normal double): 128-entry table of (1 / c_i, ln c_i) + degree-7 log1p
+__device__ __forceinline__ double log_pos(double t, const double* __restrict__ tab) {
   const int hi = __double2hiint(t);
   const int i = (hi >> 13) & (kLogEntries - 1);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(t));
@@ -269,8 +269,12 @@ __device__ __forceinline__ double pow_pos(double t, double alpha, const double* 
   p = fma(p, r, -0.5);
   p = fma(p, r, 1.0);
   const double e = (double)((hi >> 20) - 1023);
-  const double lg = fma(e, 0.6931471805599453094, fma(p, r, lc.y));
-  const double y = alpha * lg;
+  return fma(e, 0.6931471805599453094, fma(p, r, lc.y));
+}
+
+// e^y for |y| < 2^26: 32-entry 2^(j/32) table + degree-6 polynomial; |y| beyond ~690 saturates
+// instead of overflowing
+__device__ __forceinline__ double exp_scaled(double y, const double* __restrict__ tab) {
   const double v = fma(y, 46.16624130844682903551 /* 32 / ln 2 */, kRoundMagic);
   const double kf = v - kRoundMagic;
   double q = fma(-kf, 0.0216608493924982895 /* hi(ln2 / 32) */, y);
@@ -285,6 +289,11 @@ __device__ __forceinline__ double pow_pos(double t, double alpha, const double* 
   const double res = tab[kTabExp + (k & (kExpEntries - 1))] * w;   // in [1, 2) * (1 +- 0.011)
   const int scale = min(max(k >> 5, -1000), 1000);
   return __hiloint2double(__double2hiint(res) + (scale << 20), __double2loint(res));
+}
+
+// t^alpha for t > 0 (normal double); |alpha ln t| beyond ~690 saturates instead of overflowing
+__device__ __forceinline__ double pow_pos(double t, double alpha, const double* __restrict__ tab) {
+  return exp_scaled(alpha * log_pos(t, tab), tab);
 }
 
 struct DrawParams {
@@ -345,8 +354,8 @@ __device__ __forceinline__ double baseline_occupation(double logm, double mass,
 // issue turn only every ~24-32 cycles, tools/fp64_mix.cu; the plan pads G to a multiple of U with
 // zero-weight nodes) and accumulated into the two rows (secondary-percentile bins) of the group.
 // A group with a single row points its second row at an all-zero weight row.
-template <bool SAT, bool DECORATED, bool MODULATE, int U>
-__device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, const DrawParams& p,
+template <bool SAT, bool DECORATED, bool MODULATE, int U, typename Params>
+__device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, const Params& p,
                                                  double split, const double* __restrict__ tab,
                                                  double& occ0, double& occ1) {
   const int G = plan.n_gauss_pad;
@@ -420,6 +429,11 @@ __device__ __forceinline__ void occupation_item(const OccPlan& plan, const tc_mo
                                                 const double* __restrict__ tab, Store store) {
   if (model.modulate_with_cenocc) {   // rare: keep one generic instantiation
     occupation_item_impl<true, true, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
+  } else if (plan.unroll == 2 * kOccUnroll) {
+    if (model.decorated)
+      occupation_item_impl<true, false, 2 * kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
+    else
+      occupation_item_impl<false, false, 2 * kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
   } else if (plan.unroll == kOccUnroll) {
     if (model.decorated)
       occupation_item_impl<true, false, kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
@@ -940,6 +954,276 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// family 1: Leauthaud11 occupations (halotools Leauthaud11Cens / Leauthaud11Sats over the
+// Behroozi10SmHm stellar-to-halo-mass relation; call sites tabcorr.py:556-563)
+//
+//   <N_cen>(M) = 0.5 (1 - erf((log10 M*_thr - log10 M*(M)) / (sqrt(2) sigma_logM*)))
+//   <N_sat>(M) = exp(-M_cut / (M h)) (M h / M_sat)^alphasat  [x <N_cen>(M) if modulate_with_cenocc]
+//   M_sat = 1e12 bsat (M_knee / 1e12)^betasat,  M_cut = 1e12 bcut (M_knee / 1e12)^betacut,
+//   M_knee = h 10^(log10 M_h(M*_thr)),  h = 0.7
+// log10 M_h(log10 M*) is Behroozi et al. (2010) eq. 21 with parameters x_0 + x_a (a - 1) at the
+// model redshift.  halotools inverts it numerically: it tabulates log10 M_h on the 100 knots
+// log10 M* = linspace(8.5, 12.5, 100) and evaluates the interpolating cubic spline (scipy
+// InterpolatedUnivariateSpline, k = 3: not-a-knot end conditions, cubic extrapolation) of log10 M*
+// over log10 M_h.  Parity means reproducing that spline, not the exact inverse, so every draw
+// builds the same table and solves the same not-a-knot system (Thomas algorithm) in shared
+// memory; a node is then a 7-step binary search and one cubic.  A draw whose table is not
+// strictly increasing (halotools raises there) gets NaN occupations.
+//
+// This family does not run inside the fused kernel (its per-draw spline does not fit beside the W
+// tiles): occupation_l11_kernel writes occ[B, N] and the contraction runs on the occupation
+// input of predict_kernel.  Restated from memory of halotools -- parity unpinned, see DESIGN.md.
+// ------------------------------------------------------------------------------------------
+constexpr int kL11Knots = 100;
+constexpr int kL11DrawsPerBlock = 32;
+constexpr double kL11LittleH = 0.7;
+constexpr double kL11LogMsLo = 8.5, kL11LogMsHi = 12.5;
+
+struct L11Draw {
+  // knot k: x = log10 M_h of the knot, y/z/w = c1, c2, c3 of the cubic on [knot k, knot k + 1):
+  // log10 M* = s_k + t (c1 + t (c2 + t c3)), t = log10 M - x
+  double4 knot[kL11Knots];
+  double inv_scatter;   // 1 / (sqrt(2) sigma)
+  double neg_mcut;      // -M_cut
+  double inv_msat;      // 1 / M_sat
+  double alphasat;
+  double a_cen, a_sat;  // assembly-bias strengths (0 unless decorated)
+  double bad;           // NaN if the table is not strictly increasing, else 0
+  double pad;
+};
+
+struct L11Params {
+  const L11Draw* d;
+  double threshold;
+  double a_cen, a_sat;
+};
+
+__device__ __forceinline__ double l11_knot_logms(int k) {
+  // numpy.linspace(8.5, 12.5, 100): arange(100) * step + start, last element set to stop
+  return k == kL11Knots - 1 ? kL11LogMsHi
+                            : (double)k * ((kL11LogMsHi - kL11LogMsLo) / (kL11Knots - 1)) + kL11LogMsLo;
+}
+
+// Behroozi10SmHm.mean_log_halo_mass: log10 M_h [h = 1 units] of log10 M* [h = 1 units]
+__device__ double l11_log_halo_mass(double log_ms, double logm0, double logm1, double beta,
+                                    double delta, double gamma) {
+  const double ms = exp10(log_ms) / (kL11LittleH * kL11LittleH);   // h = 1 -> h = 0.7
+  const double ratio = ms / exp10(logm0);
+  const double log_mh = logm1 + beta * log10(ratio) +
+                        pow(ratio, delta) / (1.0 + pow(ratio, -gamma)) - 0.5;
+  return log10(exp10(log_mh) * kL11LittleH);                       // back to h = 1
+}
+
+__device__ __forceinline__ double l11_log_mstar(double logm, const L11Draw* d) {
+  int i = 0;   // largest knot index in [0, kL11Knots - 2] with x_i <= logm (0 if none)
+#pragma unroll
+  for (int step = 64; step >= 1; step >>= 1) {
+    const int j = i + step;
+    if (j <= kL11Knots - 2 && d->knot[j].x <= logm) i = j;
+  }
+  const double4 c = d->knot[i];
+  const double t = logm - c.x;
+  return fma(t, fma(t, fma(t, c.w, c.z), c.y), l11_knot_logms(i));
+}
+
+template <bool SAT, bool MODULATE>
+__device__ __forceinline__ double baseline_occupation(double logm, double mass, const L11Params& p,
+                                                      const double* __restrict__ tab) {
+  if (!SAT) {
+    const double x = (l11_log_mstar(logm, p.d) - p.threshold) * p.d->inv_scatter;
+    return half_erfc_neg(x, tab) + p.d->bad;
+  }
+  const double mh = mass * kL11LittleH;
+  double y = fma(p.d->alphasat, log_pos(mh * p.d->inv_msat, tab), p.d->neg_mcut / mh);
+  y = fmin(fmax(y, -800.0), 800.0);
+  double f = exp_scaled(y, tab);
+  if (MODULATE) {
+    const double x = (l11_log_mstar(logm, p.d) - p.threshold) * p.d->inv_scatter;
+    f *= half_erfc_neg(x, tab);
+  }
+  return f + p.d->bad;
+}
+
+// Spline tables and per-draw constants of one block of draws, by the whole CTA.
+__device__ void l11_prepare_block(L11Draw* draws, int n_block, long long draw0,
+                                  long long n_draws, const double* __restrict__ theta,
+                                  long long theta_ds, long long theta_ps, const tc_model& model) {
+  const double a1 = 1.0 / (1.0 + model.redshift) - 1.0;   // a - 1
+  // (1) knot abscissae and per-draw constants
+  for (int idx = threadIdx.x; idx < n_block * (kL11Knots + 1); idx += blockDim.x) {
+    const int b = idx / (kL11Knots + 1), k = idx - b * (kL11Knots + 1);
+    const long long draw = min(draw0 + b, n_draws - 1);
+    const double* th = theta + draw * theta_ds;
+    const double logm0 = fma(th[1 * theta_ps], a1, th[0]);
+    const double logm1 = fma(th[3 * theta_ps], a1, th[2 * theta_ps]);
+    const double beta = fma(th[5 * theta_ps], a1, th[4 * theta_ps]);
+    const double delta = fma(th[7 * theta_ps], a1, th[6 * theta_ps]);
+    const double gamma = fma(th[9 * theta_ps], a1, th[8 * theta_ps]);
+    if (k < kL11Knots) {
+      draws[b].knot[k].x = l11_log_halo_mass(l11_knot_logms(k), logm0, logm1, beta, delta, gamma);
+    } else {
+      const double knee = exp10(l11_log_halo_mass(model.threshold, logm0, logm1, beta, delta, gamma)) *
+                          kL11LittleH / 1e12;
+      const double msat = 1e12 * th[12 * theta_ps] * pow(knee, th[15 * theta_ps]);
+      const double mcut = 1e12 * th[13 * theta_ps] * pow(knee, th[14 * theta_ps]);
+      draws[b].inv_scatter = 1.0 / (1.4142135623730951 * th[10 * theta_ps]);
+      draws[b].neg_mcut = -mcut;
+      draws[b].inv_msat = 1.0 / msat;
+      draws[b].alphasat = th[11 * theta_ps];
+      draws[b].a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
+      draws[b].a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;
+    }
+  }
+  __syncthreads();
+  // (2) second derivatives m_k of the not-a-knot spline s(x): one thread per draw (Thomas).
+  // interior equations h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 (d_i - d_{i-1}),
+  // d_i = (s_{i+1} - s_i) / h_i, with m_0 and m_{n-1} eliminated through the continuity of the
+  // third derivative at knots 1 and n - 2.  Scratch: knot[i].y = modified upper diagonal,
+  // knot[i].z = modified right-hand side, knot[i].w = m_i.
+  if (threadIdx.x < n_block) {
+    L11Draw& D = draws[threadIdx.x];
+    constexpr int n = kL11Knots;
+    bool increasing = true;
+    double h_prev = D.knot[1].x - D.knot[0].x;            // h_0
+    double d_prev = (l11_knot_logms(1) - l11_knot_logms(0)) / h_prev;
+    increasing = increasing && h_prev > 0.0;
+    double cp = 0.0, rp = 0.0;                            // c'_{i-1}, r'_{i-1}
+    for (int i = 1; i <= n - 2; i++) {
+      const double h = D.knot[i + 1].x - D.knot[i].x;     // h_i
+      increasing = increasing && h > 0.0;
+      const double d = (l11_knot_logms(i + 1) - l11_knot_logms(i)) / h;
+      double lower = h_prev, diag = 2.0 * (h_prev + h), upper = h;
+      if (i == 1) {
+        lower = 0.0;
+        diag = 3.0 * h_prev + 2.0 * h + h_prev * h_prev / h;
+        upper = h - h_prev * h_prev / h;
+      }
+      if (i == n - 2) {
+        lower = h_prev - h * h / h_prev;
+        diag = 2.0 * h_prev + 3.0 * h + h * h / h_prev;
+        upper = 0.0;
+      }
+      const double rhs = 6.0 * (d - d_prev);
+      const double inv = 1.0 / (diag - lower * cp);
+      cp = upper * inv;
+      rp = (rhs - lower * rp) * inv;
+      D.knot[i].y = cp;
+      D.knot[i].z = rp;
+      h_prev = h;
+      d_prev = d;
+    }
+    double m_next = 0.0;
+    for (int i = n - 2; i >= 1; i--) {
+      const double m = D.knot[i].z - D.knot[i].y * m_next;
+      D.knot[i].w = m;
+      m_next = m;
+    }
+    {
+      const double h0 = D.knot[1].x - D.knot[0].x, h1 = D.knot[2].x - D.knot[1].x;
+      D.knot[0].w = D.knot[1].w - h0 / h1 * (D.knot[2].w - D.knot[1].w);
+      const double ha = D.knot[n - 1].x - D.knot[n - 2].x, hb = D.knot[n - 2].x - D.knot[n - 3].x;
+      D.knot[n - 1].w = D.knot[n - 2].w + ha / hb * (D.knot[n - 2].w - D.knot[n - 3].w);
+    }
+    D.bad = increasing ? 0.0 : CUDART_NAN;
+  }
+  __syncthreads();
+  // (3) cubic coefficients per interval: read (x, m) of both ends, then overwrite y/z/w
+  constexpr int kPer = (kL11DrawsPerBlock * (kL11Knots - 1) + kThreads - 1) / kThreads;
+  double c1[kPer], c2[kPer], c3[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; q++) {
+    const int idx = threadIdx.x + q * blockDim.x;
+    if (idx < n_block * (kL11Knots - 1)) {
+      const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
+      const double4 k0 = draws[b].knot[k], k1 = draws[b].knot[k + 1];
+      const double h = k1.x - k0.x;
+      const double d = (l11_knot_logms(k + 1) - l11_knot_logms(k)) / h;
+      c1[q] = d - h * (2.0 * k0.w + k1.w) * (1.0 / 6.0);
+      c2[q] = 0.5 * k0.w;
+      c3[q] = (k1.w - k0.w) / (6.0 * h);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kPer; q++) {
+    const int idx = threadIdx.x + q * blockDim.x;
+    if (idx < n_block * (kL11Knots - 1)) {
+      const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
+      draws[b].knot[k].y = c1[q];
+      draws[b].knot[k].z = c2[q];
+      draws[b].knot[k].w = c3[q];
+    }
+  }
+  __syncthreads();
+}
+
+template <bool DECORATED, bool MODULATE, int U, typename Store>
+__device__ __forceinline__ void occupation_item_l11(const OccPlan& plan, const tc_model& model,
+                                                    const L11Draw* d, int g_begin, int g_end,
+                                                    const double* __restrict__ tab, Store store) {
+  L11Params p;
+  p.d = d;
+  p.threshold = model.threshold;
+  p.a_cen = d->a_cen;
+  p.a_sat = d->a_sat;
+  const bool sat = g_begin >= plan.n_cen_groups;
+  for (int grp = g_begin + (threadIdx.x >> 3 & 3); grp < g_end; grp += 4) {
+    double occ0, occ1;
+    if (sat)
+      occupation_group<true, DECORATED, MODULATE, U>(plan, grp, p, model.split, tab, occ0, occ1);
+    else
+      occupation_group<false, DECORATED, false, U>(plan, grp, p, model.split, tab, occ0, occ1);
+    const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
+    store(row0, occ0, plan.row_nh[row0]);
+    if (row1 >= 0) store(row1, occ1, plan.row_nh[row1]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) occupation_l11_kernel(const OccArgs args) {
+  extern __shared__ __align__(16) double l11_smem[];
+  double* tab = l11_smem;
+  L11Draw* draws = reinterpret_cast<L11Draw*>(l11_smem + kTabDoubles);
+  load_math_tables(tab);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_ranges = args.n_ranges_cen + args.n_ranges_sat;
+  const long long n_blocks = (args.n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;
+  for (long long block = blockIdx.x; block < n_blocks; block += gridDim.x) {
+    const long long draw0 = block * kL11DrawsPerBlock;
+    const int n_block = (int)min((long long)kL11DrawsPerBlock, args.n_draws - draw0);
+    __syncthreads();   // the previous block's tables are no longer read
+    l11_prepare_block(draws, n_block, draw0, args.n_draws, args.theta, args.theta_ds,
+                      args.theta_ps, args.model);
+    // one warp per item = 8 draws x one group range; four groups in flight per warp
+    const int n_items = (kL11DrawsPerBlock / 8) * n_ranges;
+    for (int item = warp; item < n_items; item += kWarps) {
+      const int sub = item / n_ranges, q = item - sub * n_ranges;
+      const int b = min(sub * 8 + (lane & 7), n_block - 1);
+      const long long draw = draw0 + sub * 8 + (lane & 7);
+      const bool live = draw < args.n_draws;
+      int g_begin, g_end;
+      occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
+      auto store = [&](int row, double occ, double) {
+        const int dst = args.pad_to_row[row];
+        if (live && dst >= 0) args.occ_out[draw * args.n_rows + dst] = occ;
+      };
+      const bool u5 = args.plan.unroll == kOccUnroll;
+      const bool mod = args.model.modulate_with_cenocc != 0;
+      if (args.model.decorated) {
+        if (mod) { if (u5) occupation_item_l11<true, true, kOccUnroll>(args.plan, args.model, draws + b, g_begin, g_end, tab, store);
+                   else occupation_item_l11<true, true, 2>(args.plan, args.model, draws + b, g_begin, g_end, tab, store); }
+        else     { if (u5) occupation_item_l11<true, false, kOccUnroll>(args.plan, args.model, draws + b, g_begin, g_end, tab, store);
+                   else occupation_item_l11<true, false, 2>(args.plan, args.model, draws + b, g_begin, g_end, tab, store); }
+      } else {
+        if (mod) { if (u5) occupation_item_l11<false, true, kOccUnroll>(args.plan, args.model, draws + b, g_begin, g_end, tab, store);
+                   else occupation_item_l11<false, true, 2>(args.plan, args.model, draws + b, g_begin, g_end, tab, store); }
+        else     { if (u5) occupation_item_l11<false, false, kOccUnroll>(args.plan, args.model, draws + b, g_begin, g_end, tab, store);
+                   else occupation_item_l11<false, false, 2>(args.plan, args.model, draws + b, g_begin, g_end, tab, store); }
+      }
+    }
+  }
+}
+
 // element-wise evaluation of the table-driven math, for the accuracy tests (tc_debug_math)
 __global__ void debug_math_kernel(int kind, const double* x, const double* y, double* out,
                                   long long n) {
@@ -1382,7 +1666,10 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   }
   const int n_groups = (int)groups.size();
   // the kernel evaluates `unroll` nodes per iteration
-  const int unroll = tune("OCC_UNROLL", kOccUnroll) == kOccUnroll && G % kOccUnroll == 0 ? kOccUnroll : 2;
+  const int want_unroll = tune("OCC_UNROLL", kOccUnroll);
+  const int unroll = want_unroll == 2 * kOccUnroll && G % (2 * kOccUnroll) == 0 ? 2 * kOccUnroll
+                     : want_unroll >= kOccUnroll && G % kOccUnroll == 0     ? kOccUnroll
+                                                                              : 2;
   const int GP = round_up(G, unroll);
   std::vector<double> node_logm((size_t)n_groups * GP), node_m((size_t)n_groups * GP);
   std::vector<int> grp_rows((size_t)n_groups * kGroupRows, -1), grp_is_sat(n_groups);
@@ -1623,6 +1910,13 @@ const char* tc_last_error(void) { return g_last_error.c_str(); }
 
 int tc_version(void) { return TC_VERSION; }
 
+int tc_model_n_theta(const tc_model* model) {
+  if (!model) return fail(TC_EINVAL, "tc_model_n_theta: model is NULL");
+  if (model->family == TC_FAMILY_ZHENG07) return TC_N_THETA;
+  if (model->family == TC_FAMILY_LEAUTHAUD11) return TC_N_THETA_LEAUTHAUD11;
+  return fail(TC_EUNSUPPORTED, "tc_model_n_theta: unknown model family");
+}
+
 int tc_table_create(tc_table** out, int mode, int n_rows, int n_r, int n_tables,
                     const double* n_h, const double* log_min, const double* log_max,
                     const double* sec_pct, const double* dist_index, const int32_t* is_sat,
@@ -1698,7 +1992,8 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   if (!t || !model || !theta || !occ) return fail(TC_EINVAL, "tc_occupation_batch: NULL argument");
   if (theta_ld != 0 && theta_ld < n_draws)
     return fail(TC_EINVAL, "tc_occupation_batch: theta_ld must be 0 or >= n_draws");
-  if (model->family != 0) return fail(TC_EUNSUPPORTED, "tc_occupation_batch: unknown model family");
+  if (model->family != TC_FAMILY_ZHENG07 && model->family != TC_FAMILY_LEAUTHAUD11)
+    return fail(TC_EUNSUPPORTED, "tc_occupation_batch: unknown model family");
   if (n_draws <= 0) return TC_OK;
   std::lock_guard<std::mutex> lock(t->mutex);
   DeviceGuard guard(t->device);
@@ -1707,17 +2002,36 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   if (rc != TC_OK) return rc;
   int n_sm = 0;
   if ((rc = device_sms(t->device, &n_sm))) return rc;
+  const int n_theta = model->family == TC_FAMILY_LEAUTHAUD11 ? TC_N_THETA_LEAUTHAUD11 : TC_N_THETA;
   OccArgs args{};
   args.plan = t->layouts[0].plans[n_gauss].dev;
   args.model = *model;
   args.theta = theta;
-  args.theta_ds = theta_ld ? 1 : TC_N_THETA;
+  args.theta_ds = theta_ld ? 1 : n_theta;
   args.theta_ps = theta_ld ? theta_ld : 1;
   args.n_draws = n_draws;
   args.n_rows = t->n_rows;
   args.pad_to_row = t->layouts[0].dev.pad_to_row;
   args.occ_out = occ;
   pick_ranges(args.plan, 1, &args.n_ranges_cen, &args.n_ranges_sat);
+  if (model->family == TC_FAMILY_LEAUTHAUD11) {
+    const size_t smem = kTabDoubles * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
+    static std::mutex m;
+    static std::map<int, bool> configured;
+    {
+      std::lock_guard<std::mutex> lock_attr(m);
+      if (!configured[t->device]) {
+        TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[t->device] = true;
+      }
+    }
+    const long long n_blocks = (n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(n_blocks, n_sm));
+    occupation_l11_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(args);
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+  }
   const long long n_items = (n_draws + 7) / 8 * (args.n_ranges_cen + args.n_ranges_sat);
   int grid = (int)std::max<long long>(1, std::min<long long>((n_items + kWarps - 1) / kWarps,
                                                              (long long)n_sm));
@@ -1749,8 +2063,10 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   if (theta && !model) return fail(TC_EINVAL, "tc_predict_batch: model is NULL");
   if (theta && theta_ld != 0 && theta_ld < n_draws)
     return fail(TC_EINVAL, "tc_predict_batch: theta_ld must be 0 or >= n_draws");
-  if (theta && model->family != 0)
-    return fail(TC_EUNSUPPORTED, "tc_predict_batch: unknown model family");
+  if (theta && model->family != TC_FAMILY_ZHENG07)
+    return fail(TC_EUNSUPPORTED, "tc_predict_batch: the fused occupation phase implements "
+                                 "TC_FAMILY_ZHENG07 only; evaluate tc_occupation_batch and pass "
+                                 "its result as occ_dev");
   if (precision != TC_PRECISION_FP64 && precision != TC_PRECISION_3XTF32)
     return fail(TC_EINVAL, "tc_predict_batch: precision must be TC_PRECISION_FP64 or _3XTF32");
   if (precision == TC_PRECISION_3XTF32 && t->mode != TC_MODE_AUTO)

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from . import h5mini
-from .models import ModelSpec, resolve_model, ASSEMBIAS_KEYS
+from .models import resolve_model, spec_from_params
 from .tabcorr import (TabCorr, DeviceTableGroup, _to_device_f64, _torch, _h5py,
                       theta_to_device)
 from .table import Table
@@ -257,8 +257,7 @@ class Interpolator:
             if key not in params:
                 raise ValueError('The key {} is not present in the parameter dictionary of the '
                                  'model.'.format(key))
-        decorated = all(k in params for k in ASSEMBIAS_KEYS)
-        spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
+        spec = resolve_model(model) if model is not None else spec_from_params(params)
         device = self._groups[0][0].device
         theta = theta_to_device(params, spec, device)
         n_draws = theta.shape[0]
@@ -313,6 +312,15 @@ class Interpolator:
             for i in self.unique_gal_type_index:
                 self.tabcorr_list[i]._check_consistency(model)
         spec = resolve_model(model)
+        if spec.family != 0:
+            # families outside the fused kernel: the batch path with one draw
+            params = {k: np.atleast_1d(np.float64(v)) for k, v in model.param_dict.items()
+                      if np.ndim(v) == 0}
+            ngal, xi = self.predict_batch(params, separate_gal_type, n_gauss_prim, extrapolate,
+                                          model=spec)
+            if separate_gal_type:
+                return ({k: v[0] for k, v in ngal.items()}, {k: v[0] for k, v in xi.items()})
+            return ngal[0], xi[0]
         from .models import theta_from_params
         values = theta_from_params(model.param_dict, 1, spec)[0]
         x_values = [np.float64(model.param_dict[key]) for key in self._keys]

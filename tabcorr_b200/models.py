@@ -7,9 +7,10 @@ The reference evaluates ``model.mean_occupation_centrals/satellites`` of a halot
 
 * a halotools model (recognised by the class names of its occupation components -- halotools
   itself is never imported),
-* the light-weight stand-ins below (``PrebuiltHodModelFactory('zheng07' | 'hearin15-zheng07')``),
-* or any duck-typed object with a zheng07 ``param_dict`` (plus optional ``decorated`` / ``split`` /
-  ``modulate_with_cenocc`` attributes)
+* the light-weight stand-ins below (``PrebuiltHodModelFactory('zheng07' | 'decorated-zheng07' |
+  'leauthaud11' | 'hearin15')``),
+* or any duck-typed object with a zheng07 or leauthaud11 ``param_dict`` (plus optional
+  ``decorated`` / ``split`` / ``modulate_with_cenocc`` / ``threshold`` / ``redshift`` attributes)
 
 to a kernel family descriptor.  Anything else raises ``NotImplementedError`` -- there is no CPU
 fallback; occupations computed elsewhere can still be passed to ``predict`` as an ndarray
@@ -24,6 +25,17 @@ ZHENG07_KEYS = ('logMmin', 'sigma_logM', 'logM0', 'logM1', 'alpha')
 ASSEMBIAS_KEYS = ('mean_occupation_centrals_assembias_param1',
                   'mean_occupation_satellites_assembias_param1')
 THETA_KEYS = ZHENG07_KEYS + ASSEMBIAS_KEYS
+
+# halotools Leauthaud11Cens / Leauthaud11Sats over Behroozi10SmHm: param_dict keys in the order
+# of the kernel's parameter vector (include/tabcorr_b200.h, TC_FAMILY_LEAUTHAUD11)
+LEAUTHAUD11_KEYS = ('smhm_m0_0', 'smhm_m0_a', 'smhm_m1_0', 'smhm_m1_a', 'smhm_beta_0',
+                    'smhm_beta_a', 'smhm_delta_0', 'smhm_delta_a', 'smhm_gamma_0', 'smhm_gamma_a',
+                    'scatter_model_param1', 'alphasat', 'bsat', 'bcut', 'betacut', 'betasat')
+# Behroozi et al. (2010) table 2 / Leauthaud et al. (2011) values halotools ships as defaults
+LEAUTHAUD11_DEFAULTS = (10.72, 0.59, 12.35, 0.3, 0.43, 0.18, 0.56, 0.18, 1.54, 2.52, 0.2,
+                        1.0, 10.62, 1.47, -0.13, 0.859)
+FAMILY_ZHENG07, FAMILY_LEAUTHAUD11 = 0, 1
+FAMILY_KEYS = {FAMILY_ZHENG07: ZHENG07_KEYS, FAMILY_LEAUTHAUD11: LEAUTHAUD11_KEYS}
 
 # Zheng et al. (2007) table 1 (SDSS), the values halotools' ``PrebuiltHodModelFactory('zheng07',
 # threshold=...)`` loads.  Restated from the paper; -18 and -21 are cross-checked against the
@@ -44,14 +56,46 @@ ZHENG07_PUBLISHED = {
 class ModelSpec:
     """What the kernel needs to know about a model (mirrors ``tc_model`` in the C ABI)."""
 
-    def __init__(self, family=0, decorated=False, modulate_with_cenocc=False, split=0.5):
+    def __init__(self, family=0, decorated=False, modulate_with_cenocc=False, split=0.5,
+                 threshold=0.0, redshift=0.0):
         self.family = int(family)
+        if self.family not in FAMILY_KEYS:
+            raise NotImplementedError('unknown occupation family {}'.format(family))
         self.decorated = bool(decorated)
         self.modulate_with_cenocc = bool(modulate_with_cenocc)
         self.split = float(split)
+        self.threshold = float(threshold)   # leauthaud11: log10 stellar-mass threshold
+        self.redshift = float(redshift)     # leauthaud11: redshift of the SMHM parameters
+
+    @property
+    def occupation_keys(self):
+        """The family's occupation parameters (without the assembly-bias strengths)."""
+        return FAMILY_KEYS[self.family]
+
+    @property
+    def theta_keys(self):
+        """param_dict keys of the kernel's parameter vector, in kernel order."""
+        return FAMILY_KEYS[self.family] + ASSEMBIAS_KEYS
+
+    @property
+    def n_theta(self):
+        return len(self.theta_keys)
 
     def key(self):
-        return (self.family, self.decorated, self.modulate_with_cenocc, self.split)
+        return (self.family, self.decorated, self.modulate_with_cenocc, self.split,
+                self.threshold, self.redshift)
+
+
+def spec_from_params(params):
+    """Family of a bare parameter dict (no model object): zheng07, decorated when the two
+    assembly-bias strengths are present.  Other families need ``model=`` (they carry constants
+    that are not in ``param_dict``)."""
+    if all(k in params for k in ZHENG07_KEYS):
+        return ModelSpec(FAMILY_ZHENG07, decorated=all(k in params for k in ASSEMBIAS_KEYS))
+    if any(k in params for k in LEAUTHAUD11_KEYS):
+        raise ValueError('leauthaud11 parameters need model= (a model instance or ModelSpec '
+                         'carrying threshold and redshift)')
+    return ModelSpec(FAMILY_ZHENG07, decorated=all(k in params for k in ASSEMBIAS_KEYS))
 
 
 class Zheng07Model:
@@ -91,6 +135,39 @@ class Zheng07Model:
                                         'satellites_occupation': sats}
 
 
+class Leauthaud11Model:
+    """Stand-in for ``PrebuiltHodModelFactory('leauthaud11')`` / ``('hearin15')`` as far as the
+    prediction path is concerned (``tabcorr/tabcorr.py:496-563``): stellar-mass threshold sample
+    over the Behroozi et al. (2010) stellar-to-halo-mass relation."""
+
+    tabcorr_b200_family = FAMILY_LEAUTHAUD11
+
+    def __init__(self, threshold=10.5, redshift=0.0, prim_haloprop_key='halo_mvir',
+                 sec_haloprop_key='halo_nfw_conc', decorated=False, split=0.5,
+                 modulate_with_cenocc=True, central_assembias_strength=1.0,
+                 satellite_assembias_strength=0.2, **ignored):
+        self.param_dict = dict(zip(LEAUTHAUD11_KEYS, LEAUTHAUD11_DEFAULTS))
+        self.decorated = bool(decorated)
+        self.split = float(split)
+        self.modulate_with_cenocc = bool(modulate_with_cenocc)
+        if self.decorated:
+            self.param_dict[ASSEMBIAS_KEYS[0]] = float(central_assembias_strength)
+            self.param_dict[ASSEMBIAS_KEYS[1]] = float(satellite_assembias_strength)
+        self.threshold = float(threshold)
+        self.redshift = float(redshift)
+        self.gal_types = ['centrals', 'satellites']
+        cens = SimpleNamespace(prim_haloprop_key=prim_haloprop_key, threshold=self.threshold,
+                               redshift=self.redshift)
+        sats = SimpleNamespace(prim_haloprop_key=prim_haloprop_key, threshold=self.threshold,
+                               redshift=self.redshift,
+                               modulate_with_cenocc=self.modulate_with_cenocc)
+        if self.decorated:
+            cens.sec_haloprop_key = sec_haloprop_key
+            sats.sec_haloprop_key = sec_haloprop_key
+        self._input_model_dictionary = {'centrals_occupation': cens,
+                                        'satellites_occupation': sats}
+
+
 def PrebuiltHodModelFactory(model_nickname, **kwargs):
     """Stand-in for ``halotools.empirical_models.PrebuiltHodModelFactory`` (README.md:47,
     tests/conftest.py:29-35) for the model families the occupation kernel implements."""
@@ -99,9 +176,22 @@ def PrebuiltHodModelFactory(model_nickname, **kwargs):
         return Zheng07Model(**kwargs)
     if name in ('hearin15-zheng07', 'decorated-zheng07', 'zheng07-decorated'):
         return Zheng07Model(decorated=True, **kwargs)
+    if name == 'leauthaud11':
+        return Leauthaud11Model(**kwargs)
+    if name == 'hearin15':
+        return Leauthaud11Model(decorated=True, **kwargs)
     raise NotImplementedError(
         "model '{}' is not implemented by the occupation kernel (available: 'zheng07', "
-        "'decorated-zheng07')".format(model_nickname))
+        "'decorated-zheng07', 'leauthaud11', 'hearin15')".format(model_nickname))
+
+
+def _single_scatter(component):
+    """halotools' LogNormalScatterModel has one ``scatter_model_param<i>`` per abscissa; the
+    kernel implements the (default) constant scatter."""
+    extra = [k for k in getattr(component, 'param_dict', {})
+             if k.startswith('scatter_model_param') and k != 'scatter_model_param1']
+    if extra:
+        raise NotImplementedError('mass-dependent stellar-mass scatter is not implemented')
 
 
 def _constant_split(component):
@@ -121,7 +211,8 @@ def resolve_model(model):
         return model
     if hasattr(model, 'tabcorr_b200_family'):
         return ModelSpec(model.tabcorr_b200_family, model.decorated, model.modulate_with_cenocc,
-                         model.split)
+                         model.split, getattr(model, 'threshold', 0.0),
+                         getattr(model, 'redshift', 0.0))
     components = getattr(model, '_input_model_dictionary', None)
     if components is not None and 'centrals_occupation' in components:
         cens = components['centrals_occupation']
@@ -134,6 +225,20 @@ def resolve_model(model):
             if _constant_split(sats) != split:
                 raise NotImplementedError('different splits for centrals and satellites')
             return ModelSpec(0, True, getattr(sats, 'modulate_with_cenocc', False), split)
+        if names in (('Leauthaud11Cens', 'Leauthaud11Sats'),
+                     ('AssembiasLeauthaud11Cens', 'AssembiasLeauthaud11Sats')):
+            decorated = names[0].startswith('Assembias')
+            split = 0.5
+            if decorated:
+                split = _constant_split(cens)
+                if _constant_split(sats) != split:
+                    raise NotImplementedError('different splits for centrals and satellites')
+            _single_scatter(cens)
+            if float(sats.threshold) != float(cens.threshold):
+                raise NotImplementedError('different thresholds for centrals and satellites')
+            return ModelSpec(FAMILY_LEAUTHAUD11, decorated,
+                             getattr(sats, 'modulate_with_cenocc', True), split,
+                             float(cens.threshold), float(getattr(cens, 'redshift', 0.0)))
         raise NotImplementedError(
             'occupation components {} are not implemented by the CUDA occupation kernel; '
             'pass precomputed occupations as an ndarray instead'.format(names))
@@ -142,31 +247,43 @@ def resolve_model(model):
         return ModelSpec(0, getattr(model, 'decorated', False),
                          getattr(model, 'modulate_with_cenocc', False),
                          getattr(model, 'split', 0.5))
+    if param_dict is not None and all(k in param_dict for k in LEAUTHAUD11_KEYS):
+        if not hasattr(model, 'threshold'):
+            raise NotImplementedError('a leauthaud11 model needs a `threshold` attribute')
+        return ModelSpec(FAMILY_LEAUTHAUD11, getattr(model, 'decorated', False),
+                         getattr(model, 'modulate_with_cenocc', True),
+                         getattr(model, 'split', 0.5), float(model.threshold),
+                         float(getattr(model, 'redshift', 0.0)))
     raise NotImplementedError(
-        'cannot map {!r} to a kernel occupation family (zheng07, decorated zheng07)'.format(model))
+        'cannot map {!r} to a kernel occupation family (zheng07, leauthaud11 and their '
+        'decorated versions)'.format(model))
 
 
 def theta_columns(params, spec=None):
-    """The ``TC_N_THETA`` columns (arrays ``[B]`` or scalars) of a parameter dict in kernel order;
-    raises ``ValueError`` for missing parameters like :func:`theta_from_params`."""
-    missing = [k for k in ZHENG07_KEYS if k not in params]
+    """The columns (arrays ``[B]`` or scalars) of a parameter dict in the kernel order of the
+    family (``spec.theta_keys``); raises ``ValueError`` for missing parameters like
+    :func:`theta_from_params`."""
+    if spec is None:
+        spec = ModelSpec()
+    missing = [k for k in spec.occupation_keys if k not in params]
     if missing:
         raise ValueError('missing occupation parameters: {}'.format(', '.join(missing)))
-    if spec is not None and spec.decorated:
+    if spec.decorated:
         missing = [k for k in ASSEMBIAS_KEYS if k not in params]
         if missing:
             raise ValueError('missing assembly-bias parameters: {}'.format(', '.join(missing)))
-    return [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in THETA_KEYS]
+    return [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in spec.theta_keys]
 
 
 def theta_from_params(params, n_draws=None, spec=None, alloc=None):
-    """``[B, 7]`` float64 array in kernel order from a dict of scalars/arrays keyed by halotools
-    parameter names.  Missing assembly-bias strengths default to 0.  ``alloc(shape)`` may supply
-    the output buffer (e.g. pinned host memory)."""
+    """``[B, n_theta]`` float64 array in kernel order from a dict of scalars/arrays keyed by
+    halotools parameter names (``n_theta`` = 7 for zheng07, 18 for leauthaud11).  Missing
+    assembly-bias strengths default to 0.  ``alloc(shape)`` may supply the output buffer (e.g.
+    pinned host memory)."""
     columns = theta_columns(params, spec)
     if n_draws is None:
         n_draws = max([c.shape[0] for c in columns if c.ndim > 0] + [1])
-    shape = (n_draws, len(THETA_KEYS))
+    shape = (n_draws, len(columns))
     theta = np.empty(shape, dtype=np.float64) if alloc is None else alloc(shape)
     for j, column in enumerate(columns):
         theta[:, j] = column

@@ -112,6 +112,28 @@ def make_draws(n_draws, seed=1, decorated=False, extra=None):
     return draws
 
 
+def make_draws_leauthaud11(n_draws, seed=1, decorated=False, extra=None):
+    """Independent uniform leauthaud11 draws around the halotools defaults (Behroozi et al. 2010
+    table 2, Leauthaud et al. 2011), ``dict[str, ndarray[n_draws]]``; ranges keep the
+    stellar-to-halo-mass relation monotonic."""
+    rng = np.random.default_rng(seed)
+    ranges = {
+        'smhm_m0_0': (10.4, 11.0), 'smhm_m0_a': (0.4, 0.8), 'smhm_m1_0': (12.0, 12.7),
+        'smhm_m1_a': (0.1, 0.5), 'smhm_beta_0': (0.35, 0.5), 'smhm_beta_a': (0.1, 0.25),
+        'smhm_delta_0': (0.4, 0.7), 'smhm_delta_a': (0.1, 0.25), 'smhm_gamma_0': (1.2, 1.9),
+        'smhm_gamma_a': (2.0, 3.0), 'scatter_model_param1': (0.1, 0.4), 'alphasat': (0.8, 1.2),
+        'bsat': (8.0, 13.0), 'bcut': (0.5, 3.0), 'betacut': (-0.3, 0.1), 'betasat': (0.6, 1.1),
+    }
+    draws = {key: rng.uniform(lo, hi, n_draws) for key, (lo, hi) in ranges.items()}
+    if decorated:
+        for key in ASSEMBIAS_KEYS:
+            draws[key] = rng.uniform(-1.0, 1.0, n_draws)
+    if extra:
+        for key, (lo, hi) in extra.items():
+            draws[key] = rng.uniform(lo, hi, n_draws)
+    return draws
+
+
 def make_grid_tables(axes, n_mass=30, n_sec=2, n_r=14, mode='auto', kind='wp', seed=7,
                      n_h_scale=1.0):
     """Tables on a full rectangular grid, as ``scripts/tabulate_snapshot.py:158-165,240-254`` writes

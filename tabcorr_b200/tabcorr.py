@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from . import h5mini
-from .models import (ModelSpec, THETA_KEYS, ASSEMBIAS_KEYS, resolve_model, theta_columns,
+from .models import (ModelSpec, THETA_KEYS, resolve_model, spec_from_params, theta_columns,
                      theta_from_params)
 from .table import Table
 
@@ -169,19 +169,24 @@ class DeviceTableGroup:
     @staticmethod
     def _model_struct(spec):
         return _lib.tc_model(spec.family, int(spec.decorated), int(spec.modulate_with_cenocc), 0,
-                             spec.split)
+                             spec.split, spec.threshold, spec.redshift)
 
-    def occupation(self, spec, n_gauss, theta):
-        """theta: CUDA tensor [B, 7] -> CUDA tensor [B, n_rows] (mean_occupation)."""
+    def occupation(self, spec, n_gauss, theta, theta_columns=False):
+        """theta: CUDA tensor ``[B, n_theta]`` (or ``[n_theta, B]`` with ``theta_columns``) ->
+        CUDA tensor ``[B, n_rows]`` (mean_occupation)."""
         torch = _torch()
         self.plan(n_gauss)
-        n_draws = theta.shape[0]
+        n_draws = theta.shape[1] if theta_columns else theta.shape[0]
+        n_theta = theta.shape[0] if theta_columns else theta.shape[1]
+        if n_theta != spec.n_theta:
+            raise ValueError('the parameter array has {} columns, the model family needs {} '
+                             '({})'.format(n_theta, spec.n_theta, ', '.join(spec.theta_keys)))
         occ = torch.zeros((n_draws, self.n_rows), dtype=torch.float64, device=self.device)
         model = self._model_struct(spec)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.tc_occupation_batch(
-            self.handle, ctypes.byref(model), int(n_gauss), theta.data_ptr(), 0, n_draws,
-            occ.data_ptr(), stream))
+            self.handle, ctypes.byref(model), int(n_gauss), theta.data_ptr(),
+            theta.stride(0) if theta_columns else 0, n_draws, occ.data_ptr(), stream))
         return occ
 
     def predict_one(self, spec, n_gauss, values, separate):
@@ -189,6 +194,16 @@ class DeviceTableGroup:
         ``ngal [T, 1|2]``, ``xi [T, R, C]`` (copies).  Latency path, see ``_SingleDrawBuffers``."""
         torch = _torch()
         self.plan(n_gauss)
+        if spec.family != 0:
+            # families outside the fused kernel: occupation kernel + contraction (no latency path)
+            theta = _to_device_f64(np.asarray(values, dtype=np.float64)[np.newaxis, :], self.device)
+            n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
+            ngal = torch.empty((1, self.n_tables, n_ng), dtype=torch.float64, device=self.device)
+            xi = torch.empty((1, self.n_tables, self.n_r * n_comp), dtype=torch.float64,
+                             device=self.device)
+            self.predict_into(spec, n_gauss, theta, None, separate, ngal, 0, xi, 0)
+            return (ngal[0].cpu().numpy(),
+                    xi[0].cpu().numpy().reshape(self.n_tables, self.n_r, n_comp))
         with self._lock:
             if self._single is None:
                 self._single = _SingleDrawBuffers(self)
@@ -212,8 +227,13 @@ class DeviceTableGroup:
                      theta_columns=False, precision=_lib.TC_PRECISION_FP64):
         """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
         and ``xi`` starting at table offset ``*_offset`` (in doubles within a draw).  ``theta`` is
-        ``[B, 7]``, or ``[7, B]`` (one contiguous column per parameter) with ``theta_columns``."""
+        ``[B, n_theta]``, or ``[n_theta, B]`` (one contiguous column per parameter) with
+        ``theta_columns``.  Families the fused kernel does not implement (leauthaud11) run the
+        occupation kernel first and contract its output."""
         torch = _torch()
+        if theta is not None and spec is not None and spec.family != 0:
+            occ = self.occupation(spec, n_gauss, theta, theta_columns=theta_columns)
+            theta, theta_columns = None, False
         n_draws = (theta.shape[1] if theta_columns else theta.shape[0]) if theta is not None \
             else occ.shape[0]
         theta_ld = theta.stride(0) if (theta is not None and theta_columns) else 0
@@ -433,16 +453,16 @@ class TabCorr:
         torch = _torch()
         group = self._ensure_device()
         if isinstance(params, dict):
-            decorated = all(k in params for k in ASSEMBIAS_KEYS)
-            spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
+            spec = resolve_model(model) if model is not None else spec_from_params(params)
             theta = theta_to_device(params, spec, group.device)
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             theta = _to_device_f64(params, group.device)
-            if theta.ndim != 2 or theta.shape[1] not in (5, len(THETA_KEYS)):
-                raise ValueError('params must be a dict of arrays or a [B, 5|7] array ordered as '
-                                 '{}'.format(', '.join(THETA_KEYS)))
-            if theta.shape[1] == 5:
+            if theta.ndim != 2 or theta.shape[1] not in (spec.n_theta - 2, spec.n_theta):
+                raise ValueError('params must be a dict of arrays or a [B, {}|{}] array ordered as '
+                                 '{}'.format(spec.n_theta - 2, spec.n_theta,
+                                             ', '.join(spec.theta_keys)))
+            if theta.shape[1] == spec.n_theta - 2:
                 theta = torch.cat([theta, torch.zeros((theta.shape[0], 2), dtype=torch.float64,
                                                       device=theta.device)], dim=1)
         return spec, theta
@@ -456,7 +476,8 @@ class TabCorr:
         params : dict of arrays ``[B]`` or array/tensor ``[B, 5|7]``
             Occupation parameters keyed by their halotools names (``logMmin, sigma_logM, logM0,
             logM1, alpha`` and, for decorated models, the two ``*_assembias_param1``), or the
-            same as columns in that order.  Ignored when ``occupation`` is given.
+            same as columns in that order.  With a leauthaud11 / hearin15 ``model`` the keys are
+            ``models.LEAUTHAUD11_KEYS`` (16 | 18 columns).  Ignored when ``occupation`` is given.
         separate_gal_type : bool, optional
             Split the result by galaxy type like ``predict`` does.
         n_gauss_prim : int, optional
@@ -522,24 +543,24 @@ class TabCorr:
         group = self._ensure_device()
         device = group.device
         if isinstance(params, dict):
-            decorated = all(k in params for k in ASSEMBIAS_KEYS)
-            spec = resolve_model(model) if model is not None else ModelSpec(decorated=decorated)
+            spec = resolve_model(model) if model is not None else spec_from_params(params)
             columns = theta_columns(params, spec)
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             array = np.asarray(params, dtype=np.float64)
-            if array.ndim != 2 or array.shape[1] not in (5, len(THETA_KEYS)):
-                raise ValueError('params must be a dict of arrays or a [B, 5|7] array ordered as '
-                                 '{}'.format(', '.join(THETA_KEYS)))
+            if array.ndim != 2 or array.shape[1] not in (spec.n_theta - 2, spec.n_theta):
+                raise ValueError('params must be a dict of arrays or a [B, {}|{}] array ordered as '
+                                 '{}'.format(spec.n_theta - 2, spec.n_theta,
+                                             ', '.join(spec.theta_keys)))
             columns = [array[:, j] for j in range(array.shape[1])]
-            columns += [np.float64(0.0)] * (len(THETA_KEYS) - len(columns))
+            columns += [np.float64(0.0)] * (spec.n_theta - len(columns))
         n_draws = max([c.shape[0] for c in columns if np.ndim(c) > 0] + [1])
         n_ng, n_comp = (2 if separate else 1), group.n_comp(separate)
         f64 = torch.float64
         # parameters are staged one contiguous column per parameter (a strided fill of [B, 7] rows
         # costs 4x more host time); chunk [lo, hi) owns the block [7 lo, 7 hi) viewed as
         # [7, hi - lo], so that every chunk is one contiguous host-to-device copy
-        n_theta = len(THETA_KEYS)
+        n_theta = spec.n_theta
         theta_pin = torch.empty(n_draws * n_theta, dtype=f64, pin_memory=True)
         ngal_pin = torch.empty((n_draws, n_ng), dtype=f64, pin_memory=True)
         xi_pin = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, pin_memory=True)

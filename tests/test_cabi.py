@@ -43,7 +43,16 @@ def test_version_and_constants(lib):
     text = open(HEADER).read()
     assert lib.tc_version() == int(re.search(r'#define TC_VERSION (\d+)', text).group(1))
     assert int(re.search(r'#define TC_N_THETA (\d+)', text).group(1)) == _lib.TC_N_THETA
-    assert ctypes.sizeof(_lib.tc_model) == 24  # 4 x int32 + double, as declared in the header
+    assert int(re.search(r'#define TC_N_THETA_LEAUTHAUD11 (\d+)', text).group(1)) == \
+        _lib.TC_N_THETA_LEAUTHAUD11
+    assert ctypes.sizeof(_lib.tc_model) == 40  # 4 x int32 + 3 doubles, as declared in the header
+    from tabcorr_b200 import models
+    for family, n_theta in ((_lib.TC_FAMILY_ZHENG07, _lib.TC_N_THETA),
+                            (_lib.TC_FAMILY_LEAUTHAUD11, _lib.TC_N_THETA_LEAUTHAUD11)):
+        spec = models.ModelSpec(family)
+        model = _lib.tc_model(family, 0, 0, 0, 0.5, 10.5, 0.0)
+        assert lib.tc_model_n_theta(ctypes.byref(model)) == n_theta == spec.n_theta
+    assert lib.tc_model_n_theta(ctypes.byref(_lib.tc_model(9, 0, 0, 0, 0.5, 0.0, 0.0))) == -3
 
 
 def test_argument_errors_do_not_need_a_device(lib):

@@ -1,0 +1,176 @@
+"""GPU parity tests of the leauthaud11 / hearin15 occupation family
+against the numpy/scipy oracle on the same seeded inputs, through the reference-shaped Python API.
+
+The occupation formulas restate halotools from memory (parity unpinned, see oracle/ header); what
+these tests pin is that the CUDA kernel computes exactly what the oracle states, including
+halotools' numerical inversion of the stellar-to-halo-mass relation (100-knot not-a-knot spline).
+Tolerance: rtol 1e-10 on (ngal, xi) like the zheng07 path; occupations to 5e-11 absolute/relative.
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def tb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import tabcorr_b200
+    return tabcorr_b200
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import tabcorr_oracle
+    return tabcorr_oracle
+
+
+def close(actual, ref, rtol=RTOL):
+    actual, ref = np.asarray(actual), np.asarray(ref)
+    scale = np.abs(ref).max(axis=-1, keepdims=True) if ref.ndim else np.abs(ref)
+    np.testing.assert_allclose(actual, ref, rtol=rtol, atol=float(rtol) * 1e-3 * np.max(scale))
+
+
+def table_pair(tb, orc, name):
+    kw, _ = cases.SYNTHETIC[name]
+    tab = tb.synthetic.make_table(**kw)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                            tab['attrs']['mode'])
+    return halotab, table
+
+
+VARIANTS = [
+    dict(threshold=10.5, redshift=0.0, decorated=False, modulate_with_cenocc=True),
+    dict(threshold=11.0, redshift=0.5, decorated=False, modulate_with_cenocc=False),
+    dict(threshold=10.5, redshift=0.0, decorated=True, modulate_with_cenocc=True),
+    dict(threshold=10.0, redshift=1.0, decorated=True, modulate_with_cenocc=False, split=0.3),
+]
+
+
+@pytest.mark.parametrize('variant', range(len(VARIANTS)))
+@pytest.mark.parametrize('n_gauss', [10, 3])
+def test_occupation_matches_oracle(tb, orc, variant, n_gauss):
+    kw = VARIANTS[variant]
+    halotab, table = table_pair(tb, orc, 'syn240')
+    draws = tb.synthetic.make_draws_leauthaud11(9, seed=21 + variant, decorated=kw['decorated'])
+    spec = tb.models.ModelSpec(tb.models.FAMILY_LEAUTHAUD11, kw['decorated'],
+                               kw['modulate_with_cenocc'], kw.get('split', 0.5),
+                               kw['threshold'], kw['redshift'])
+    occ = halotab.mean_occupation_batch(draws, n_gauss_prim=n_gauss, model=spec).cpu().numpy()
+    assert occ.shape == (9, 240)
+    for i in range(9):
+        model = orc.Leauthaud11Oracle(cases.draws_row(draws, i), **kw)
+        ref = orc.mean_occupation(table, model, n_gauss)
+        np.testing.assert_allclose(occ[i], ref, rtol=5e-11, atol=5e-11 * max(1.0, ref.max()))
+    assert occ.max() > 1.0 and 0.0 < occ[:, :120].max() <= 1.0 + 1e-12
+
+
+@pytest.mark.parametrize('name', ['syn240', 'syncross', 'synmulti'])
+def test_predict_batch_matches_oracle(tb, orc, name):
+    halotab, table = table_pair(tb, orc, name)
+    kw = dict(threshold=10.5, redshift=0.0, decorated=True, modulate_with_cenocc=True)
+    draws = tb.synthetic.make_draws_leauthaud11(40, seed=5, decorated=True)
+    stand_in = tb.PrebuiltHodModelFactory('hearin15', threshold=10.5, redshift=0.0)
+    ngal, xi = halotab.predict_batch(draws, model=stand_in)
+    ngal_sep, xi_sep = halotab.predict_batch(draws, model=stand_in, separate_gal_type=True)
+    for i in range(0, 40, 3):
+        model = orc.Leauthaud11Oracle(cases.draws_row(draws, i), **kw)
+        occ = orc.mean_occupation(table, model)
+        ngal_ref, xi_ref = orc.predict(table, occ)
+        close(ngal[i], ngal_ref)
+        close(xi[i].ravel(), np.ravel(xi_ref))
+        ngal_ref, xi_ref = orc.predict(table, occ, separate_gal_type=True)
+        total = np.max(np.sum([np.abs(v) for v in xi_ref.values()], axis=0))
+        for key in xi_ref:
+            np.testing.assert_allclose(xi_sep[key][i], xi_ref[key], rtol=RTOL,
+                                       atol=RTOL * 1e-3 * total)
+        for key in ngal_ref:
+            close(ngal_sep[key][i], ngal_ref[key])
+
+
+def test_model_api_and_array_input(tb, orc):
+    halotab, table = table_pair(tb, orc, 'syn36x3')
+    model = tb.PrebuiltHodModelFactory('leauthaud11', threshold=10.8, redshift=0.02)
+    model.param_dict['alphasat'] = 1.1
+    spec = tb.models.resolve_model(model)
+    assert (spec.family, spec.decorated, spec.modulate_with_cenocc, spec.threshold) == \
+        (1, False, True, 10.8)
+    ref_model = orc.Leauthaud11Oracle(model.param_dict, threshold=10.8, redshift=0.02)
+    occ_ref = orc.mean_occupation(table, ref_model)
+    np.testing.assert_allclose(halotab.mean_occupation(model), occ_ref, rtol=5e-11, atol=5e-11)
+    ngal_ref, xi_ref = orc.predict(table, occ_ref)
+    ngal, xi = halotab.predict(model)
+    assert isinstance(ngal, np.floating) and xi.shape == tuple(table.tpcf_shape)
+    close(ngal, ngal_ref)
+    close(xi, xi_ref)
+    # [B, 16] array in kernel order == dict input; bare dicts of this family need model=
+    theta = np.array([[model.param_dict[k] for k in tb.models.LEAUTHAUD11_KEYS]] * 3)
+    ngal_a, xi_a = halotab.predict_batch(theta, model=model)
+    assert np.array_equal(ngal_a, np.repeat(ngal_a[:1], 3)) and np.array_equal(xi_a[0], xi_a[2])
+    close(ngal_a[0], ngal_ref)
+    close(xi_a[0], xi_ref)
+    with pytest.raises(ValueError, match='model='):
+        halotab.predict_batch({k: np.array([v]) for k, v in model.param_dict.items()})
+    with pytest.raises(ValueError, match='columns|ordered'):
+        halotab.predict_batch(theta[:, :7], model=model)
+    # the optional 3xTF32 contraction also accepts this family's occupations
+    ngal_t, xi_t = halotab.predict_batch(theta, model=model, precision='3xtf32')
+    close(xi_t[0], xi_ref, rtol=1e-6)
+
+
+def test_interpolator_with_leauthaud11(tb, orc):
+    tables, param_table, _ = cases.grid_case('grid2d')
+    halotabs = [tb.TabCorr.from_arrays(t['gal_type'], t['tpcf_matrix'], t['tpcf_shape'],
+                                       t['attrs'], upload=False) for t in tables]
+    interp = tb.Interpolator(halotabs, param_table)
+    oracle_tables = [orc.OracleTable(t['gal_type'], t['tpcf_matrix'], t['tpcf_shape'],
+                                     t['attrs']['mode']) for t in tables]
+    ointerp = orc.OracleInterpolator(oracle_tables, param_table)
+    model = tb.PrebuiltHodModelFactory('hearin15', threshold=10.5)
+    model.param_dict.update(alpha_s=1.03, log_eta=-0.11)
+    ref_model = orc.Leauthaud11Oracle(
+        {k: v for k, v in model.param_dict.items() if k not in ('alpha_s', 'log_eta')},
+        threshold=10.5, decorated=True)
+    ref_model.param_dict.update(alpha_s=1.03, log_eta=-0.11)
+    ngal_ref, xi_ref = ointerp.predict(ref_model)
+    ngal, xi = interp.predict(model)
+    close(ngal, ngal_ref)
+    close(xi, xi_ref)
+
+
+def test_non_monotonic_relation_gives_nan(tb, orc):
+    halotab, _ = table_pair(tb, orc, 'syn36x3')
+    model = tb.PrebuiltHodModelFactory('leauthaud11')
+    model.param_dict.update(smhm_beta_0=-3.0)   # halo mass falls with stellar mass
+    with pytest.raises(ValueError):
+        orc.Leauthaud11Oracle(model.param_dict).mean_log_stellar_mass(np.array([1e12]))
+    occ = halotab.mean_occupation(model)
+    assert np.all(np.isnan(occ))
+
+
+def test_fused_entry_point_rejects_the_family(tb):
+    from tabcorr_b200 import _lib
+    halotab = tb.TabCorr.from_arrays(**{k: v for k, v in tb.synthetic.make_table(
+        n_mass=4, n_sec=1, n_r=3).items()})
+    group = halotab._ensure_device()
+    group.plan(10)
+    import torch
+    theta = torch.zeros((2, 18), dtype=torch.float64, device='cuda')
+    out = torch.zeros((2, 8), dtype=torch.float64, device='cuda')
+    work = torch.zeros(1 << 20, dtype=torch.uint8, device='cuda')
+    model = _lib.tc_model(1, 0, 1, 0, 0.5, 10.5, 0.0)
+    status = group.lib.tc_predict_batch(group.handle, ctypes.byref(model), 10, theta.data_ptr(), 0,
+                                        None, 2, 0, 0, out.data_ptr(), 1, out.data_ptr() + 64, 3,
+                                        work.data_ptr(), work.numel(), None)
+    assert status == -3 and b'tc_occupation_batch' in group.lib.tc_last_error()

@@ -77,3 +77,63 @@ def test_table_set_groups_and_scatters():
         ts.predict_batch({'a': a}, index + 0.5)
     with pytest.raises(ValueError):
         TableSet([])
+
+
+def test_leauthaud11_oracle_inverts_the_smhm_relation():
+    """The oracle's halotools-style inversion (100-knot interpolating spline) is the not-a-knot
+    cubic spline and inverts mean_log_halo_mass to the spline's accuracy."""
+    from scipy.interpolate import CubicSpline
+    from oracle import tabcorr_oracle as orc
+    model = orc.Leauthaud11Oracle(redshift=0.3)
+    knots = np.linspace(8.5, 12.5, 100)
+    table = model.mean_log_halo_mass(knots)
+    assert np.all(np.diff(table) > 0)
+    log_mh = np.linspace(table[0] - 0.2, 15.3, 57)   # includes the extrapolated low-mass end
+    ours = model.mean_log_stellar_mass(10**log_mh)
+    np.testing.assert_allclose(ours, CubicSpline(table, knots, bc_type='not-a-knot')(log_mh),
+                               rtol=0, atol=2e-11)
+    inside = (log_mh > table[0]) & (log_mh < table[-1])
+    np.testing.assert_allclose(model.mean_log_halo_mass(ours[inside]), log_mh[inside], atol=1e-5)
+    # occupations: centrals rise from 0 to 1 through 0.5 at M_h(threshold), satellites ~ power law
+    m_thr = 10**model.mean_log_halo_mass(model.threshold)
+    assert abs(model.mean_occupation_centrals(prim_haloprop=np.array([m_thr]))[0] - 0.5) < 1e-5
+    sats = model.mean_occupation_satellites(prim_haloprop=np.array([1e14, 2e14]))
+    assert 1.9 < sats[1] / sats[0] < 2.2
+
+
+def test_resolve_model_families():
+    from types import SimpleNamespace
+    from tabcorr_b200 import models
+
+    def component(name, **attrs):
+        return type(name, (), {})().__class__ and _with(type(name, (), {})(), attrs)
+
+    def _with(obj, attrs):
+        for k, v in attrs.items():
+            setattr(obj, k, v)
+        return obj
+
+    cens = component('Leauthaud11Cens', threshold=10.5, redshift=0.1, prim_haloprop_key='halo_mvir',
+                     param_dict={'scatter_model_param1': 0.2})
+    sats = component('Leauthaud11Sats', threshold=10.5, modulate_with_cenocc=True,
+                     prim_haloprop_key='halo_mvir')
+    model = SimpleNamespace(_input_model_dictionary={'centrals_occupation': cens,
+                                                     'satellites_occupation': sats})
+    spec = models.resolve_model(model)
+    assert spec.key() == (1, False, True, 0.5, 10.5, 0.1) and spec.n_theta == 18
+    assert spec.theta_keys[:16] == models.LEAUTHAUD11_KEYS
+    cens.param_dict['scatter_model_param2'] = 0.3
+    with pytest.raises(NotImplementedError, match='scatter'):
+        models.resolve_model(model)
+    model = models.PrebuiltHodModelFactory('hearin15', threshold=11.0, redshift=0.5)
+    spec = models.resolve_model(model)
+    assert spec.key() == (1, True, True, 0.5, 11.0, 0.5)
+    theta = models.theta_from_params(model.param_dict, 1, spec)
+    assert theta.shape == (1, 18) and theta[0, 16] == 1.0 and theta[0, 17] == 0.2
+    with pytest.raises(ValueError, match='missing occupation parameters'):
+        models.theta_from_params({'alphasat': 1.0}, 1, spec)
+    with pytest.raises(ValueError, match='model='):
+        models.spec_from_params({k: 1.0 for k in models.LEAUTHAUD11_KEYS})
+    with pytest.raises(NotImplementedError):
+        models.PrebuiltHodModelFactory('tinker13')
+    assert models.spec_from_params({k: 1.0 for k in models.THETA_KEYS}).decorated
