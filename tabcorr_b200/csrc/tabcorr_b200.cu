@@ -90,6 +90,7 @@ struct OccPlan {       // device pointers, one per (layout, n_gauss)
   int zero_row;             // index of an all-zero row of row_c (second row of 1-row groups)
   const double* node_logm;  // [n_groups, G]  log10 of the node masses
   const double* node_m;     // [n_groups, G]  node masses
+  const double* node_inv_m; // [n_groups, G]  1 / node mass
   const int* grp_rows;      // [n_groups, kGroupRows] padded row index or -1
   const int* grp_is_sat;    // [n_groups]
   const double* row_c;      // [n_pad, G] normalised quadrature weights
@@ -298,6 +299,19 @@ __device__ __forceinline__ double pow_pos(double t, double alpha, const double* 
 
 struct DrawParams {
   double logMmin, inv_sigma, m0, inv_m1, alpha, a_cen, a_sat;
+  // node arrays handed to baseline_occupation as (first, second); zheng07 satellites need the
+  // mass only, unless they are modulated by the central occupation (log10 mass, mass)
+  static __device__ __forceinline__ const double* first_nodes(const OccPlan& plan, bool sat,
+                                                              bool modulate) {
+    return sat && !modulate ? plan.node_m : plan.node_logm;
+  }
+  static __device__ __forceinline__ const double* second_nodes(const OccPlan& plan) {
+    return plan.node_m;
+  }
+  static __device__ __forceinline__ bool needs_second(bool sat, bool modulate) {
+    return sat && modulate;
+  }
+  __device__ __forceinline__ void begin_group(double) {}
 };
 
 // theta points at the draw's first parameter; consecutive parameters are `ps` doubles apart
@@ -355,15 +369,16 @@ __device__ __forceinline__ double baseline_occupation(double logm, double mass,
 // zero-weight nodes) and accumulated into the two rows (secondary-percentile bins) of the group.
 // A group with a single row points its second row at an all-zero weight row.
 template <bool SAT, bool DECORATED, bool MODULATE, int U, typename Params>
-__device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, const Params& p,
+__device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, Params& p,
                                                  double split, const double* __restrict__ tab,
                                                  double& occ0, double& occ1) {
   const int G = plan.n_gauss_pad;
   const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
   const double* c0 = plan.row_c + (size_t)row0 * G;
   const double* c1 = plan.row_c + (size_t)(row1 >= 0 ? row1 : plan.zero_row) * G;
-  const double* node = (SAT && !MODULATE ? plan.node_m : plan.node_logm) + (size_t)grp * G;
-  const double* node2 = plan.node_m + (size_t)grp * G;
+  const double* node = Params::first_nodes(plan, SAT, MODULATE) + (size_t)grp * G;
+  const double* node2 = Params::second_nodes(plan) + (size_t)grp * G;
+  p.begin_group(node[0]);
   double k0 = 0.0, k1 = 0.0, ratio = 0.0;
   bool split_ok = false;
   if (DECORATED) {
@@ -380,8 +395,8 @@ __device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, c
     double f[U];
 #pragma unroll
     for (int u = 0; u < U; u++)
-      f[u] = baseline_occupation<SAT, MODULATE>(node[g + u], SAT && MODULATE ? node2[g + u]
-                                                                             : node[g + u], p, tab);
+      f[u] = baseline_occupation<SAT, MODULATE>(
+          node[g + u], Params::needs_second(SAT, MODULATE) ? node2[g + u] : node[g + u], p, tab);
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (DECORATED) {
@@ -968,7 +983,7 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
 // InterpolatedUnivariateSpline, k = 3: not-a-knot end conditions, cubic extrapolation) of log10 M*
 // over log10 M_h.  Parity means reproducing that spline, not the exact inverse, so every draw
 // builds the same table and solves the same not-a-knot system (Thomas algorithm) in shared
-// memory; a node is then a 7-step binary search and one cubic.  A draw whose table is not
+// memory; a mass bin is then one 7-step binary search, and a node a short walk and one cubic.  A draw whose table is not
 // strictly increasing (halotools raises there) gets NaN occupations.
 //
 // This family does not run inside the fused kernel (its per-draw spline does not fit beside the W
@@ -976,27 +991,52 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
 // input of predict_kernel.  Restated from memory of halotools -- parity unpinned, see DESIGN.md.
 // ------------------------------------------------------------------------------------------
 constexpr int kL11Knots = 100;
-constexpr int kL11DrawsPerBlock = 32;
+constexpr int kL11DrawsPerBlock = 64;     // 64 x 3.2 KB of spline tables + math tables < 227 KB
 constexpr double kL11LittleH = 0.7;
 constexpr double kL11LogMsLo = 8.5, kL11LogMsHi = 12.5;
+constexpr double kLn10 = 2.302585092994045684;
 
 struct L11Draw {
-  // knot k: x = log10 M_h of the knot, y/z/w = c1, c2, c3 of the cubic on [knot k, knot k + 1):
+  // knot k: x = log10 M_h of the knot; y, z, w = c1, c3, c2 of the cubic on [knot k, knot k + 1):
   // log10 M* = s_k + t (c1 + t (c2 + t c3)), t = log10 M - x
   double4 knot[kL11Knots];
-  double inv_scatter;   // 1 / (sqrt(2) sigma)
-  double neg_mcut;      // -M_cut
-  double inv_msat;      // 1 / M_sat
+  double inv_scatter;     // 1 / (sqrt(2) sigma)
+  double neg_mcut_h;      // -M_cut / h
+  double ln_h_over_msat;  // ln(h / M_sat)
   double alphasat;
-  double a_cen, a_sat;  // assembly-bias strengths (0 unless decorated)
-  double bad;           // NaN if the table is not strictly increasing, else 0
-  double pad;
+  double a_cen, a_sat;    // assembly-bias strengths (0 unless decorated)
+  double bad;             // NaN if the table is not strictly increasing, else 0
+  double pad[3];          // sizeof = 25 x 128 + 80 bytes: the same knot of 8 consecutive draws
+                          // falls into 8 different 16-byte bank groups
 };
+static_assert(sizeof(L11Draw) % 128 == 80, "L11Draw stride chosen against bank conflicts");
 
 struct L11Params {
   const L11Draw* d;
   double threshold;
   double a_cen, a_sat;
+  int hint;   // knot interval of the group's first node: the nodes of a mass bin ascend from it
+  double next_x[3];   // abscissae of the next three knots (+inf past the last interval)
+  // baseline_occupation receives (log10 mass, 1 / mass)
+  static __device__ __forceinline__ const double* first_nodes(const OccPlan& plan, bool, bool) {
+    return plan.node_logm;
+  }
+  static __device__ __forceinline__ const double* second_nodes(const OccPlan& plan) {
+    return plan.node_inv_m;
+  }
+  static __device__ __forceinline__ bool needs_second(bool sat, bool) { return sat; }
+  __device__ __forceinline__ void begin_group(double logm) {
+    int i = 0;   // largest knot index in [0, kL11Knots - 2] with x_i <= logm (0 if none)
+#pragma unroll
+    for (int step = 64; step >= 1; step >>= 1) {
+      const int j = i + step;
+      if (j <= kL11Knots - 2 && d->knot[j].x <= logm) i = j;
+    }
+    hint = i;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      next_x[j] = i + 1 + j <= kL11Knots - 2 ? d->knot[i + 1 + j].x : CUDART_INF;
+  }
 };
 
 __device__ __forceinline__ double l11_knot_logms(int k) {
@@ -1005,41 +1045,42 @@ __device__ __forceinline__ double l11_knot_logms(int k) {
                             : (double)k * ((kL11LogMsHi - kL11LogMsLo) / (kL11Knots - 1)) + kL11LogMsLo;
 }
 
-// Behroozi10SmHm.mean_log_halo_mass: log10 M_h [h = 1 units] of log10 M* [h = 1 units]
-__device__ double l11_log_halo_mass(double log_ms, double logm0, double logm1, double beta,
-                                    double delta, double gamma) {
-  const double ms = exp10(log_ms) / (kL11LittleH * kL11LittleH);   // h = 1 -> h = 0.7
-  const double ratio = ms / exp10(logm0);
-  const double log_mh = logm1 + beta * log10(ratio) +
-                        pow(ratio, delta) / (1.0 + pow(ratio, -gamma)) - 0.5;
-  return log10(exp10(log_mh) * kL11LittleH);                       // back to h = 1
+// Behroozi10SmHm.mean_log_halo_mass: log10 M_h [h = 1 units] of log10 M* [h = 1 units].  halotools
+// converts M* -> M* / h^2 and M_h -> M_h h through 10** and log10; here the conversions are added
+// in log space (differences at the 1e-16 level).
+__device__ __forceinline__ double l11_log_halo_mass(double log_ms, double logm0, double logm1,
+                                                    double beta, double delta, double gamma) {
+  const double log_h = -0.15490195998574316929;   // log10(0.7)
+  const double lr = log_ms - 2.0 * log_h - logm0;  // log10(M* / M0) in h = 0.7 units
+  return logm1 + beta * lr + exp10(delta * lr) / (1.0 + exp10(-gamma * lr)) - 0.5 + log_h;
 }
 
-__device__ __forceinline__ double l11_log_mstar(double logm, const L11Draw* d) {
-  int i = 0;   // largest knot index in [0, kL11Knots - 2] with x_i <= logm (0 if none)
-#pragma unroll
-  for (int step = 64; step >= 1; step >>= 1) {
-    const int j = i + step;
-    if (j <= kL11Knots - 2 && d->knot[j].x <= logm) i = j;
-  }
-  const double4 c = d->knot[i];
+__device__ __forceinline__ double l11_log_mstar(double logm, const L11Params& p) {
+  // the nodes of a group ascend from the hinted interval and a mass bin spans few knots: three
+  // branch-free steps against the cached abscissae, then (rarely) a linear walk
+  int i = p.hint + (p.next_x[0] <= logm ? 1 : 0) + (p.next_x[1] <= logm ? 1 : 0) +
+          (p.next_x[2] <= logm ? 1 : 0);
+  if (p.next_x[2] <= logm)
+    while (i < kL11Knots - 2 && p.d->knot[i + 1].x <= logm) i++;
+  const double4 c = p.d->knot[i];
   const double t = logm - c.x;
-  return fma(t, fma(t, fma(t, c.w, c.z), c.y), l11_knot_logms(i));
+  return fma(t, fma(t, fma(t, c.z, c.w), c.y), l11_knot_logms(i));
 }
 
 template <bool SAT, bool MODULATE>
-__device__ __forceinline__ double baseline_occupation(double logm, double mass, const L11Params& p,
+__device__ __forceinline__ double baseline_occupation(double logm, double inv_mass,
+                                                      const L11Params& p,
                                                       const double* __restrict__ tab) {
   if (!SAT) {
-    const double x = (l11_log_mstar(logm, p.d) - p.threshold) * p.d->inv_scatter;
+    const double x = (l11_log_mstar(logm, p) - p.threshold) * p.d->inv_scatter;
     return half_erfc_neg(x, tab) + p.d->bad;
   }
-  const double mh = mass * kL11LittleH;
-  double y = fma(p.d->alphasat, log_pos(mh * p.d->inv_msat, tab), p.d->neg_mcut / mh);
+  // exp(-M_cut / (M h)) (M h / M_sat)^alphasat = exp(alphasat (ln M + ln(h / M_sat)) - M_cut / (M h))
+  double y = fma(p.d->alphasat, fma(logm, kLn10, p.d->ln_h_over_msat), p.d->neg_mcut_h * inv_mass);
   y = fmin(fmax(y, -800.0), 800.0);
   double f = exp_scaled(y, tab);
   if (MODULATE) {
-    const double x = (l11_log_mstar(logm, p.d) - p.threshold) * p.d->inv_scatter;
+    const double x = (l11_log_mstar(logm, p) - p.threshold) * p.d->inv_scatter;
     f *= half_erfc_neg(x, tab);
   }
   return f + p.d->bad;
@@ -1063,13 +1104,14 @@ __device__ void l11_prepare_block(L11Draw* draws, int n_block, long long draw0,
     if (k < kL11Knots) {
       draws[b].knot[k].x = l11_log_halo_mass(l11_knot_logms(k), logm0, logm1, beta, delta, gamma);
     } else {
-      const double knee = exp10(l11_log_halo_mass(model.threshold, logm0, logm1, beta, delta, gamma)) *
-                          kL11LittleH / 1e12;
-      const double msat = 1e12 * th[12 * theta_ps] * pow(knee, th[15 * theta_ps]);
-      const double mcut = 1e12 * th[13 * theta_ps] * pow(knee, th[14 * theta_ps]);
+      // Leauthaud11Sats._update_satellite_params: knee = h M_h(threshold) / 1e12
+      const double log_knee = l11_log_halo_mass(model.threshold, logm0, logm1, beta, delta, gamma) +
+                              log10(kL11LittleH) - 12.0;
+      const double msat = 1e12 * th[12 * theta_ps] * exp10(th[15 * theta_ps] * log_knee);
+      const double mcut = 1e12 * th[13 * theta_ps] * exp10(th[14 * theta_ps] * log_knee);
       draws[b].inv_scatter = 1.0 / (1.4142135623730951 * th[10 * theta_ps]);
-      draws[b].neg_mcut = -mcut;
-      draws[b].inv_msat = 1.0 / msat;
+      draws[b].neg_mcut_h = -mcut / kL11LittleH;
+      draws[b].ln_h_over_msat = log(kL11LittleH / msat);
       draws[b].alphasat = th[11 * theta_ps];
       draws[b].a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
       draws[b].a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;
@@ -1080,80 +1122,71 @@ __device__ void l11_prepare_block(L11Draw* draws, int n_block, long long draw0,
   // interior equations h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 (d_i - d_{i-1}),
   // d_i = (s_{i+1} - s_i) / h_i, with m_0 and m_{n-1} eliminated through the continuity of the
   // third derivative at knots 1 and n - 2.  Scratch: knot[i].y = modified upper diagonal,
-  // knot[i].z = modified right-hand side, knot[i].w = m_i.
-  if (threadIdx.x < n_block) {
-    L11Draw& D = draws[threadIdx.x];
-    constexpr int n = kL11Knots;
-    bool increasing = true;
-    double h_prev = D.knot[1].x - D.knot[0].x;            // h_0
-    double d_prev = (l11_knot_logms(1) - l11_knot_logms(0)) / h_prev;
-    increasing = increasing && h_prev > 0.0;
-    double cp = 0.0, rp = 0.0;                            // c'_{i-1}, r'_{i-1}
-    for (int i = 1; i <= n - 2; i++) {
-      const double h = D.knot[i + 1].x - D.knot[i].x;     // h_i
-      increasing = increasing && h > 0.0;
-      const double d = (l11_knot_logms(i + 1) - l11_knot_logms(i)) / h;
-      double lower = h_prev, diag = 2.0 * (h_prev + h), upper = h;
-      if (i == 1) {
-        lower = 0.0;
-        diag = 3.0 * h_prev + 2.0 * h + h_prev * h_prev / h;
-        upper = h - h_prev * h_prev / h;
+  // knot[i].z = modified right-hand side, knot[i].w = m_i.  The draws are spread over the warps
+  // (one lane group per SM sub-partition) because the recurrences are latency bound.
+  {
+    const int lanes = (n_block + kWarps - 1) / kWarps;              // draws per warp
+    const int b = (threadIdx.x >> 5) * lanes + (threadIdx.x & 31);
+    if ((threadIdx.x & 31) < lanes && b < n_block) {
+      L11Draw& D = draws[b];
+      constexpr int n = kL11Knots;
+      double h_prev = D.knot[1].x - D.knot[0].x;            // h_0
+      bool increasing = h_prev > 0.0;
+      double d_prev = (l11_knot_logms(1) - l11_knot_logms(0)) / h_prev;
+      double cp = 0.0, rp = 0.0;                            // c'_{i-1}, r'_{i-1}
+      for (int i = 1; i <= n - 2; i++) {
+        const double h = D.knot[i + 1].x - D.knot[i].x;     // h_i
+        increasing = increasing && h > 0.0;
+        const double d = (l11_knot_logms(i + 1) - l11_knot_logms(i)) / h;
+        double lower = h_prev, diag = 2.0 * (h_prev + h), upper = h;
+        if (i == 1) {
+          lower = 0.0;
+          diag = 3.0 * h_prev + 2.0 * h + h_prev * h_prev / h;
+          upper = h - h_prev * h_prev / h;
+        }
+        if (i == n - 2) {
+          lower = h_prev - h * h / h_prev;
+          diag = 2.0 * h_prev + 3.0 * h + h * h / h_prev;
+          upper = 0.0;
+        }
+        const double rhs = 6.0 * (d - d_prev);
+        const double inv = 1.0 / (diag - lower * cp);
+        cp = upper * inv;
+        rp = (rhs - lower * rp) * inv;
+        D.knot[i].y = cp;
+        D.knot[i].z = rp;
+        h_prev = h;
+        d_prev = d;
       }
-      if (i == n - 2) {
-        lower = h_prev - h * h / h_prev;
-        diag = 2.0 * h_prev + 3.0 * h + h * h / h_prev;
-        upper = 0.0;
+      double m_next = 0.0;
+      for (int i = n - 2; i >= 1; i--) {
+        const double m = D.knot[i].z - D.knot[i].y * m_next;
+        D.knot[i].w = m;
+        m_next = m;
       }
-      const double rhs = 6.0 * (d - d_prev);
-      const double inv = 1.0 / (diag - lower * cp);
-      cp = upper * inv;
-      rp = (rhs - lower * rp) * inv;
-      D.knot[i].y = cp;
-      D.knot[i].z = rp;
-      h_prev = h;
-      d_prev = d;
-    }
-    double m_next = 0.0;
-    for (int i = n - 2; i >= 1; i--) {
-      const double m = D.knot[i].z - D.knot[i].y * m_next;
-      D.knot[i].w = m;
-      m_next = m;
-    }
-    {
       const double h0 = D.knot[1].x - D.knot[0].x, h1 = D.knot[2].x - D.knot[1].x;
       D.knot[0].w = D.knot[1].w - h0 / h1 * (D.knot[2].w - D.knot[1].w);
       const double ha = D.knot[n - 1].x - D.knot[n - 2].x, hb = D.knot[n - 2].x - D.knot[n - 3].x;
       D.knot[n - 1].w = D.knot[n - 2].w + ha / hb * (D.knot[n - 2].w - D.knot[n - 3].w);
-    }
-    D.bad = increasing ? 0.0 : CUDART_NAN;
-  }
-  __syncthreads();
-  // (3) cubic coefficients per interval: read (x, m) of both ends, then overwrite y/z/w
-  constexpr int kPer = (kL11DrawsPerBlock * (kL11Knots - 1) + kThreads - 1) / kThreads;
-  double c1[kPer], c2[kPer], c3[kPer];
-#pragma unroll
-  for (int q = 0; q < kPer; q++) {
-    const int idx = threadIdx.x + q * blockDim.x;
-    if (idx < n_block * (kL11Knots - 1)) {
-      const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
-      const double4 k0 = draws[b].knot[k], k1 = draws[b].knot[k + 1];
-      const double h = k1.x - k0.x;
-      const double d = (l11_knot_logms(k + 1) - l11_knot_logms(k)) / h;
-      c1[q] = d - h * (2.0 * k0.w + k1.w) * (1.0 / 6.0);
-      c2[q] = 0.5 * k0.w;
-      c3[q] = (k1.w - k0.w) / (6.0 * h);
+      D.bad = increasing ? 0.0 : CUDART_NAN;
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int q = 0; q < kPer; q++) {
-    const int idx = threadIdx.x + q * blockDim.x;
-    if (idx < n_block * (kL11Knots - 1)) {
-      const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
-      draws[b].knot[k].y = c1[q];
-      draws[b].knot[k].z = c2[q];
-      draws[b].knot[k].w = c3[q];
-    }
+  // (3) cubic coefficients per interval: c1 and c3 go to the (now dead) y and z slots -- only x
+  // and w (= m) of knots k, k + 1 are read in this pass -- then w becomes c2 = m / 2
+  for (int idx = threadIdx.x; idx < n_block * (kL11Knots - 1); idx += blockDim.x) {
+    const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
+    const double x0 = draws[b].knot[k].x, x1 = draws[b].knot[k + 1].x;
+    const double m0 = draws[b].knot[k].w, m1 = draws[b].knot[k + 1].w;
+    const double h = x1 - x0;
+    const double d = (l11_knot_logms(k + 1) - l11_knot_logms(k)) / h;
+    draws[b].knot[k].y = d - h * (2.0 * m0 + m1) * (1.0 / 6.0);
+    draws[b].knot[k].z = (m1 - m0) / (6.0 * h);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_block * (kL11Knots - 1); idx += blockDim.x) {
+    const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
+    draws[b].knot[k].w *= 0.5;
   }
   __syncthreads();
 }
@@ -1167,6 +1200,7 @@ __device__ __forceinline__ void occupation_item_l11(const OccPlan& plan, const t
   p.threshold = model.threshold;
   p.a_cen = d->a_cen;
   p.a_sat = d->a_sat;
+  p.hint = 0;
   const bool sat = g_begin >= plan.n_cen_groups;
   for (int grp = g_begin + (threadIdx.x >> 3 & 3); grp < g_end; grp += 4) {
     double occ0, occ1;
@@ -1704,6 +1738,14 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   int rc;
   if ((rc = upload(node_logm, &d_logm))) return rc; ph.allocations.push_back(d_logm);
   if ((rc = upload(node_m, &d_m))) return rc; ph.allocations.push_back(d_m);
+  {
+    std::vector<double> node_inv_m(node_m.size());
+    for (size_t k = 0; k < node_m.size(); k++) node_inv_m[k] = 1.0 / node_m[k];
+    double* d_inv;
+    if ((rc = upload(node_inv_m, &d_inv))) return rc;
+    ph.allocations.push_back(d_inv);
+    ph.dev.node_inv_m = d_inv;
+  }
   if ((rc = upload(grp_rows, &d_rows))) return rc; ph.allocations.push_back(d_rows);
   if ((rc = upload(grp_is_sat, &d_sat))) return rc; ph.allocations.push_back(d_sat);
   if ((rc = upload(row_c, &d_c))) return rc; ph.allocations.push_back(d_c);
