@@ -13,7 +13,9 @@ rank 0 with one NCCL gather per step, inside the timed region.
 
 Prints ONE JSON line.  `value` is device-timed throughput with the parameters already in HBM;
 `e2e` is the same metric through the public API ``TabCorr.predict_batch`` with host numpy inputs
-and outputs (pinned H2D + D2H inside the timed region, wall clock).
+and outputs (pinned H2D + D2H inside the timed region, wall clock); on N > 1 GPUs through
+``predict_batch_sharded(..., gather='host')``: every rank copies its rows into one shared,
+CUDA-registered host segment over its own PCIe link and rank 0 reads the whole result there.
 """
 
 import argparse
@@ -308,7 +310,8 @@ def run_gpu_arm(args):
     def e2e_step():
         if world == 1:
             return halotab.predict_batch(draws, n_gauss_prim=N_GAUSS)
-        return predict_batch_sharded(halotab, all_draws, n_gauss_prim=N_GAUSS, dst=0)
+        return predict_batch_sharded(halotab, all_draws, n_gauss_prim=N_GAUSS, dst=0,
+                                     gather='host')
 
     for _ in range(4):  # also warms torch's pinned-memory cache (results of two calls stay alive)
         host_result = e2e_step()
@@ -342,8 +345,8 @@ def run_gpu_arm(args):
         n_pad = (n_rows + 15) // 16 * 16
         executed = 2.0 * N_R * 64.0 * (n_pad // 8) * (n_pad // 8 + 1) / 2 * n_draws
         roofline = {
-            'bound': 'tensor', 'kernel': 'predict_kernel<8, auto> (fused occupation + DMMA '
-                                         'quadratic form)',
+            'bound': 'tensor', 'kernel': 'predict_kernel<7, auto> (fused occupation + DMMA quadratic '
+                                         'form; 2 W tiles of 56 draws at N=240)',
             'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
             'frac': achieved / peak.value, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
             'traffic_unit': 'bytes of DRAM read + write per launch',

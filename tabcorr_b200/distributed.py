@@ -5,9 +5,19 @@ collective: rank r of W evaluates the contiguous slice
 ``[B r / W, B (r + 1) / W)`` of the draws on its own replica of the table, and the per-rank result
 slabs ``[B_r, 1 + R]`` are collected with ONE ``gather`` (NCCL over NVLink on GPUs, gloo in the CPU
 tests).  One process per GPU, launched with ``torch.distributed.run``.
+
+When the caller wants the results in HOST memory (the reference's API returns numpy arrays), a
+device-side gather funnels every rank's rows through rank ``dst``'s PCIe link.  On one node
+``predict_batch_sharded(..., gather='host')`` avoids that: the ranks share one POSIX
+shared-memory segment, registered with CUDA in every process, and each GPU copies its own rows
+into its slice over its own PCIe link; the only collective left is a barrier.
 """
 
+import atexit
+
 import numpy as np
+
+_SEGMENTS = {}   # (group id, n_bytes) -> SharedHostArray
 
 
 def shard_bounds(n_draws, rank, world_size):
@@ -59,8 +69,116 @@ def gather_rows(local, n_total, dst=0, group=None):
     return torch.cat(pieces, dim=0)
 
 
+class SharedHostArray:
+    """A float64 host buffer all ranks of one node map (``multiprocessing.shared_memory``), page
+    locked for CUDA in every process (``cudaHostRegister``) so that device-to-host copies into it
+    are asynchronous DMA transfers."""
+
+    def __init__(self, n_doubles, group=None):
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        rank = dist.get_rank(group)
+        n_bytes = max(8, 8 * int(n_doubles))
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=n_bytes)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group else 0,
+                                   group=group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:   # the creator unlinks; keep Python's resource tracker from doing it twice
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, 'shared_memory')
+            except Exception:
+                pass
+        self.owner = rank == 0
+        self.array = np.ndarray((n_bytes // 8,), dtype=np.float64, buffer=self.shm.buf)
+        self.tensor = torch.from_numpy(self.array)
+        self.registered = False
+        if torch.cuda.is_available():
+            status = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), n_bytes, 0)
+            self.registered = int(status) == 0
+        dist.barrier(group=group)   # every rank has mapped the segment before anyone may unlink
+
+    def close(self):
+        import torch
+        if self.shm is None:
+            return
+        if self.registered:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            except Exception:
+                pass
+        self.tensor = self.array = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
+        self.shm = None
+
+
+def _shared_segment(n_doubles, group=None):
+    key = (id(group), int(n_doubles))
+    if key not in _SEGMENTS:
+        for old_key in [k for k in _SEGMENTS if k[0] == key[0]]:   # one live segment per group
+            _SEGMENTS.pop(old_key).close()
+        _SEGMENTS[key] = SharedHostArray(n_doubles, group)
+    return _SEGMENTS[key]
+
+
+@atexit.register
+def _close_segments():
+    for segment in list(_SEGMENTS.values()):
+        segment.close()
+    _SEGMENTS.clear()
+
+
+def single_node(group=None):
+    """True when all ranks of the group run on the same host."""
+    import socket
+    import torch.distributed as dist
+    names = [None] * dist.get_world_size(group)
+    dist.all_gather_object(names, socket.gethostname(), group=group)
+    return len(set(names)) == 1
+
+
+def _predict_batch_shared_host(halotab, params, n_total, n_gauss_prim, model, dst, group,
+                               predict_kwargs):
+    """Every rank evaluates its slice host-to-host and writes the results into its rows of a
+    shared, CUDA-registered host segment; ``dst`` returns views of it."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    shape = tuple(halotab.tpcf_shape)
+    n_r = int(np.prod(shape))
+    segment = _shared_segment(n_total * (1 + n_r), group)
+    ngal_all = segment.tensor[:n_total].view(n_total, 1)
+    xi_all = segment.tensor[n_total:n_total * (1 + n_r)].view(n_total, n_r, 1)
+    lo, hi = shard_bounds(n_total, rank, world)
+    if hi > lo:
+        local = shard_params(params, rank, world)
+        if hasattr(halotab, '_predict_batch_pipelined'):
+            halotab.predict_batch(local, n_gauss_prim=n_gauss_prim, model=model,
+                                  out=(ngal_all[lo:hi], xi_all[lo:hi]), **predict_kwargs)
+        else:   # Interpolator, TableSet, test stand-ins: results to the host, then into the slice
+            ngal, xi = halotab.predict_batch(local, n_gauss_prim=n_gauss_prim, model=model,
+                                             as_numpy=False, **predict_kwargs)
+            ngal_all[lo:hi].copy_(ngal.reshape(-1, 1), non_blocking=True)
+            xi_all[lo:hi].copy_(xi.reshape(hi - lo, n_r, 1), non_blocking=True)
+            if ngal.is_cuda:
+                torch.cuda.current_stream(ngal.device).synchronize()
+    dist.barrier(group=group)   # every slice has landed in host memory
+    if rank != dst:
+        return None
+    return ngal_all.numpy()[:, 0], xi_all.numpy().reshape((n_total,) + shape)
+
+
 def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, group=None,
-                          n_chunks=3, **predict_kwargs):
+                          n_chunks=3, gather='nccl', **predict_kwargs):
     """``halotab.predict_batch`` over all ranks of the process group.
 
     ``params`` holds ALL draws on every rank (dict of ``[B]`` arrays or ``[B, k]`` array); each
@@ -71,6 +189,12 @@ def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, g
     on ``dst``, the device-to-host copy of the gathered piece c - 1 overlap the kernels of the
     next piece, so that rank ``dst``'s PCIe link -- which carries every rank's results -- is busy
     during the computation instead of after it.  Results do not depend on ``n_chunks``.
+
+    ``gather``: 'nccl' (default) is that device-side gather; 'host' (one node only) lets every
+    rank copy its rows into a shared, CUDA-registered host segment over its own PCIe link, with a
+    barrier as the only collective -- the arrays ``dst`` gets back are views of that segment and
+    stay valid until the next call with another batch size; 'auto' picks 'host' when all ranks
+    share a node.
     """
     import torch
     import torch.distributed as dist
@@ -80,6 +204,11 @@ def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, g
         n_total = max(np.shape(v)[0] for v in params.values() if np.ndim(v) > 0)
     else:
         n_total = len(params)
+    if gather not in ('nccl', 'host', 'auto'):
+        raise ValueError("gather must be 'nccl', 'host' or 'auto'")
+    if world > 1 and gather != 'nccl' and (gather == 'host' or single_node(group)):
+        return _predict_batch_shared_host(halotab, params, n_total, n_gauss_prim, model, dst,
+                                          group, predict_kwargs)
     local = shard_params(params, rank, world)
     lo_rank, hi_rank = shard_bounds(n_total, rank, world)
     n_local = hi_rank - lo_rank

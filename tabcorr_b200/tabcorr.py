@@ -468,7 +468,8 @@ class TabCorr:
         return spec, theta
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, model=None,
-                      occupation=None, as_numpy=True, pipeline_chunk='auto', precision='fp64'):
+                      occupation=None, as_numpy=True, pipeline_chunk='auto', precision='fp64',
+                      out=None):
         """Predict number density and correlation function for B parameter sets at once.
 
         Parameters
@@ -494,6 +495,11 @@ class TabCorr:
             auto-correlation tables on the TF32 tensor cores with split operands (relative error
             ~1e-7, about twice the throughput); occupations stay FP64.  Cross-correlation tables
             always use FP64 (they are bound by the occupation arithmetic).
+        out : tuple of two host tensors/arrays, optional
+            Pre-allocated destination of the host results: ``ngal [B, 1|2]`` and ``xi [B, R, C]``
+            float64 (C = 1, or 3 / 2 with ``separate_gal_type``), ideally pinned or
+            ``cudaHostRegister``-ed memory (e.g. the shared segment ``predict_batch_sharded`` lets
+            every rank write its slice into).  The returned arrays are views of them.
         pipeline_chunk : 'auto', int or sequence of int, optional
             With host inputs and host outputs the draws are cut into chunks whose host-to-device
             copy, kernels and device-to-host copy overlap on three CUDA streams.  An int is a
@@ -513,11 +519,13 @@ class TabCorr:
         precision = _lib.precision_code(precision)
         if group.mode != 'auto':
             precision = _lib.TC_PRECISION_FP64
+        if out is not None and not as_numpy:
+            raise ValueError('out= holds host results; it cannot be combined with as_numpy=False')
         if (occupation is None and as_numpy and not isinstance(params, torch.Tensor) and
                 (isinstance(pipeline_chunk, (str, list, tuple)) or
                  (pipeline_chunk and pipeline_chunk > 0))):
             return self._predict_batch_pipelined(params, model, separate, int(n_gauss_prim),
-                                                 pipeline_chunk, precision)
+                                                 pipeline_chunk, precision, out)
         if occupation is not None:
             occ = _to_device_f64(occupation, group.device)
             if occ.ndim != 2 or occ.shape[1] != group.n_rows:
@@ -532,10 +540,30 @@ class TabCorr:
         xi = torch.empty((n_draws, group.n_r, n_comp), dtype=torch.float64, device=group.device)
         group.predict_into(spec, int(n_gauss_prim), theta, occ, separate, ngal, 0, xi, 0,
                            precision=precision)
+        if out is not None:
+            ngal_out, xi_out = self._host_out(out, n_draws, ngal.shape[1], n_comp)
+            ngal_out.copy_(ngal, non_blocking=True)
+            xi_out.copy_(xi, non_blocking=True)
+            torch.cuda.current_stream(group.device).synchronize()
+            return self._format_batch(ngal_out.numpy(), xi_out.numpy(), separate, False)
         return self._format_batch(ngal, xi, separate, as_numpy)
 
+    def _host_out(self, out, n_draws, n_ng, n_comp):
+        """Validate ``out=(ngal, xi)`` and return it as two float64 host tensors."""
+        torch = _torch()
+        group = self._ensure_device()
+        tensors = []
+        for member, shape in zip(out, ((n_draws, n_ng), (n_draws, group.n_r, n_comp))):
+            tensor = member if isinstance(member, torch.Tensor) else torch.from_numpy(member)
+            if (tensor.dtype != torch.float64 or tensor.is_cuda or not tensor.is_contiguous() or
+                    tuple(tensor.shape) != shape):
+                raise ValueError('out must hold contiguous float64 host arrays of shapes {} and '
+                                 '{}'.format((n_draws, n_ng), (n_draws, group.n_r, n_comp)))
+            tensors.append(tensor)
+        return tensors
+
     def _predict_batch_pipelined(self, params, model, separate, n_gauss, chunk,
-                                 precision=_lib.TC_PRECISION_FP64):
+                                 precision=_lib.TC_PRECISION_FP64, out=None):
         """Host parameters in, host results out: the draws are cut into chunks; chunk i + 1 is
         staged in pinned memory and copied to the device while chunk i is evaluated and chunk
         i - 1 is copied back (copy streams + events; the kernels stay on the current stream)."""
@@ -562,8 +590,11 @@ class TabCorr:
         # [7, hi - lo], so that every chunk is one contiguous host-to-device copy
         n_theta = spec.n_theta
         theta_pin = torch.empty(n_draws * n_theta, dtype=f64, pin_memory=True)
-        ngal_pin = torch.empty((n_draws, n_ng), dtype=f64, pin_memory=True)
-        xi_pin = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, pin_memory=True)
+        if out is not None:
+            ngal_pin, xi_pin = self._host_out(out, n_draws, n_ng, n_comp)
+        else:
+            ngal_pin = torch.empty((n_draws, n_ng), dtype=f64, pin_memory=True)
+            xi_pin = torch.empty((n_draws, group.n_r, n_comp), dtype=f64, pin_memory=True)
         theta_np = theta_pin.numpy()
         theta = torch.empty(n_draws * n_theta, dtype=f64, device=device)
         ngal = torch.empty((n_draws, n_ng), dtype=f64, device=device)

@@ -54,6 +54,7 @@ class OracleBackedTable:
         self.orc = orc
         tab = synthetic.make_table(n_mass=5, n_sec=2, n_r=4, seed=5)
         self.table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+        self.tpcf_shape = self.table.tpcf_shape
 
     def predict_batch(self, params, n_gauss_prim=10, model=None, as_numpy=True):
         n = len(params['logMmin'])
@@ -97,6 +98,15 @@ def _worker(rank, world, port, n_draws, out_dir):
             np.save(os.path.join(out_dir, 'xi.npy'), result[1])
         else:
             assert result is None
+        # 3. the same through the shared host segment (no gather: every rank writes its rows)
+        assert tcd.single_node()
+        for mode in ('host', 'auto'):
+            shared = tcd.predict_batch_sharded(halotab, draws, n_gauss_prim=4, dst=0, gather=mode)
+            if rank == 0:
+                assert np.array_equal(shared[0], result[0]) and np.array_equal(shared[1], result[1])
+            else:
+                assert shared is None
+        assert len(tcd._SEGMENTS) == 1   # cached across calls of the same size
         dist.barrier()
     finally:
         dist.destroy_process_group()

@@ -300,3 +300,31 @@ def test_3xtf32_mode_scope(tb, golden_dir):
     b = interp.predict_batch(grid_draws, precision='3xtf32')
     np.testing.assert_allclose(b[0], a[0], rtol=TF32_RTOL)
     np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6 * np.abs(a[1]).max())
+
+
+def test_predict_batch_out_argument(tb):
+    """out=(ngal, xi): results land in caller-provided host memory (pipelined and direct path)."""
+    import torch
+    tab = tb.synthetic.make_table(n_mass=12, n_sec=2, n_r=7)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    draws = tb.synthetic.make_draws(40000, seed=3)
+    ngal_ref, xi_ref = halotab.predict_batch(draws)
+    ngal = torch.empty((40000, 1), dtype=torch.float64, pin_memory=True)
+    xi = np.empty((40000, 7, 1))
+    got = halotab.predict_batch(draws, out=(ngal, xi))
+    assert np.array_equal(got[0], ngal_ref) and np.array_equal(got[1], xi_ref)
+    assert np.array_equal(ngal.numpy()[:, 0], ngal_ref) and np.array_equal(xi[:, :, 0], xi_ref)
+    assert got[1].base is not None   # a view of the caller's buffer
+    xi[:] = 0
+    halotab.predict_batch(draws, out=(ngal, xi), pipeline_chunk=0)
+    assert np.array_equal(xi[:, :, 0], xi_ref)
+    sep = (np.empty((40000, 2)), np.empty((40000, 7, 3)))
+    ngal_d, xi_d = halotab.predict_batch(draws, separate_gal_type=True, out=sep)
+    ref_d = halotab.predict_batch(draws, separate_gal_type=True)
+    for key in xi_d:
+        assert np.array_equal(xi_d[key], ref_d[1][key])
+    with pytest.raises(ValueError, match='out must hold'):
+        halotab.predict_batch(draws, out=(np.empty((40000, 2)), xi))
+    with pytest.raises(ValueError, match='as_numpy'):
+        halotab.predict_batch(draws, out=(ngal, xi), as_numpy=False)

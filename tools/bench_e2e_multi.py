@@ -17,23 +17,24 @@ tab = synthetic.make_table(n_mass=60, n_sec=2, n_r=20)
 halotab = tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], tab['attrs'], device=local)
 draws = synthetic.make_draws(per_gpu * world, seed=1)
 ref = None
-for n_chunks in (1, 2, 3, 4, 6, 8):
+for n_chunks in (3, 'host'):
+    kw = dict(gather='host') if n_chunks == 'host' else dict(n_chunks=n_chunks)
     for _ in range(4):
-        out = predict_batch_sharded(halotab, draws, n_chunks=n_chunks)
+        out = predict_batch_sharded(halotab, draws, **kw)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     reps = 10
     for _ in range(reps):
-        out = predict_batch_sharded(halotab, draws, n_chunks=n_chunks)
+        out = predict_batch_sharded(halotab, draws, **kw)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     dt = (time.perf_counter() - t0) / reps
     if rank == 0:
         if ref is None:
-            ref = out
+            ref = (out[0].copy(), out[1].copy())
         same = bool(np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1]))
         print(json.dumps({'n_gpus': world, 'n_chunks': n_chunks, 'ms': dt * 1e3, 'preds_per_s': per_gpu * world / dt, 'same': same}), flush=True)
 if world > 1:
