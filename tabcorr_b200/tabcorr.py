@@ -124,6 +124,7 @@ class DeviceTableGroup:
         self._workspace = None
         self._copy_streams = None
         self._single = None
+        self._small = None
         self._lock = threading.Lock()
 
     def __del__(self):
@@ -223,6 +224,34 @@ class DeviceTableGroup:
                 self.n_tables, self.n_r, n_comp).copy()
         return ngal, xi
 
+    def predict_small(self, spec, n_gauss, columns, n_draws, separate, precision):
+        """Up to ``SMALL_BATCH`` parameter sets (``columns``: one array or scalar per kernel
+        parameter) -> host arrays ``ngal [B, T * (1|2)]``, ``xi [B, T * R * C]`` (copies).  The
+        ensemble-sampler regime: like :meth:`predict_one` the parameters and the results live in
+        persistent pinned host memory that the kernels read and write directly, so a call is one
+        ctypes call and one stream synchronisation -- no allocations, no copy launches."""
+        torch = _torch()
+        self.plan(n_gauss)
+        with self._lock:
+            if self._small is None:
+                self._small = _SmallBatchBuffers(self, SMALL_BATCH)
+            buf = self._small
+            for j, column in enumerate(columns):
+                buf.theta_np[j, :n_draws] = column
+            n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
+            ngal_cols, xi_cols = self.n_tables * n_ng, self.n_tables * self.n_r * n_comp
+            model = self._model_struct(spec)
+            stream = torch.cuda.current_stream(self.device)
+            _lib.check(self.lib.tc_predict_batch(
+                self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(),
+                buf.capacity, None, int(n_draws), int(separate), int(precision),
+                buf.ngal.data_ptr(), ngal_cols, buf.xi.data_ptr(), xi_cols,
+                buf.workspace.data_ptr(), buf.workspace.numel(), stream.cuda_stream))
+            stream.synchronize()
+            ngal = buf.ngal_np[:n_draws * ngal_cols].reshape(n_draws, ngal_cols).copy()
+            xi = buf.xi_np[:n_draws * xi_cols].reshape(n_draws, xi_cols).copy()
+        return ngal, xi
+
     def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset,
                      theta_columns=False, precision=_lib.TC_PRECISION_FP64):
         """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
@@ -269,6 +298,29 @@ class _SingleDrawBuffers:
         self.theta_np, self.ngal_np, self.xi_np = (self.theta.numpy(), self.ngal.numpy(),
                                                    self.xi.numpy())
         need = max(int(group.lib.tc_predict_workspace_bytes(group.handle, 1, sep))
+                   for sep in (0, 1))
+        self.workspace = torch.empty(max(need, 8), dtype=torch.uint8, device=group.device)
+
+
+SMALL_BATCH = 1024   # batches up to this size take the zero-copy path of predict_batch
+
+
+class _SmallBatchBuffers:
+    """Persistent pinned buffers of the small-batch fast path (``DeviceTableGroup.predict_small``):
+    parameters as one contiguous column per parameter (``theta_ld = capacity``), results for
+    ``capacity`` draws, workspace on the device."""
+
+    def __init__(self, group, capacity):
+        torch = _torch()
+        f64 = torch.float64
+        self.capacity = int(capacity)
+        self.theta = torch.zeros((len(THETA_KEYS), self.capacity), dtype=f64, pin_memory=True)
+        self.ngal = torch.zeros(self.capacity * 2 * group.n_tables, dtype=f64, pin_memory=True)
+        self.xi = torch.zeros(self.capacity * group.n_tables * group.n_r * 3, dtype=f64,
+                              pin_memory=True)
+        self.theta_np, self.ngal_np, self.xi_np = (self.theta.numpy(), self.ngal.numpy(),
+                                                   self.xi.numpy())
+        need = max(int(group.lib.tc_predict_workspace_bytes(group.handle, self.capacity, sep))
                    for sep in (0, 1))
         self.workspace = torch.empty(max(need, 8), dtype=torch.uint8, device=group.device)
 
@@ -521,6 +573,11 @@ class TabCorr:
             precision = _lib.TC_PRECISION_FP64
         if out is not None and not as_numpy:
             raise ValueError('out= holds host results; it cannot be combined with as_numpy=False')
+        if (occupation is None and as_numpy and out is None and
+                not isinstance(params, torch.Tensor)):
+            small = self._predict_batch_small(params, model, separate, int(n_gauss_prim), precision)
+            if small is not None:
+                return small
         if (occupation is None and as_numpy and not isinstance(params, torch.Tensor) and
                 (isinstance(pipeline_chunk, (str, list, tuple)) or
                  (pipeline_chunk and pipeline_chunk > 0))):
@@ -547,6 +604,29 @@ class TabCorr:
             torch.cuda.current_stream(group.device).synchronize()
             return self._format_batch(ngal_out.numpy(), xi_out.numpy(), separate, False)
         return self._format_batch(ngal, xi, separate, as_numpy)
+
+    def _predict_batch_small(self, params, model, separate, n_gauss, precision):
+        """The zero-copy path for host batches of at most ``SMALL_BATCH`` draws of a family the
+        fused kernel implements; None when the batch does not qualify."""
+        if isinstance(params, dict):
+            spec = resolve_model(model) if model is not None else spec_from_params(params)
+            if spec.family != 0:
+                return None
+            columns = theta_columns(params, spec)
+        else:
+            spec = resolve_model(model) if model is not None else ModelSpec()
+            array = np.asarray(params, dtype=np.float64)
+            if spec.family != 0 or array.ndim != 2 or array.shape[1] not in (5, 7):
+                return None   # the general path reports shape errors
+            columns = [array[:, j] for j in range(array.shape[1])]
+            columns += [np.float64(0.0)] * (7 - len(columns))
+        n_draws = max([c.shape[0] for c in columns if np.ndim(c) > 0] + [1])
+        if n_draws > SMALL_BATCH or any(np.ndim(c) > 0 and c.shape[0] != n_draws for c in columns):
+            return None
+        group = self._ensure_device()
+        ngal, xi = group.predict_small(spec, n_gauss, columns, n_draws, separate, precision)
+        return self._format_batch(ngal, xi.reshape(n_draws, group.n_r, group.n_comp(separate)),
+                                  separate, False)
 
     def _host_out(self, out, n_draws, n_ng, n_comp):
         """Validate ``out=(ngal, xi)`` and return it as two float64 host tensors."""

@@ -328,3 +328,36 @@ def test_predict_batch_out_argument(tb):
         halotab.predict_batch(draws, out=(np.empty((40000, 2)), xi))
     with pytest.raises(ValueError, match='as_numpy'):
         halotab.predict_batch(draws, out=(ngal, xi), as_numpy=False)
+
+
+def test_small_batches_take_the_zero_copy_path_and_agree_bitwise(tb):
+    """Batches up to SMALL_BATCH draws run through persistent pinned buffers; same kernels, so
+    the results equal those of the general path bit for bit."""
+    from tabcorr_b200 import tabcorr as tc_mod
+    tab = tb.synthetic.make_table(n_mass=12, n_sec=2, n_r=7)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    big = tb.synthetic.make_draws(3000, seed=9, decorated=True)
+    ngal_ref, xi_ref = halotab.predict_batch(big)            # general (pipelined) path
+    sep_ref = halotab.predict_batch(big, separate_gal_type=True)
+    for n in (1, 7, 64, tc_mod.SMALL_BATCH):
+        small = {k: v[:n] for k, v in big.items()}
+        ngal, xi = halotab.predict_batch(small)
+        assert halotab._ensure_device()._small is not None
+        assert ngal.shape == (n,) and xi.shape == (n, 7)
+        assert np.array_equal(ngal, ngal_ref[:n]) and np.array_equal(xi, xi_ref[:n])
+        ngal_d, xi_d = halotab.predict_batch(small, separate_gal_type=True)
+        for key in xi_d:
+            assert np.array_equal(xi_d[key], sep_ref[1][key][:n])
+        for key in ngal_d:
+            assert np.array_equal(ngal_d[key], sep_ref[0][key][:n])
+    # array input, scalars broadcast, results are copies (a second call must not overwrite them)
+    theta = np.stack([big[k][:5] for k in tb.models.THETA_KEYS], axis=1)
+    decorated = tb.models.ModelSpec(decorated=True)   # arrays carry no keys: the model says so
+    first = halotab.predict_batch(theta, model=decorated)
+    second = halotab.predict_batch(theta[::-1].copy(), model=decorated)
+    assert np.array_equal(first[1], xi_ref[:5]) and np.array_equal(second[1], xi_ref[:5][::-1])
+    mixed = dict({k: v[:4] for k, v in big.items()}, alpha=1.0)
+    ref = halotab.predict_batch(dict({k: v[:4] for k, v in big.items()}, alpha=np.ones(4)),
+                                pipeline_chunk=0, as_numpy=False)
+    assert np.array_equal(halotab.predict_batch(mixed)[1], ref[1].cpu().numpy())
