@@ -134,6 +134,16 @@ int tc_predict_batch(tc_table* table, const tc_model* model, int n_gauss, const 
                      int64_t ngal_stride, double* xi_dev, int64_t xi_stride, void* workspace_dev,
                      size_t workspace_bytes, void* stream);
 
+/* TabCorr.predict(model) (tabcorr.py:580-650) for ONE parameter set whose TC_N_THETA parameters
+ * are read from HOST memory at call time and travel to the kernel in its launch arguments -- the
+ * latency path of the reference's MCMC idiom (README.md:72-74): no parameter upload, and no
+ * mapped-host reads by every thread block.  Outputs and workspace as in tc_predict_batch with
+ * n_draws = 1 (they may live in mapped pinned host memory).  TC_FAMILY_ZHENG07 only. */
+int tc_predict_one(tc_table* table, const tc_model* model, int n_gauss, const double* theta_host,
+                   int separate, int precision, double* ngal_dev, int64_t ngal_stride,
+                   double* xi_dev, int64_t xi_stride, void* workspace_dev, size_t workspace_bytes,
+                   void* stream);
+
 /* Interpolator.__init__ (tabcorr/interpolator.py:39-61): n_dims axes with n_knots[d] sorted knots
  * (concatenated in knots_host) and the spline matrices a[d] of shape [n_knots[d]-1, 4, n_knots[d]]
  * (spline_interpolation_matrix, interpolator.py:219-272; concatenated in a_host).

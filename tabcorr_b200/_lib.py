@@ -35,7 +35,7 @@ TC_FAMILY_LEAUTHAUD11 = 1
 SYMBOLS = (
     'tc_last_error', 'tc_version', 'tc_model_n_theta', 'tc_table_create', 'tc_table_destroy', 'tc_table_n_rows',
     'tc_table_n_r', 'tc_table_n_tables', 'tc_table_plan', 'tc_occupation_batch',
-    'tc_predict_workspace_bytes', 'tc_predict_batch', 'tc_interp_create', 'tc_interp_destroy',
+    'tc_predict_workspace_bytes', 'tc_predict_batch', 'tc_predict_one', 'tc_interp_create', 'tc_interp_destroy',
     'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math')
 
 
@@ -95,6 +95,10 @@ def load():
         vp, ctypes.POINTER(tc_model), ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64,
         ctypes.c_int, ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_size_t,
         vp]
+    lib.tc_predict_one.restype = ctypes.c_int
+    lib.tc_predict_one.argtypes = [
+        vp, ctypes.POINTER(tc_model), ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp,
+        ctypes.c_int64, vp, ctypes.c_int64, vp, ctypes.c_size_t, vp]
     lib.tc_interp_create.restype = ctypes.c_int
     lib.tc_interp_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, c_int32_p, c_double_p,
                                      c_double_p, c_int32_p, ctypes.c_int]

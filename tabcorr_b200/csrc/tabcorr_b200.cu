@@ -506,6 +506,8 @@ struct PredictArgs {
   const double* theta;   // parameter draws or nullptr: theta[draw * theta_ds + k * theta_ps]
   long long theta_ds, theta_ps;
   const double* occ;     // [B, n_rows] or nullptr
+  int theta_is_inline;   // one draw whose parameters travel in the launch arguments
+  double theta_inline[TC_N_THETA];
   long long n_draws;
   long long n_tiles;
   double* parts;         // [n_tiles, n_parts, BM]
@@ -524,6 +526,7 @@ struct PredictCtrl {
   int first_lo, last_hi;        // chunk range of the CTA's first / last tile
   int n_local;                  // tiles this CTA works on
   long long tile_first;
+  double theta_inline[TC_N_THETA];   // shared-memory copy of the inline parameters
 };
 
 // One contraction chunk by one warp.  W is the draw tile in B-fragment order.
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
   load_math_tables(tab);
 
   const int n_occ = NT * (args.n_ranges_cen + args.n_ranges_sat);
-  if (tid == 0) {
+  {
     // The grid cuts the total COST (n_tiles x per-tile chunk cost) into equal contiguous ranges, so
     // that every CTA gets the same amount of DMMA work whatever the number of draws; a CTA
     // recomputes the weights of the (at most two) tiles it shares with its neighbours.
@@ -757,33 +760,40 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
                               total_cost % gridDim.x * (blockIdx.x + 1) / gridDim.x;
     long long tile_first = cost_lo / tile_cost;
     long long tile_last = min((cost_hi + tile_cost - 1) / tile_cost, args.n_tiles);  // exclusive
-    // first chunk whose start cost is >= the range boundary (neighbouring CTAs search the same
-    // value, so their chunk ranges meet exactly)
-    auto first_chunk_at = [&](long long bound) {
-      if (bound <= 0) return 0;
-      if (bound >= tile_cost) return lay.n_chunks;
-      int lo = 0, hi = lay.n_chunks;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (lay.chunk_cost_prefix[mid] < bound) lo = mid + 1; else hi = mid;
-      }
-      return lo;
-    };
-    int first_lo = first_chunk_at(cost_lo - tile_first * tile_cost);
-    if (first_lo >= lay.n_chunks) { tile_first++; first_lo = 0; }
-    int last_hi = lay.n_chunks;
-    if (tile_last > tile_first) {
-      last_hi = first_chunk_at(cost_hi - (tile_last - 1) * tile_cost);
-      if (last_hi <= (tile_last - 1 == tile_first ? first_lo : 0)) { tile_last--; last_hi = lay.n_chunks; }
+    // first chunk whose start cost is >= the range boundary = number of prefix entries below it
+    // (neighbouring CTAs count against the same value, so their chunk ranges meet exactly).  The
+    // whole CTA counts in parallel: one round trip to L2 instead of a dependent binary search, which
+    // is what a one-draw call waits for.
+    const long long bound_lo = cost_lo - tile_first * tile_cost;
+    const long long bound_hi = cost_hi - (tile_last - 1) * tile_cost;
+    int below_lo = 0, below_hi = 0;
+    for (int base = 0; base < lay.n_chunks; base += kThreads) {
+      const int i = base + tid;
+      const long long start = i < lay.n_chunks ? lay.chunk_cost_prefix[i] : tile_cost;
+      below_lo += __syncthreads_count(i < lay.n_chunks && start < bound_lo);
+      below_hi += __syncthreads_count(i < lay.n_chunks && start < bound_hi);
     }
-    ctrl->tile_first = tile_first;
-    ctrl->n_local = (int)max(tile_last - tile_first, 0LL);
-    ctrl->first_lo = first_lo;
-    ctrl->last_hi = last_hi;
-    ctrl->next = 0;
-    ctrl->full[0] = ctrl->full[1] = ctrl->empty[0] = ctrl->empty[1] = 0;
+    if (tid == 0) {
+      int first_lo = bound_lo <= 0 ? 0 : bound_lo >= tile_cost ? lay.n_chunks : below_lo;
+      if (first_lo >= lay.n_chunks) { tile_first++; first_lo = 0; }
+      int last_hi = lay.n_chunks;
+      if (tile_last > tile_first) {
+        last_hi = bound_hi <= 0 ? 0 : bound_hi >= tile_cost ? lay.n_chunks : below_hi;
+        if (last_hi <= (tile_last - 1 == tile_first ? first_lo : 0)) { tile_last--; last_hi = lay.n_chunks; }
+      }
+      ctrl->tile_first = tile_first;
+      ctrl->n_local = (int)max(tile_last - tile_first, 0LL);
+      ctrl->first_lo = first_lo;
+      ctrl->last_hi = last_hi;
+      ctrl->next = 0;
+      ctrl->full[0] = ctrl->full[1] = ctrl->empty[0] = ctrl->empty[1] = 0;
+    }
+    if (args.theta_is_inline && tid < TC_N_THETA) ctrl->theta_inline[tid] = args.theta_inline[tid];
   }
   __syncthreads();
+  // parameters of the draws: device (or mapped host) memory, or the launch arguments of a
+  // one-draw call (a mapped-host read costs every CTA a PCIe round trip: 14 us per call)
+  const double* theta_base = args.theta_is_inline ? ctrl->theta_inline : args.theta;
   const int n_local = ctrl->n_local;
   const long long tile_first = ctrl->tile_first;
   const int first_lo = ctrl->first_lo, last_hi = ctrl->last_hi;
@@ -823,10 +833,10 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       const int b = 8 * nt + (lane & 7);
       long long draw = (tile_first + j) * BM + b;
       if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: recompute the last draw
-      if (args.theta != nullptr) {
+      if (theta_base != nullptr) {
         int g_begin, g_end;
         occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
-        occupation_item(args.plan, args.model, args.theta + draw * args.theta_ds, args.theta_ps,
+        occupation_item(args.plan, args.model, theta_base + draw * args.theta_ds, args.theta_ps,
                         g_begin, g_end, tab,
                         [&](int row, double occ, double nh) {
                           store_weight<NT, MODE>(Ws, row, b, occ * nh);
@@ -2094,12 +2104,22 @@ size_t tc_predict_workspace_bytes(const tc_table* t, int64_t n_draws, int separa
   return plan_workspace(t->layouts[separate ? 1 : 0], n_draws, n_sm).total;
 }
 
-int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
-                     int64_t theta_ld, const double* occ, int64_t n_draws, int separate,
-                     int precision, double* ngal,
-                     int64_t ngal_stride, double* xi, int64_t xi_stride, void* workspace,
-                     size_t workspace_bytes, void* stream_) {
+}  // extern "C"
+
+namespace {
+
+// tc_predict_batch / tc_predict_one.  theta_inline: host pointer to the TC_N_THETA parameters of a
+// single draw, passed to the kernel in its launch arguments (theta and occ are NULL then).
+int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
+                 int64_t theta_ld, const double* occ, const double* theta_inline, int64_t n_draws,
+                 int separate, int precision, double* ngal, int64_t ngal_stride, double* xi,
+                 int64_t xi_stride, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!t || !ngal || !xi) return fail(TC_EINVAL, "tc_predict_batch: NULL argument");
+  if (theta_inline) {
+    if (theta || occ || n_draws != 1)
+      return fail(TC_EINVAL, "tc_predict_one: one draw with host parameters only");
+    theta = theta_inline;   // validated like device parameters below; never dereferenced on the device
+  }
   if ((theta == nullptr) == (occ == nullptr))
     return fail(TC_EINVAL, "tc_predict_batch: exactly one of theta_dev and occ_dev must be given");
   if (theta && !model) return fail(TC_EINVAL, "tc_predict_batch: model is NULL");
@@ -2149,9 +2169,15 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
   args.lay = L.dev;
   args.plan = L.plans[plan_g].dev;
   if (model) args.model = *model;
-  args.theta = theta;
+  args.theta = theta_inline ? nullptr : theta;
   args.theta_ds = theta_ld ? 1 : TC_N_THETA;
   args.theta_ps = theta_ld ? theta_ld : 1;
+  if (theta_inline) {
+    args.theta_is_inline = 1;
+    args.theta_ds = 0;
+    args.theta_ps = 1;
+    for (int k = 0; k < TC_N_THETA; k++) args.theta_inline[k] = theta_inline[k];
+  }
   args.occ = occ;
   args.n_draws = n_draws;
   args.n_tiles = ws.n_tiles;
@@ -2220,6 +2246,27 @@ int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const doub
     g_profile.recorded = true;
   }
   return TC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tc_predict_batch(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
+                     int64_t theta_ld, const double* occ, int64_t n_draws, int separate,
+                     int precision, double* ngal, int64_t ngal_stride, double* xi,
+                     int64_t xi_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  return predict_impl(t, model, n_gauss, theta, theta_ld, occ, nullptr, n_draws, separate,
+                      precision, ngal, ngal_stride, xi, xi_stride, workspace, workspace_bytes,
+                      stream);
+}
+
+int tc_predict_one(tc_table* t, const tc_model* model, int n_gauss, const double* theta_host,
+                   int separate, int precision, double* ngal, int64_t ngal_stride, double* xi,
+                   int64_t xi_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!theta_host) return fail(TC_EINVAL, "tc_predict_one: theta_host is NULL");
+  return predict_impl(t, model, n_gauss, nullptr, 0, nullptr, theta_host, 1, separate, precision,
+                      ngal, ngal_stride, xi, xi_stride, workspace, workspace_bytes, stream);
 }
 
 int tc_profile_enable(int on) {

@@ -224,9 +224,9 @@ class Interpolator:
             slot = 0
             for (group, members), workspace in zip(self._groups, buf['workspace']):
                 group.plan(n_gauss)
-                _lib.check(self._lib.tc_predict_batch(
-                    group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(), 0,
-                    None, 1, int(separate), _lib.TC_PRECISION_FP64,
+                _lib.check(self._lib.tc_predict_one(
+                    group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(),
+                    int(separate), _lib.TC_PRECISION_FP64,
                     buf['ngal_t'].data_ptr() + 8 * slot * n_ng,
                     n_tables * n_ng, buf['xi_t'].data_ptr() + 8 * slot * n_cols, n_tables * n_cols,
                     workspace.data_ptr(), workspace.numel(), stream.cuda_stream))

@@ -213,10 +213,10 @@ class DeviceTableGroup:
             n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
             model = self._model_struct(spec)
             stream = torch.cuda.current_stream(self.device)
-            _lib.check(self.lib.tc_predict_batch(
-                self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(), 0, None, 1,
-                int(separate), _lib.TC_PRECISION_FP64, buf.ngal.data_ptr(), self.n_tables * n_ng, buf.xi.data_ptr(),
-                self.n_tables * self.n_r * n_comp, buf.workspace.data_ptr(),
+            _lib.check(self.lib.tc_predict_one(
+                self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(),
+                int(separate), _lib.TC_PRECISION_FP64, buf.ngal.data_ptr(), self.n_tables * n_ng,
+                buf.xi.data_ptr(), self.n_tables * self.n_r * n_comp, buf.workspace.data_ptr(),
                 buf.workspace.numel(), stream.cuda_stream))
             stream.synchronize()
             ngal = buf.ngal_np[:self.n_tables * n_ng].reshape(self.n_tables, n_ng).copy()
@@ -242,11 +242,19 @@ class DeviceTableGroup:
             ngal_cols, xi_cols = self.n_tables * n_ng, self.n_tables * self.n_r * n_comp
             model = self._model_struct(spec)
             stream = torch.cuda.current_stream(self.device)
-            _lib.check(self.lib.tc_predict_batch(
-                self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(),
-                buf.capacity, None, int(n_draws), int(separate), int(precision),
-                buf.ngal.data_ptr(), ngal_cols, buf.xi.data_ptr(), xi_cols,
-                buf.workspace.data_ptr(), buf.workspace.numel(), stream.cuda_stream))
+            if n_draws == 1:   # parameters in the launch arguments
+                buf.one_np[:] = buf.theta_np[:, 0]
+                _lib.check(self.lib.tc_predict_one(
+                    self.handle, ctypes.byref(model), int(n_gauss), buf.one.data_ptr(),
+                    int(separate), int(precision), buf.ngal.data_ptr(), ngal_cols,
+                    buf.xi.data_ptr(), xi_cols, buf.workspace.data_ptr(), buf.workspace.numel(),
+                    stream.cuda_stream))
+            else:
+                _lib.check(self.lib.tc_predict_batch(
+                    self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(),
+                    buf.capacity, None, int(n_draws), int(separate), int(precision),
+                    buf.ngal.data_ptr(), ngal_cols, buf.xi.data_ptr(), xi_cols,
+                    buf.workspace.data_ptr(), buf.workspace.numel(), stream.cuda_stream))
             stream.synchronize()
             ngal = buf.ngal_np[:n_draws * ngal_cols].reshape(n_draws, ngal_cols).copy()
             xi = buf.xi_np[:n_draws * xi_cols].reshape(n_draws, xi_cols).copy()
@@ -315,6 +323,8 @@ class _SmallBatchBuffers:
         f64 = torch.float64
         self.capacity = int(capacity)
         self.theta = torch.zeros((len(THETA_KEYS), self.capacity), dtype=f64, pin_memory=True)
+        self.one = torch.zeros(len(THETA_KEYS), dtype=f64)   # plain host memory: read at call time
+        self.one_np = self.one.numpy()
         self.ngal = torch.zeros(self.capacity * 2 * group.n_tables, dtype=f64, pin_memory=True)
         self.xi = torch.zeros(self.capacity * group.n_tables * group.n_r * 3, dtype=f64,
                               pin_memory=True)
