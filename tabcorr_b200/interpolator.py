@@ -244,12 +244,17 @@ class Interpolator:
         return self.tabcorr_list[0]._format_batch(ngal, xi, separate, False)
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
-                      model=None, as_numpy=True, precision='fp64'):
+                      model=None, as_numpy=True, precision='fp64', defer_range_check=False):
         """Interpolated predictions for B parameter sets.
 
         ``params`` is a dict of arrays ``[B]`` holding the occupation parameters and one entry per
         interpolation axis (the column names of ``param_dict_table``).  Returns ``(ngal [B],
         xi [B, *tpcf_shape])`` or per-gal-type dicts, like :meth:`predict`.
+
+        ``defer_range_check`` (device results only): do not synchronise to test the
+        out-of-range flag; return ``(ngal, xi, flag)`` with ``flag`` a one-element int32 CUDA
+        tensor that is non-zero when a draw lay outside the knot hull without ``extrapolate``
+        (its outputs are NaN) -- callers that issue several batches check once at the end.
         """
         torch = _torch()
         self._ensure_device()
@@ -292,6 +297,11 @@ class Interpolator:
             _lib.check(self._lib.tc_interp_apply_batch(
                 self._interp, x.data_ptr(), n_draws, data.data_ptr(), n_cols, out.data_ptr(),
                 int(bool(extrapolate)), flag.data_ptr(), stream))
+        if defer_range_check:
+            if as_numpy:
+                raise ValueError('defer_range_check needs as_numpy=False')
+            return self.tabcorr_list[0]._format_batch(
+                ngal, xi.view(n_draws, n_r, n_comp), separate, False) + (flag,)
         if int(flag.item()) != 0:
             raise ValueError('The x-coordinates are outside of the interpolation range and '
                              'extrapolation is turned off.')

@@ -50,14 +50,28 @@ class TableSet:
         counts = np.bincount(table_index, minlength=len(self.tables))
         out = None
         start = 0
+        flags = []
+        order_dev = None   # uploaded once through pinned memory: a pageable copy per group would
+        #                    block the host until the previous group's kernels have finished
         for t, count in enumerate(counts):
             if count == 0:
                 continue
             rows = order[start:start + count]
             start += count
             sub = {k: (np.asarray(v)[rows] if np.ndim(v) > 0 else v) for k, v in params.items()}
-            result = self.tables[t].predict_batch(sub, separate_gal_type=separate_gal_type,
-                                                  as_numpy=False, **predict_kwargs)
+            table = self.tables[t]
+            if hasattr(table, 'tabcorr_list'):
+                # an Interpolator: no synchronisation per table, the out-of-range flags of all
+                # groups are tested once at the end, so the host prepares group t + 1 while the
+                # device evaluates group t
+                result = table.predict_batch(sub, separate_gal_type=separate_gal_type,
+                                             as_numpy=False, defer_range_check=True,
+                                             **predict_kwargs)
+                flags.append(result[2])
+                result = result[:2]
+            else:
+                result = table.predict_batch(sub, separate_gal_type=separate_gal_type,
+                                             as_numpy=False, **predict_kwargs)
             flat, spec = _flatten(result)
             if out is None:
                 out = [torch.empty((n_draws,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
@@ -65,11 +79,21 @@ class TableSet:
                 out_spec = spec
             elif spec != out_spec:
                 raise ValueError('tables of a TableSet must produce identically shaped results')
-            index = torch.from_numpy(rows).to(flat[0].device)
+            if order_dev is None:
+                if flat[0].is_cuda:
+                    pinned = torch.empty(n_draws, dtype=torch.int64, pin_memory=True)
+                    pinned.numpy()[:] = order
+                    order_dev = pinned.to(flat[0].device, non_blocking=True)
+                else:
+                    order_dev = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64))
+            index = order_dev[start - count:start]
             for dst, src in zip(out, flat):
                 dst.index_copy_(0, index, src)
         if out is None:
             raise ValueError('empty batch')
+        if flags and int(torch.stack([f.reshape(()) for f in flags]).max().item()) != 0:
+            raise ValueError('The x-coordinates are outside of the interpolation range and '
+                             'extrapolation is turned off.')
         if as_numpy:
             out = [_to_host(x) for x in out]
         return _unflatten(out, out_spec)

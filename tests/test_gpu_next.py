@@ -90,6 +90,16 @@ def test_table_set_per_draw_cosmology(tb):
             assert np.array_equal(xi_sep[key][rows], xi_c[key])
     with pytest.raises(ValueError):
         table_set.predict_batch(draws, index + 1)
+    # one draw outside the knot hull of the LAST group: the deferred range check still raises
+    outside = {k: v.copy() for k, v in draws.items()}
+    outside['alpha_s'][np.flatnonzero(index == 2)[-1]] = 1.5
+    with pytest.raises(ValueError, match='interpolation range'):
+        table_set.predict_batch(outside, index)
+    ngal_x, xi_x = table_set.predict_batch(outside, index, extrapolate=True)
+    assert np.all(np.isfinite(xi_x)) and np.array_equal(ngal_x[index == 0], ngal[index == 0])
+    ngal_f, xi_f, flag = interps[0].predict_batch({k: v[:3] for k, v in draws.items()},
+                                                  as_numpy=False, defer_range_check=True)
+    assert int(flag.item()) == 0 and ngal_f.is_cuda
     # plain TabCorr members work too
     plain = tb.TableSet([interp.tabcorr_list[0] for interp in interps])
     ngal_p, xi_p = plain.predict_batch(draws, index)
