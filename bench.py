@@ -122,7 +122,7 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -377,13 +377,32 @@ def run_gpu_arm(args):
         }
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline_single(args.cpu_sample)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def emit(line):
+    """Print the ONE JSON line on the real stdout (see main: fd 1 is pointed at stderr while the
+    benchmark runs, so that nothing a library prints -- e.g. NCCL's version banner -- lands beside
+    the JSON line)."""
+    text = json.dumps(line) + '\n'
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
     parser.add_argument('--steps', type=int, default=20)
