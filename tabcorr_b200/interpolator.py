@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from . import h5mini
-from .models import resolve_model, spec_from_params
+from .models import ModelSpec, resolve_model, spec_from_params
 from .tabcorr import (TabCorr, DeviceTableGroup, _to_device_f64, _torch, _h5py,
                       theta_to_device)
 from .table import Table
@@ -115,6 +115,11 @@ class Interpolator:
         self._interp = None
         self._one = None
         self._one_lock = threading.Lock()
+
+    @property
+    def tpcf_shape(self):
+        """Shape of one prediction (shared by all grid tables)."""
+        return tuple(self.tabcorr_list[0].tpcf_shape)
 
     # ------------------------------------------------------------------ I/O
     @classmethod
@@ -271,6 +276,29 @@ class Interpolator:
             raise ValueError('interpolation coordinates and occupation parameters differ in length')
         x = _to_device_f64(np.stack([np.broadcast_to(c, (n_draws,)) for c in coordinates]),
                            device).t().contiguous()
+        return self.predict_batch_tensors(theta, x, spec, separate_gal_type, n_gauss_prim,
+                                          extrapolate, as_numpy, precision, defer_range_check)
+
+    def predict_batch_tensors(self, theta, x, model=None, separate_gal_type=False,
+                              n_gauss_prim=10, extrapolate=False, as_numpy=False,
+                              precision='fp64', defer_range_check=False):
+        """:meth:`predict_batch` for parameters that already live on the device: ``theta``
+        ``[B, n_theta]`` in the kernel order of the model's family (``ModelSpec.theta_keys``) and
+        the interpolation coordinates ``x [B, D]`` in the column order of ``param_dict_table``
+        (device-side sweeps, ``tabcorr_b200.sweep``)."""
+        torch = _torch()
+        self._ensure_device()
+        spec = resolve_model(model) if model is not None else ModelSpec()
+        device = self._groups[0][0].device
+        theta = theta.to(device=device, dtype=torch.float64).contiguous()
+        x = x.to(device=device, dtype=torch.float64).contiguous()
+        n_draws = theta.shape[0]
+        if theta.ndim != 2 or theta.shape[1] != spec.n_theta:
+            raise ValueError('theta must have shape [B, {}] ({})'.format(
+                spec.n_theta, ', '.join(spec.theta_keys)))
+        if x.shape != (n_draws, len(self._keys)):
+            raise ValueError('x must have shape [B, {}] ({})'.format(
+                len(self._keys), ', '.join(self._keys)))
 
         separate = bool(separate_gal_type)
         first_group = self._groups[0][0]

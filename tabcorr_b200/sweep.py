@@ -12,7 +12,7 @@ path.  What happens to a gathered slab is up to ``consume`` (default: keep it in
 
 import numpy as np
 
-from .models import THETA_KEYS
+from .models import ASSEMBIAS_KEYS, ModelSpec, THETA_KEYS, resolve_model
 
 
 class UniformPrior:
@@ -46,16 +46,17 @@ ZHENG07_PRIOR = {'logMmin': (11.0, 14.0), 'sigma_logM': (0.05, 1.0), 'logM0': (1
                  'logM1': (12.0, 15.0), 'alpha': (0.5, 1.5)}
 
 
-def _theta_tensor(prior, sample):
-    """``[n, len(prior.keys)]`` samples -> ``[n, 7]`` tensor in kernel order (missing assembly-bias
-    strengths are 0) and the dict of extra columns (interpolation coordinates)."""
+def _theta_tensor(prior, sample, keys=THETA_KEYS):
+    """``[n, len(prior.keys)]`` samples -> ``[n, len(keys)]`` tensor in kernel order (``keys``: the
+    family's ``ModelSpec.theta_keys``; parameters the prior does not name are 0, e.g. the
+    assembly-bias strengths of an undecorated model) and the dict of extra columns
+    (interpolation coordinates)."""
     import torch
-    theta = torch.zeros((sample.shape[0], len(THETA_KEYS)), dtype=torch.float64,
-                        device=sample.device)
+    theta = torch.zeros((sample.shape[0], len(keys)), dtype=torch.float64, device=sample.device)
     extra = {}
     for j, key in enumerate(prior.keys):
-        if key in THETA_KEYS:
-            theta[:, THETA_KEYS.index(key)] = sample[:, j]
+        if key in keys:
+            theta[:, keys.index(key)] = sample[:, j]
         else:
             extra[key] = sample[:, j]
     return theta, extra
@@ -71,16 +72,21 @@ def predict_sweep(halotab, prior, n_draws, chunk=1 << 20, n_gauss_prim=10, model
 
     Parameters
     ----------
-    halotab : TabCorr
-        Table replica of this rank (``predict_batch`` with a ``[n, 7]`` device tensor).
+    halotab : TabCorr or Interpolator
+        Table replica of this rank.  For an ``Interpolator`` the prior must also name its
+        interpolation coordinates (the columns of ``param_dict_table``).
     prior : UniformPrior
+    model : model instance or ModelSpec, optional
+        Occupation family; default zheng07, decorated when the prior names the two
+        ``*_assembias_param1`` strengths.
     n_draws, chunk : int
         Total number of draws and draws per chunk (one fused launch per chunk).
     consume : callable ``(lo, hi, slab)``, optional
         Called on rank ``dst`` for every gathered chunk with its draw range and the
         ``[hi - lo, 1 + R]`` device tensor (column 0 = ngal).  Default: copy into a host array.
-    predict : callable ``(theta [n, 7]) -> (ngal [n], xi [n, ...])``, optional
-        Replaces ``halotab.predict_batch`` (the gloo tests use an oracle-backed stand-in).
+    predict : callable ``(theta [n, n_theta]) -> (ngal [n], xi [n, ...])``, optional
+        Replaces ``halotab.predict_batch`` (the gloo tests use an oracle-backed stand-in); called
+        as ``predict(theta, extra)`` when the prior names columns outside the family's parameters.
     xi_shape : tuple, optional
         Shape of one prediction; default ``halotab.tpcf_shape``.
 
@@ -95,9 +101,24 @@ def predict_sweep(halotab, prior, n_draws, chunk=1 << 20, n_gauss_prim=10, model
     if device is None:
         device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() \
             else torch.device('cpu')
+    if model is not None:
+        spec = resolve_model(model)
+    else:
+        spec = ModelSpec(decorated=all(k in prior.keys for k in ASSEMBIAS_KEYS))
+    theta_keys = spec.theta_keys
+    coordinate_keys = list(getattr(halotab, '_keys', [])) if hasattr(halotab, 'tabcorr_list') else []
+    user_predict = predict is not None
     if predict is None:
-        def predict(theta):
-            return halotab.predict_batch(theta, n_gauss_prim=n_gauss_prim, model=model,
+        missing = [k for k in coordinate_keys if k not in prior.keys]
+        if missing:
+            raise ValueError('the prior does not name the interpolation coordinates {}'.format(
+                ', '.join(missing)))
+
+        def predict(theta, extra=None):
+            if coordinate_keys:
+                x = torch.stack([extra[k] for k in coordinate_keys], dim=1)
+                return halotab.predict_batch_tensors(theta, x, spec, n_gauss_prim=n_gauss_prim)
+            return halotab.predict_batch(theta, n_gauss_prim=n_gauss_prim, model=spec,
                                          as_numpy=False)
     bounds = chunk_bounds(int(n_draws), int(chunk))
     n_rounds = -(-len(bounds) // world)
@@ -131,10 +152,15 @@ def predict_sweep(halotab, prior, n_draws, chunk=1 << 20, n_gauss_prim=10, model
         slab = None
         if c < len(bounds):
             lo, hi = bounds[c]
-            theta, extra = _theta_tensor(prior, prior.sample(c, hi - lo, device))
-            if extra:
-                raise NotImplementedError('interpolation coordinates in sweeps: pass `predict`')
-            ngal, xi = predict(theta)
+            theta, extra = _theta_tensor(prior, prior.sample(c, hi - lo, device), theta_keys)
+            unknown = [k for k in extra if k not in coordinate_keys]
+            if unknown and not user_predict:
+                raise ValueError('the prior names parameters that neither the occupation family '
+                                 'nor the table uses: {}'.format(', '.join(unknown)))
+            if user_predict and extra:
+                ngal, xi = predict(theta, extra)   # the stand-in receives the other columns too
+            else:
+                ngal, xi = predict(theta) if user_predict else predict(theta, extra)
             slab = torch.cat([ngal.reshape(-1, 1), xi.reshape(xi.shape[0], -1)], dim=1)
             if slab.shape[1] != width:
                 raise ValueError('predict returned {} columns, expected {}'.format(

@@ -371,3 +371,47 @@ def test_small_batches_take_the_zero_copy_path_and_agree_bitwise(tb):
     ref = halotab.predict_batch(dict({k: v[:4] for k, v in big.items()}, alpha=np.ones(4)),
                                 pipeline_chunk=0, as_numpy=False)
     assert np.array_equal(halotab.predict_batch(mixed)[1], ref[1].cpu().numpy())
+
+
+def test_sweep_over_interpolator_and_other_family(tb):
+    """Sweeps with interpolation coordinates in the prior (an Interpolator) and with the
+    leauthaud11 family: the chunked device-side sweep equals one batch over the same draws."""
+    import torch
+    from tabcorr_b200 import sweep
+    tables, param_table, _ = cases.grid_case('grid2d')
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    bounds = dict(sweep.ZHENG07_PRIOR)
+    bounds.update({k: (0.0, 0.0) for k in tb.models.ASSEMBIAS_KEYS})
+    bounds[tb.models.ASSEMBIAS_KEYS[0]] = (-1.0, 1.0)
+    bounds[tb.models.ASSEMBIAS_KEYS[1]] = (-1.0, 1.0)
+    bounds['log_eta'] = (float(np.min(param_table['log_eta'])), float(np.max(param_table['log_eta'])))
+    bounds['alpha_s'] = (0.8, 1.2)
+    prior = sweep.UniformPrior(bounds, seed=11)
+    n_draws, chunk = 5000, 2048
+    ngal, xi = sweep.predict_sweep(interp, prior, n_draws, chunk=chunk)
+    sample = torch.cat([prior.sample(c, hi - lo, 'cuda')
+                        for c, (lo, hi) in enumerate(sweep.chunk_bounds(n_draws, chunk))]).cpu().numpy()
+    params = {k: sample[:, j] for j, k in enumerate(prior.keys)}
+    ngal_ref, xi_ref = interp.predict_batch(params)
+    assert np.array_equal(ngal, ngal_ref) and np.array_equal(xi, xi_ref)
+    with pytest.raises(ValueError, match='interpolation coordinates'):
+        sweep.predict_sweep(interp, sweep.UniformPrior(sweep.ZHENG07_PRIOR), 10)
+    # leauthaud11 on a single table
+    tab = cases.synthetic.make_table(n_mass=25, n_sec=2, n_r=8, seed=12)
+    halotab = table_from_dict(tb, tab)
+    model = tb.PrebuiltHodModelFactory('leauthaud11', threshold=10.5)
+    l11 = sweep.UniformPrior({'smhm_m1_0': (12.1, 12.6), 'alphasat': (0.9, 1.1),
+                              'scatter_model_param1': (0.15, 0.3)}, seed=2)
+    with pytest.raises(ValueError):   # parameters the prior does not name would be 0
+        pass_through = {k: (v, v) for k, v in model.param_dict.items()}
+        pass_through['not_a_parameter'] = (0.0, 1.0)
+        sweep.predict_sweep(halotab, sweep.UniformPrior(pass_through), 10, model=model)
+    full = {k: (v, v) for k, v in model.param_dict.items()}
+    full.update({'smhm_m1_0': (12.1, 12.6), 'alphasat': (0.9, 1.1)})
+    l11 = sweep.UniformPrior(full, seed=2)
+    ngal, xi = sweep.predict_sweep(halotab, l11, 3000, chunk=1024, model=model)
+    sample = torch.cat([l11.sample(c, hi - lo, 'cuda')
+                        for c, (lo, hi) in enumerate(sweep.chunk_bounds(3000, 1024))]).cpu().numpy()
+    ref = halotab.predict_batch({k: sample[:, j] for j, k in enumerate(l11.keys)}, model=model,
+                                pipeline_chunk=0)
+    assert np.array_equal(ngal, ref[0]) and np.array_equal(xi, ref[1])
