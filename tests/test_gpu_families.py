@@ -174,3 +174,33 @@ def test_fused_entry_point_rejects_the_family(tb):
                                         None, 2, 0, 0, out.data_ptr(), 1, out.data_ptr() + 64, 3,
                                         work.data_ptr(), work.numel(), None)
     assert status == -3 and b'tc_occupation_batch' in group.lib.tc_last_error()
+
+
+def test_full_size_properties(tb):
+    """BASELINE-size batch (1e5 hearin15 draws, N=240, R=20): the size-independent properties the
+    reference's own tests use (sum of parts == total, rtol 1e-6 there; G convergence) plus
+    invariance to the batch split."""
+    kw, _ = cases.SYNTHETIC['syn240']
+    tab = tb.synthetic.make_table(**kw)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    model = tb.PrebuiltHodModelFactory('hearin15', threshold=10.5)
+    n = 100000
+    draws = tb.synthetic.make_draws_leauthaud11(n, seed=31, decorated=True)
+    ngal, xi = halotab.predict_batch(draws, model=model)
+    assert np.all(np.isfinite(ngal)) and np.all(np.isfinite(xi)) and np.all(ngal > 0)
+    ngal_sep, xi_sep = halotab.predict_batch(draws, model=model, separate_gal_type=True)
+    np.testing.assert_allclose(ngal_sep['centrals'] + ngal_sep['satellites'], ngal, rtol=1e-13)
+    total = sum(xi_sep.values())
+    scale = np.sum([np.abs(v) for v in xi_sep.values()], axis=0).max(axis=1, keepdims=True)
+    assert np.max(np.abs(total - xi) / scale) < 1e-12
+    # the same draws in two halves and in reverse order give the same numbers bit for bit
+    half = {k: v[n // 2:] for k, v in draws.items()}
+    ngal_h, xi_h = halotab.predict_batch(half, model=model)
+    assert np.array_equal(ngal_h, ngal[n // 2:]) and np.array_equal(xi_h, xi[n // 2:])
+    # Gauss-Legendre convergence at the default parameters, like the reference's own test (random
+    # draws with a stellar-mass scatter of 0.1 dex have a central step sharper than a mass bin)
+    ngal_10, xi_10 = halotab.predict(model, n_gauss_prim=10)
+    ngal_100, xi_100 = halotab.predict(model, n_gauss_prim=100)
+    np.testing.assert_allclose(ngal_10, ngal_100, rtol=1e-4)
+    np.testing.assert_allclose(xi_10, xi_100, rtol=1e-3)
