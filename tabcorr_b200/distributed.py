@@ -146,6 +146,26 @@ def single_node(group=None):
     return len(set(names)) == 1
 
 
+def shared_host_fits(n_doubles, group=None):
+    """True when /dev/shm has room for a segment of ``n_doubles`` float64 (decided on rank 0 and
+    broadcast, so that all ranks take the same path; touching pages of an over-committed tmpfs
+    segment would raise SIGBUS) or when an equal segment is already mapped."""
+    import os
+    import torch.distributed as dist
+    if (id(group), int(n_doubles)) in _SEGMENTS:
+        return True
+    fits = [True]
+    if dist.get_rank(group) == 0:
+        try:
+            stat = os.statvfs('/dev/shm')
+            fits[0] = stat.f_bavail * stat.f_frsize >= 8 * int(n_doubles) + (16 << 20)
+        except OSError:
+            fits[0] = False
+    dist.broadcast_object_list(fits, src=dist.get_global_rank(group, 0) if group else 0,
+                               group=group)
+    return bool(fits[0])
+
+
 def _predict_batch_shared_host(halotab, params, n_total, n_gauss_prim, model, dst, group,
                                predict_kwargs):
     """Every rank evaluates its slice host-to-host and writes the results into its rows of a
@@ -207,8 +227,11 @@ def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, g
     if gather not in ('nccl', 'host', 'auto'):
         raise ValueError("gather must be 'nccl', 'host' or 'auto'")
     if world > 1 and gather != 'nccl' and (gather == 'host' or single_node(group)):
-        return _predict_batch_shared_host(halotab, params, n_total, n_gauss_prim, model, dst,
-                                          group, predict_kwargs)
+        n_doubles = n_total * (1 + int(np.prod(halotab.tpcf_shape)))
+        if shared_host_fits(n_doubles, group):
+            return _predict_batch_shared_host(halotab, params, n_total, n_gauss_prim, model, dst,
+                                              group, predict_kwargs)
+        # /dev/shm too small for the result: the device-side gather below needs no host segment
     local = shard_params(params, rank, world)
     lo_rank, hi_rank = shard_bounds(n_total, rank, world)
     n_local = hi_rank - lo_rank
