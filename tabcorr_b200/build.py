@@ -11,11 +11,14 @@ OUTPUT = os.path.join(HERE, 'libtabcorr_b200.so')
 
 
 def build(force=False, verbose=False):
-    """Compile ``csrc/tabcorr_b200.cu`` for sm_100a into ``libtabcorr_b200.so`` (skipped when the
-    library is newer than its sources unless ``force``)."""
+    """Compile ``csrc/tabcorr_b200.cu`` (which includes ``csrc/*.cuh``) for sm_100a into
+    ``libtabcorr_b200.so`` (skipped when the library is newer than its sources unless ``force``)."""
     header = os.path.join(os.path.dirname(HERE), 'include', 'tabcorr_b200.h')
+    csrc = os.path.dirname(SOURCE)   # one translation unit: tabcorr_b200.cu includes the .cuh files
+    sources = [header] + [os.path.join(csrc, name) for name in os.listdir(csrc)
+                          if name.endswith(('.cu', '.cuh'))]
     if (not force and os.path.isfile(OUTPUT) and
-            os.path.getmtime(OUTPUT) >= max(os.path.getmtime(SOURCE), os.path.getmtime(header))):
+            os.path.getmtime(OUTPUT) >= max(os.path.getmtime(path) for path in sources)):
         return OUTPUT
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -1,0 +1,593 @@
+// tabcorr_b200 -- host-side table preparation: padded layouts, DMMA fragment streams, quadrature
+// plans, tile / workspace heuristics, math-table upload, launch helpers.
+//
+// Part of the single translation unit tabcorr_b200.cu (see its header comment and DESIGN.md).
+#pragma once
+
+#include "common.cuh"
+#include "device_math.cuh"
+#include "occupation.cuh"
+#include "predict_kernel.cuh"
+#include "leauthaud11.cuh"
+#include "aux_kernels.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// host-side table preparation
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int upload(const std::vector<T>& host, T** dev) {
+  *dev = nullptr;
+  size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+  TC_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), bytes));
+  if (!host.empty())
+    TC_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return TC_OK;
+}
+
+struct PlanHost {
+  OccPlan dev{};
+  std::vector<void*> allocations;
+};
+
+struct Layout {
+  bool built = false;
+  bool built32 = false;   // afrag32 (3xTF32 mode) is built on first use
+  LayoutDev dev{};
+  std::vector<int> row_to_pad;
+  std::vector<void*> allocations;
+  std::map<int, PlanHost> plans;  // by n_gauss
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Tuning knobs for experiments (tools/bench_variants.py): TC_TUNE_<NAME>=<int> in the environment.
+int tune(const char* name, int fallback) {
+  const char* v = std::getenv((std::string("TC_TUNE_") + name).c_str());
+  return v && *v ? std::atoi(v) : fallback;
+}
+
+}  // namespace
+
+struct tc_table {
+  int device = 0;
+  int mode = 0;
+  int n_rows = 0, n_r = 0, n_tables = 0, n_cen = 0;
+  std::vector<double> n_h, log_min, log_max, pct, dist;
+  bool has_dist = false;
+  std::vector<int> is_sat;
+  std::vector<std::vector<double>> matrices;  // host copies, kept to build the split layout lazily
+  std::map<int, std::pair<std::vector<double>, std::vector<double>>> rules;  // n_gauss -> (x, w)
+  Layout layouts[2];  // [separate]
+  std::mutex mutex;
+};
+
+struct tc_interp {
+  int device = 0;
+  InterpDev dev{};
+  int sum_knots = 0;
+  std::vector<void*> allocations;
+};
+
+namespace {
+
+// Build the padded row order and the A-fragment stream of one layout.
+int build_layout(tc_table* t, int separate) {
+  Layout& L = t->layouts[separate];
+  if (L.built) return TC_OK;
+  const int N = t->n_rows, R = t->n_r, T = t->n_tables;
+  const int Reff = R * T;
+  const int n_cen = t->n_cen, n_sat = N - n_cen;
+  // centrals first (stable); in the split layout the satellite block starts on a 16-row tile
+  const int nc_pad = separate ? round_up(n_cen, 16) : n_cen;
+  const int n_pad = std::max(16, round_up(nc_pad + n_sat, 16));
+  L.row_to_pad.assign(N, -1);
+  std::vector<int> pad_to_row(n_pad, -1);
+  {
+    int ic = 0, is = nc_pad;
+    for (int i = 0; i < N; i++) {
+      int p = t->is_sat[i] ? is++ : ic++;
+      L.row_to_pad[i] = p;
+      pad_to_row[p] = i;
+    }
+  }
+  const int T16 = n_pad / 16;
+  std::vector<Chunk> chunks;
+  std::vector<std::vector<int>> out_lists;
+  std::vector<double2> afrag;
+  long long ks_per_r = 0;
+  int n_parts = 0;
+
+  if (t->mode == TC_MODE_AUTO) {
+    ks_per_r = 2LL * T16 * (T16 + 1);
+    afrag.assign((size_t)Reff * ks_per_r * 32 + 32, make_double2(0.0, 0.0));
+    // M'[i][j] (j <= i) = M[i][j] (i == j) or 2 M[i][j]: the reference's packed prefactor sum
+    // (tabcorr.py:638-642) written as a lower-triangular matrix product.
+    for (int tb = 0; tb < T; tb++) {
+      const double* packed = t->matrices[tb].data();
+      const size_t P = (size_t)N * (N + 1) / 2;
+      for (int r = 0; r < R; r++) {
+        const double* m = packed + (size_t)r * P;
+        double2* dst = afrag.data() + (size_t)(tb * R + r) * ks_per_r * 32;
+        for (int i = 0; i < N; i++) {
+          const int pi = L.row_to_pad[i];
+          for (int j = 0; j <= i; j++) {
+            const int pj = L.row_to_pad[j];
+            double val = m[(size_t)i * (i + 1) / 2 + j];
+            if (i != j) val *= 2.0;
+            const int hi = std::max(pi, pj), lo = std::min(pi, pj);
+            const int mt = hi / 16, rr = hi % 16, ks = lo / 4, tg = lo % 4;
+            double2& d = dst[((size_t)2 * mt * (mt + 1) + ks) * 32 + (rr % 8) * 4 + tg];
+            if (rr < 8) d.x = val; else d.y = val;
+          }
+        }
+      }
+    }
+    // chunks: per radial bin, the tile range cut into pieces of similar cost
+    const int n_comp = separate ? 3 : 1;
+    out_lists.assign((size_t)Reff * n_comp, {});
+    const int c16 = nc_pad / 16;  // first satellite tile (split layout)
+    int pieces = std::max(1, std::min(T16, (tune("CHUNKS", 6 * kWarps) + Reff - 1) / Reff));
+    auto add_range = [&](int r, int mt_lo, int mt_hi, int k_begin, int k_cap, int comp, int np) {
+      // cost of tile mt ~ number of k-steps
+      auto cost = [&](int mt) { return std::max(0, std::min(4 * (mt + 1), k_cap) - k_begin); };
+      long long total = 0;
+      for (int mt = mt_lo; mt < mt_hi; mt++) total += cost(mt);
+      if (total == 0) return;
+      np = std::max(1, std::min(np, mt_hi - mt_lo));
+      long long acc = 0;
+      int start = mt_lo, piece = 0;
+      for (int mt = mt_lo; mt < mt_hi; mt++) {
+        acc += cost(mt);
+        bool last = mt == mt_hi - 1;
+        if (last || acc * np >= total * (piece + 1)) {
+          Chunk c{};
+          c.r = r; c.mt0 = start; c.mt1 = mt + 1; c.k_begin = k_begin; c.k_cap = k_cap;
+          c.part_row = n_parts++;
+          chunks.push_back(c);
+          out_lists[(size_t)r * n_comp + comp].push_back(c.part_row);
+          start = mt + 1;
+          piece++;
+        }
+      }
+    };
+    const int kinf = 1 << 28;
+    for (int r = 0; r < Reff; r++) {
+      if (!separate) {
+        add_range(r, 0, T16, 0, kinf, 0, pieces);
+      } else {
+        add_range(r, 0, c16, 0, kinf, 0, pieces);              // centrals-centrals
+        add_range(r, c16, T16, 0, nc_pad / 4, 1, pieces);       // centrals-satellites
+        add_range(r, c16, T16, nc_pad / 4, kinf, 2, pieces);    // satellites-satellites
+      }
+    }
+  } else {
+    const int n_rt = (Reff + 15) / 16;
+    ks_per_r = n_pad / 4;
+    afrag.assign((size_t)n_rt * ks_per_r * 32 + 32, make_double2(0.0, 0.0));
+    for (int tb = 0; tb < T; tb++) {
+      const double* m = t->matrices[tb].data();
+      for (int r = 0; r < R; r++) {
+        const int re = tb * R + r, rt = re / 16, rr = re % 16;
+        for (int i = 0; i < N; i++) {
+          const int pi = L.row_to_pad[i];
+          double2& d = afrag[((size_t)rt * ks_per_r + pi / 4) * 32 + (rr % 8) * 4 + pi % 4];
+          if (rr < 8) d.x = m[(size_t)r * N + i]; else d.y = m[(size_t)r * N + i];
+        }
+      }
+    }
+    const int n_comp = separate ? 2 : 1;
+    out_lists.assign((size_t)Reff * n_comp, {});
+    const int ks_total = n_pad / 4;
+    // k-ranges: split at the centrals/satellites boundary (split layout) and into pieces
+    std::vector<std::pair<int, int>> segs;
+    if (separate) {
+      segs.push_back({0, nc_pad / 4});
+      segs.push_back({nc_pad / 4, ks_total});
+    } else {
+      segs.push_back({0, ks_total});
+    }
+    const int want = std::max(1, (4 * kWarps + n_rt - 1) / n_rt / (int)segs.size());
+    for (int rt = 0; rt < n_rt; rt++) {
+      for (size_t sg = 0; sg < segs.size(); sg++) {
+        const int lo = segs[sg].first, hi = segs[sg].second;
+        if (hi <= lo) continue;
+        const int np = std::max(1, std::min(want, (hi - lo + 7) / 8));
+        for (int pc = 0; pc < np; pc++) {
+          Chunk c{};
+          c.r = rt;
+          c.k_begin = lo + (int)((long long)(hi - lo) * pc / np);
+          c.k_cap = lo + (int)((long long)(hi - lo) * (pc + 1) / np);
+          if (c.k_cap <= c.k_begin) continue;
+          c.part_row = n_parts;
+          n_parts += 16;
+          chunks.push_back(c);
+          for (int rr = 0; rr < 16; rr++) {
+            const int re = rt * 16 + rr;
+            if (re < Reff) out_lists[(size_t)re * n_comp + sg].push_back(c.part_row + rr);
+          }
+        }
+      }
+    }
+  }
+  auto chunk_cost = [&](const Chunk& c) {
+    if (t->mode != TC_MODE_AUTO) return (long long)(c.k_cap - c.k_begin);
+    long long s = 0;
+    for (int mt = c.mt0; mt < c.mt1; mt++)
+      s += std::max(0, std::min(4 * (mt + 1), c.k_cap) - c.k_begin);
+    return s;
+  };
+  // longest chunks first (only the end of a CTA's last tile is sensitive to the order)
+  std::stable_sort(chunks.begin(), chunks.end(),
+                   [&](const Chunk& a, const Chunk& b) { return chunk_cost(a) > chunk_cost(b); });
+
+  std::vector<long long> cost_prefix(chunks.size() + 1, 0);
+  for (size_t c = 0; c < chunks.size(); c++)
+    cost_prefix[c + 1] = cost_prefix[c] + std::max<long long>(1, chunk_cost(chunks[c]));
+
+  std::vector<int> out_ptr(out_lists.size() + 1, 0), out_parts;
+  for (size_t o = 0; o < out_lists.size(); o++) {
+    out_ptr[o + 1] = out_ptr[o] + (int)out_lists[o].size();
+    out_parts.insert(out_parts.end(), out_lists[o].begin(), out_lists[o].end());
+  }
+
+  double2* d_afrag; Chunk* d_chunks; int *d_out_ptr, *d_out_parts, *d_pad_to_row;
+  long long* d_cost_prefix;
+  int rc;
+  if ((rc = upload(cost_prefix, &d_cost_prefix))) return rc;
+  L.allocations.push_back(d_cost_prefix);
+  if ((rc = upload(afrag, &d_afrag))) return rc;
+  L.allocations.push_back(d_afrag);
+  if ((rc = upload(chunks, &d_chunks))) return rc;
+  L.allocations.push_back(d_chunks);
+  if ((rc = upload(out_ptr, &d_out_ptr))) return rc;
+  L.allocations.push_back(d_out_ptr);
+  if ((rc = upload(out_parts, &d_out_parts))) return rc;
+  L.allocations.push_back(d_out_parts);
+  if ((rc = upload(pad_to_row, &d_pad_to_row))) return rc;
+  L.allocations.push_back(d_pad_to_row);
+
+  L.dev.n_rows = N;
+  L.dev.n_pad = n_pad;
+  L.dev.nc_pad = nc_pad;
+  L.dev.n_parts = std::max(n_parts, 1);
+  L.dev.n_chunks = (int)chunks.size();
+  L.dev.n_out = (int)out_lists.size();
+  L.dev.ks_per_r = ks_per_r;
+  L.dev.afrag = d_afrag;
+  L.dev.chunks = d_chunks;
+  L.dev.chunk_cost_prefix = d_cost_prefix;
+  L.dev.out_ptr = d_out_ptr;
+  L.dev.out_parts = d_out_parts;
+  L.dev.pad_to_row = d_pad_to_row;
+  L.built = true;
+  return TC_OK;
+}
+
+// round an FP32 value to TF32 (10 explicit mantissa bits), ties to even
+float tf32_round_host(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, sizeof(u));
+  u += 0xfffu + ((u >> 13) & 1u);
+  u &= 0xffffe000u;
+  std::memcpy(&x, &u, sizeof(u));
+  return x;
+}
+
+// A-fragment stream of the 3xTF32 mode: the same lower-triangular M' as build_layout, in m16n8k8
+// fragments (16-row tiles x k8-steps of 8 columns), every entry split into TF32 high and low part.
+int build_afrag32(tc_table* t, int separate) {
+  Layout& L = t->layouts[separate];
+  if (L.built32) return TC_OK;
+  if (t->mode != TC_MODE_AUTO)
+    return fail(TC_EUNSUPPORTED, "the 3xTF32 mode exists for auto-correlation tables only");
+  const int N = t->n_rows, R = t->n_r, T = t->n_tables, Reff = R * T;
+  const int T16 = L.dev.n_pad / 16;
+  const long long ks8_per_r = (long long)T16 * (T16 + 1);
+  std::vector<float4> frag((size_t)Reff * ks8_per_r * 64 + 64, make_float4(0.f, 0.f, 0.f, 0.f));
+  const size_t P = (size_t)N * (N + 1) / 2;
+  for (int tb = 0; tb < T; tb++) {
+    const double* packed = t->matrices[tb].data();
+    for (int r = 0; r < R; r++) {
+      const double* m = packed + (size_t)r * P;
+      float4* dst = frag.data() + (size_t)(tb * R + r) * ks8_per_r * 64;
+      for (int i = 0; i < N; i++) {
+        const int pi = L.row_to_pad[i];
+        for (int j = 0; j <= i; j++) {
+          const int pj = L.row_to_pad[j];
+          double val = m[(size_t)i * (i + 1) / 2 + j];
+          if (i != j) val *= 2.0;
+          const int hi_r = std::max(pi, pj), lo_c = std::min(pi, pj);
+          const int mt = hi_r / 16, rr = hi_r % 16, ks = lo_c / 8, kk = lo_c % 8;
+          const int lane = (rr % 8) * 4 + (kk % 4), reg = (rr / 8) + 2 * (kk / 4);
+          const float hi = tf32_round_host((float)val);
+          const float lo = tf32_round_host((float)(val - (double)hi));
+          float4* block = dst + ((size_t)mt * (mt + 1) + ks) * 64;
+          reinterpret_cast<float*>(&block[lane])[reg] = hi;
+          reinterpret_cast<float*>(&block[32 + lane])[reg] = lo;
+        }
+      }
+    }
+  }
+  float4* d_frag;
+  int rc;
+  if ((rc = upload(frag, &d_frag))) return rc;
+  L.allocations.push_back(d_frag);
+  L.dev.afrag32 = d_frag;
+  L.dev.ks8_per_r = ks8_per_r;
+  L.built32 = true;
+  return TC_OK;
+}
+
+// Quadrature plan of a layout for one Gauss-Legendre rule (tabcorr.py:543-552,568-578).
+int build_plan(tc_table* t, int separate, int n_gauss) {
+  Layout& L = t->layouts[separate];
+  if (L.plans.count(n_gauss)) return TC_OK;
+  auto rule = t->rules.find(n_gauss);
+  if (rule == t->rules.end())
+    return fail(TC_EINVAL, "no quadrature rule registered for n_gauss=" + std::to_string(n_gauss) +
+                               " (call tc_table_plan first)");
+  const std::vector<double>& x01 = rule->second.first;
+  const std::vector<double>& wq = rule->second.second;
+  const int N = t->n_rows, G = n_gauss, n_pad = L.dev.n_pad;
+
+  struct Group { double lo, hi; int sat; std::vector<int> rows; };
+  std::vector<Group> groups;
+  for (int pass = 0; pass < 2; pass++) {  // centrals groups first
+    for (int i = 0; i < N; i++) {
+      if ((t->is_sat[i] != 0) != (pass == 1)) continue;
+      bool placed = false;
+      for (auto& gq : groups) {
+        if (gq.sat == pass && gq.lo == t->log_min[i] && gq.hi == t->log_max[i] &&
+            (int)gq.rows.size() < kGroupRows) {
+          gq.rows.push_back(i);
+          placed = true;
+          break;
+        }
+      }
+      if (!placed) groups.push_back(Group{t->log_min[i], t->log_max[i], pass, {i}});
+    }
+  }
+  const int n_groups = (int)groups.size();
+  // the kernel evaluates `unroll` nodes per iteration
+  // (tried: 10 nodes in flight -- no gain, tools/bench_variants.py)
+  const int unroll = tune("OCC_UNROLL", kOccUnroll) == kOccUnroll && G % kOccUnroll == 0 ? kOccUnroll : 2;
+  const int GP = round_up(G, unroll);
+  std::vector<double> node_logm((size_t)n_groups * GP), node_m((size_t)n_groups * GP);
+  std::vector<int> grp_rows((size_t)n_groups * kGroupRows, -1), grp_is_sat(n_groups);
+  std::vector<double> row_c((size_t)(n_pad + 1) * GP, 0.0), row_nh(n_pad, 0.0), row_pct(n_pad, 0.0);
+  for (int q = 0; q < n_groups; q++) {
+    const Group& gq = groups[q];
+    grp_is_sat[q] = gq.sat;
+    for (int k = 0; k < G; k++) {
+      // prim_haloprop = 10**(log_min + d_log * x) and halotools' log10(prim_haloprop)
+      double m = std::pow(10.0, gq.lo + (gq.hi - gq.lo) * x01[k]);
+      node_m[(size_t)q * GP + k] = m;
+      node_logm[(size_t)q * GP + k] = std::log10(m);
+    }
+    for (int k = G; k < GP; k++) {  // zero-weight padding node
+      node_m[(size_t)q * GP + k] = node_m[(size_t)q * GP];
+      node_logm[(size_t)q * GP + k] = node_logm[(size_t)q * GP];
+    }
+    for (size_t s = 0; s < gq.rows.size(); s++) {
+      const int i = gq.rows[s], p = L.row_to_pad[i];
+      grp_rows[(size_t)q * kGroupRows + s] = p;
+      row_nh[p] = t->n_h[i];
+      row_pct[p] = t->pct[i];
+      const double n = t->has_dist ? t->dist[i] + 1.0 : 0.0;  // tabcorr.py:568-574
+      double norm = 0.0;
+      for (int k = 0; k < G; k++) norm += wq[k] * std::pow(node_m[(size_t)q * GP + k], n);
+      for (int k = 0; k < G; k++)
+        row_c[(size_t)p * GP + k] = wq[k] * std::pow(node_m[(size_t)q * GP + k], n) / norm;
+    }
+  }
+  PlanHost ph;
+  double *d_logm, *d_m, *d_c, *d_nh, *d_pct; int *d_rows, *d_sat;
+  int rc;
+  if ((rc = upload(node_logm, &d_logm))) return rc; ph.allocations.push_back(d_logm);
+  if ((rc = upload(node_m, &d_m))) return rc; ph.allocations.push_back(d_m);
+  {
+    std::vector<double> node_inv_m(node_m.size());
+    for (size_t k = 0; k < node_m.size(); k++) node_inv_m[k] = 1.0 / node_m[k];
+    double* d_inv;
+    if ((rc = upload(node_inv_m, &d_inv))) return rc;
+    ph.allocations.push_back(d_inv);
+    ph.dev.node_inv_m = d_inv;
+  }
+  if ((rc = upload(grp_rows, &d_rows))) return rc; ph.allocations.push_back(d_rows);
+  if ((rc = upload(grp_is_sat, &d_sat))) return rc; ph.allocations.push_back(d_sat);
+  if ((rc = upload(row_c, &d_c))) return rc; ph.allocations.push_back(d_c);
+  if ((rc = upload(row_nh, &d_nh))) return rc; ph.allocations.push_back(d_nh);
+  if ((rc = upload(row_pct, &d_pct))) return rc; ph.allocations.push_back(d_pct);
+  ph.dev.n_groups = n_groups;
+  ph.dev.n_cen_groups = 0;
+  for (int q = 0; q < n_groups; q++) ph.dev.n_cen_groups += grp_is_sat[q] ? 0 : 1;
+  ph.dev.n_gauss = G;
+  ph.dev.n_gauss_pad = GP;
+  ph.dev.unroll = unroll;
+  ph.dev.zero_row = n_pad;
+  ph.dev.node_logm = d_logm;
+  ph.dev.node_m = d_m;
+  ph.dev.grp_rows = d_rows;
+  ph.dev.grp_is_sat = d_sat;
+  ph.dev.row_c = d_c;
+  ph.dev.row_nh = d_nh;
+  ph.dev.row_pct = d_pct;
+  L.plans[n_gauss] = ph;
+  return TC_OK;
+}
+
+size_t predict_smem_bytes(int n_pad, int nt, int n_buf) {
+  return ((size_t)n_buf * n_pad * 8 * nt + kTabDoubles) * sizeof(double) + sizeof(PredictCtrl);
+}
+
+// Draw-tile width (8 nt draws) and number of W buffers.  Two buffers let the occupation of the
+// next tile overlap the contraction of the current one, but halve the tile width that fits in
+// shared memory, and the width is what the table stream from L2 is amortised over: measured on
+// B200, N = 240: 2 x 56 draws = 1 x 64 draws (4.03 ms per 1e5 draws), N = 500: 1 x 48 draws beats
+// 2 x 24 draws (16.9 vs 18.1 ms).  So two buffers are used while they leave at least 40 draws;
+// within a buffer count the widest tile that fits, narrower only while the batch is too small to
+// give every SM a tile.
+void pick_tile(int n_pad, long long n_draws, int n_sm, int* nt_out, int* n_buf_out) {
+  *nt_out = 0;
+  *n_buf_out = 0;
+  const int forced = tune("NBUF", 0);
+  auto widest = [&](int n_buf) {
+    for (int nt = 8; nt >= 1; nt--)
+      if (predict_smem_bytes(n_pad, nt, n_buf) <= (size_t)kSmemLimit) return nt;
+    return 0;
+  };
+  int n_buf = widest(2) >= 5 ? 2 : 1;
+  if (forced == 1 || forced == 2) n_buf = forced;
+  if (widest(n_buf) == 0) n_buf = 1;
+  int best = 0;
+  for (int nt = 8; nt >= 1; nt--) {
+    if (predict_smem_bytes(n_pad, nt, n_buf) > (size_t)kSmemLimit) continue;
+    best = nt;  // the largest that fits, shrinking while the grid would not fill the device
+    if ((n_draws + 8 * nt - 1) / (8 * nt) >= n_sm) break;
+  }
+  if (best) {
+    *nt_out = best;
+    *n_buf_out = n_buf;
+  }
+}
+
+struct Workspace {
+  size_t parts_bytes, ngal_bytes, total;
+  long long n_tiles;
+  int nt, n_buf;
+};
+
+Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
+  Workspace w{};
+  pick_tile(L.dev.n_pad, n_draws, n_sm, &w.nt, &w.n_buf);
+  if (w.nt == 0) return w;
+  const int bm = 8 * w.nt;
+  w.n_tiles = (n_draws + bm - 1) / bm;
+  w.parts_bytes = (size_t)w.n_tiles * L.dev.n_parts * bm * sizeof(double);
+  w.ngal_bytes = (size_t)w.n_tiles * 2 * bm * sizeof(double);
+  w.total = w.parts_bytes + w.ngal_bytes;
+  return w;
+}
+
+// Occupation items per n-tile: about kOccItemsPerTile / nt group ranges, split between centrals and
+// satellites in proportion to their groups (at least one each where the type exists).
+constexpr int kOccItemsPerTile = 14;
+
+void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat) {
+  const int cen = plan.n_cen_groups, sat = plan.n_groups - plan.n_cen_groups;
+  const int want = std::max(2, (tune("OCC_ITEMS", kOccItemsPerTile) + nt - 1) / nt);
+  auto share = [&](int count) {
+    if (count == 0) return 0;
+    const int units = (count + 3) / 4;
+    return std::max(1, std::min(units, (int)std::lround((double)want * count / (cen + sat))));
+  };
+  *n_cen = share(cen);
+  *n_sat = share(sat);
+  if (*n_cen + *n_sat == 0) *n_cen = 1;  // table without rows cannot happen; keep n_occ > 0
+}
+
+// Coefficient tables of the occupation math (see half_erfc_neg / pow_pos), computed in long double.
+int ensure_math_tables(int device) {
+  static std::mutex m;
+  static std::map<int, bool> done;
+  std::lock_guard<std::mutex> lock(m);
+  if (done[device]) return TC_OK;
+  std::vector<double> tab(kTabDoubles, 0.0);
+  const int n = kErfDeg + 1;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  tab[kErfIntervals - 1] = 1.0;  // saturated columns: 0 below the first, 1 above the last interval
+  for (int i = 0; i < kErfIntervals - 2; i++) {
+    const long double xc = -6.0L + 0.5L * i;  // x = xc + s / 4 with s in [-1, 1]; t = s / 2
+    std::vector<long double> fs(n), sn(n);
+    for (int j = 0; j < n; j++) {
+      sn[j] = cosl(pi * (j + 0.5L) / n);
+      fs[j] = 0.5L * erfcl(-(xc + 0.25L * sn[j]));
+    }
+    // Chebyshev coefficients of the interpolant, then Chebyshev -> monomial in s
+    std::vector<long double> a(n, 0.0L);
+    for (int k = 0; k < n; k++) {
+      long double sum = 0.0L;
+      for (int j = 0; j < n; j++) sum += fs[j] * cosl(k * pi * (j + 0.5L) / n);
+      a[k] = (k == 0 ? 1.0L : 2.0L) * sum / n;
+    }
+    std::vector<long double> mono(n, 0.0L), t0(n, 0.0L), t1(n, 0.0L), t2(n, 0.0L);
+    t0[0] = 1.0L;                 // T_0
+    t1[1] = 1.0L;                 // T_1
+    for (int d = 0; d < n; d++) mono[d] += a[0] * t0[d] + (n > 1 ? a[1] * t1[d] : 0.0L);
+    for (int k = 2; k < n; k++) {  // T_k = 2 s T_{k-1} - T_{k-2}
+      for (int d = 0; d < n; d++) t2[d] = (d > 0 ? 2.0L * t1[d - 1] : 0.0L) - t0[d];
+      for (int d = 0; d < n; d++) mono[d] += a[k] * t2[d];
+      t0 = t1;
+      t1 = t2;
+    }
+    long double scale = 1.0L;    // s = 2 t
+    for (int d = 0; d < n; d++) {
+      tab[(size_t)d * kErfStride + i + 1] = (double)(mono[d] * scale);
+      scale *= 2.0L;
+    }
+  }
+  for (int i = 0; i < kLogEntries; i++) {
+    const double inv_c = (double)(1.0L / (1.0L + (i + 0.5L) / kLogEntries));
+    tab[kTabLog + 2 * i] = inv_c;
+    tab[kTabLog + 2 * i + 1] = (double)(-logl((long double)inv_c));
+  }
+  for (int j = 0; j < kExpEntries; j++) tab[kTabExp + j] = (double)exp2l((long double)j / kExpEntries);
+  TC_CUDA(cudaMemcpyToSymbol(g_math_tables, tab.data(), sizeof(double) * kTabDoubles));
+  done[device] = true;
+  return TC_OK;
+}
+
+int device_sms(int device, int* n_sm) {
+  static std::mutex m;
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lock(m);
+  auto it = cache.find(device);
+  if (it == cache.end()) {
+    int v = 0;
+    TC_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    it = cache.emplace(device, v).first;
+  }
+  *n_sm = it->second;
+  return TC_OK;
+}
+
+template <int NT, int MODE>
+int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
+  static std::mutex m;
+  static std::map<int, bool> configured;
+  int dev = 0;
+  TC_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(m);
+    if (!configured[dev]) {
+      TC_CUDA(cudaFuncSetAttribute(predict_kernel<NT, MODE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+      configured[dev] = true;
+    }
+  }
+  predict_kernel<NT, MODE><<<grid, kThreads, smem, stream>>>(args);
+  TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+// optional per-kernel timing for bench.py (tc_profile_enable / tc_profile_read)
+struct Profile {
+  bool enabled = false;
+  bool recorded = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+Profile g_profile;
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; (void)cudaGetLastError(); return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) { ok = false; (void)cudaGetLastError(); }
+  }
+  ~DeviceGuard() { if (prev >= 0) (void)cudaSetDevice(prev); }
+};
+
+}  // namespace

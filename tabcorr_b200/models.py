@@ -3,7 +3,7 @@
 The reference evaluates ``model.mean_occupation_centrals/satellites`` of a halotools
 ``HodModelFactory`` on the CPU (``tabcorr/tabcorr.py:556-563``).  Here the model object only
 *describes* the occupation functions: the arithmetic runs in the CUDA occupation kernel
-(``csrc/tabcorr_b200.cu``).  ``resolve_model`` maps
+(``csrc/occupation.cuh``, ``csrc/leauthaud11.cuh``).  ``resolve_model`` maps
 
 * a halotools model (recognised by the class names of its occupation components -- halotools
   itself is never imported),

@@ -4,7 +4,8 @@ markdown kept under profiles/:  python tools/ncu_summary.py gpurun_out/prof.ncu-
 
 Prints the headline metrics (duration, DRAM bytes, pipe utilisation, stall reasons), the SASS
 opcode mix with its share of the warp-stall samples, and the sample share of the code regions
-named by source line ranges of csrc/tabcorr_b200.cu (needs -lineinfo, which build.py passes).
+delimited by the first and the last DMMA of the kernel (-lineinfo, which build.py passes, also maps
+the ncu source page to csrc/*.cuh).
 """
 
 import csv
