@@ -471,13 +471,18 @@ Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
   return w;
 }
 
-// Occupation items per n-tile: about kOccItemsPerTile / nt group ranges, split between centrals and
-// satellites in proportion to their groups (at least one each where the type exists).
+// Occupation items per n-tile: about `items` / nt group ranges, split between centrals and
+// satellites in proportion to their groups (at least one each where the type exists).  Auto
+// tables: 14 items per tile, taken in the gaps of the contraction.  Cross tables are bound by
+// the occupation arithmetic itself (2 R N flops per draw), so the items are what the 12 warps
+// balance: 48 smaller ones (measured: N = 240 0.84 -> 0.71 ms per 1e5 draws, N = 1104 3.12 -> 3.04).
 constexpr int kOccItemsPerTile = 14;
+constexpr int kOccItemsPerTileCross = 48;
 
-void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat) {
+void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat,
+                 int items = kOccItemsPerTile) {
   const int cen = plan.n_cen_groups, sat = plan.n_groups - plan.n_cen_groups;
-  const int want = std::max(2, (tune("OCC_ITEMS", kOccItemsPerTile) + nt - 1) / nt);
+  const int want = std::max(2, (tune("OCC_ITEMS", items) + nt - 1) / nt);
   auto share = [&](int count) {
     if (count == 0) return 0;
     const int units = (count + 3) / 4;

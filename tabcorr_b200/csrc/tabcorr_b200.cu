@@ -266,7 +266,8 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   args.ngal_tile = reinterpret_cast<double*>(static_cast<char*>(workspace) + ws.parts_bytes);
 
   args.n_buf = ws.n_buf;
-  pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat);
+  pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat,
+              t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile);
   {
     // occupation items take every occ_stride-th slot of the first 70 % of a tile's work list (an
     // item runs for tens of microseconds beside DMMA warps that starve its scalar FP64, so the

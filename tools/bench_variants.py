@@ -28,6 +28,8 @@ SHAPES = [
     ('cfg5 N=500 R=20 wp', 125, 2, 20, 'auto', 'wp', False),
     ('bolplanck-like N=60 R=19 wp', 30, 1, 19, 'auto', 'wp', False),
     ('cross N=1104 R=13 ds', 276, 2, 13, 'cross', 'wp', False),
+    ('cross N=60 R=19 ds', 30, 1, 19, 'cross', 'wp', False),
+    ('cross N=240 R=19 ds', 60, 2, 19, 'cross', 'wp', False),
 ]
 
 
