@@ -89,6 +89,27 @@ def cpu_baseline_single(n_sample):
                           n_sample, DRAWS_PER_GPU)}
 
 
+def parity_vs_cpu(ngal_gpu, xi_gpu, n_check=256):
+    """Max relative deviation of the GPU results from the CPU port on the first draws of the
+    workload (BASELINE.md section 3 asks for it beside the timings)."""
+    from oracle import tabcorr_oracle as orc
+    from tabcorr_b200 import synthetic
+    tab = synthetic.make_table(n_mass=N_MASS, n_sec=N_SEC, n_r=N_R)
+    draws = synthetic.make_draws(DRAWS_PER_GPU, seed=1)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    model = orc.Zheng07Oracle()
+    n_check = min(n_check, len(ngal_gpu))
+    dev_ngal = dev_xi = 0.0
+    for i in range(n_check):
+        for key, values in draws.items():
+            model.param_dict[key] = values[i]
+        ngal, xi = orc.predict(table, orc.mean_occupation(table, model, N_GAUSS))
+        dev_ngal = max(dev_ngal, abs(ngal_gpu[i] / ngal - 1.0))
+        dev_xi = max(dev_xi, float(np.max(np.abs(xi_gpu[i] - xi)) / np.max(np.abs(xi))))
+    return {'draws_checked': n_check, 'max_rel_dev_ngal': dev_ngal, 'max_rel_dev_xi': dev_xi,
+            'tolerance': 1e-10, 'ok': bool(dev_ngal < 1e-10 and dev_xi < 1e-10)}
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's algorithm on all host cores (multiprocessing fan-out,
     one table copy per worker), same workload/metric; each step is a bounded sample."""
@@ -377,6 +398,9 @@ def run_gpu_arm(args):
         }
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline_single(args.cpu_sample)
+            if n_draws == DRAWS_PER_GPU:
+                line['parity_vs_cpu'] = parity_vs_cpu(ngal[:, 0].cpu().numpy(),
+                                                      xi[:, :, 0].cpu().numpy())
         emit(line)
     if world > 1:
         dist.barrier()
