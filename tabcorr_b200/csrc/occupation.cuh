@@ -133,11 +133,12 @@ template <bool DECORATED, bool MODULATE, int U, typename Store>
 __device__ __forceinline__ void occupation_item_impl(const OccPlan& plan, const tc_model& model,
                                                      const double* __restrict__ theta_row,
                                                      long long theta_ps, int g_begin, int g_end,
-                                                     const double* __restrict__ tab, Store store) {
+                                                     const double* __restrict__ tab, Store store,
+                                                     int first, int stride) {
   DrawParams p = load_draw(theta_row, theta_ps);
   if (!model.decorated) p.a_cen = p.a_sat = 0.0;  // strengths are ignored unless decorated
   const bool sat = g_begin >= plan.n_cen_groups;
-  for (int grp = g_begin + (threadIdx.x >> 3 & 3); grp < g_end; grp += 4) {
+  for (int grp = g_begin + first; grp < g_end; grp += stride) {
     double occ0, occ1;
     if (sat)
       occupation_group<true, DECORATED, MODULATE, U>(plan, grp, p, model.split, tab, occ0, occ1);
@@ -149,23 +150,30 @@ __device__ __forceinline__ void occupation_item_impl(const OccPlan& plan, const 
   }
 }
 
+// `first` / `stride`: which groups of the range this lane takes.  A batch gives a lane the draw
+// lane & 7 and the groups (lane >> 3) + 4 k; a one-draw call (the latency path) has a single
+// parameter set, so all 32 lanes spread over the groups (first = lane, stride = 32) instead of
+// 24 of them recomputing the same draw.
 template <typename Store>
 __device__ __forceinline__ void occupation_item(const OccPlan& plan, const tc_model& model,
                                                 const double* __restrict__ theta_row,
                                                 long long theta_ps, int g_begin, int g_end,
-                                                const double* __restrict__ tab, Store store) {
+                                                const double* __restrict__ tab, Store store,
+                                                int first, int stride) {
+#define TC_OCC_ITEM(DEC_, MOD_, U_)                                                              \
+  occupation_item_impl<DEC_, MOD_, U_>(plan, model, theta_row, theta_ps, g_begin, g_end, tab,   \
+                                       store, first, stride)
   if (model.modulate_with_cenocc) {   // rare: keep one generic instantiation
-    occupation_item_impl<true, true, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
+    TC_OCC_ITEM(true, true, 2);
   } else if (plan.unroll == kOccUnroll) {
-    if (model.decorated)
-      occupation_item_impl<true, false, kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
-    else
-      occupation_item_impl<false, false, kOccUnroll>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
+    if (model.decorated) TC_OCC_ITEM(true, false, kOccUnroll);
+    else TC_OCC_ITEM(false, false, kOccUnroll);
   } else if (model.decorated) {
-    occupation_item_impl<true, false, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
+    TC_OCC_ITEM(true, false, 2);
   } else {
-    occupation_item_impl<false, false, 2>(plan, model, theta_row, theta_ps, g_begin, g_end, tab, store);
+    TC_OCC_ITEM(false, false, 2);
   }
+#undef TC_OCC_ITEM
 }
 
 // Group range q of n_ranges = n_ranges_cen + n_ranges_sat: each galaxy type's groups are cut into
@@ -221,7 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
                     [&](int row, double occ, double) {
                       const int dst = args.pad_to_row[row];
                       if (live && dst >= 0) args.occ_out[draw * args.n_rows + dst] = occ;
-                    });
+                    },
+                    threadIdx.x >> 3 & 3, 4);
   }
 }
 

@@ -363,7 +363,9 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       if (j >= n_buf) flag_wait(&ctrl->empty[buf], (j / n_buf) * kWarps);
       double* Ws = smem + buf * tile_doubles;
       const int nt = idx % NT, q = idx / NT;
-      const int b = 8 * nt + (lane & 7);
+      // a one-draw call spreads all 32 lanes over the groups of the range (column 0 of the tile)
+      const bool one_draw = args.n_draws == 1;
+      const int b = one_draw ? 0 : 8 * nt + (lane & 7);
       long long draw = (tile_first + j) * BM + b;
       if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: recompute the last draw
       if (theta_base != nullptr) {
@@ -373,7 +375,8 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
                         g_begin, g_end, tab,
                         [&](int row, double occ, double nh) {
                           store_weight<NT, MODE>(Ws, row, b, occ * nh);
-                        });
+                        },
+                        one_draw ? lane : (lane >> 3), one_draw ? 32 : 4);
       } else {
         const int n_q = args.n_ranges_cen + args.n_ranges_sat;
         const int r_begin = (int)((long long)lay.n_pad * q / n_q);
