@@ -382,3 +382,66 @@ def test_device_math_accuracy(tb):
     _lib.check(lib.tc_debug_math(1, td.data_ptr(), ad.data_ptr(), out.data_ptr(), len(t), None))
     got = out.cpu().numpy()
     assert np.max(np.abs(got / t**alpha - 1)) < 1e-13
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_random_ragged_shuffled_tables(tb, seed):
+    """Randomised table shapes against the oracle: random numbers of mass / secondary bins, empty
+    (mass, sec) cells dropped at random (tabcorr.py:346-351 does that), rows in RANDOM order (the
+    kernels re-order centrals first internally), auto or cross, with or without the legacy
+    dist-index column, random n_gauss_prim and batch size; total and per-gal-type results."""
+    from oracle import tabcorr_oracle as orc
+    rng = np.random.default_rng(1000 + seed)
+    n_mass, n_sec = int(rng.integers(3, 40)), int(rng.integers(1, 4))
+    mode = 'auto' if rng.random() < 0.65 else 'cross'
+    n_r = int(rng.integers(1, 9))
+    kind = 'multipole' if (mode == 'auto' and rng.random() < 0.3) else 'wp'
+    tab = cases.synthetic.make_table(n_mass=n_mass, n_sec=n_sec, n_r=n_r, mode=mode, kind=kind,
+                                     seed=seed)
+    gal_type, n = tab['gal_type'], len(tab['gal_type'])
+    if mode == 'auto':   # dense symmetric form to re-pack after dropping / permuting rows
+        rows, cols = np.tril_indices(n)
+        dense = np.zeros((n_r, n, n))
+        dense[:, rows, cols] = tab['tpcf_matrix']
+        dense[:, cols, rows] = tab['tpcf_matrix']
+    keep = np.flatnonzero(rng.random(n) > 0.2)
+    if len(keep) < 2:
+        keep = np.arange(n)
+    keep = rng.permutation(keep)
+    gal_type = gal_type[keep]
+    if mode == 'auto':
+        sub = dense[:, keep][:, :, keep]
+        rows, cols = np.tril_indices(len(keep))
+        matrix = sub[:, rows, cols]
+    else:
+        matrix = tab['tpcf_matrix'][:, keep]
+    if rng.random() < 0.3:   # legacy table without the mass-function slope column
+        names = [k for k in gal_type.dtype.names if k != 'prim_haloprop_dist_index']
+        legacy = np.zeros(len(gal_type), dtype=[(k, gal_type.dtype[k]) for k in names])
+        for k in names:
+            legacy[k] = gal_type[k]
+        gal_type = legacy
+    n_gauss = int(rng.choice([1, 2, 3, 5, 7, 10, 12]))
+    n_draws = int(rng.integers(1, 300))
+    decorated = bool(rng.random() < 0.6)
+    draws = cases.synthetic.make_draws(n_draws, seed=seed, decorated=decorated)
+    halotab = tb.TabCorr.from_arrays(gal_type, matrix, tab['tpcf_shape'], tab['attrs'])
+    table = orc.OracleTable(gal_type, matrix, tab['tpcf_shape'], mode)
+    ngal, xi = halotab.predict_batch(draws, n_gauss_prim=n_gauss)
+    ngal_sep, xi_sep = halotab.predict_batch(draws, n_gauss_prim=n_gauss, separate_gal_type=True)
+    occ = halotab.mean_occupation_batch(draws, n_gauss_prim=n_gauss).cpu().numpy()
+    for i in sorted(set([0, n_draws // 2, n_draws - 1])):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=decorated)
+        occ_ref = orc.mean_occupation(table, model, n_gauss)
+        np.testing.assert_allclose(occ[i], occ_ref, rtol=1e-11, atol=1e-13 * max(1.0, occ_ref.max()))
+        ngal_ref, xi_ref = orc.predict(table, occ_ref)
+        close(ngal[i], ngal_ref)
+        close(xi[i], xi_ref)
+        ngal_ref, xi_ref = orc.predict(table, occ_ref, separate_gal_type=True)
+        assert sorted(xi_sep) == sorted(xi_ref) and sorted(ngal_sep) == sorted(ngal_ref)
+        total = np.max(np.sum([np.abs(v) for v in xi_ref.values()], axis=0))
+        for key in xi_ref:
+            np.testing.assert_allclose(xi_sep[key][i], xi_ref[key], rtol=RTOL,
+                                       atol=RTOL * 1e-3 * max(total, 1e-300))
+        for key in ngal_ref:
+            close(ngal_sep[key][i], ngal_ref[key])
