@@ -347,7 +347,7 @@ def test_small_batches_take_the_zero_copy_path_and_agree_bitwise(tb):
     tab = tb.synthetic.make_table(n_mass=12, n_sec=2, n_r=7)
     halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
                                      tab['attrs'])
-    big = tb.synthetic.make_draws(3000, seed=9, decorated=True)
+    big = tb.synthetic.make_draws(tc_mod.SMALL_BATCH + 1000, seed=9, decorated=True)
     ngal_ref, xi_ref = halotab.predict_batch(big)            # general (pipelined) path
     sep_ref = halotab.predict_batch(big, separate_gal_type=True)
     for n in (1, 7, 64, tc_mod.SMALL_BATCH):
