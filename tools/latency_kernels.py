@@ -1,12 +1,16 @@
+"""CUDA-event durations of predict_kernel / finalize_kernel for 1, 64 and 1024 draws with the
+parameters and the results in device memory or in mapped pinned host memory (what the zero-copy
+paths cost inside the kernels).  python tools/latency_kernels.py"""
 import os, sys, ctypes, json
-sys.path.insert(0, os.getcwd())
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np, torch, tabcorr_b200
 from tabcorr_b200 import _lib, synthetic
 from tabcorr_b200.models import ModelSpec, theta_from_params
 lib = _lib.load()
 for name in ('N60', 'N240'):
     if name == 'N60':
-        h = tabcorr_b200.TabCorr.read('tests/golden/bolplanck_wp.hdf5')
+        h = tabcorr_b200.TabCorr.read(os.path.join(ROOT, 'tests', 'golden', 'bolplanck_wp.hdf5'))
     else:
         tab = synthetic.make_table(n_mass=60, n_sec=2, n_r=20)
         h = tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], tab['attrs'])
