@@ -119,3 +119,27 @@ def test_header_prototypes_match_the_binding(lib):
     assert _lib.precision_code('3xTF32') == 1 and _lib.precision_code('fp64') == 0
     with pytest.raises(ValueError):
         _lib.precision_code('bf16')
+
+
+def test_header_is_valid_c99(tmp_path):
+    """include/tabcorr_b200.h and the plain-C client compile as C99 with -Wall -Werror (the ABI is
+    C, not C++); linking against the in-tree library resolves every symbol the client uses."""
+    import shutil
+    import subprocess
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    if shutil.which('gcc') is None or not os.path.isfile(os.path.join(cuda, 'include',
+                                                                       'cuda_runtime_api.h')):
+        pytest.skip('gcc or the CUDA runtime headers are not available')
+    root = os.path.dirname(os.path.dirname(HEADER))
+    source = os.path.join(root, 'tests', 'c_client', 'predict_client.c')
+    obj = str(tmp_path / 'client.o')
+    # the header alone is pedantic C99 (CUDA's own runtime headers are not)
+    alone = tmp_path / 'header_only.c'
+    alone.write_text('#include "tabcorr_b200.h"\nint main(void) { return TC_VERSION > 0 ? 0 : 1; }\n')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-c', str(alone), '-o',
+                    str(tmp_path / 'header_only.o'), '-I', os.path.dirname(HEADER)], check=True)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-c', source, '-o', obj,
+                    '-I', os.path.dirname(HEADER), '-I', os.path.join(cuda, 'include')], check=True)
+    subprocess.run(['gcc', '-o', str(tmp_path / 'client'), obj, '-L', os.path.dirname(_lib.LIB_PATH),
+                    '-l:libtabcorr_b200.so', '-L', os.path.join(cuda, 'lib64'), '-lcudart'],
+                   check=True)
