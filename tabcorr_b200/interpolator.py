@@ -192,35 +192,56 @@ class Interpolator:
             self._interp = None
 
     # ------------------------------------------------------------------ prediction
-    def _predict_one(self, spec, n_gauss, values, x_values, separate, extrapolate):
-        """Latency path of :meth:`predict`: one parameter set, persistent buffers, parameters,
-        coordinates, results and the out-of-range flag in pinned host memory that the kernels
-        access directly; one stream synchronisation, no copies, no allocations."""
+    def _small_capacity(self):
+        """Draws the persistent buffers of :meth:`_predict_small` hold: ``SMALL_BATCH``, less for
+        large grids (the per-table results of all draws stay below 64 MB of device memory)."""
+        from .tabcorr import SMALL_BATCH
+        self._ensure_device()
+        per_draw = len(self.tabcorr_list) * self._groups[0][0].n_r * 3 * 8
+        return int(max(1, min(SMALL_BATCH, (64 << 20) // per_draw)))
+
+    def _predict_small(self, spec, n_gauss, columns, x_columns, n_draws, separate, extrapolate,
+                       precision=_lib.TC_PRECISION_FP64):
+        """Latency path of :meth:`predict` and of small :meth:`predict_batch` calls (at most
+        ``SMALL_BATCH`` host draws): persistent buffers; the parameters (one pinned column per
+        parameter; in the launch arguments for a single draw), the coordinates, the results and
+        the out-of-range flag live in pinned host memory that the kernels access directly; one
+        stream synchronisation, no copies, no allocations.  ``columns`` / ``x_columns``: one array
+        ``[B]`` or scalar per kernel parameter / interpolation axis."""
         torch = _torch()
         self._ensure_device()
         first_group = self._groups[0][0]
         device = first_group.device
         n_tables = len(self.tabcorr_list)
         n_r = first_group.n_r
+        n_axes = len(self._keys)
         with self._one_lock:
             if self._one is None:
                 f64 = torch.float64
+                cap = self._small_capacity()
                 self._one = {
-                    'theta': torch.zeros(7, dtype=f64, pin_memory=True),
-                    'x': torch.zeros(len(self._keys), dtype=f64, pin_memory=True),
+                    'cap': cap,
+                    'theta': torch.zeros((7, cap), dtype=f64, pin_memory=True),
+                    'one': torch.zeros(7, dtype=f64),
+                    'x': torch.zeros((cap, n_axes), dtype=f64, pin_memory=True),
                     'flag': torch.zeros(1, dtype=torch.int32, pin_memory=True),
-                    'ngal': torch.zeros(2, dtype=f64, pin_memory=True),
-                    'xi': torch.zeros(n_r * 3, dtype=f64, pin_memory=True),
-                    'ngal_t': torch.zeros(n_tables * 2, dtype=f64, device=device),
-                    'xi_t': torch.zeros(n_tables * n_r * 3, dtype=f64, device=device),
+                    'ngal': torch.zeros(cap * 2, dtype=f64, pin_memory=True),
+                    'xi': torch.zeros(cap * n_r * 3, dtype=f64, pin_memory=True),
+                    'ngal_t': torch.zeros(cap * n_tables * 2, dtype=f64, device=device),
+                    'xi_t': torch.zeros(cap * n_tables * n_r * 3, dtype=f64, device=device),
                     'workspace': [torch.empty(max(8, max(
-                        int(self._lib.tc_predict_workspace_bytes(group.handle, 1, sep))
+                        int(self._lib.tc_predict_workspace_bytes(group.handle, cap, sep))
                         for sep in (0, 1))), dtype=torch.uint8, device=device)
                         for group, _ in self._groups],
                 }
             buf = self._one
-            buf['theta'].numpy()[:] = values
-            buf['x'].numpy()[:] = x_values
+            cap = buf['cap']
+            theta_np = buf['theta'].numpy()
+            for j, column in enumerate(columns):
+                theta_np[j, :n_draws] = column
+            x_np = buf['x'].numpy()
+            for d, column in enumerate(x_columns):
+                x_np[:n_draws, d] = column
             buf['flag'].numpy()[0] = 0
             n_ng, n_comp = (2 if separate else 1), first_group.n_comp(separate)
             n_cols = n_r * n_comp
@@ -229,24 +250,39 @@ class Interpolator:
             slot = 0
             for (group, members), workspace in zip(self._groups, buf['workspace']):
                 group.plan(n_gauss)
-                _lib.check(self._lib.tc_predict_one(
-                    group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(),
-                    int(separate), _lib.TC_PRECISION_FP64,
-                    buf['ngal_t'].data_ptr() + 8 * slot * n_ng,
-                    n_tables * n_ng, buf['xi_t'].data_ptr() + 8 * slot * n_cols, n_tables * n_cols,
-                    workspace.data_ptr(), workspace.numel(), stream.cuda_stream))
+                ngal_ptr = buf['ngal_t'].data_ptr() + 8 * slot * n_ng
+                xi_ptr = buf['xi_t'].data_ptr() + 8 * slot * n_cols
+                if n_draws == 1:
+                    buf['one'].numpy()[:] = theta_np[:, 0]
+                    _lib.check(self._lib.tc_predict_one(
+                        group.handle, ctypes.byref(model), int(n_gauss), buf['one'].data_ptr(),
+                        int(separate), int(precision), ngal_ptr, n_tables * n_ng, xi_ptr,
+                        n_tables * n_cols, workspace.data_ptr(), workspace.numel(),
+                        stream.cuda_stream))
+                else:
+                    _lib.check(self._lib.tc_predict_batch(
+                        group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(),
+                        cap, None, int(n_draws), int(separate), int(precision), ngal_ptr,
+                        n_tables * n_ng, xi_ptr, n_tables * n_cols, workspace.data_ptr(),
+                        workspace.numel(), stream.cuda_stream))
                 slot += len(members)
             for data, cols, out in ((buf['ngal_t'], n_ng, buf['ngal']), (buf['xi_t'], n_cols, buf['xi'])):
                 _lib.check(self._lib.tc_interp_apply_batch(
-                    self._interp, buf['x'].data_ptr(), 1, data.data_ptr(), cols, out.data_ptr(),
-                    int(bool(extrapolate)), buf['flag'].data_ptr(), stream.cuda_stream))
+                    self._interp, buf['x'].data_ptr(), int(n_draws), data.data_ptr(), cols,
+                    out.data_ptr(), int(bool(extrapolate)), buf['flag'].data_ptr(),
+                    stream.cuda_stream))
             stream.synchronize()
             if int(buf['flag'].numpy()[0]) != 0:
                 raise ValueError('The x-coordinates are outside of the interpolation range and '
                                  'extrapolation is turned off.')
-            ngal = buf['ngal'].numpy()[:n_ng].reshape(1, n_ng).copy()
-            xi = buf['xi'].numpy()[:n_cols].reshape(1, n_r, n_comp).copy()
+            ngal = buf['ngal'].numpy()[:n_draws * n_ng].reshape(n_draws, n_ng).copy()
+            xi = buf['xi'].numpy()[:n_draws * n_cols].reshape(n_draws, n_r, n_comp).copy()
         return self.tabcorr_list[0]._format_batch(ngal, xi, separate, False)
+
+    def _predict_one(self, spec, n_gauss, values, x_values, separate, extrapolate):
+        """One parameter set through :meth:`_predict_small`."""
+        return self._predict_small(spec, n_gauss, list(values), list(x_values), 1, separate,
+                                   extrapolate)
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, extrapolate=False,
                       model=None, as_numpy=True, precision='fp64', defer_range_check=False):
@@ -268,6 +304,18 @@ class Interpolator:
                 raise ValueError('The key {} is not present in the parameter dictionary of the '
                                  'model.'.format(key))
         spec = resolve_model(model) if model is not None else spec_from_params(params)
+        if as_numpy and not defer_range_check and spec.family == 0:
+            from .models import theta_columns
+            columns = theta_columns(params, spec)
+            x_columns = [np.asarray(params[key], dtype=np.float64) for key in self._keys]
+            sizes = [c.shape[0] for c in columns + x_columns if np.ndim(c) > 0]
+            n_small = max(sizes + [1])
+            first_mode = self._groups[0][0].mode
+            if n_small <= self._small_capacity() and all(size == n_small for size in sizes):
+                code = _lib.precision_code(precision) if first_mode == 'auto' \
+                    else _lib.TC_PRECISION_FP64
+                return self._predict_small(spec, int(n_gauss_prim), columns, x_columns, n_small,
+                                           bool(separate_gal_type), extrapolate, code)
         device = self._groups[0][0].device
         theta = theta_to_device(params, spec, device)
         n_draws = theta.shape[0]

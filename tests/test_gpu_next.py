@@ -415,3 +415,38 @@ def test_sweep_over_interpolator_and_other_family(tb):
     ref = halotab.predict_batch({k: sample[:, j] for j, k in enumerate(l11.keys)}, model=model,
                                 pipeline_chunk=0)
     assert np.array_equal(ngal, ref[0]) and np.array_equal(xi, ref[1])
+
+
+def test_interpolator_small_batches_agree_bitwise(tb):
+    """Interpolator.predict_batch with few host draws takes the zero-copy path (persistent pinned
+    buffers); the results equal the general path's bit for bit, errors are reported alike."""
+    tables, param_table, _ = cases.grid_case('grid2d')
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    cap = interp._small_capacity()
+    assert 1 <= cap <= 4096
+    extra = {'alpha_s': (0.8, 1.2), 'log_eta': (float(np.min(param_table['log_eta'])),
+                                               float(np.max(param_table['log_eta'])))}
+    big = cases.synthetic.make_draws(cap + 500, seed=14, decorated=True, extra=extra)
+    ngal_ref, xi_ref = interp.predict_batch(big)             # general path
+    sep_ref = interp.predict_batch(big, separate_gal_type=True)
+    for n in (1, 5, 64, cap):
+        small = {k: v[:n] for k, v in big.items()}
+        ngal, xi = interp.predict_batch(small)
+        assert interp._one is not None and ngal.shape == (n,)
+        assert np.array_equal(ngal, ngal_ref[:n]) and np.array_equal(xi, xi_ref[:n])
+        ngal_d, xi_d = interp.predict_batch(small, separate_gal_type=True)
+        for key in xi_d:
+            assert np.array_equal(xi_d[key], sep_ref[1][key][:n])
+        for key in ngal_d:
+            assert np.array_equal(ngal_d[key], sep_ref[0][key][:n])
+    outside = {k: v[:9].copy() for k, v in big.items()}
+    outside['alpha_s'][4] = 1.7
+    with pytest.raises(ValueError, match='interpolation range'):
+        interp.predict_batch(outside)
+    ngal_x, xi_x = interp.predict_batch(outside, extrapolate=True)
+    assert np.all(np.isfinite(xi_x)) and np.array_equal(ngal_x[:4], ngal_ref[:4])
+    # scalars broadcast; the single-model API still agrees with the batch
+    model = tb.PrebuiltHodModelFactory('decorated-zheng07', threshold=-20)
+    model.param_dict.update({k: float(v[3]) for k, v in big.items()})
+    ngal_1, xi_1 = interp.predict(model)
+    assert ngal_1 == ngal_ref[3] and np.array_equal(xi_1, xi_ref[3])
