@@ -37,7 +37,7 @@ N_MASS, N_SEC, N_R, N_GAUSS = 60, 2, 20, 10
 DRAWS_PER_GPU = 100000
 # dram__bytes_read.sum + dram__bytes_write.sum of predict_kernel for this workload (one launch =
 # 1e5 draws), from the committed ncu capture; only reported for the default batch size
-NCU_DRAM_BYTES_PER_LAUNCH = 22611712 + 14923520
+NCU_DRAM_BYTES_PER_LAUNCH = 31631104 + 13955840
 METRIC = 'HOD predictions/sec (ngal+wp)'
 UNIT = 'predictions/s'
 
