@@ -11,6 +11,8 @@ from .interpolator import Interpolator  # noqa: F401,E402
 from . import database  # noqa: F401,E402
 from .tableset import TableSet  # noqa: F401,E402
 from . import sweep  # noqa: F401,E402
+from . import distributed  # noqa: F401,E402
+from . import synthetic  # noqa: F401,E402
 from .multipole import tabcorr_s_mu_to_multipole, tpcf_multipole  # noqa: F401,E402
 from . import models  # noqa: F401,E402
 from .models import PrebuiltHodModelFactory  # noqa: F401,E402
