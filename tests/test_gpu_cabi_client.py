@@ -86,3 +86,27 @@ def test_c_client_matches_python_api(client, tmp_path, name, separate):
     else:
         assert np.array_equal(ngal.cpu().numpy(), ngal_c[:, 0])
         assert np.array_equal(xi.cpu().numpy().reshape(n_draws, n_r), xi_c[:, :, 0])
+
+
+def test_integration_md_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would add)
+    is executed as written -- only the library path is substituted -- and agrees with the
+    package's own binding bit for bit."""
+    import re
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import tabcorr_b200 as tb
+    from tabcorr_b200 import _lib
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = re.search(r'```python\n(# tabcorr/_b200\.py.*?)```', text, flags=re.S).group(1)
+    block = block.replace("'libtabcorr_b200.so'", repr(_lib.LIB_PATH))
+    namespace = {}
+    exec(compile(block, 'INTEGRATION.md', 'exec'), namespace)
+    halotab = tb.TabCorr.read(os.path.join(ROOT, 'tests', 'golden', 'bolplanck_wp.hdf5'))
+    handle = namespace['upload'](halotab)
+    draws = tb.synthetic.make_draws(300, seed=8)
+    theta = tb.models.theta_from_params(draws, None, tb.models.ModelSpec())
+    ngal, xi = namespace['predict_batch'](handle, theta, 19)
+    ngal_ref, xi_ref = halotab.predict_batch(draws)
+    assert np.array_equal(ngal, ngal_ref) and np.array_equal(xi, xi_ref)
