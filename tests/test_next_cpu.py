@@ -137,3 +137,30 @@ def test_resolve_model_families():
     with pytest.raises(NotImplementedError):
         models.PrebuiltHodModelFactory('tinker13')
     assert models.spec_from_params({k: 1.0 for k in models.THETA_KEYS}).decorated
+
+
+def test_leauthaud11_oracle_known_answers():
+    """Regression pins of the leauthaud11 restatement (computed by this oracle when it was
+    written -- NOT reference values: halotools is absent, see the oracle header)."""
+    from oracle import tabcorr_oracle as orc
+    mass = 10**np.array([11.5, 12.5, 13.5, 14.5])
+    model = orc.Leauthaud11Oracle()
+    np.testing.assert_allclose(
+        model.mean_occupation_centrals(prim_haloprop=mass, sec_haloprop_percentile=np.full(4, .3)),
+        [0.00041245588971217106, 0.59916378405937, 0.9768642259131576, 0.9995655939151888],
+        rtol=1e-10)
+    np.testing.assert_allclose(
+        model.mean_occupation_satellites(prim_haloprop=mass, sec_haloprop_percentile=np.full(4, .3)),
+        [1.108321904656615e-08, 0.04272086498081341, 1.2170524513583085, 13.168140436737644],
+        rtol=1e-10)
+    model = orc.Leauthaud11Oracle(threshold=11.0, redshift=0.5, decorated=True,
+                                  modulate_with_cenocc=False)
+    pct = np.array([.2, .8, .2, .8])
+    np.testing.assert_allclose(
+        model.mean_occupation_centrals(prim_haloprop=mass, sec_haloprop_percentile=pct),
+        [5.797862190348724e-13, 0.006104036664566104, 0.15264881029766253, 0.9135468664557148],
+        rtol=1e-9)
+    np.testing.assert_allclose(
+        model.mean_occupation_satellites(prim_haloprop=mass, sec_haloprop_percentile=pct),
+        [6.870067016061366e-06, 0.007813292140338041, 0.03746174399873051, 1.1654583688653277],
+        rtol=1e-10)
