@@ -450,3 +450,43 @@ def test_interpolator_small_batches_agree_bitwise(tb):
     model.param_dict.update({k: float(v[3]) for k, v in big.items()})
     ngal_1, xi_1 = interp.predict(model)
     assert ngal_1 == ngal_ref[3] and np.array_equal(xi_1, xi_ref[3])
+
+
+def test_concurrent_host_threads(tb):
+    """SURVEY 8(b) ownership/threading: the reference mutates `self` lazily on the first call;
+    here the derived tables are immutable and the persistent latency buffers are guarded, so host
+    threads may share one table (and one Interpolator) -- every call returns what a serial call
+    returns."""
+    import threading
+    tab = tb.synthetic.make_table(n_mass=20, n_sec=2, n_r=9)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    tables, param_table, _ = cases.grid_case('grid1dx')
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    lo, hi = float(np.min(param_table['log_eta'])), float(np.max(param_table['log_eta']))
+    n_threads, n_calls = 4, 40
+    draws = [tb.synthetic.make_draws(7 + 13 * k, seed=50 + k, decorated=True,
+                                     extra={'log_eta': (lo, hi)}) for k in range(n_threads)]
+    serial = [(halotab.predict_batch(d), halotab.predict_batch(d, n_gauss_prim=3),
+               interp.predict_batch(d)) for d in draws]
+    errors = []
+
+    def worker(k):
+        try:
+            for call in range(n_calls):
+                a = halotab.predict_batch(draws[k])
+                b = halotab.predict_batch(draws[k], n_gauss_prim=3)
+                c = interp.predict_batch(draws[k])
+                for got, ref in zip((a, b, c), serial[k]):
+                    if not (np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])):
+                        errors.append((k, call))
+                        return
+        except Exception as exc:   # pragma: no cover - reported below
+            errors.append((k, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert errors == []
