@@ -156,6 +156,8 @@ class DeviceTableGroup:
         return 3 if self.mode == 'auto' else 2
 
     def _workspace_for(self, n_draws, separate):
+        """Scratch buffer of the current stream (kernels of different streams may overlap, so
+        every stream that launches on this table gets its own)."""
         torch = _torch()
         need = int(self.lib.tc_predict_workspace_bytes(self.handle, int(n_draws), int(separate)))
         if need == 0 and n_draws > 0:
@@ -163,9 +165,14 @@ class DeviceTableGroup:
                 'table too large for the CUDA kernel: the weights of 8 draws x {} halo bins do not '
                 'fit the 227 KB shared-memory tile (at most ~3500 bins are supported)'.format(
                     self.n_rows))
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        if self._workspace is None:
+            self._workspace = {}
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        current = self._workspace.get(stream)
+        if current is None or current.numel() < need:
+            current = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._workspace[stream] = current
+        return current
 
     @staticmethod
     def _model_struct(spec):

@@ -490,3 +490,34 @@ def test_concurrent_host_threads(tb):
     for t in threads:
         t.join()
     assert errors == []
+
+
+def test_two_streams_share_a_table(tb):
+    """Launches on different CUDA streams may overlap: each stream has its own scratch buffer."""
+    import threading
+    import torch
+    tab = tb.synthetic.make_table(n_mass=30, n_sec=2, n_r=6)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    draws = [tb.synthetic.make_draws(20000, seed=60 + k) for k in range(2)]
+    theta = [torch.from_numpy(tb.models.theta_from_params(d, None, tb.models.ModelSpec())).cuda()
+             for d in draws]
+    serial = [halotab.predict_batch(t, as_numpy=False) for t in theta]
+    torch.cuda.synchronize()
+    results = [None, None]
+
+    def worker(k):
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for _ in range(10):
+                results[k] = halotab.predict_batch(theta[k], as_numpy=False)
+        stream.synchronize()
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(2):
+        assert torch.equal(results[k][0], serial[k][0]) and torch.equal(results[k][1], serial[k][1])
+    assert len(halotab._ensure_device()._workspace) >= 2
