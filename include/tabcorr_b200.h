@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 103
+#define TC_VERSION 104
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -166,6 +166,11 @@ int tc_interp_apply_batch(tc_interp* interp, const double* x_dev, int64_t n_draw
 /* Live FP64 tensor (DMMA) peak of the device in TFLOP/s, the roofline denominator bench.py
  * reports (MEASURED_PEAKS.json carries no FP64 figure). */
 int tc_measure_dmma_peak(int device, double* tflops_out);
+
+/* Live FP64 ALU (DFMA) peak of the device in TFLOP/s: the roofline denominator of the paths that
+ * are bound by the occupation arithmetic (cross tables tabcorr.py:648-649, mean_occupation
+ * tabcorr.py:465-578), where bench.py reports node evaluations/s. */
+int tc_measure_dfma_peak(int device, double* tflops_out);
 
 /* Element-wise evaluation of the occupation kernel's table-driven math on the current device, for
  * accuracy tests: kind 0: out = 0.5 (1 + erf(x)); kind 1: out = x^y for x > 0. */

@@ -255,8 +255,16 @@ def mean_occupation(table, model, n_gauss_prim=10, **occ_kwargs):
     gt = table.gal_type
     log_min = gt['log_prim_haloprop_min']
     d_log = gt['log_prim_haloprop_max'] - log_min
-    x_gauss, w_gauss = np.polynomial.legendre.leggauss(n_gauss_prim)  # :544
-    x_gauss = (x_gauss + 1) / 2  # :546
+    # :543-546 the reference caches the Gauss-Legendre rule on the table object
+    cache = getattr(table, '_gauss_cache', None)
+    if cache is None or len(cache[0]) != n_gauss_prim:
+        x_gauss, w_gauss = np.polynomial.legendre.leggauss(n_gauss_prim)  # :544
+        cache = ((x_gauss + 1) / 2, w_gauss)  # :546
+        try:
+            table._gauss_cache = cache
+        except AttributeError:
+            pass
+    x_gauss, w_gauss = cache
     prim = 10**(log_min + d_log * x_gauss[:, np.newaxis]).T.ravel()  # :548-549
     pct = np.repeat(gt['sec_haloprop_percentile'], n_gauss_prim)  # :550-551
     names = np.repeat(table.gal_type_names, n_gauss_prim)  # :552

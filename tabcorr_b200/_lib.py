@@ -36,7 +36,7 @@ SYMBOLS = (
     'tc_last_error', 'tc_version', 'tc_model_n_theta', 'tc_table_create', 'tc_table_destroy', 'tc_table_n_rows',
     'tc_table_n_r', 'tc_table_n_tables', 'tc_table_plan', 'tc_occupation_batch',
     'tc_predict_workspace_bytes', 'tc_predict_batch', 'tc_predict_one', 'tc_interp_create', 'tc_interp_destroy',
-    'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math')
+    'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_measure_dfma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math')
 
 
 class TabCorrB200Error(RuntimeError):
@@ -109,6 +109,8 @@ def load():
                                           ctypes.c_int, vp, vp]
     lib.tc_measure_dmma_peak.restype = ctypes.c_int
     lib.tc_measure_dmma_peak.argtypes = [ctypes.c_int, c_double_p]
+    lib.tc_measure_dfma_peak.restype = ctypes.c_int
+    lib.tc_measure_dfma_peak.argtypes = [ctypes.c_int, c_double_p]
     lib.tc_profile_enable.restype = ctypes.c_int
     lib.tc_profile_enable.argtypes = [ctypes.c_int]
     lib.tc_profile_read.restype = ctypes.c_int

@@ -100,4 +100,21 @@ __global__ void dmma_peak_kernel(double* out, int iters) {
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 ALU (DFMA) peak: 8 independent chains per thread.  The roofline denominator of the paths
+// bound by the occupation arithmetic (cross tables, mean_occupation_batch).
+__global__ void dfma_peak_kernel(double* out, int iters) {
+  const double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9 * threadIdx.x;
+  double c[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) c[i] = i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = fma(c[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
