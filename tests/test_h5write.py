@@ -156,3 +156,138 @@ def test_reader_rejects_damaged_files_cleanly(tmp_path, golden_dir):
         tabcorr_b200.TabCorr.read(bad, upload=False)
     with pytest.raises(OSError):
         tabcorr_b200.TabCorr.read(tmp_path / 'missing.hdf5', upload=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# region-by-region comparison of write(read(fixture)) with the h5py-written fixture
+# ---------------------------------------------------------------------------------------------
+_MESSAGE_NAMES = {0x0000: 'nil', 0x0001: 'dataspace', 0x0003: 'datatype', 0x0005: 'fill_value',
+                  0x0008: 'layout', 0x000C: 'attribute', 0x0010: 'continuation',
+                  0x0011: 'symbol_table', 0x0012: 'modification_time'}
+
+
+def _regions(fname):
+    """Decompose a classic-format HDF5 file into address-free regions:
+    {(object path, region name): bytes}.  Addresses inside messages (data address of the layout
+    message, B-tree / heap addresses of the symbol-table message, global-heap references of
+    variable-length string attributes) are replaced by what they point to, so that two files
+    with the same content but a different placement of their blocks compare equal."""
+    f = h5mini.File(fname)
+    r = f._r
+    out = {('', 'superblock[0:24]'): bytes(r.buf[0:24]),
+           ('', 'superblock.addresses'): bytes(r.buf[24:40]) + bytes(r.buf[48:56]),
+           ('', 'superblock.eof == file size'): struct.pack('<?', r.u64(40) == len(r.raw))}
+
+    def visit(obj, path):
+        counts = {}
+        for mtype, flags, body, size in obj._messages:
+            name = _MESSAGE_NAMES.get(mtype, hex(mtype))
+            data = bytes(r.buf[body:body + size])
+            if mtype in (0x0000, 0x0010):      # padding / continuation: placement only
+                counts[name] = counts.get(name, 0) + 1
+                continue
+            if mtype == 0x0012:
+                counts[name] = counts.get(name, 0) + 1
+                continue
+            if mtype == 0x0008:                # layout v3 contiguous: version, class, address, size
+                assert data[0] == 3 and data[1] == 1
+                address, nbytes = struct.unpack_from('<QQ', data, 2)
+                out[(path, 'layout')] = data[:2] + struct.pack('<Q', nbytes)
+                out[(path, 'raw data')] = bytes(r.buf[address + r.base:address + r.base + nbytes])
+                continue
+            if mtype == 0x0011:
+                btree, heap = struct.unpack_from('<QQ', data, 0)
+                links = r.group_links(btree + r.base, heap + r.base)
+                out[(path, 'links in B-tree order')] = '\x00'.join(links).encode()
+                continue
+            if mtype == 0x000C:
+                version = data[0]
+                name_size, dt_size, ds_size = struct.unpack_from('<HHH', data, 2)
+                attr = data[8:8 + name_size].rstrip(b'\x00').decode()
+                p = 8 + (name_size + 7) // 8 * 8
+                dtype = data[p:p + dt_size]
+                p += (dt_size + 7) // 8 * 8
+                space = data[p:p + ds_size]
+                p += (ds_size + 7) // 8 * 8
+                value = data[p:]
+                if dtype[0] & 0x0f == 9:       # vlen: length, global heap address, index
+                    length, gaddr, gidx = struct.unpack_from('<IQI', value, 0)
+                    value = struct.pack('<I', length) + r.global_heap_object(gaddr + r.base, gidx)
+                out[(path, 'attribute {!r}: header'.format(attr))] = bytes([version]) + data[2:8]
+                out[(path, 'attribute {!r}: datatype'.format(attr))] = dtype
+                out[(path, 'attribute {!r}: dataspace'.format(attr))] = space
+                out[(path, 'attribute {!r}: value'.format(attr))] = value
+                continue
+            out[(path, name)] = bytes([flags]) + data
+        for name, count in counts.items():
+            out[(path, 'count of {} messages'.format(name))] = struct.pack('<I', count)
+        out[(path, 'object header version')] = bytes(r.buf[obj._addr:obj._addr + 2])
+        if isinstance(obj, h5mini.Group):
+            for key in obj.keys():
+                visit(obj[key], (path + '/' + key) if path else key)
+
+    visit(f, '')
+    return out
+
+
+@pytest.mark.parametrize('name', ['bolplanck_wp.hdf5', 'bolplanck_ds.hdf5', 'ds_efficient.hdf5'])
+def test_rewritten_fixture_equals_the_h5py_file_region_by_region(tmp_path, golden_dir, name):
+    """``write(read(fixture))`` against the file h5py + astropy wrote (the reference's
+    ``TabCorr.write``, tabcorr/tabcorr.py:418-463, ``Interpolator.write``,
+    tabcorr/interpolator.py:98-122): every dataspace, datatype, fill-value and layout message,
+    every attribute (header, datatype, dataspace, value), every group's links and every
+    dataset's raw bytes are IDENTICAL; the complete list of differences is enumerated below and
+    is placement/bookkeeping only (libhdf5 is absent here, so this is the strongest evidence
+    available that libhdf5 will read these files as it reads its own)."""
+    source = os.path.join(golden_dir, name)
+    if name == 'ds_efficient.hdf5':
+        obj = tabcorr_b200.Interpolator.read(source)
+    else:
+        obj = tabcorr_b200.TabCorr.read(source, upload=False)
+    out = tmp_path / name
+    obj.write(out)
+    ref, new = _regions(source), _regions(out)
+    if name == 'bolplanck_ds.hdf5':
+        # the fixture holds arg_1, arg_2 (arg_0, the particle positions, fell under the
+        # max_args_size rule, tabcorr.py:450-453); read() collects the existing keys in order
+        # (:401-404) and write() enumerates them from 0 again (:450) -- in the reference too
+        renamed = {}
+        for (path, region), value in ref.items():
+            path = {'tpcf_args/arg_1': 'tpcf_args/arg_0', 'tpcf_args/arg_2': 'tpcf_args/arg_1'}.get(
+                path, path)
+            if (path, region) == ('tpcf_args', 'links in B-tree order'):
+                value = b'arg_0\x00arg_1'
+            renamed[(path, region)] = value
+        ref = renamed
+
+    differences = set()
+    for key in sorted(set(ref) | set(new)):
+        if ref.get(key) != new.get(key):
+            differences.add(key)
+    # what may differ, and why:
+    allowed = set()
+    for path, region in differences:
+        # libhdf5 stamps every dataset with a modification time and pads object headers with
+        # NIL messages / continuation blocks; the writer emits neither (all optional)
+        if region.startswith('count of '):
+            allowed.add((path, region))
+        # h5py stored 'simname' as a fixed-length string (numpy bytes_ from astropy metadata);
+        # the writer stores every str attribute as a variable-length string like 'tpcf'/'mode'
+        # (both decode to the same str in h5py and in TabCorr.read, tabcorr.py:395-397)
+        if region in ("attribute 'simname': datatype", "attribute 'simname': value",
+                      "attribute 'simname': header"):
+            allowed.add((path, region))
+        # the legacy root attribute 'spline' of old Interpolator files is not read by
+        # Interpolator.read (interpolator.py:72-96) and not written by Interpolator.write
+        if path == '' and region.startswith("attribute 'spline'"):
+            allowed.add((path, region))
+        # base/free-space/driver addresses: the fixture has a non-trivial free-space state
+        if (path, region) == ('', 'superblock.addresses'):
+            allowed.add((path, region))
+    assert differences <= allowed, sorted(differences - allowed)
+    # and the regions that carry the content are all there
+    assert sum(1 for _, region in ref if region == 'raw data') == \
+        sum(1 for _, region in new if region == 'raw data') > 0
+    for key, value in ref.items():
+        if key[1] == 'raw data':
+            assert new[key] == value, key
