@@ -36,8 +36,12 @@ if ROOT not in sys.path:
 N_MASS, N_SEC, N_R, N_GAUSS = 60, 2, 20, 10
 DRAWS_PER_GPU = 100000
 # dram__bytes_read.sum + dram__bytes_write.sum of predict_kernel for this workload (one launch =
-# 1e5 draws), from the committed ncu capture; only reported for the default batch size
+# 1e5 draws).  NOT measured by this run: the constant is copied from the committed ncu --set full
+# capture named in NCU_TRAFFIC_SOURCE; only reported for the default batch size
 NCU_DRAM_BYTES_PER_LAUNCH = 31631104 + 13955840
+NCU_TRAFFIC_SOURCE = 'profiles/r01_predict_kernel_N240_R20.md'
+# algorithmic HBM bytes per launch: 7 parameters in, 1 + R results out per draw, the table once
+ALGORITHMIC_BYTES_PER_DRAW = 8 * 7 + 8 * (1 + N_R)
 METRIC = 'HOD predictions/sec (ngal+wp)'
 UNIT = 'predictions/s'
 
@@ -56,6 +60,16 @@ def workload_config(n_draws):
 def algorithmic_flops(n, r):
     """dense W.M_r plus row-dot, per prediction."""
     return 2.0 * r * n * n + 2.0 * r * n
+
+
+def executed_flops(n, r, mode='auto'):
+    """Tensor flops the kernel issues per prediction: the lower triangle of the padded table in
+    8 x 8 DMMA blocks (auto: the reference's packed prefactor-2 sum, tabcorr/tabcorr.py:626-647);
+    cross tables: a 16-bin tile of radial bins times the padded rows."""
+    n_pad = (n + 15) // 16 * 16
+    if mode == 'auto':
+        return 2.0 * r * 64.0 * (n_pad // 8) * (n_pad // 8 + 1) / 2
+    return 2.0 * ((r + 15) // 16 * 16) * n_pad
 
 
 # ---------------------------------------------------------------------------------------------
@@ -144,6 +158,158 @@ def run_reference_arm(args):
         'gpu_launches': 0,
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, short device-timed runs (the `configs` block)
+# ---------------------------------------------------------------------------------------------
+# FP64 instructions the occupation kernel issues per quadrature-node evaluation (DFMA + DADD +
+# DMUL of the ncu capture in profiles/r01_occupation_kernel_N240.md: 94.0e6 warp instructions for
+# 1.2e8 evaluations x 32 lanes); each counted as one FMA = 2 flops against the DFMA peak
+FP64_OPS_PER_EVALUATION = 25.1
+
+
+def run_configs(args, world, rank, local_rank, lib, peak_dmma):
+    """BASELINE.json configs[0..4] beside the headline: real bolplanck tables (cfg1), decorated
+    multipoles (cfg3), database-style Interpolator + per-draw cosmology (cfg4) and, on any
+    number of GPUs, the fixed-size sweep of configs[4].  One dict per configuration."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import tabcorr_b200
+    from tabcorr_b200 import _lib, synthetic, sweep
+    from tabcorr_b200.models import ModelSpec, theta_from_params
+
+    out = []
+    n_draws = args.config_draws
+    reps = 3
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    golden = os.path.join(ROOT, 'tests', 'golden')
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(reps):
+            flush.fill_(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.median(ms))
+
+    def table_of(tab):
+        return tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'],
+                                                tab['tpcf_shape'], tab['attrs'],
+                                                device=local_rank)
+
+    def device_ms(halotab, draws, decorated=False, **kw):
+        spec = ModelSpec(decorated=decorated)
+        theta = torch.from_numpy(theta_from_params(draws, None, spec)).cuda()
+        return timed(lambda: halotab.predict_batch(theta, model=spec, as_numpy=False, **kw))
+
+    def frac(n, r, mode, ms, n_d):
+        return executed_flops(n, r, mode) * n_d / (ms * 1e-3) / (peak_dmma * 1e12)
+
+    if rank == 0:
+        peak_dfma = ctypes.c_double()
+        _lib.check(lib.tc_measure_dfma_peak(local_rank, ctypes.byref(peak_dfma)))
+        # ---- cfg1: the README workflow's real tables ------------------------------------------
+        draws = synthetic.make_draws(n_draws, seed=1)
+        halotab = tabcorr_b200.TabCorr.read(os.path.join(golden, 'bolplanck_wp.hdf5'),
+                                            device=local_rank)
+        ms = device_ms(halotab, draws)
+        out.append({'config': 'cfg1 real bolplanck_wp.hdf5 (auto, N=60, R=19), zheng07',
+                    'n_draws': n_draws, 'ms': ms, 'preds_per_s': n_draws / ms * 1e3,
+                    'executed_frac': frac(60, 19, 'auto', ms, n_draws)})
+        halotab = tabcorr_b200.TabCorr.read(os.path.join(golden, 'bolplanck_ds.hdf5'),
+                                            device=local_rank)
+        ms = device_ms(halotab, draws)
+        evals = n_draws * 60.0 * N_GAUSS / (ms * 1e-3)
+        out.append({'config': 'cfg1 real bolplanck_ds.hdf5 (cross, N=60, R=19), zheng07',
+                    'n_draws': n_draws, 'ms': ms, 'preds_per_s': n_draws / ms * 1e3,
+                    'bound': 'fp64 alu (occupation arithmetic; 2RN contraction flops per draw)',
+                    'occupation_evaluations_per_s': evals,
+                    'fp64_ops_per_evaluation': FP64_OPS_PER_EVALUATION,
+                    'dfma_peak_tflops': peak_dfma.value,
+                    'fp64_alu_frac': evals * FP64_OPS_PER_EVALUATION * 2.0 /
+                    (peak_dfma.value * 1e12)})
+        # ---- cfg3: multipoles, decorated zheng07 ----------------------------------------------
+        tab = synthetic.make_table(n_mass=N_MASS, n_sec=N_SEC, n_r=42, kind='multipole',
+                                   tpcf_shape=(3, 14))
+        draws_dec = synthetic.make_draws(n_draws, seed=1, decorated=True)
+        ms = device_ms(table_of(tab), draws_dec, decorated=True, n_gauss_prim=N_GAUSS)
+        out.append({'config': 'cfg3 N=240 R=3x14 multipoles, decorated zheng07, G=10',
+                    'n_draws': n_draws, 'ms': ms, 'preds_per_s': n_draws / ms * 1e3,
+                    'executed_frac': frac(240, 42, 'auto', ms, n_draws)})
+        # ---- cfg4: database-style Interpolator, per-draw cosmology ----------------------------
+        axes = {'alpha_s': np.linspace(0.8, 1.2, 4), 'log_eta': np.log10(np.geomspace(1 / 3, 3, 4))}
+        interps = []
+        for c in range(8):
+            tables, param_table = synthetic.make_grid_tables(
+                axes, n_mass=30, n_sec=2, n_r=14, kind='wp', seed=100 + c, n_h_scale=1 + 0.1 * c)
+            interps.append(tabcorr_b200.Interpolator([table_of(t) for t in tables], param_table))
+        table_set = tabcorr_b200.TableSet(interps)
+        extra = {k: (float(v.min()), float(v.max())) for k, v in axes.items()}
+        draws4 = synthetic.make_draws(n_draws, seed=2, extra=extra)
+        index = np.random.default_rng(3).integers(0, 8, n_draws)
+        table_set.predict_batch(draws4, index)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            table_set.predict_batch(draws4, index)
+        ms_set = (time.perf_counter() - t0) / reps * 1e3
+        one = {k: v[index == 0] for k, v in draws4.items()}
+        n_one = int((index == 0).sum())
+        ms_one = timed(lambda: interps[0].predict_batch(one, as_numpy=False))
+        out.append({'config': 'cfg4 database-style wp Interpolator T=16 (N=120, R=14), 8 cosmologies '
+                              'by TableSet, per-draw cosmology',
+                    'n_draws': n_draws, 'tableset_host_to_host_ms': ms_set,
+                    'tableset_preds_per_s_host_to_host': n_draws / ms_set * 1e3,
+                    'single_interpolator_draws': n_one, 'single_interpolator_ms': ms_one,
+                    'single_interpolator_preds_per_s': n_one / ms_one * 1e3,
+                    'executed_frac_single_interpolator': frac(120, 14 * 16, 'auto', ms_one, n_one)})
+        del table_set, interps
+
+    # ---- cfg5: fixed-size sweep sharded over the GPUs (strong scaling, gather to rank 0) -----
+    tab = synthetic.make_table(n_mass=125, n_sec=2, n_r=20)
+    halotab = table_of(tab)
+    prior = sweep.UniformPrior(sweep.ZHENG07_PRIOR, seed=5)
+    totals = {'n': 0}
+
+    def consume(lo, hi, slab):
+        totals['n'] += hi - lo
+
+    def run(n):
+        totals['n'] = 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sweep.predict_sweep(halotab, prior, n, chunk=args.sweep_chunk, consume=consume)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return time.perf_counter() - t0
+
+    run(min(args.sweep_draws, world * args.sweep_chunk))
+    seconds = run(args.sweep_draws)
+    if world > 1:
+        t = torch.tensor([seconds], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds = float(t.item())
+    if rank == 0:
+        out.append({'config': 'cfg5 sweep N=500 R=20 wp zheng07: {} draws in total (fixed, strong '
+                              'scaling) generated on the device, chunks of {}, gather to rank 0'
+                              .format(args.sweep_draws, args.sweep_chunk),
+                    'n_gpus': world, 'n_draws': args.sweep_draws, 'seconds': seconds,
+                    'preds_per_s': args.sweep_draws / seconds,
+                    'executed_frac_per_gpu': executed_flops(500, 20) * args.sweep_draws / seconds /
+                    (peak_dmma * 1e12) / world})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -269,6 +435,7 @@ def run_gpu_arm(args):
     n_draws = args.draws
     tab = synthetic.make_table(n_mass=N_MASS, n_sec=N_SEC, n_r=N_R)
     n_rows = len(tab['gal_type'])
+    table_bytes = int(np.asarray(tab['tpcf_matrix']).size * 8)
     halotab = tabcorr_b200.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'],
                                                tab['tpcf_shape'], tab['attrs'], device=local_rank)
     all_draws = synthetic.make_draws(n_draws * world, seed=1)
@@ -357,29 +524,40 @@ def run_gpu_arm(args):
         same = (np.array_equal(ngal_host[:n_draws], ngal[:, 0].cpu().numpy()) and
                 np.array_equal(xi_host[:n_draws], xi[:, :, 0].cpu().numpy()))
 
+    peak = ctypes.c_double()
+    _lib.check(lib.tc_measure_dmma_peak(local_rank, ctypes.byref(peak)))
+    # free the headline workload's buffers before the other configurations allocate theirs
+    del flush
+    configs = None
+    if not args.no_configs:
+        configs = run_configs(args, world, rank, local_rank, lib, peak.value)
+
     if rank == 0:
-        peak = ctypes.c_double()
-        _lib.check(lib.tc_measure_dmma_peak(local_rank, ctypes.byref(peak)))
-        flops = algorithmic_flops(n_rows, N_R) * n_draws
         k_ms = float(np.mean(kernel_ms))
-        achieved = flops / (k_ms * 1e-3) * 1e-12
-        n_pad = (n_rows + 15) // 16 * 16
-        executed = 2.0 * N_R * 64.0 * (n_pad // 8) * (n_pad // 8 + 1) / 2 * n_draws
+        executed = executed_flops(n_rows, N_R) * n_draws
+        dense = algorithmic_flops(n_rows, N_R) * n_draws
+        achieved = executed / (k_ms * 1e-3) * 1e-12
         roofline = {
             'bound': 'tensor', 'kernel': 'predict_kernel<7, auto> (fused occupation + DMMA quadratic '
                                          'form; 2 W tiles of 56 draws at N=240)',
             'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
-            'frac': achieved / peak.value, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
-            'traffic_unit': 'bytes of DRAM read + write per launch',
-            'traffic_source': 'ncu --set full capture of this command, '
-                              'profiles/r01_predict_kernel_N240_R20.md',
+            'frac': achieved / peak.value,
+            'flops_per_prediction': executed_flops(n_rows, N_R),
+            'note': 'achieved = tensor flops the kernel executes (lower triangle of the symmetric '
+                    'table, 2*R*64*T8(T8+1)/2 with T8 = n_pad/8: what ncu counts as DMMA) / kernel '
+                    'time; the symmetric-minimal count R*N*(N+1) is {:.0f} per prediction'.format(
+                        N_R * n_rows * (n_rows + 1.0)),
             'peak_source': 'FP64 DMMA (mma.sync m8n8k4 f64) peak measured live by '
                            'tc_measure_dmma_peak; MEASURED_PEAKS.json has no FP64 figure',
-            'flops_per_prediction': algorithmic_flops(n_rows, N_R),
-            'note': 'achieved counts the dense algorithmic flops 2RN^2+2RN (SURVEY 8d); the '
-                    'kernel multiplies only the lower triangle, executed_* count those flops',
-            'executed_tflops': executed / (k_ms * 1e-3) * 1e-12,
-            'executed_frac': executed / (k_ms * 1e-3) * 1e-12 / peak.value,
+            'dense_equivalent_tflops': dense / (k_ms * 1e-3) * 1e-12,
+            'dense_equivalent_note': 'SURVEY 8(d) dense count 2RN^2+2RN per prediction over the '
+                                     'same time; exceeds the peak because only half of the '
+                                     'symmetric product is executed -- not a roofline fraction',
+            'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
+            'traffic_unit': 'bytes of DRAM read + write per launch',
+            'traffic_source': 'constant copied from the ncu --set full capture summarised in ' +
+                              NCU_TRAFFIC_SOURCE + ' (not measured by this run)',
+            'algorithmic_bytes_per_launch': ALGORITHMIC_BYTES_PER_DRAW * n_draws + table_bytes,
             'kernel_ms': k_ms, 'finalize_ms': float(np.mean(finalize_ms)),
             'kernel_share_of_step': float(np.sum(kernel_ms) / total_ms) if world == 1 else None,
         }
@@ -393,9 +571,11 @@ def run_gpu_arm(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'timing': 'wall clock around predict_batch calls'},
             'gpu_launches': 2 * args.steps,  # predict_kernel + finalize_kernel per timed step
-             'roofline': roofline, 'clocks': clocks,
+            'roofline': roofline, 'clocks': clocks,
             'results_consistent': bool(same),
         }
+        if configs is not None:
+            line['configs'] = configs
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline_single(args.cpu_sample)
             if n_draws == DRAWS_PER_GPU:
@@ -436,6 +616,13 @@ def main():
     parser.add_argument('--cpu-sample', type=int, default=8000,
                         help='draws of the workload timed for cpu_baseline')
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    parser.add_argument('--no-configs', action='store_true',
+                        help='skip the `configs` block (the other BASELINE.json configurations)')
+    parser.add_argument('--config-draws', type=int, default=100000,
+                        help='draws of the cfg1/cfg3/cfg4 runs of the `configs` block')
+    parser.add_argument('--sweep-draws', type=int, default=1 << 24,
+                        help='total draws of the cfg5 sweep (fixed for any number of GPUs)')
+    parser.add_argument('--sweep-chunk', type=int, default=1 << 20)
     args = parser.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -11,6 +11,6 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpu
 cat gpurun_out/bench.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 cat gpurun_out/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_kernel -s 3 -c 1 -o gpurun_out/prof_predict -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-configs > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_kernel -s 3 -c 1 -o gpurun_out/prof_predict -f python bench.py --steps 2 --warmup 3 --no-cpu --no-configs > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out
