@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 104
+#define TC_VERSION 105
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -35,8 +35,10 @@ extern "C" {
 
 /* Arithmetic of the auto-mode contraction.  FP64: DMMA tensor cores, parity with the reference
  * to rtol 1e-10.  3XTF32 (optional, auto tables only): table entries and tracer weights split into
- * TF32 high + low parts, hi*hi + lo*hi + hi*lo accumulated in FP32 on the TF32 tensor cores,
- * row-dot and normalisation in FP64; relative error ~1e-7 of the term magnitudes (tested 1e-6).
+ * TF32 high + low parts, the products that matter to 22 bits accumulated in FP32 on the TF32 tensor
+ * cores -- tcgen05.mma with TMEM accumulators and TMA-staged operands for batches on tables of at
+ * most 256 padded rows (csrc/tcgen05_contract.cuh), the warp-level m16n8k8 MMA otherwise -- row-dot
+ * and normalisation in FP64; relative error ~1e-7 of the term magnitudes (tested 1e-6).
  * The occupation arithmetic is FP64 in both. */
 #define TC_PRECISION_FP64 0
 #define TC_PRECISION_3XTF32 1
@@ -115,6 +117,12 @@ int tc_occupation_batch(tc_table* table, const tc_model* model, int n_gauss,
 
 /* Scratch bytes tc_predict_batch needs for n_draws (separate = separate_gal_type). */
 size_t tc_predict_workspace_bytes(const tc_table* table, int64_t n_draws, int separate);
+
+/* The same for a given precision: TC_PRECISION_3XTF32 on eligible tables (auto mode, total
+ * predictions, at most 256 padded rows) adds the operand images of the tcgen05 contraction; with
+ * the smaller FP64 workspace that mode runs on the warp-level TF32 MMA instead. */
+size_t tc_predict_workspace_bytes_for(const tc_table* table, int64_t n_draws, int separate,
+                                      int precision);
 
 /* TabCorr.predict (tabcorr.py:580-683) for B draws, fused occupation + contraction.
  * Exactly one of theta_dev (layout above; evaluated with `model` and the n_gauss plan) and

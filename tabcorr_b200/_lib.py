@@ -35,7 +35,7 @@ TC_FAMILY_LEAUTHAUD11 = 1
 SYMBOLS = (
     'tc_last_error', 'tc_version', 'tc_model_n_theta', 'tc_table_create', 'tc_table_destroy', 'tc_table_n_rows',
     'tc_table_n_r', 'tc_table_n_tables', 'tc_table_plan', 'tc_occupation_batch',
-    'tc_predict_workspace_bytes', 'tc_predict_batch', 'tc_predict_one', 'tc_interp_create', 'tc_interp_destroy',
+    'tc_predict_workspace_bytes', 'tc_predict_workspace_bytes_for', 'tc_predict_batch', 'tc_predict_one', 'tc_interp_create', 'tc_interp_destroy',
     'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_measure_dfma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math')
 
 
@@ -90,6 +90,8 @@ def load():
                                         ctypes.c_int64, ctypes.c_int64, vp, vp]
     lib.tc_predict_workspace_bytes.restype = ctypes.c_size_t
     lib.tc_predict_workspace_bytes.argtypes = [vp, ctypes.c_int64, ctypes.c_int]
+    lib.tc_predict_workspace_bytes_for.restype = ctypes.c_size_t
+    lib.tc_predict_workspace_bytes_for.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
     lib.tc_predict_batch.restype = ctypes.c_int
     lib.tc_predict_batch.argtypes = [
         vp, ctypes.POINTER(tc_model), ctypes.c_int, vp, ctypes.c_int64, vp, ctypes.c_int64,

@@ -185,9 +185,132 @@ size_t tc_predict_workspace_bytes(const tc_table* t, int64_t n_draws, int separa
   return plan_workspace(t->layouts[separate ? 1 : 0], n_draws, n_sm).total;
 }
 
+size_t tc_predict_workspace_bytes_for(const tc_table* t, int64_t n_draws, int separate,
+                                      int precision) {
+  size_t need = tc_predict_workspace_bytes(t, n_draws, separate);
+  if (need == 0 || precision != TC_PRECISION_3XTF32 || !tcgen_eligible(t, separate ? 1 : 0))
+    return need;
+  return std::max(need, plan_tcgen_workspace(t, n_draws).total);
+}
+
 }  // extern "C"
 
 namespace {
+
+// The 3xTF32 contraction on tcgen05 (csrc/tcgen05_contract.cuh): weights_image_kernel (FP64
+// occupations -> operand images) -> tcgen_contract_kernel -> finalize_kernel.  The caller holds
+// the table mutex and has validated the arguments.
+int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double* theta,
+                  int64_t theta_ld, int64_t n_draws, double* ngal, int64_t ngal_stride, double* xi,
+                  int64_t xi_stride, void* workspace, cudaStream_t stream, int n_sm) {
+  int rc = build_tcgen(t);
+  if (rc != TC_OK) return rc;
+  if ((rc = build_plan(t, 0, n_gauss))) return rc;
+  Layout& L = t->layouts[0];
+  const TcgenWorkspace ws = plan_tcgen_workspace(t, n_draws);
+  char* base = static_cast<char*>(workspace);
+  base += (256 - reinterpret_cast<uintptr_t>(base) % 256) % 256;
+  uint8_t* a_img = reinterpret_cast<uint8_t*>(base);
+  float* c_img = reinterpret_cast<float*>(base + ws.a_bytes);
+  double* parts = reinterpret_cast<double*>(base + ws.a_bytes + ws.c_bytes);
+  double* ngal_tile = reinterpret_cast<double*>(base + ws.a_bytes + ws.c_bytes + ws.parts_bytes);
+  double* ngal_parts = reinterpret_cast<double*>(base + ws.a_bytes + ws.c_bytes + ws.parts_bytes +
+                                                 ws.ngal_bytes);
+  int* error_flag = reinterpret_cast<int*>(base + ws.a_bytes + ws.c_bytes + ws.parts_bytes +
+                                           ws.ngal_bytes + ws.ngal_parts_bytes);
+  TC_CUDA(cudaMemsetAsync(error_flag, 0, sizeof(int), stream));
+  const bool profile = g_profile.enabled;
+  if (profile) TC_CUDA(cudaEventRecord(g_profile.ev[0], stream));
+
+  WeightsImageArgs wa{};
+  wa.plan = L.plans[n_gauss].dev;
+  wa.model = *model;
+  wa.theta = theta;
+  wa.theta_ds = theta_ld ? 1 : TC_N_THETA;
+  wa.theta_ps = theta_ld ? theta_ld : 1;
+  wa.n_draws = n_draws;
+  pick_ranges(wa.plan, 1, &wa.n_ranges_cen, &wa.n_ranges_sat);
+  if (wa.n_ranges_cen + wa.n_ranges_sat > ws.n_ranges_max)
+    return fail(TC_EUNSUPPORTED, "tcgen05 path: too many occupation ranges");
+  wa.kp = L.tcgen.kp;
+  wa.n_pad = L.dev.n_pad;
+  wa.n_rows = t->n_rows;
+  wa.a_img = a_img;
+  wa.c_img = c_img;
+  wa.ngal_parts = ngal_parts;
+  wa.ngal_ld = ws.n_tiles * kTcM;
+  {
+    const long long n_items = (n_draws + 7) / 8 * (wa.n_ranges_cen + wa.n_ranges_sat);
+    const int grid = (int)std::max<long long>(
+        1, std::min<long long>((n_items + kWarps - 1) / kWarps, (long long)n_sm));
+    weights_image_kernel<<<grid, kThreads, 0, stream>>>(wa);
+    TC_CUDA(cudaGetLastError());
+  }
+
+  TcgenArgs ta{};
+  ta.tc = L.tcgen;
+  ta.a_img = a_img;
+  ta.c_img = c_img;
+  ta.ngal_parts = ngal_parts;
+  ta.ngal_ld = wa.ngal_ld;
+  ta.n_ranges_cen = wa.n_ranges_cen;
+  ta.n_ranges_sat = wa.n_ranges_sat;
+  ta.n_pad = L.dev.n_pad;
+  ta.n_rows = t->n_rows;
+  ta.seg = tune("TCGEN_SEG", 2);
+  if (ta.seg != 1 && ta.seg != 2 && ta.seg != 4) ta.seg = 2;
+  if (ta.seg > L.tcgen.n_kb) ta.seg = 1;
+  ta.n_tiles = ws.n_tiles;
+  ta.parts = parts;
+  ta.ngal_tile = ngal_tile;
+  ta.error_flag = error_flag;
+  const size_t smem = (size_t)kTcM * L.tcgen.kp * 4 + (size_t)kTcStages * kTcStageBytes +
+                      kTcBarriers * 8 + 16;
+  {
+    static std::mutex m;
+    static std::map<int, bool> configured;
+    std::lock_guard<std::mutex> lock_attr(m);
+    if (!configured[t->device]) {
+      TC_CUDA(cudaFuncSetAttribute(tcgen_contract_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+      configured[t->device] = true;
+    }
+  }
+  const int grid = (int)std::min<long long>(ws.n_tiles, n_sm);
+  tcgen_contract_kernel<<<grid, kTcThreads, smem, stream>>>(ta);
+  TC_CUDA(cudaGetLastError());
+  if (profile) TC_CUDA(cudaEventRecord(g_profile.ev[1], stream));
+
+  FinalizeArgs fa{};
+  fa.lay = L.dev;
+  fa.lay.n_parts = L.tcgen.n_parts;
+  fa.lay.out_ptr = L.tcgen.out_ptr;
+  fa.lay.out_parts = L.tcgen.out_parts;
+  fa.parts = parts;
+  fa.ngal_tile = ngal_tile;
+  fa.n_draws = n_draws;
+  fa.bm = kTcM;
+  fa.mode = TC_MODE_AUTO;
+  fa.separate = 0;
+  fa.n_tables = t->n_tables;
+  fa.ngal_out = ngal;
+  fa.ngal_stride = ngal_stride;
+  fa.xi_out = xi;
+  fa.xi_stride = xi_stride;
+  const int n_out = L.dev.n_out;
+  const int outs_per_block = 256 / kTcM;
+  int fy = std::max(1, std::min(64, (n_out + outs_per_block - 1) / outs_per_block));
+  if (ws.n_tiles > 4LL * n_sm) fy = 1;
+  finalize_kernel<<<dim3((unsigned)ws.n_tiles, fy), 256, 0, stream>>>(fa);
+  TC_CUDA(cudaGetLastError());
+  tcgen_poison_kernel<<<64, 256, 0, stream>>>(error_flag, xi, n_draws, xi_stride, n_out);
+  TC_CUDA(cudaGetLastError());
+  if (profile) {
+    TC_CUDA(cudaEventRecord(g_profile.ev[2], stream));
+    g_profile.recorded = true;
+  }
+  return TC_OK;
+}
 
 // tc_predict_batch / tc_predict_one.  theta_inline: host pointer to the TC_N_THETA parameters of a
 // single draw, passed to the kernel in its launch arguments (theta and occ are NULL then).
@@ -223,6 +346,18 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   if (!guard.ok) return fail(TC_ECUDA, "tc_predict_batch: cannot select the table's CUDA device");
   int rc = build_layout(t, separate);
   if (rc != TC_OK) return rc;
+  if (precision == TC_PRECISION_3XTF32 && theta && !theta_inline && tcgen_eligible(t, separate) &&
+      n_draws >= tune("TCGEN_MIN_DRAWS", 2048) && workspace &&
+      workspace_bytes >= plan_tcgen_workspace(t, n_draws).total) {
+    // Blackwell-native contraction (tcgen05 + TMEM + TMA); smaller batches, split predictions,
+    // precomputed occupations and larger tables take the warp-level TF32 MMA below
+    int n_sm_tc = 0;
+    if ((rc = device_sms(t->device, &n_sm_tc))) return rc;
+    if (ngal_stride < (int64_t)t->n_tables || xi_stride < (int64_t)t->n_tables * t->n_r)
+      return fail(TC_EINVAL, "tc_predict_batch: output stride smaller than one draw's outputs");
+    return predict_tcgen(t, model, n_gauss, theta, theta_ld, n_draws, ngal, ngal_stride, xi,
+                         xi_stride, workspace, stream, n_sm_tc);
+  }
   if (precision == TC_PRECISION_3XTF32 && (rc = build_afrag32(t, separate))) return rc;
   Layout& L = t->layouts[separate];
   if (!theta && t->rules.empty()) {

@@ -155,11 +155,12 @@ class DeviceTableGroup:
             return 1
         return 3 if self.mode == 'auto' else 2
 
-    def _workspace_for(self, n_draws, separate):
+    def _workspace_for(self, n_draws, separate, precision=_lib.TC_PRECISION_FP64):
         """Scratch buffer of the current stream (kernels of different streams may overlap, so
         every stream that launches on this table gets its own)."""
         torch = _torch()
-        need = int(self.lib.tc_predict_workspace_bytes(self.handle, int(n_draws), int(separate)))
+        need = int(self.lib.tc_predict_workspace_bytes_for(self.handle, int(n_draws),
+                                                           int(separate), int(precision)))
         if need == 0 and n_draws > 0:
             raise _lib.TabCorrB200Error(
                 'table too large for the CUDA kernel: the weights of 8 draws x {} halo bins do not '
@@ -284,7 +285,7 @@ class DeviceTableGroup:
         if theta is not None:
             self.plan(n_gauss)
         with self._lock:
-            workspace = self._workspace_for(n_draws, separate)
+            workspace = self._workspace_for(n_draws, separate, precision)
             model = self._model_struct(spec if spec is not None else ModelSpec())
             stream = torch.cuda.current_stream(self.device).cuda_stream
             ngal_flat = ngal.view(n_draws, -1)
