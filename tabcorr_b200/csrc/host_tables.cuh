@@ -329,47 +329,52 @@ bool tcgen_eligible(const tc_table* t, int separate) {
   if (t->mode != TC_MODE_AUTO || separate) return false;
   if (tune("TCGEN", 1) == 0) return false;
   const int n_pad = std::max(16, round_up(t->n_rows, 16));
-  return round_up(n_pad, kTcKB) <= kTcMaxKp;
+  return round_up(n_pad, kTcKS) <= kTcMaxKp;
 }
 
 // Table stream of the tcgen05 contraction: the dense symmetric M_r in padded row order, split into
-// TF32 high and low parts, cut into stages {lo, hi} of 128 rows (2 radial bins x 64 table rows) x
-// 32 k in the canonical K-major UMMA layout, in the order the kernel consumes them.
+// TF32 high and low parts, as planes of 128 rows (2 radial bins x 64 table rows) x 64 k in the
+// canonical K-major UMMA layout, in the order the kernel consumes them: column block, radial-bin
+// pair, {all low planes, all high planes}; two K segments form one 64 KB bulk copy.
 int build_tcgen(tc_table* t) {
   Layout& L = t->layouts[0];
   if (L.built_tc) return TC_OK;
   const int N = t->n_rows, R = t->n_r, T = t->n_tables, Reff = R * T;
   const int n_pad = L.dev.n_pad;
   TcgenDev& tc = L.tcgen;
-  tc.kp = round_up(n_pad, kTcKB);
-  tc.n_kb = tc.kp / kTcKB;
+  tc.kp = round_up(n_pad, kTcKS);
+  tc.n_seg = tc.kp / kTcKS;
+  tc.n_pairs = (tc.n_seg + 1) / 2;
   tc.n_ib = (N + kTcNI - 1) / kTcNI;
+  tc.n_reff = Reff;
   tc.n_rp = (Reff + kTcRB - 1) / kTcRB;
-  tc.n_parts = tc.n_ib * kTcRB * tc.n_rp;
-  const size_t n_stages = (size_t)tc.n_ib * tc.n_rp * tc.n_kb;
-  std::vector<uint8_t> img(n_stages * kTcStageBytes, 0);
+  tc.n_parts = tc.n_ib * kTcRB * tc.n_rp;         // [column block][radial bin]
+  const size_t rp_bytes = (size_t)2 * tc.n_pairs * kTcCopyBytes;
+  std::vector<uint8_t> img((size_t)tc.n_ib * tc.n_rp * rp_bytes, 0);
   const size_t P = (size_t)N * (N + 1) / 2;
   std::vector<int> pad_to_row(tc.kp, -1);
   for (int i = 0; i < N; i++) pad_to_row[L.row_to_pad[i]] = i;
   for (int ib = 0; ib < tc.n_ib; ib++) {
     for (int rp = 0; rp < tc.n_rp; rp++) {
-      for (int kb = 0; kb < tc.n_kb; kb++) {
-        uint8_t* stage = img.data() + (((size_t)ib * tc.n_rp + rp) * tc.n_kb + kb) * kTcStageBytes;
+      uint8_t* base = img.data() + ((size_t)ib * tc.n_rp + rp) * rp_bytes;
+      for (int sg = 0; sg < tc.n_seg; sg++) {
+        uint8_t* lo_plane = base + (size_t)(sg / 2) * kTcCopyBytes + (size_t)(sg % 2) * kTcPlaneBytes;
+        uint8_t* hi_plane = lo_plane + (size_t)tc.n_pairs * kTcCopyBytes;
         for (int n = 0; n < kTcN; n++) {
           const int re = rp * kTcRB + n / kTcNI, pi = ib * kTcNI + n % kTcNI;
           if (re >= Reff || pi >= tc.kp || pad_to_row[pi] < 0) continue;
           const int i = pad_to_row[pi];
           const double* m = t->matrices[re / R].data() + (size_t)(re % R) * P;
-          for (int k = 0; k < kTcKB; k++) {
-            const int pj = kb * kTcKB + k;
+          for (int k = 0; k < kTcKS; k++) {
+            const int pj = sg * kTcKS + k;
             if (pad_to_row[pj] < 0) continue;
             const int j = pad_to_row[pj];
             const double val = i >= j ? m[(size_t)i * (i + 1) / 2 + j] : m[(size_t)j * (j + 1) / 2 + i];
             const float hi = tf32_round_host((float)val);
             const float lo = tf32_round_host((float)(val - (double)hi));
-            const size_t off = canon_offset(n, k, 1024);
-            std::memcpy(stage + off, &lo, 4);
-            std::memcpy(stage + kTcPlaneBytes + off, &hi, 4);
+            const size_t off = canon_offset(n, k, kTcSbo);
+            std::memcpy(lo_plane + off, &lo, 4);
+            std::memcpy(hi_plane + off, &hi, 4);
           }
         }
       }
@@ -406,15 +411,14 @@ struct TcgenWorkspace {
 TcgenWorkspace plan_tcgen_workspace(const tc_table* t, long long n_draws) {
   TcgenWorkspace w{};
   const int n_pad = std::max(16, round_up(t->n_rows, 16));
-  const int kp = round_up(n_pad, kTcKB);
+  const int kp = round_up(n_pad, kTcKS);
   const int n_ib = (t->n_rows + kTcNI - 1) / kTcNI;
-  const int n_rp = (t->n_r * t->n_tables + kTcRB - 1) / kTcRB;
   auto align = [](size_t b) { return (b + 255) / 256 * 256; };
   w.n_tiles = (n_draws + kTcM - 1) / kTcM;
   w.n_ranges_max = 64;
   w.a_bytes = align((size_t)w.n_tiles * kTcM * kp * 4);
   w.c_bytes = align((size_t)w.n_tiles * n_pad * kTcM * 4);
-  w.parts_bytes = align((size_t)w.n_tiles * n_ib * kTcRB * n_rp * kTcM * 8);
+  w.parts_bytes = align((size_t)w.n_tiles * n_ib * kTcRB * ((t->n_r * t->n_tables + kTcRB - 1) / kTcRB) * kTcM * 8);
   w.ngal_bytes = align((size_t)w.n_tiles * 2 * kTcM * 8);
   w.ngal_parts_bytes = align((size_t)w.n_ranges_max * w.n_tiles * kTcM * 8);
   w.total = w.a_bytes + w.c_bytes + w.parts_bytes + w.ngal_bytes + w.ngal_parts_bytes + 256;

@@ -210,7 +210,7 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
   const TcgenWorkspace ws = plan_tcgen_workspace(t, n_draws);
   char* base = static_cast<char*>(workspace);
   base += (256 - reinterpret_cast<uintptr_t>(base) % 256) % 256;
-  uint8_t* a_img = reinterpret_cast<uint8_t*>(base);
+  float* h_img = reinterpret_cast<float*>(base);
   float* c_img = reinterpret_cast<float*>(base + ws.a_bytes);
   double* parts = reinterpret_cast<double*>(base + ws.a_bytes + ws.c_bytes);
   double* ngal_tile = reinterpret_cast<double*>(base + ws.a_bytes + ws.c_bytes + ws.parts_bytes);
@@ -235,7 +235,7 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
   wa.kp = L.tcgen.kp;
   wa.n_pad = L.dev.n_pad;
   wa.n_rows = t->n_rows;
-  wa.a_img = a_img;
+  wa.h_img = h_img;
   wa.c_img = c_img;
   wa.ngal_parts = ngal_parts;
   wa.ngal_ld = ws.n_tiles * kTcM;
@@ -249,7 +249,7 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
 
   TcgenArgs ta{};
   ta.tc = L.tcgen;
-  ta.a_img = a_img;
+  ta.h_img = h_img;
   ta.c_img = c_img;
   ta.ngal_parts = ngal_parts;
   ta.ngal_ld = wa.ngal_ld;
@@ -257,15 +257,17 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
   ta.n_ranges_sat = wa.n_ranges_sat;
   ta.n_pad = L.dev.n_pad;
   ta.n_rows = t->n_rows;
-  ta.seg = tune("TCGEN_SEG", 2);
-  if (ta.seg != 1 && ta.seg != 2 && ta.seg != 4) ta.seg = 2;
-  if (ta.seg > L.tcgen.n_kb) ta.seg = 1;
   ta.n_tiles = ws.n_tiles;
   ta.parts = parts;
   ta.ngal_tile = ngal_tile;
   ta.error_flag = error_flag;
-  const size_t smem = (size_t)kTcM * L.tcgen.kp * 4 + (size_t)kTcStages * kTcStageBytes +
-                      kTcBarriers * 8 + 16;
+  static long long* debug_buf = nullptr;
+  if (tune("TCGEN_DEBUG", 0)) {
+    if (!debug_buf) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&debug_buf), 1024 * 8 * sizeof(long long)));
+    TC_CUDA(cudaMemsetAsync(debug_buf, 0, 1024 * 8 * sizeof(long long), stream));
+    ta.debug = debug_buf;
+  }
+  const size_t smem = (size_t)kTcStages * kTcCopyBytes + kTcBarriers * 8 + 16;
   {
     static std::mutex m;
     static std::map<int, bool> configured;
@@ -276,9 +278,18 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
       configured[t->device] = true;
     }
   }
-  const int grid = (int)std::min<long long>(ws.n_tiles, n_sm);
+  const int grid = (int)std::min<long long>(ws.n_tiles * L.tcgen.n_ib, n_sm);
   tcgen_contract_kernel<<<grid, kTcThreads, smem, stream>>>(ta);
   TC_CUDA(cudaGetLastError());
+  if (ta.debug) {   // developer aid: cycle breakdown of CTA 0, 1 and the last one on stderr
+    TC_CUDA(cudaStreamSynchronize(stream));
+    std::vector<long long> h((size_t)grid * 8);
+    TC_CUDA(cudaMemcpy(h.data(), ta.debug, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int c : {0, 1, grid - 1})
+      std::fprintf(stderr, "tcgen cta %d: mma total %lld wait_a %lld wait_acc %lld wait_full %lld | "
+                   "epi total %lld a_store %lld c_load %lld wait_acc_full %lld\n", c, h[c * 8], h[c * 8 + 1],
+                   h[c * 8 + 2], h[c * 8 + 3], h[c * 8 + 4], h[c * 8 + 5], h[c * 8 + 6], h[c * 8 + 7]);
+  }
   if (profile) TC_CUDA(cudaEventRecord(g_profile.ev[1], stream));
 
   FinalizeArgs fa{};
@@ -347,10 +358,11 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   int rc = build_layout(t, separate);
   if (rc != TC_OK) return rc;
   if (precision == TC_PRECISION_3XTF32 && theta && !theta_inline && tcgen_eligible(t, separate) &&
-      n_draws >= tune("TCGEN_MIN_DRAWS", 2048) && workspace &&
+      n_draws >= tune("TCGEN_MIN_DRAWS", 1) && workspace &&
       workspace_bytes >= plan_tcgen_workspace(t, n_draws).total) {
-    // Blackwell-native contraction (tcgen05 + TMEM + TMA); smaller batches, split predictions,
-    // precomputed occupations and larger tables take the warp-level TF32 MMA below
+    // Blackwell-native contraction (tcgen05 + TMEM + TMA) for every batch size, so that results do
+    // not depend on how a batch is cut; split predictions, precomputed occupations, the one-draw
+    // latency call and larger tables take the warp-level TF32 MMA below
     int n_sm_tc = 0;
     if ((rc = device_sms(t->device, &n_sm_tc))) return rc;
     if (ngal_stride < (int64_t)t->n_tables || xi_stride < (int64_t)t->n_tables * t->n_r)

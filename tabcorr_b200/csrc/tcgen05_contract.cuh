@@ -15,14 +15,26 @@
 // dropped l^T M l is 2^-22 relative.  The occupation arithmetic stays FP64 (weights_image_kernel).
 //
 // Data flow per CTA (persistent, one per SM, 192 threads):
-//   warp 4 (one lane)  TMA producer: the draw tile's h image (128 x Kp TF32, 128 KB at N = 240) and
-//                      the table stream, 32 KB stages {Ml, Mh} of 128 table rows x 32 k
-//   warp 5 (one lane)  MMA issuer: per accumulator block (64 table rows i x 2 radial bins) and
-//                      k-block 8 tcgen05.mma (M = 128 draws, N = 128, K = 8), accumulators in TMEM,
-//                      optionally one accumulator per K segment (FP32 accumulation error)
-//   warps 0-3          epilogue: tcgen05.ld of the lane's 128 columns, FP32 products with c_i,
-//                      FP64 sums, one scratch row per (column block, radial bin) for finalize_kernel
-// All operand images are pre-formatted in the canonical K-major no-swizzle UMMA layout (8-row x
+//   warps 0-3          thread m owns TMEM lane m = draw m of the tile.  Per tile they write the
+//                      draw tile h (128 x Kp TF32) into TMEM columns [0, Kp) with tcgen05.st -- the
+//                      MMA's A operand lives in tensor memory, so shared memory holds nothing but
+//                      the table stream -- and run the epilogue: tcgen05.ld of an accumulator,
+//                      FP32 products with c_i, FP64 sums, one scratch row per (column block,
+//                      radial bin) for finalize_kernel
+//   warp 4 (one lane)  TMA producer: the table stream in 64 KB bulk copies (two K segments of one
+//                      plane, Ml or Mh, for 2 radial bins x 64 table rows) through a ring of three
+//                      stages (cp.async.bulk + mbarrier).  A bulk copy costs ~470 cycles whatever
+//                      its size (tools/tcgen_micro.cu): 64 KB copies stream at 110 B/cycle/SM.
+//   warp 5 (one lane)  MMA issuer: tcgen05.mma kind::tf32, M = 128 draws, N = 128, K = 8, A from
+//                      TMEM, B from shared memory, into one of two 128-column accumulators.  The
+//                      issue loops are fully unrolled with constant operand offsets: descriptor
+//                      arithmetic on the uniform datapath costs ~100 cycles per MMA otherwise,
+//                      more than the 64 cycles the tensor core needs (tools/tcgen_micro.cu).
+// Accumulation chains: the tensor core truncates its FP32 accumulator (and the aligned products)
+// towards zero, a bias of ~3e-8 of the running sum per MMA of a same-sign chain (measured).  So the
+// low-plane products of all K, 2^-11 of the result, form one chain of their own, and the high
+// plane is cut into chains of 8 MMAs (one K segment of 64) that the epilogue adds in FP64.
+// The table images are pre-formatted in the canonical K-major no-swizzle UMMA layout (8-row x
 // 16-byte core matrices), so every copy is one contiguous bulk transfer.
 #pragma once
 
@@ -32,22 +44,35 @@
 namespace {
 
 constexpr int kTcM = 128;                 // draws per tile = UMMA M = TMEM lanes
-constexpr int kTcNI = 64;                 // table rows i per accumulator block
+constexpr int kTcNI = 64;                 // table rows i per column block
 constexpr int kTcRB = 2;                  // radial bins per MMA
 constexpr int kTcN = kTcNI * kTcRB;       // UMMA N
-constexpr int kTcKB = 32;                 // k per table stage (4 MMAs of K = 8 per plane)
+constexpr int kTcKS = 64;                 // k per segment (8 MMAs of K = 8)
+constexpr int kTcPlaneBytes = kTcN * kTcKS * 4;        // 32 KB: one plane (lo or hi) of one segment
+constexpr int kTcCopyBytes = 2 * kTcPlaneBytes;        // a bulk copy carries two segments of a plane
 constexpr int kTcStages = 3;
-constexpr int kTcPlaneBytes = kTcN * kTcKB * 4;        // 16 KB
-constexpr int kTcStageBytes = 2 * kTcPlaneBytes;       // {lo, hi}
-constexpr int kTcThreads = 192;
-constexpr int kTcMaxKp = 256;             // A image of 128 draws x Kp x 4 B must leave 3 stages
+constexpr int kTcSbo = (kTcKS / 4) * 128;              // bytes between 8-row groups of a plane
+constexpr int kTcChain = 4;               // MMAs per high-plane accumulation chain (K = 32)
+constexpr int kTcThreads = 320;           // warps 0-3, 6-9: epilogue; 4: TMA producer; 5: MMA issuer
+constexpr int kTcEpiWarps = 8;            // 2 groups (radial bin of the pair) x 4 lane quarters
+constexpr int kTcMaxKp = 256;             // the draw tile occupies Kp TMEM columns
 constexpr int kTcTmemCols = 512;
-constexpr int kTcBarriers = 16;
+constexpr int kTcAccCol = 256;            // accumulator ring: 2 x 128 columns behind the draw tile
+constexpr int kTcAccBufs = 2;
+constexpr int kTcBarriers = 2 * kTcStages + 1 + 2 * kTcAccBufs;
+// cycle counters of the roles (TC_TUNE_TCGEN_DEBUG=1 prints them); compile with -DTC_TCGEN_DEBUG
+#ifdef TC_TCGEN_DEBUG
+constexpr bool kTcDebug = true;
+#else
+constexpr bool kTcDebug = false;
+#endif
 
 struct TcgenDev {
-  int kp;        // table rows padded to a multiple of 32 (K extent of the images)
-  int n_kb;      // kp / 32
+  int kp;        // table rows padded to a multiple of 64 (K extent of the images)
+  int n_seg;     // kp / 64: K segments
+  int n_pairs;   // segment pairs = bulk copies per plane
   int n_ib;      // column blocks of 64 table rows
+  int n_reff;    // radial bins x tables
   int n_rp;      // radial-bin pairs
   int n_parts;   // scratch rows per tile: n_ib * 2 n_rp
   const uint8_t* b_img;
@@ -57,17 +82,17 @@ struct TcgenDev {
 
 struct TcgenArgs {
   TcgenDev tc;
-  const uint8_t* a_img;      // [n_tiles][128 x kp TF32, canonical layout]
-  const float* c_img;        // [n_tiles][n_pad][128]
+  const float* h_img;        // [n_tiles][kp / 32][128 draws][32]  TF32-rounded weights
+  const float* c_img;        // [n_tiles][n_pad][128]              2 w - h
   const double* ngal_parts;  // [n_ranges][ngal_ld] number densities per occupation range
   long long ngal_ld;
   int n_ranges_cen, n_ranges_sat;
   int n_pad, n_rows;
-  int seg;                   // K segments with their own TMEM accumulator (1, 2 or 4)
   long long n_tiles;
   double* parts;             // [n_tiles][n_parts][128]
   double* ngal_tile;         // [n_tiles][2][128]
   int* error_flag;
+  long long* debug;          // optional [grid][8] cycle counters (TC_TUNE_TCGEN_DEBUG), else nullptr
 };
 
 // ------------------------------------------------------------------------------------------
@@ -134,6 +159,57 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the A operand in tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-uniform issue: the whole warp executes the instruction stream and one elected lane issues.
+// Inside a lane-0-only branch the compiler moves every operand to a uniform register per MMA
+// (4 R2UR + an ELECT loop, ~100 cycles); with uniform control flow the operands stay in uniform
+// registers and MMAs issue back to back.
+__device__ __forceinline__ void umma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem,
+                                                   uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
+      ::"r"(bar)
+      : "memory");
+}
+// Bounded wait whose failure is sticky and never changes the control flow of the caller.
+__device__ __forceinline__ void mbar_wait_sticky(uint32_t bar, uint32_t parity, bool& failed) {
+  if (failed) return;
+  if (!mbar_wait(bar, parity)) failed = true;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&v)[8]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+      "%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+        "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+        "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -156,6 +232,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
 }
 
+// 64 consecutive columns of the thread's lane: two loads in flight, one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t* q = r + 32 * h;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]),
+          "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]),
+          "=r"(q[14]), "=r"(q[15]), "=r"(q[16]), "=r"(q[17]), "=r"(q[18]), "=r"(q[19]),
+          "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]), "=r"(q[25]),
+          "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+        : "r"(taddr + 32 * h)
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 64; j++) v[j] = __uint_as_float(r[j]);
+}
+
 // byte offset of element (row, k) in a canonical K-major no-swizzle image whose 8-row groups are
 // `sbo` bytes apart (k counted from the start of the image's K extent)
 __host__ __device__ __forceinline__ size_t canon_offset(int row, int k, size_t sbo) {
@@ -170,30 +269,55 @@ constexpr uint32_t kTcIdesc = (1u << 4)                       // D format F32
 // ------------------------------------------------------------------------------------------
 // the contraction kernel
 // ------------------------------------------------------------------------------------------
+// One accumulation chain: NKS MMAs over consecutive k-steps of a plane in shared memory.
+// b_lo is the low word of the descriptor of the chain's first k-step (address and leading offset),
+// b_hi the high word; a k-step advances the address field by 256 bytes = 16 units and the TMEM
+// operand by 8 columns.  Executed by the whole MMA warp (see umma_tf32_ts_elect).
+template <int NKS>
+__device__ __forceinline__ void issue_chain(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t accumulate_first) {
+#pragma unroll
+  for (int ks = 0; ks < NKS; ks++)
+    umma_tf32_ts_elect(d_tmem, a_tmem + ks * 8, ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + ks * 16),
+                       kTcIdesc, ks == 0 ? accumulate_first : 1u);
+}
+__device__ __forceinline__ void issue_chain_n(int n_ks, uint32_t d_tmem, uint32_t a_tmem,
+                                              uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t accumulate_first) {
+  if (n_ks == 8) {
+    issue_chain<8>(d_tmem, a_tmem, b_lo, b_hi, accumulate_first);
+  } else if (n_ks == 4) {
+    issue_chain<4>(d_tmem, a_tmem, b_lo, b_hi, accumulate_first);
+  } else {
+    for (int ks = 0; ks < n_ks; ks++)
+      umma_tf32_ts_elect(d_tmem, a_tmem + ks * 8,
+                         ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + ks * 16), kTcIdesc,
+                         ks == 0 ? accumulate_first : 1u);
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tcgen_contract_kernel(const TcgenArgs args) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   const TcgenDev& tc = args.tc;
-  const uint32_t a_bytes = (uint32_t)kTcM * tc.kp * 4;
-  uint8_t* a_s = tc_smem;
-  uint8_t* b_s = tc_smem + a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + kTcStages * kTcStageBytes);
+  uint8_t* b_s = tc_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + kTcStages * kTcCopyBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTcBarriers);
-  // barriers: full[3], empty[3], a_full, a_empty, acc_full[4], acc_empty[4]
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3);
-  const uint32_t bar_a_full = smem_u32(bars + 6), bar_a_empty = smem_u32(bars + 7);
-  const uint32_t bar_acc_full = smem_u32(bars + 8), bar_acc_empty = smem_u32(bars + 12);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kTcStages);
+  const uint32_t bar_a_full = smem_u32(bars + 2 * kTcStages);
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * kTcStages + 1);
+  const uint32_t bar_acc_empty = smem_u32(bars + 2 * kTcStages + 1 + kTcAccBufs);
+  // the shuffle tells the compiler that the warp index is warp-uniform (role branches stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; s++) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_a_full, 1);
-    mbar_init(bar_a_empty, 1);
-    for (int b = 0; b < 4; b++) {
+    mbar_init(bar_a_full, 4);                  // warps 0-3 store the draw tile
+    for (int b = 0; b < kTcAccBufs; b++) {
       mbar_init(bar_acc_full + 8 * b, 1);
-      mbar_init(bar_acc_empty + 8 * b, 4);   // one arrival per epilogue warp
+      mbar_init(bar_acc_empty + 8 * b, kTcEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,34 +331,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tcgen_contract_kernel(const Tcg
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // The CTA owns all 512 columns of the SM's tensor memory, so the allocation starts at lane 0,
+  // column 0; the MMA warp relies on it (its operands stay compile-time offsets).
   const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0 && threadIdx.x == 0) atomicExch(args.error_flag, 4);
 
-  const int seg = args.seg;
-  const int acc_stride = kTcN * seg;               // TMEM columns per accumulator buffer
-  const int n_acc = kTcTmemCols / acc_stride;      // 4, 2 or 1 buffers
-  const int n_jobs = tc.n_ib * tc.n_rp;            // accumulator blocks per tile
-  bool ok = true;
+  // Work items are (tile, column block) pairs in tile-major order; every CTA takes an equal
+  // contiguous range, so at most two of its tiles are shared with a neighbour (both load the tile).
+  const long long n_items = args.n_tiles * tc.n_ib;
+  const long long item_lo = n_items * blockIdx.x / gridDim.x;
+  const long long item_hi = n_items * (blockIdx.x + 1) / gridDim.x;
+  const size_t rp_bytes = (size_t)2 * tc.n_pairs * kTcCopyBytes;   // table stream of one (ib, rp)
+  const int n_ksteps = (args.n_pad + 7) / 8;                       // k-steps that hold table rows
+  const int n_hi_units = (n_ksteps + kTcChain - 1) / kTcChain;
 
   if (warp == 4) {
-    // ===== TMA producer ==========================================================================
+    // ===== TMA producer: the table stream ========================================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int t_local = 0;
-      for (long long tile = blockIdx.x; tile < args.n_tiles && ok; tile += gridDim.x, t_local++) {
-        if (t_local > 0) ok = mbar_wait(bar_a_empty, (t_local - 1) & 1);
-        if (!ok) break;
-        mbar_expect_tx(bar_a_full, a_bytes);
-        const uint8_t* src = args.a_img + (size_t)tile * a_bytes;
-        for (uint32_t off = 0; off < a_bytes; off += 32768)
-          bulk_g2s(smem_u32(a_s + off), src + off, min(32768u, a_bytes - off), bar_a_full);
-        for (int job = 0; job < n_jobs && ok; job++) {
-          for (int kb = 0; kb < tc.n_kb; kb++) {
+      bool ok = true;
+      for (long long item = item_lo; item < item_hi && ok; item++) {
+        const int ib = (int)(item % tc.n_ib);
+        for (int rp = 0; rp < tc.n_rp && ok; rp++) {
+          const uint8_t* src = tc.b_img + ((size_t)ib * tc.n_rp + rp) * rp_bytes;
+          for (int cp = 0; cp < 2 * tc.n_pairs; cp++) {       // low plane pairs, then high plane pairs
+            const int pair = cp % tc.n_pairs;
+            const uint32_t bytes = (uint32_t)min(2, tc.n_seg - 2 * pair) * kTcPlaneBytes;
             ok = mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             if (!ok) break;
-            mbar_expect_tx(bar_full + 8 * stage, kTcStageBytes);
-            bulk_g2s(smem_u32(b_s + stage * kTcStageBytes),
-                     tc.b_img + ((size_t)job * tc.n_kb + kb) * kTcStageBytes, kTcStageBytes,
+            mbar_expect_tx(bar_full + 8 * stage, bytes);
+            bulk_g2s(smem_u32(b_s + stage * kTcCopyBytes), src + (size_t)cp * kTcCopyBytes, bytes,
                      bar_full + 8 * stage);
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
           }
@@ -243,114 +370,205 @@ __global__ void __launch_bounds__(kTcThreads, 1) tcgen_contract_kernel(const Tcg
       if (!ok) atomicExch(args.error_flag, 1);
     }
   } else if (warp == 5) {
-    // ===== MMA issuer ============================================================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int t_local = 0;
-      long long job_count = 0;
-      const uint32_t sbo_a = (uint32_t)tc.kp * 32;   // 8-row groups of the A image
-      for (long long tile = blockIdx.x; tile < args.n_tiles && ok; tile += gridDim.x, t_local++) {
-        ok = mbar_wait(bar_a_full, t_local & 1);
-        if (!ok) break;
+    // ===== MMA issuer: warp-uniform control flow, one elected lane issues ==========================
+    // The instruction stream of this warp is the critical path (uniform-datapath instructions
+    // issue every ~6 cycles): a chain of 4 MMAs is 256 cycles of tensor-core work, so the loops
+    // below are unrolled to constant operand offsets and carry no index arithmetic.
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t buf = 0, emp_par0 = 1, emp_par1 = 1;   // accumulator ring: next buffer, wait parities
+    long long tile_prev = -1;
+    int t_local = 0;
+    bool failed = false;
+    long long t_wait_a = 0, t_wait_acc = 0, t_wait_full = 0;
+    const long long t_begin = clock64();
+    const bool dbg = kTcDebug && args.debug != nullptr;
+    const uint32_t b_hi_word = (uint32_t)(kTcSbo >> 4) | (1u << 14);   // stride offset, version 1
+    auto acquire_acc = [&]() -> uint32_t {          // returns the accumulator's first TMEM column
+      const uint32_t b = buf;
+      const long long t0 = dbg ? clock64() : 0;
+      mbar_wait_sticky(bar_acc_empty + 8 * b, b ? emp_par1 : emp_par0, failed);
+      if (dbg) t_wait_acc += clock64() - t0;
+      tc_fence_after();
+      if (b) emp_par1 ^= 1; else emp_par0 ^= 1;
+      buf ^= 1;
+      return kTcAccCol + b * kTcN;
+    };
+    for (long long item = item_lo; item < item_hi; item++) {
+      const long long tile = item / tc.n_ib;
+      if (tile != tile_prev) {                 // wait for the draw tile in tensor memory
+        const long long t0 = dbg ? clock64() : 0;
+        mbar_wait_sticky(bar_a_full, t_local & 1, failed);
+        if (dbg) t_wait_a += clock64() - t0;
         tc_fence_after();
-        for (int job = 0; job < n_jobs && ok; job++, job_count++) {
-          const int buf = (int)(job_count % n_acc);
-          const uint32_t use = (uint32_t)(job_count / n_acc);
-          ok = mbar_wait(bar_acc_empty + 8 * buf, (use & 1) ^ 1);
-          if (!ok) break;
-          tc_fence_after();
-          int seg_prev = -1;
-          for (int kb = 0; kb < tc.n_kb; kb++) {
-            ok = mbar_wait(bar_full + 8 * stage, phase);
-            if (!ok) break;
+        tile_prev = tile;
+        t_local++;
+      }
+      for (int rp = 0; rp < tc.n_rp; rp++) {
+        // ---- low plane: one chain over all K ----------------------------------------------------
+        {
+          const uint32_t d_tmem = acquire_acc();
+          const uint32_t acc_bar = bar_acc_full + 8 * ((d_tmem - kTcAccCol) / kTcN);
+          for (int pair = 0; pair < tc.n_pairs; pair++) {
+            const long long t0 = dbg ? clock64() : 0;
+            mbar_wait_sticky(bar_full + 8 * stage, phase, failed);
+            if (dbg) t_wait_full += clock64() - t0;
             tc_fence_after();
-            const int s = kb * seg / tc.n_kb;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_stride + s * kTcN);
-            const uint32_t a_addr = smem_u32(a_s) + (uint32_t)kb * 8 * 128;
-            const uint32_t b_addr = smem_u32(b_s + stage * kTcStageBytes);
-#pragma unroll
-            for (int plane = 0; plane < 2; plane++) {      // low parts first
-#pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                const uint64_t ad = umma_desc(a_addr + ks * 256, 128, sbo_a);
-                const uint64_t bd = umma_desc(b_addr + plane * kTcPlaneBytes + ks * 256, 128, 1024);
-                umma_tf32(d_tmem, ad, bd, kTcIdesc, (s != seg_prev && plane == 0 && ks == 0) ? 0u : 1u);
-              }
+            const uint32_t b_lo = ((smem_u32(b_s + stage * kTcCopyBytes) & 0x3FFFFu) >> 4) | (8u << 16);
+            const int ks_left = n_ksteps - pair * 16;          // k-steps of this pair with table rows
+            if (ks_left >= 16) {
+              issue_chain<8>(d_tmem, (uint32_t)(pair * 128), b_lo, b_hi_word, pair == 0 ? 0u : 1u);
+              issue_chain<8>(d_tmem, (uint32_t)(pair * 128 + 64), b_lo + (kTcPlaneBytes >> 4),
+                             b_hi_word, 1u);
+            } else {
+              for (int ks = 0; ks < ks_left; ks++)
+                umma_tf32_ts_elect(d_tmem, (uint32_t)(pair * 128 + ks * 8),
+                                   ((uint64_t)b_hi_word << 32) |
+                                       (uint64_t)(b_lo + (ks >> 3) * (kTcPlaneBytes >> 4) + (ks & 7) * 16),
+                                   kTcIdesc, (pair == 0 && ks == 0) ? 0u : 1u);
             }
-            seg_prev = s;
-            umma_commit(bar_empty + 8 * stage);     // the stage is free once these MMAs have read it
+            umma_commit_elect(bar_empty + 8 * stage);
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(bar_acc_full + 8 * buf);      // accumulators complete
+          umma_commit_elect(acc_bar);
         }
-        umma_commit(bar_a_empty);                   // the draw tile may be overwritten
+        // ---- high plane: chains of kTcChain k-steps, each into its own accumulator ----------------
+        for (int pair = 0; pair < tc.n_pairs; pair++) {
+          const long long t0 = dbg ? clock64() : 0;
+          mbar_wait_sticky(bar_full + 8 * stage, phase, failed);
+          if (dbg) t_wait_full += clock64() - t0;
+          tc_fence_after();
+          const uint32_t b_lo = ((smem_u32(b_s + stage * kTcCopyBytes) & 0x3FFFFu) >> 4) | (8u << 16);
+          const int ks_left = n_ksteps - pair * 16;
+#pragma unroll
+          for (int q = 0; q < 16 / kTcChain; q++) {           // the chains of the pair of planes
+            const int n = ks_left - q * kTcChain;             // k-steps left for this chain
+            if (n > 0) {
+              const uint32_t d_tmem = acquire_acc();
+              const uint32_t acc_bar = bar_acc_full + 8 * ((d_tmem - kTcAccCol) / kTcN);
+              const uint32_t a_tmem = (uint32_t)(pair * 128 + q * kTcChain * 8);
+              const uint32_t b_q = b_lo + (uint32_t)((q * kTcChain) >> 3) * (kTcPlaneBytes >> 4) +
+                                   (uint32_t)((q * kTcChain) & 7) * 16;
+              if (n >= kTcChain) {
+                issue_chain<kTcChain>(d_tmem, a_tmem, b_q, b_hi_word, 0u);
+              } else {
+                for (int ks = 0; ks < n; ks++)
+                  umma_tf32_ts_elect(d_tmem, a_tmem + ks * 8,
+                                     ((uint64_t)b_hi_word << 32) | (uint64_t)(b_q + ks * 16), kTcIdesc,
+                                     ks == 0 ? 0u : 1u);
+              }
+              umma_commit_elect(acc_bar);
+            }
+          }
+          umma_commit_elect(bar_empty + 8 * stage);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
       }
-      if (!ok) atomicExch(args.error_flag, 2);
+    }
+    if (failed && lane == 0) atomicExch(args.error_flag, 2);
+    if (dbg && lane == 0) {
+      long long* d = args.debug + (size_t)blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = t_wait_a; d[2] = t_wait_acc; d[3] = t_wait_full;
     }
   } else {
-    // ===== epilogue warps: thread m owns TMEM lane m = draw m of the tile ==========================
-    const int m = threadIdx.x;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    long long job_count = 0;
+    // ===== epilogue warps.  Thread m owns TMEM lane m = draw m of the tile.  Eight warps in two
+    // groups: group g takes radial bin g of the pair (64 accumulator columns).  What a short chain
+    // waits for is the hand-off of the accumulator (commit -> load -> arrive -> next chain), not the
+    // arithmetic (TC_TUNE_TCGEN_DEBUG counters): the accumulator is handed back right after the
+    // TMEM load.  Tried and measured slower: 16 warps of 32 columns (arrivals on one mbarrier
+    // serialise), one polling lane per warp plus a named barrier and a single arrival. ==============
+    const int quarter = warp & 3;                       // TMEM lanes a warp may access: 32 (warp % 4)
+    const int rr = warp < 4 ? 0 : 1;                    // warps 0-3, 6-9
+    const int m = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t unit_count = 0;
+    long long tile_prev = -1;
+    bool ok = true;
+    const bool dbg = kTcDebug && args.debug != nullptr;
+    long long t_store = 0, t_cload = 0, t_wait = 0;
+    const long long t_begin = clock64();
     const int n_ranges = args.n_ranges_cen + args.n_ranges_sat;
-    for (long long tile = blockIdx.x; tile < args.n_tiles && ok; tile += gridDim.x) {
-      {
-        double nc = 0.0, ns = 0.0;
-        for (int q = 0; q < n_ranges; q++) {
-          const double v = args.ngal_parts[(size_t)q * args.ngal_ld + tile * kTcM + m];
-          if (q < args.n_ranges_cen) nc += v; else ns += v;
-        }
-        args.ngal_tile[(tile * 2 + 0) * kTcM + m] = nc;
-        args.ngal_tile[(tile * 2 + 1) * kTcM + m] = ns;
-      }
-      double* parts = args.parts + (size_t)tile * tc.n_parts * kTcM + m;
-      for (int ib = 0; ib < tc.n_ib && ok; ib++) {
-        float c[kTcNI];
+    const int n_chunks = tc.kp / 32;
+    for (long long item = item_lo; item < item_hi && ok; item++) {
+      const long long tile = item / tc.n_ib;
+      const int ib = (int)(item - tile * tc.n_ib);
+      const long long t_s0 = dbg ? clock64() : 0;
+      if (tile != tile_prev && rr == 0) {
+        // Every MMA that reads the previous tile has completed: this thread has waited for the
+        // accumulator of the last chain, whose commit follows all earlier MMAs.
+        const float4* src = reinterpret_cast<const float4*>(
+            args.h_img + ((size_t)tile * n_chunks * kTcM + m) * 32);
+        for (int ch = 0; ch < n_chunks; ch++) {
+          float4 v[8];
 #pragma unroll
-        for (int j = 0; j < kTcNI; j++) {
-          const int i = ib * kTcNI + j;
-          c[j] = i < args.n_rows ? args.c_img[((size_t)tile * args.n_pad + i) * kTcM + m] : 0.0f;
+          for (int j = 0; j < 8; j++) v[j] = __ldg(src + (size_t)ch * kTcM * 8 + j);
+          tmem_st32(lane_base + (uint32_t)(ch * 32), v);
         }
-        for (int rp = 0; rp < tc.n_rp; rp++, job_count++) {
-          const int buf = (int)(job_count % n_acc);
-          const uint32_t use = (uint32_t)(job_count / n_acc);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full);
+        {
+          // number densities of the tile (both CTAs that share a tile write the same values)
+          double nc = 0.0, ns = 0.0;
+          for (int q = 0; q < n_ranges; q++) {
+            const double v = args.ngal_parts[(size_t)q * args.ngal_ld + tile * kTcM + m];
+            if (q < args.n_ranges_cen) nc += v; else ns += v;
+          }
+          args.ngal_tile[(tile * 2 + 0) * kTcM + m] = nc;
+          args.ngal_tile[(tile * 2 + 1) * kTcM + m] = ns;
+        }
+      }
+      tile_prev = tile;
+      const long long t_s1 = dbg ? clock64() : 0;
+      double* parts = args.parts + ((size_t)tile * tc.n_parts + (size_t)ib * 2 * tc.n_rp) * kTcM + m;
+      float c[kTcNI];
+#pragma unroll
+      for (int j = 0; j < kTcNI; j++) {
+        const int i = ib * kTcNI + j;
+        c[j] = i < args.n_rows ? args.c_img[((size_t)tile * args.n_pad + i) * kTcM + m] : 0.0f;
+      }
+      if (dbg) {
+        float keep = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTcNI; j++) keep += c[j];
+        if (keep == 1.2345e-30f) t_wait++;       // forces the loads to complete before the clock
+        t_store += t_s1 - t_s0;
+        t_cload += clock64() - t_s1;
+      }
+      for (int rp = 0; rp < tc.n_rp && ok; rp++) {
+        double sum = 0.0;
+        for (int u = 0; u <= n_hi_units; u++, unit_count++) {   // the low chain, then the high chains
+          const uint32_t buf = unit_count & 1, use = unit_count >> 1;
+          const long long t_w0 = dbg ? clock64() : 0;
           ok = mbar_wait(bar_acc_full + 8 * buf, use & 1);
           ok = __all_sync(0xffffffffu, ok);
+          if (dbg) t_wait += clock64() - t_w0;
           if (!ok) break;
           tc_fence_after();
-#pragma unroll
-          for (int rr = 0; rr < kTcRB; rr++) {
-            double sum = 0.0;
-#pragma unroll
-            for (int ch = 0; ch < kTcNI / 32; ch++) {
-              const uint32_t col = (uint32_t)(buf * acc_stride + rr * kTcNI + ch * 32);
-              float v[32];
-              tmem_ld32(tmem_base + lane_base + col, v);
-              for (int s = 1; s < seg; s++) {
-                float u[32];
-                tmem_ld32(tmem_base + lane_base + col + s * kTcN, u);
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] += u[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float p = v[j] * c[ch * 32 + j];
-                p = fmaf(v[j + 1], c[ch * 32 + j + 1], p);
-                p = fmaf(v[j + 2], c[ch * 32 + j + 2], p);
-                p = fmaf(v[j + 3], c[ch * 32 + j + 3], p);
-                sum += (double)p;
-              }
-            }
-            parts[(size_t)(ib * 2 * tc.n_rp + 2 * rp + rr) * kTcM] = sum;
-          }
+          float v[kTcNI];
+          tmem_ld64(lane_base + (uint32_t)(kTcAccCol + buf * kTcN + rr * kTcNI), v);
+          // hand the accumulator back before the arithmetic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+#pragma unroll
+          for (int j = 0; j < kTcNI; j += 8) {
+            float p = v[j] * c[j];
+#pragma unroll
+            for (int e = 1; e < 8; e++) p = fmaf(v[j + e], c[j + e], p);
+            sum += (double)p;
+          }
         }
+        if (!ok) break;
+        parts[(size_t)(2 * rp + rr) * kTcM] = sum;
       }
     }
     if (!ok && lane == 0) atomicExch(args.error_flag, 3);
+    if (dbg && threadIdx.x == 0) {
+      long long* d = args.debug + (size_t)blockIdx.x * 8;
+      d[4] = clock64() - t_begin; d[5] = t_store; d[6] = t_cload; d[7] = t_wait;
+    }
   }
 
   tc_fence_before();
@@ -373,7 +591,7 @@ struct WeightsImageArgs {
   long long n_draws;
   int n_ranges_cen, n_ranges_sat;
   int kp, n_pad, n_rows;
-  uint8_t* a_img;
+  float* h_img;
   float* c_img;
   double* ngal_parts;
   long long ngal_ld;
@@ -388,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) weights_image_kernel(const Weight
   const long long n_blocks = (args.n_draws + 7) / 8;
   const long long n_items = n_blocks * n_ranges;
   const long long warp0 = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const size_t a_bytes = (size_t)kTcM * args.kp * 4, sbo_a = (size_t)args.kp * 32;
+  const int n_chunks = args.kp / 32;
   for (long long item = warp0; item < n_items; item += (long long)gridDim.x * kWarps) {
     const long long block = item / n_ranges;
     const int q = (int)(item - block * n_ranges);
@@ -396,13 +614,15 @@ __global__ void __launch_bounds__(kThreads, 1) weights_image_kernel(const Weight
     const bool live = draw < args.n_draws;
     const long long tile = draw / kTcM;
     const int m = (int)(draw - tile * kTcM);
-    uint8_t* a_tile = args.a_img + (size_t)tile * a_bytes;
+    // h image: [tile][row / 32][draw][row % 32], so that the thread owning a TMEM lane reads 128
+    // contiguous bytes per 32-column store
+    float* h_tile = args.h_img + ((size_t)tile * n_chunks * kTcM + m) * 32;
     float* c_tile = args.c_img + (size_t)tile * args.n_pad * kTcM + m;
     int g_begin, g_end;
     occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
     if (q == 0 && live) {   // K padding of the draw's image row (the table stream is zero there too)
       for (int row = args.n_rows + (lane >> 3); row < args.kp; row += 4)
-        *reinterpret_cast<float*>(a_tile + canon_offset(m, row, sbo_a)) = 0.0f;
+        h_tile[(size_t)(row >> 5) * kTcM * 32 + (row & 31)] = 0.0f;
     }
     double total = 0.0;
     occupation_item(args.plan, args.model,
@@ -413,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) weights_image_kernel(const Weight
                       const float h = to_tf32((float)w);
                       total += w;
                       if (live) {
-                        *reinterpret_cast<float*>(a_tile + canon_offset(m, row, sbo_a)) = h;
+                        h_tile[(size_t)(row >> 5) * kTcM * 32 + (row & 31)] = h;
                         c_tile[(size_t)row * kTcM] = (float)(2.0 * w - (double)h);
                       }
                     },

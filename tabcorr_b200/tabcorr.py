@@ -339,8 +339,11 @@ class _SmallBatchBuffers:
                               pin_memory=True)
         self.theta_np, self.ngal_np, self.xi_np = (self.theta.numpy(), self.ngal.numpy(),
                                                    self.xi.numpy())
-        need = max(int(group.lib.tc_predict_workspace_bytes(group.handle, self.capacity, sep))
-                   for sep in (0, 1))
+        # large enough for either precision: the 3xTF32 mode then takes the same (tcgen05) path for
+        # small and large batches, so its results do not depend on how a batch is cut
+        need = max(int(group.lib.tc_predict_workspace_bytes_for(group.handle, self.capacity, sep,
+                                                                prec))
+                   for sep in (0, 1) for prec in (_lib.TC_PRECISION_FP64, _lib.TC_PRECISION_3XTF32))
         self.workspace = torch.empty(max(need, 8), dtype=torch.uint8, device=group.device)
 
 

@@ -521,3 +521,62 @@ def test_two_streams_share_a_table(tb):
     for k in range(2):
         assert torch.equal(results[k][0], serial[k][0]) and torch.equal(results[k][1], serial[k][1])
     assert len(halotab._ensure_device()._workspace) >= 2
+
+
+# ---------------------------------------------------------------------------------------------
+# the 3xTF32 mode on tcgen05 / TMEM / TMA (csrc/tcgen05_contract.cuh) against the other paths
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('kw,n_draws', [
+    (dict(n_mass=60, n_sec=2, n_r=20), 5000),        # headline shape: 4 column blocks, 4 K segments
+    (dict(n_mass=60, n_sec=2, n_r=7), 300),          # odd number of radial bins (half-used MMA)
+    (dict(n_mass=30, n_sec=1, n_r=19), 129),         # one column block, one segment, 2 tiles
+    (dict(n_mass=13, n_sec=1, n_r=3), 1),            # 26 rows: padding everywhere, one draw
+    (dict(n_mass=47, n_sec=1, n_r=5), 777),          # 94 rows: partial second column block
+    (dict(n_mass=64, n_sec=2, n_r=2), 2500),         # 256 rows: the largest eligible table
+])
+def test_tcgen05_contraction_against_fp64_and_warp_level_tf32(tb, kw, n_draws, monkeypatch):
+    """Batches on auto tables of at most 256 padded rows run the 3xTF32 mode on the
+    5th-generation tensor cores.  Same accuracy bar as the warp-level path (1e-6 of the sum of the
+    term magnitudes); the two TF32 paths agree with each other to 2e-6; results do not depend on
+    how a batch is cut; ngal is the FP64 value."""
+    import torch
+    from tabcorr_b200.models import ModelSpec, theta_from_params
+    tab = cases.synthetic.make_table(**kw)
+    halotab = table_from_dict(tb, tab)
+    draws = cases.synthetic.make_draws(n_draws, seed=77)
+    theta = torch.from_numpy(theta_from_params(draws, None, ModelSpec())).cuda()
+    ngal, xi = halotab.predict_batch(theta, as_numpy=False)
+    _, scale = _abs_table(tb, tab).predict_batch(theta, as_numpy=False)
+    ngal_t, xi_t = halotab.predict_batch(theta, as_numpy=False, precision='3xtf32')
+    assert torch.isfinite(xi_t).all()
+    err = ((xi_t - xi).abs() / scale).max().item()
+    assert err < TF32_RTOL, err
+    assert not torch.equal(xi_t, xi)
+    np.testing.assert_allclose(ngal_t.cpu().numpy(), ngal.cpu().numpy(), rtol=1e-13)
+    # the warp-level TF32 MMA path (TC_TUNE_TCGEN=0) is the other arithmetic of the same mode
+    monkeypatch.setenv('TC_TUNE_TCGEN', '0')
+    _, xi_w = halotab.predict_batch(theta, as_numpy=False, precision='3xtf32')
+    monkeypatch.delenv('TC_TUNE_TCGEN')
+    assert not torch.equal(xi_w, xi_t)
+    assert ((xi_w - xi_t).abs() / scale).max().item() < 2 * TF32_RTOL
+    # bitwise independent of the batch: a sub-batch, and the host path cut into chunks
+    if n_draws > 3:
+        lo, hi = n_draws // 3, n_draws // 3 + max(1, n_draws // 2)
+        _, xi_sub = halotab.predict_batch(theta[lo:hi].contiguous(), as_numpy=False,
+                                          precision='3xtf32')
+        assert torch.equal(xi_sub, xi_t[lo:hi])
+        host = halotab.predict_batch(draws, precision='3xtf32')
+        assert np.array_equal(host[1], xi_t.cpu().numpy())
+
+
+def test_tcgen05_interpolator_group(tb):
+    """An Interpolator group stacks its tables as extra radial bins of one launch; the spline of
+    the 3xTF32 results stays within the mode's tolerance of the FP64 prediction."""
+    tables, param_table, grid_draws = cases.grid_case('grid2d')
+    interp = tb.Interpolator([table_from_dict(tb, t) for t in tables], param_table)
+    big = {k: np.tile(v, 40) for k, v in grid_draws.items()}
+    a = interp.predict_batch(big)
+    b = interp.predict_batch(big, precision='3xtf32')
+    np.testing.assert_allclose(b[0], a[0], rtol=TF32_RTOL)
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6 * np.abs(a[1]).max())
+    assert not np.array_equal(a[1], b[1])

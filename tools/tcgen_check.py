@@ -10,6 +10,8 @@ from tabcorr_b200.models import ModelSpec, theta_from_params
 
 shapes = [dict(n_mass=60, n_sec=2, n_r=20), dict(n_mass=30, n_sec=1, n_r=19),
           dict(n_mass=60, n_sec=2, n_r=42, kind='multipole'), dict(n_mass=60, n_sec=1, n_r=20)]
+if os.environ.get('TCGEN_SHAPES'):
+    shapes = [shapes[int(i)] for i in os.environ['TCGEN_SHAPES'].split(',')]
 n_draws = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 for shape in shapes:
     tab = synthetic.make_table(**shape)
@@ -20,7 +22,7 @@ for shape in shapes:
     ngal, xi = halotab.predict_batch(theta, as_numpy=False)
     _, scale = habs.predict_batch(theta, as_numpy=False)
     torch.cuda.synchronize()
-    for knobs in ({'TCGEN': '0'}, {'TCGEN_SEG': '1'}, {'TCGEN_SEG': '2'}, {'TCGEN_SEG': '4'}):
+    for knobs in [dict(kv.split('=') for kv in item.split(',')) for item in os.environ.get('TCGEN_KNOBS', 'TCGEN=0;TCGEN_SEG=1;TCGEN_SEG=2;TCGEN_SEG=4').split(';')]:
         for key in [k for k in os.environ if k.startswith('TC_TUNE_')]:
             del os.environ[key]
         for k, v in knobs.items():
