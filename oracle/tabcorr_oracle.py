@@ -24,7 +24,8 @@ lines it follows.  Parity status:
   be re-checked against a real halotools install when one is available.  The call sites anchoring
   them are ``tabcorr/tabcorr.py:556-563``.  The same holds for ``Leauthaud11Oracle``
   (``Leauthaud11Cens`` / ``Leauthaud11Sats`` over ``Behroozi10SmHm``: Leauthaud et al. 2011
-  eqs. 8-14, Behroozi et al. 2010 eq. 21, with halotools' h = 0.7 conversions and its numerical
+  eqs. 8-14, Behroozi et al. 2010 eq. 21, with halotools' unit conversions (h = 0.7 in
+  ``Behroozi10SmHm``, h = 0.72 in ``Leauthaud11Sats``) and its numerical
   inversion of the stellar-to-halo-mass relation by a 100-knot interpolating cubic spline).
 """
 
@@ -144,7 +145,8 @@ class Leauthaud11Oracle(Zheng07Oracle):
     threshold, ``redshift`` the redshift at which the SMHM parameters are evaluated.
     """
 
-    littleh = 0.7
+    littleh = 0.7         # Behroozi10SmHm.littleh (unit conversion of the SMHM relation)
+    littleh_sats = 0.72   # Leauthaud11Sats.littleh (its own constant, not the SMHM model's)
     DEFAULTS = dict(smhm_m0_0=10.72, smhm_m0_a=0.59, smhm_m1_0=12.35, smhm_m1_a=0.3,
                     smhm_beta_0=0.43, smhm_beta_a=0.18, smhm_delta_0=0.56, smhm_delta_a=0.18,
                     smhm_gamma_0=1.54, smhm_gamma_a=2.52, scatter_model_param1=0.2,
@@ -199,12 +201,13 @@ class Leauthaud11Oracle(Zheng07Oracle):
     def _baseline_satellites(self, prim_haloprop):
         # Leauthaud11Sats.mean_occupation with _update_satellite_params
         p = self.param_dict
-        knee_threshold = 10.0**self.mean_log_halo_mass(self.threshold) * self.littleh
+        h = self.littleh_sats
+        knee_threshold = 10.0**self.mean_log_halo_mass(self.threshold) * h
         knee_mass = 1.0e12
         msat = knee_mass * p['bsat'] * (knee_threshold / knee_mass)**p['betasat']
         mcut = knee_mass * p['bcut'] * (knee_threshold / knee_mass)**p['betacut']
         mass = np.asarray(prim_haloprop, dtype=np.float64)
-        out = np.exp(-mcut / (mass * self.littleh)) * (mass * self.littleh / msat)**p['alphasat']
+        out = np.exp(-mcut / (mass * h)) * (mass * h / msat)**p['alphasat']
         if self.modulate_with_cenocc:
             out = out * self._baseline_centrals(mass)
         return out

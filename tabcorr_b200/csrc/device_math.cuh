@@ -45,9 +45,11 @@ __device__ __forceinline__ void load_math_tables(double* tab) {
   for (int i = threadIdx.x; i < kTabDoubles; i += blockDim.x) tab[i] = g_math_tables[i];
 }
 
-// 0.5 (1 + erf(x)) for |x| < 2^49.  Interval i = rint(2 x + 12) is centred at x = -6 + i / 2;
-// intervals below 0 / above 24 map to two extra table columns holding the constants 0 and 1, so
-// the range clamp is two integer min/max instead of double-precision ones (7 instructions each).
+// 0.5 (1 + erf(x)).  Interval i = rint(2 x + 12) is centred at x = -6 + i / 2; intervals below 0 /
+// above 24 map to two extra table columns holding the constants 0 and 1, so the range clamp is
+// two integer min/max instead of double-precision ones (7 instructions each).  The rounding trick
+// needs |x| < 2^49: beyond |x| >= 16 (sigma_logM -> 0, infinities) the result is the step 0 / 1
+// that erf gives there, selected on the integer pipe from the sign and exponent bits.
 __device__ __forceinline__ double half_erfc_neg(double x, const double* __restrict__ tab) {
   const double v = fma(x, 2.0, 12.0 + kRoundMagic);
   const int i = __double2loint(v);
@@ -56,7 +58,10 @@ __device__ __forceinline__ double half_erfc_neg(double x, const double* __restri
   double p = c[kErfDeg * kErfStride];
 #pragma unroll
   for (int k = kErfDeg - 1; k >= 0; k--) p = fma(p, t, c[k * kErfStride]);
-  return p;
+  const int hx = __double2hiint(x);
+  const bool huge = (hx & 0x7fffffff) >= 0x40300000;        // |x| >= 16, infinity, NaN
+  const int step_hi = hx < 0 ? 0 : 0x3ff00000;              // 0.0 or 1.0
+  return huge ? __hiloint2double(step_hi, 0) : p;
 }
 
 // ln t for t > 0 (normal double): 128-entry table of (1 / c_i, ln c_i) + degree-7 log1p

@@ -16,7 +16,8 @@ namespace {
 //   <N_cen>(M) = 0.5 (1 - erf((log10 M*_thr - log10 M*(M)) / (sqrt(2) sigma_logM*)))
 //   <N_sat>(M) = exp(-M_cut / (M h)) (M h / M_sat)^alphasat  [x <N_cen>(M) if modulate_with_cenocc]
 //   M_sat = 1e12 bsat (M_knee / 1e12)^betasat,  M_cut = 1e12 bcut (M_knee / 1e12)^betacut,
-//   M_knee = h 10^(log10 M_h(M*_thr)),  h = 0.7
+//   M_knee = h 10^(log10 M_h(M*_thr)),  h = 0.72 in Leauthaud11Sats (its own littleh; the
+//   stellar-to-halo-mass relation Behroozi10SmHm converts with h = 0.7)
 // log10 M_h(log10 M*) is Behroozi et al. (2010) eq. 21 with parameters x_0 + x_a (a - 1) at the
 // model redshift.  halotools inverts it numerically: it tabulates log10 M_h on the 100 knots
 // log10 M* = linspace(8.5, 12.5, 100) and evaluates the interpolating cubic spline (scipy
@@ -32,7 +33,8 @@ namespace {
 // ------------------------------------------------------------------------------------------
 constexpr int kL11Knots = 100;
 constexpr int kL11DrawsPerBlock = 64;     // 64 x 3.2 KB of spline tables + math tables < 227 KB
-constexpr double kL11LittleH = 0.7;
+constexpr double kL11LittleH = 0.7;        // Behroozi10SmHm.littleh
+constexpr double kL11LittleHSats = 0.72;   // Leauthaud11Sats.littleh
 constexpr double kL11LogMsLo = 8.5, kL11LogMsHi = 12.5;
 constexpr double kLn10 = 2.302585092994045684;
 
@@ -146,12 +148,12 @@ __device__ void l11_prepare_block(L11Draw* draws, int n_block, long long draw0,
     } else {
       // Leauthaud11Sats._update_satellite_params: knee = h M_h(threshold) / 1e12
       const double log_knee = l11_log_halo_mass(model.threshold, logm0, logm1, beta, delta, gamma) +
-                              log10(kL11LittleH) - 12.0;
+                              log10(kL11LittleHSats) - 12.0;
       const double msat = 1e12 * th[12 * theta_ps] * exp10(th[15 * theta_ps] * log_knee);
       const double mcut = 1e12 * th[13 * theta_ps] * exp10(th[14 * theta_ps] * log_knee);
       draws[b].inv_scatter = 1.0 / (1.4142135623730951 * th[10 * theta_ps]);
-      draws[b].neg_mcut_h = -mcut / kL11LittleH;
-      draws[b].ln_h_over_msat = log(kL11LittleH / msat);
+      draws[b].neg_mcut_h = -mcut / kL11LittleHSats;
+      draws[b].ln_h_over_msat = log(kL11LittleHSats / msat);
       draws[b].alphasat = th[11 * theta_ps];
       draws[b].a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
       draws[b].a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;

@@ -112,20 +112,35 @@ class SharedHostArray:
             except Exception:
                 pass
         self.tensor = self.array = None
+        # unlink first and on its own: close() raises BufferError while a caller still holds views
+        # of the segment (they stay valid: the mapping lives until the last view is gone), and
+        # that must not leave the /dev/shm entry behind
+        if self.owner:
+            try:
+                self.shm.unlink()
+            except Exception:
+                pass
         try:
             self.shm.close()
-            if self.owner:
-                self.shm.unlink()
         except Exception:
             pass
         self.shm = None
 
 
+_SEGMENT_CALLS = {}
+
+
 def _shared_segment(n_doubles, group=None):
-    key = (id(group), int(n_doubles))
+    """Two segments per group, used alternately: the views rank ``dst`` got from call k stay
+    untouched during call k + 1 (whose writers are only ordered against dst by that call's final
+    barrier) and are reused by call k + 2, when dst's caller has long started call k + 1 -- so
+    "valid until the next call" holds without an extra barrier at entry."""
+    calls = _SEGMENT_CALLS.get(id(group), 0)
+    _SEGMENT_CALLS[id(group)] = calls + 1
+    key = (id(group), int(n_doubles), calls & 1)
     if key not in _SEGMENTS:
-        for old_key in [k for k in _SEGMENTS if k[0] == key[0]]:   # one live segment per group
-            _SEGMENTS.pop(old_key).close()
+        for old_key in [k for k in _SEGMENTS if k[0] == key[0] and (k[1] != key[1] or k[2] == key[2])]:
+            _SEGMENTS.pop(old_key).close()      # segments of another batch size are dropped
         _SEGMENTS[key] = SharedHostArray(n_doubles, group)
     return _SEGMENTS[key]
 
@@ -152,7 +167,7 @@ def shared_host_fits(n_doubles, group=None):
     segment would raise SIGBUS) or when an equal segment is already mapped."""
     import os
     import torch.distributed as dist
-    if (id(group), int(n_doubles)) in _SEGMENTS:
+    if any(k[:2] == (id(group), int(n_doubles)) for k in _SEGMENTS):
         return True
     fits = [True]
     if dist.get_rank(group) == 0:
@@ -213,8 +228,8 @@ def predict_batch_sharded(halotab, params, n_gauss_prim=10, model=None, dst=0, g
     ``gather``: 'nccl' (default) is that device-side gather; 'host' (one node only) lets every
     rank copy its rows into a shared, CUDA-registered host segment over its own PCIe link, with a
     barrier as the only collective -- the arrays ``dst`` gets back are views of that segment and
-    stay valid until the next call with another batch size; 'auto' picks 'host' when all ranks
-    share a node.
+    stay valid until the next call (two segments alternate, so the next call's writers cannot
+    touch them); 'auto' picks 'host' when all ranks share a node.
     """
     import torch
     import torch.distributed as dist

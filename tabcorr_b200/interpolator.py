@@ -150,6 +150,12 @@ class Interpolator:
     def _ensure_device(self):
         if self._groups is not None:
             return
+        from .tabcorr import _UPLOAD_LOCK
+        with _UPLOAD_LOCK:   # host threads sharing a fresh interpolator upload it once
+            if self._groups is None:
+                self._upload()
+
+    def _upload(self):
         lib = _lib.load()
         first = self.tabcorr_list[0]
         n_r = int(np.prod(first.tpcf_shape))

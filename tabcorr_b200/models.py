@@ -282,7 +282,8 @@ def theta_from_params(params, n_draws=None, spec=None, alloc=None):
     pinned host memory)."""
     columns = theta_columns(params, spec)
     if n_draws is None:
-        n_draws = max([c.shape[0] for c in columns if c.ndim > 0] + [1])
+        lengths = [c.shape[0] for c in columns if c.ndim > 0]
+        n_draws = max(lengths) if lengths else 1     # 0 for a batch of empty arrays
     shape = (n_draws, len(columns))
     theta = np.empty(shape, dtype=np.float64) if alloc is None else alloc(shape)
     for j, column in enumerate(columns):

@@ -82,6 +82,20 @@ def chunk_schedule(n_draws, chunk='auto', edge=None, largest=1 << 20):
     return bounds
 
 
+# serialises the first upload of a table / interpolator shared by several host threads
+_UPLOAD_LOCK = threading.RLock()
+
+
+def batch_size(columns):
+    """Number of draws of a list of parameter columns (arrays ``[B]`` and broadcast scalars): the
+    common array length -- 0 for empty arrays -- or 1 when every column is a scalar."""
+    lengths = [np.shape(c)[0] for c in columns if np.ndim(c) > 0]
+    return max(lengths) if lengths else 1
+
+
+MAX_STREAM_WORKSPACES = 8
+
+
 class DeviceTableGroup:
     """One gal_type table with one or more correlation matrices on the device (``tc_table``)."""
 
@@ -169,10 +183,14 @@ class DeviceTableGroup:
         if self._workspace is None:
             self._workspace = {}
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        current = self._workspace.get(stream)
+        current = self._workspace.pop(stream, None)
         if current is None or current.numel() < need:
             current = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._workspace[stream] = current
+        self._workspace[stream] = current          # most recently used last
+        while len(self._workspace) > MAX_STREAM_WORKSPACES:
+            # short-lived streams must not pin a buffer each for the table's lifetime; a buffer of
+            # an evicted stream stays alive until its kernels finish (caching allocator semantics)
+            self._workspace.pop(next(iter(self._workspace)))
         return current
 
     @staticmethod
@@ -379,8 +397,8 @@ def theta_to_device(params, spec, device):
     asynchronously and transposed on the device."""
     torch = _torch()
     columns = theta_columns(params, spec)
-    n_draws = max([c.shape[0] for c in columns if c.ndim > 0] + [1])
-    stage = torch.empty((len(columns), n_draws), dtype=torch.float64, pin_memory=True)
+    n_draws = batch_size(columns)
+    stage = torch.empty((len(columns), n_draws), dtype=torch.float64, pin_memory=n_draws > 0)
     stage_np = stage.numpy()
     for j, column in enumerate(columns):
         stage_np[j] = column
@@ -472,9 +490,11 @@ class TabCorr:
 
     def _ensure_device(self):
         if self._device_group is None:
-            self._device_group = DeviceTableGroup(
-                self.gal_type, [self.tpcf_matrix], self.attrs['mode'],
-                int(np.prod(self.tpcf_shape)), device=self._device)
+            with _UPLOAD_LOCK:   # host threads sharing a fresh table upload it once
+                if self._device_group is None:
+                    self._device_group = DeviceTableGroup(
+                        self.gal_type, [self.tpcf_matrix], self.attrs['mode'],
+                        int(np.prod(self.tpcf_shape)), device=self._device)
         return self._device_group
 
     # ------------------------------------------------------------------ model handling
@@ -642,8 +662,9 @@ class TabCorr:
                 return None   # the general path reports shape errors
             columns = [array[:, j] for j in range(array.shape[1])]
             columns += [np.float64(0.0)] * (7 - len(columns))
-        n_draws = max([c.shape[0] for c in columns if np.ndim(c) > 0] + [1])
-        if n_draws > SMALL_BATCH or any(np.ndim(c) > 0 and c.shape[0] != n_draws for c in columns):
+        n_draws = batch_size(columns)
+        if (n_draws == 0 or n_draws > SMALL_BATCH or
+                any(np.ndim(c) > 0 and c.shape[0] != n_draws for c in columns)):
             return None
         group = self._ensure_device()
         ngal, xi = group.predict_small(spec, n_gauss, columns, n_draws, separate, precision)
@@ -684,8 +705,13 @@ class TabCorr:
                                              ', '.join(spec.theta_keys)))
             columns = [array[:, j] for j in range(array.shape[1])]
             columns += [np.float64(0.0)] * (spec.n_theta - len(columns))
-        n_draws = max([c.shape[0] for c in columns if np.ndim(c) > 0] + [1])
+        n_draws = batch_size(columns)
         n_ng, n_comp = (2 if separate else 1), group.n_comp(separate)
+        if n_draws == 0:   # an empty batch gives empty results (no launch)
+            if out is not None:
+                self._host_out(out, 0, n_ng, n_comp)
+            return self._format_batch(np.empty((0, n_ng)), np.empty((0, group.n_r, n_comp)),
+                                      separate, False)
         f64 = torch.float64
         # parameters are staged one contiguous column per parameter (a strided fill of [B, 7] rows
         # costs 4x more host time); chunk [lo, hi) owns the block [7 lo, 7 hi) viewed as

@@ -100,13 +100,24 @@ def _worker(rank, world, port, n_draws, out_dir):
             assert result is None
         # 3. the same through the shared host segment (no gather: every rank writes its rows)
         assert tcd.single_node()
-        for mode in ('host', 'auto'):
+        previous = None
+        for mode in ('host', 'auto', 'host', 'host'):
             shared = tcd.predict_batch_sharded(halotab, draws, n_gauss_prim=4, dst=0, gather=mode)
             if rank == 0:
                 assert np.array_equal(shared[0], result[0]) and np.array_equal(shared[1], result[1])
+                # the views of the call before live in the other segment: the writers of this call
+                # (who may run ahead of dst) cannot have touched them
+                if previous is not None:
+                    assert not np.shares_memory(previous[1], shared[1])
+                    assert np.array_equal(previous[1], result[1])
+                previous = shared
             else:
                 assert shared is None
-        assert len(tcd._SEGMENTS) == 1   # cached across calls of the same size
+        assert len(tcd._SEGMENTS) == 2   # two alternating segments, cached across calls of one size
+        # another batch size drops them (and their /dev/shm entries)
+        fewer = {k: v[:n_draws - 2] for k, v in draws.items()}
+        tcd.predict_batch_sharded(halotab, fewer, n_gauss_prim=4, dst=0, gather='host')
+        assert len(tcd._SEGMENTS) == 1
         dist.barrier()
     finally:
         dist.destroy_process_group()

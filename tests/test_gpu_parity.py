@@ -368,13 +368,14 @@ def test_device_math_accuracy(tb):
     lib = _lib.load()
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-7, 7, 200000), np.linspace(-6.3, 6.3, 100001),
-                        [-100.0, 100.0, 0.0, -6.0, 6.0, 5.999999, -5.75, -1e-300]])
+                        [-100.0, 100.0, 0.0, -6.0, 6.0, 5.999999, -5.75, -1e-300, -15.99, 16.0,
+                         1e20, -1e20, 2.0**60, -2.0**60, np.inf, -np.inf, 1e300, -1e300]])
     xd = torch.from_numpy(x).cuda()
     out = torch.empty_like(xd)
     _lib.check(lib.tc_debug_math(0, xd.data_ptr(), None, out.data_ptr(), len(x), None))
     got = out.cpu().numpy()
     assert np.all((got >= 0) & (got <= 1))
-    assert np.max(np.abs(got - 0.5 * (1 + erf(x)))) < 3e-15
+    assert np.max(np.abs(got - 0.5 * (1 + erf(x)))) < 3e-15      # incl. |x| beyond 2^49, +-inf
     t = 10**rng.uniform(-25, 8, 300000)
     alpha = rng.uniform(0.3, 2.5, len(t))
     td, ad = torch.from_numpy(t).cuda(), torch.from_numpy(alpha).cuda()
@@ -445,3 +446,25 @@ def test_random_ragged_shuffled_tables(tb, seed):
                                        atol=RTOL * 1e-3 * max(total, 1e-300))
         for key in ngal_ref:
             close(ngal_sep[key][i], ngal_ref[key])
+
+
+def test_step_function_centrals_and_empty_batch(tb):
+    """sigma_logM -> 0 makes <N_cen> the 0 / 1 step erf gives for infinite arguments (the
+    reference divides by sigma_logM, tabcorr.py:556-559 -> halotools), and a batch of zero draws
+    returns empty results without a launch (round-1 advice)."""
+    tab = cases.synthetic.make_table(n_mass=20, n_sec=2, n_r=6, seed=9)
+    halotab = table_from_dict(tb, tab)
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
+    draws = cases.synthetic.make_draws(40, seed=5)
+    draws['sigma_logM'] = np.full(40, 1e-300)
+    ngal, xi = halotab.predict_batch(draws)
+    assert np.all(np.isfinite(ngal)) and np.all(np.isfinite(xi))
+    for i in (0, 7, 39):
+        model = orc.Zheng07Oracle(cases.draws_row(draws, i))
+        ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, model))
+        assert close(ngal[i], ngal_ref) and close(xi[i], xi_ref)
+    empty = {k: v[:0] for k, v in draws.items()}
+    ngal0, xi0 = halotab.predict_batch(empty)
+    assert ngal0.shape == (0,) and xi0.shape == (0,) + tuple(tab['tpcf_shape'])
+    ngal0, xi0 = halotab.predict_batch(empty, separate_gal_type=True)
+    assert all(v.shape == (0,) for v in ngal0.values()) and len(xi0) == 3

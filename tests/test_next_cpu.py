@@ -140,8 +140,10 @@ def test_resolve_model_families():
 
 
 def test_leauthaud11_oracle_known_answers():
-    """Regression pins of the leauthaud11 restatement (computed by this oracle when it was
-    written -- NOT reference values: halotools is absent, see the oracle header)."""
+    """Regression pins of the leauthaud11 restatement (computed by this oracle -- NOT reference
+    values: halotools is absent, see the oracle header).  Satellites use Leauthaud11Sats' own
+    littleh = 0.72, centrals Behroozi10SmHm's 0.7 (round-1 advice; the satellite pins changed by
+    1-20 % when that was corrected)."""
     from oracle import tabcorr_oracle as orc
     mass = 10**np.array([11.5, 12.5, 13.5, 14.5])
     model = orc.Leauthaud11Oracle()
@@ -151,7 +153,7 @@ def test_leauthaud11_oracle_known_answers():
         rtol=1e-10)
     np.testing.assert_allclose(
         model.mean_occupation_satellites(prim_haloprop=mass, sec_haloprop_percentile=np.full(4, .3)),
-        [1.108321904656615e-08, 0.04272086498081341, 1.2170524513583085, 13.168140436737644],
+        [1.3513600498370619e-08, 0.04373237926410932, 1.224272670440629, 13.223118443159517],
         rtol=1e-10)
     model = orc.Leauthaud11Oracle(threshold=11.0, redshift=0.5, decorated=True,
                                   modulate_with_cenocc=False)
@@ -162,5 +164,5 @@ def test_leauthaud11_oracle_known_answers():
         rtol=1e-9)
     np.testing.assert_allclose(
         model.mean_occupation_satellites(prim_haloprop=mass, sec_haloprop_percentile=pct),
-        [6.870067016061366e-06, 0.007813292140338041, 0.03746174399873051, 1.1654583688653277],
+        [7.82793499675266e-06, 0.007944292740829723, 0.03765846917308047, 1.1702449732622406],
         rtol=1e-10)
