@@ -452,6 +452,7 @@ def test_step_function_centrals_and_empty_batch(tb):
     """sigma_logM -> 0 makes <N_cen> the 0 / 1 step erf gives for infinite arguments (the
     reference divides by sigma_logM, tabcorr.py:556-559 -> halotools), and a batch of zero draws
     returns empty results without a launch (round-1 advice)."""
+    from oracle import tabcorr_oracle as orc
     tab = cases.synthetic.make_table(n_mass=20, n_sec=2, n_r=6, seed=9)
     halotab = table_from_dict(tb, tab)
     table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], 'auto')
