@@ -419,7 +419,7 @@ def run_gpu_arm(args):
     import tabcorr_b200
     from tabcorr_b200 import _lib, synthetic
     from tabcorr_b200.models import ModelSpec, theta_from_params
-    from tabcorr_b200.distributed import gather_rows, predict_batch_sharded
+    from tabcorr_b200.distributed import gather_slab_chunks, predict_batch_sharded
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -447,15 +447,23 @@ def run_gpu_arm(args):
     ngal = torch.empty((n_draws, 1), dtype=torch.float64, device=device)
     xi = torch.empty((n_draws, N_R, 1), dtype=torch.float64, device=device)
     result = torch.empty((n_draws, 1 + N_R), dtype=torch.float64, device=device)
+    full = (torch.empty((n_draws * world, 1 + N_R), dtype=torch.float64, device=device)
+            if world > 1 and rank == 0 else None)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     lib = _lib.load()
+    n_chunks = args.gather_chunks if world > 1 else 1
+    draws_per_launch = n_draws - n_draws * (n_chunks - 1) // n_chunks   # the last chunk's
+
+    def compute_chunk(c0, c1):
+        halotab.predict_into_slab(theta[c0:c1], result[c0:c1], N_GAUSS)
 
     def step():
-        group.predict_into(spec, N_GAUSS, theta, None, False, ngal, 0, xi, 0)
-        if world > 1:  # the one collective of the path: results to rank 0
-            result[:, :1].copy_(ngal)
-            result[:, 1:].copy_(xi.view(n_draws, N_R))
-            gather_rows(result, n_draws * world, dst=0)
+        if world == 1:
+            group.predict_into(spec, N_GAUSS, theta, None, False, ngal, 0, xi, 0)
+        else:
+            # the kernels write their rows of the [B, 1 + R] slab directly; the one collective of
+            # the path (results to rank 0) is issued per chunk and overlaps the next chunk's kernels
+            gather_slab_chunks(compute_chunk, result, full, n_chunks=n_chunks, dst=0)
 
     def barrier():
         if world > 1:
@@ -521,8 +529,13 @@ def run_gpu_arm(args):
     same = True
     if rank == 0:
         ngal_host, xi_host = host_result
-        same = (np.array_equal(ngal_host[:n_draws], ngal[:, 0].cpu().numpy()) and
-                np.array_equal(xi_host[:n_draws], xi[:, :, 0].cpu().numpy()))
+        if world == 1:
+            same = (np.array_equal(ngal_host[:n_draws], ngal[:, 0].cpu().numpy()) and
+                    np.array_equal(xi_host[:n_draws], xi[:, :, 0].cpu().numpy()))
+        else:   # the gathered device result of all ranks against the host-to-host result
+            gathered = full.cpu().numpy()
+            same = (np.array_equal(ngal_host, gathered[:, 0]) and
+                    np.array_equal(xi_host, gathered[:, 1:]))
 
     peak = ctypes.c_double()
     _lib.check(lib.tc_measure_dmma_peak(local_rank, ctypes.byref(peak)))
@@ -534,8 +547,8 @@ def run_gpu_arm(args):
 
     if rank == 0:
         k_ms = float(np.mean(kernel_ms))
-        executed = executed_flops(n_rows, N_R) * n_draws
-        dense = algorithmic_flops(n_rows, N_R) * n_draws
+        executed = executed_flops(n_rows, N_R) * draws_per_launch
+        dense = algorithmic_flops(n_rows, N_R) * draws_per_launch
         achieved = executed / (k_ms * 1e-3) * 1e-12
         roofline = {
             'bound': 'tensor', 'kernel': 'predict_kernel<7, auto> (fused occupation + DMMA quadratic '
@@ -557,11 +570,12 @@ def run_gpu_arm(args):
             'traffic_unit': 'bytes of DRAM read + write per launch',
             'traffic_source': 'constant copied from the ncu --set full capture summarised in ' +
                               NCU_TRAFFIC_SOURCE + ' (not measured by this run)',
-            'algorithmic_bytes_per_launch': ALGORITHMIC_BYTES_PER_DRAW * n_draws + table_bytes,
+            'algorithmic_bytes_per_launch': ALGORITHMIC_BYTES_PER_DRAW * draws_per_launch + table_bytes,
+            'draws_per_launch': draws_per_launch,
             'kernel_ms': k_ms, 'finalize_ms': float(np.mean(finalize_ms)),
             'kernel_share_of_step': float(np.sum(kernel_ms) / total_ms) if world == 1 else None,
         }
-        if n_draws != DRAWS_PER_GPU:
+        if draws_per_launch != DRAWS_PER_GPU:
             roofline['traffic'] = None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -570,7 +584,8 @@ def run_gpu_arm(args):
             'data': 'synthetic', 'config': workload_config(n_draws),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'timing': 'wall clock around predict_batch calls'},
-            'gpu_launches': 2 * args.steps,  # predict_kernel + finalize_kernel per timed step
+            # predict_kernel + finalize_kernel per chunk of a timed step
+            'gpu_launches': 2 * n_chunks * args.steps,
             'roofline': roofline, 'clocks': clocks,
             'results_consistent': bool(same),
         }
@@ -616,6 +631,8 @@ def main():
     parser.add_argument('--cpu-sample', type=int, default=8000,
                         help='draws of the workload timed for cpu_baseline')
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    parser.add_argument('--gather-chunks', type=int, default=3,
+                        help='N > 1: chunks per step whose gather overlaps the next chunk\'s kernels')
     parser.add_argument('--no-configs', action='store_true',
                         help='skip the `configs` block (the other BASELINE.json configurations)')
     parser.add_argument('--config-draws', type=int, default=100000,

@@ -69,6 +69,39 @@ def gather_rows(local, n_total, dst=0, group=None):
     return torch.cat(pieces, dim=0)
 
 
+def gather_slab_chunks(compute_chunk, slab, full, n_chunks=3, dst=0, group=None):
+    """The data-parallel step with its one collective overlapped: this rank's ``[n_local, C]``
+    result slab is produced in ``n_chunks`` row ranges -- ``compute_chunk(c0, c1)`` launches the
+    kernels that write ``slab[c0:c1]`` on the current stream (``TabCorr.predict_into_slab`` does,
+    through the output strides of the C ABI: no packing copies) -- and every range is sent to
+    rank ``dst`` with an asynchronous ``gather`` as soon as it is launched, so that the transfer
+    of range c runs while the kernels of range c + 1 do.  On ``dst`` the receive buffers are the
+    row blocks of ``full`` (``[world * n_local, C]``, rank-major like ``shard_bounds``), i.e. the
+    result is assembled in place, without a concatenation.  All ranks hold equally many rows.
+    Returns after every gather has completed (on the current stream for NCCL)."""
+    import torch.distributed as dist
+    n_local = slab.shape[0]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        compute_chunk(0, n_local)
+        if full is not None and full.data_ptr() != slab.data_ptr():
+            full.copy_(slab)
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_chunks = max(1, min(int(n_chunks), n_local)) if n_local else 1
+    cuts = [n_local * c // n_chunks for c in range(n_chunks + 1)]
+    works = []
+    for c in range(n_chunks):
+        c0, c1 = cuts[c], cuts[c + 1]
+        if c1 > c0:
+            compute_chunk(c0, c1)
+        receive = None
+        if rank == dst:
+            receive = [full[r * n_local + c0:r * n_local + c1] for r in range(world)]
+        works.append(dist.gather(slab[c0:c1], receive, dst=dst, group=group, async_op=True))
+    for work in works:
+        work.wait()
+
+
 class SharedHostArray:
     """A float64 host buffer all ranks of one node map (``multiprocessing.shared_memory``), page
     locked for CUDA in every process (``cudaHostRegister``) so that device-to-host copies into it

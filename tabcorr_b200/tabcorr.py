@@ -647,6 +647,22 @@ class TabCorr:
             return self._format_batch(ngal_out.numpy(), xi_out.numpy(), separate, False)
         return self._format_batch(ngal, xi, separate, as_numpy)
 
+    def predict_into_slab(self, theta, slab, n_gauss_prim=10, model=None, precision='fp64'):
+        """Device-resident batch whose results go straight into rows of a ``[B, 1 + R]`` CUDA
+        slab (column 0: ngal, columns 1..R: xi) -- the layout the multi-GPU gather moves
+        (``distributed.gather_slab_chunks``).  The kernels write through the output strides of
+        ``tc_predict_batch``; nothing is packed or concatenated afterwards.  ``theta``: CUDA
+        ``[B, n_theta]`` tensor in kernel order; ``slab`` may be a row range of a larger tensor."""
+        group = self._ensure_device()
+        spec = resolve_model(model) if model is not None else ModelSpec()
+        n_draws = theta.shape[0]
+        if tuple(slab.shape) != (n_draws, 1 + group.n_r) or slab.stride(1) != 1:
+            raise ValueError('slab must be a [{}, {}] tensor with unit column stride'.format(
+                n_draws, 1 + group.n_r))
+        code = _lib.precision_code(precision) if group.mode == 'auto' else _lib.TC_PRECISION_FP64
+        group.predict_into(spec, int(n_gauss_prim), theta, None, False, slab[:, :1], 0,
+                           slab[:, 1:], 0, precision=code)
+
     def _predict_batch_small(self, params, model, separate, n_gauss, precision):
         """The zero-copy path for host batches of at most ``SMALL_BATCH`` draws of a family the
         fused kernel implements; None when the batch does not qualify."""

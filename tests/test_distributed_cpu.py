@@ -89,6 +89,23 @@ def _worker(rank, world, port, n_draws, out_dir):
             assert torch.equal(full[:, 1], -2.0 * torch.arange(n_draws, dtype=torch.float64))
         else:
             assert full is None
+        # 1b. chunked slab gather: rows are produced range by range and land in place on rank 0
+        n_local = 7
+        slab = torch.full((n_local, 3), -1.0, dtype=torch.float64)
+        full_slab = torch.zeros((world * n_local, 3), dtype=torch.float64) if rank == 0 else None
+        launched = []
+
+        def compute_chunk(c0, c1):
+            launched.append((c0, c1))
+            rows = torch.arange(c0, c1, dtype=torch.float64) + 100.0 * rank
+            slab[c0:c1] = torch.stack([rows, rows * rows, -rows], dim=1)
+
+        tcd.gather_slab_chunks(compute_chunk, slab, full_slab, n_chunks=3, dst=0)
+        assert launched == [(0, 2), (2, 4), (4, 7)]
+        if rank == 0:
+            want = torch.cat([torch.arange(n_local, dtype=torch.float64) + 100.0 * r
+                              for r in range(world)])
+            assert torch.equal(full_slab[:, 0], want) and torch.equal(full_slab[:, 2], -want)
         # 2. the sharded prediction: every rank holds all draws, evaluates its slice
         halotab = OracleBackedTable()
         draws = synthetic.make_draws(n_draws, seed=21)
