@@ -419,7 +419,7 @@ def run_gpu_arm(args):
     import tabcorr_b200
     from tabcorr_b200 import _lib, synthetic
     from tabcorr_b200.models import ModelSpec, theta_from_params
-    from tabcorr_b200.distributed import gather_slab_chunks, predict_batch_sharded
+    from tabcorr_b200.distributed import PeerSlab, gather_slab_chunks, predict_batch_sharded
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -447,11 +447,17 @@ def run_gpu_arm(args):
     ngal = torch.empty((n_draws, 1), dtype=torch.float64, device=device)
     xi = torch.empty((n_draws, N_R, 1), dtype=torch.float64, device=device)
     result = torch.empty((n_draws, 1 + N_R), dtype=torch.float64, device=device)
-    full = (torch.empty((n_draws * world, 1 + N_R), dtype=torch.float64, device=device)
-            if world > 1 and rank == 0 else None)
+    full, peer = None, None
+    if world > 1 and args.gather == 'peer':
+        # rank 0's [world * B, 1 + R] result slab, mapped into every rank (CUDA IPC over NVLink)
+        peer = PeerSlab(n_draws * world, 1 + N_R, dst=0, device=local_rank)
+        full = peer.tensor
+        my_rows = peer.rows(rank * n_draws, (rank + 1) * n_draws)
+    elif world > 1 and rank == 0:
+        full = torch.empty((n_draws * world, 1 + N_R), dtype=torch.float64, device=device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     lib = _lib.load()
-    n_chunks = args.gather_chunks if world > 1 else 1
+    n_chunks = args.gather_chunks if (world > 1 and peer is None) else 1
     draws_per_launch = n_draws - n_draws * (n_chunks - 1) // n_chunks   # the last chunk's
 
     def compute_chunk(c0, c1):
@@ -460,6 +466,11 @@ def run_gpu_arm(args):
     def step():
         if world == 1:
             group.predict_into(spec, N_GAUSS, theta, None, False, ngal, 0, xi, 0)
+        elif peer is not None:
+            # the collection of the results on rank 0 is fused into the prediction: the epilogue
+            # kernel stores this rank's rows into rank 0's memory over NVLink; a barrier remains
+            halotab.predict_into_slab(theta, my_rows, N_GAUSS)
+            dist.barrier(device_ids=[local_rank])
         else:
             # the kernels write their rows of the [B, 1 + R] slab directly; the one collective of
             # the path (results to rank 0) is issued per chunk and overlaps the next chunk's kernels
@@ -581,7 +592,12 @@ def run_gpu_arm(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(n_draws),
+            'data': 'synthetic', 'config': dict(workload_config(n_draws), **(
+                {'collection': ("results stored by the epilogue kernel straight into rank 0's "
+                                'memory (CUDA IPC peer slab over NVLink) + one barrier per step'
+                                if peer is not None else
+                                'NCCL gather to rank 0 in {} chunk(s) per step'.format(n_chunks))}
+                if world > 1 else {})),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'timing': 'wall clock around predict_batch calls'},
             # predict_kernel + finalize_kernel per chunk of a timed step
@@ -597,6 +613,9 @@ def run_gpu_arm(args):
                 line['parity_vs_cpu'] = parity_vs_cpu(ngal[:, 0].cpu().numpy(),
                                                       xi[:, :, 0].cpu().numpy())
         emit(line)
+    if peer is not None:
+        del full
+        peer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -631,7 +650,10 @@ def main():
     parser.add_argument('--cpu-sample', type=int, default=8000,
                         help='draws of the workload timed for cpu_baseline')
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    parser.add_argument('--gather-chunks', type=int, default=3,
+    parser.add_argument('--gather', default='nccl', choices=['peer', 'nccl'],
+                        help="N > 1: 'peer' = results stored straight into rank 0's memory by the "
+                             "epilogue kernel (CUDA IPC / NVLink), 'nccl' = chunked NCCL gather")
+    parser.add_argument('--gather-chunks', type=int, default=1,
                         help='N > 1: chunks per step whose gather overlaps the next chunk\'s kernels')
     parser.add_argument('--no-configs', action='store_true',
                         help='skip the `configs` block (the other BASELINE.json configurations)')

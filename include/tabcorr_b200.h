@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 105
+#define TC_VERSION 106
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -170,6 +170,18 @@ int tc_interp_destroy(tc_interp* interp);
 int tc_interp_apply_batch(tc_interp* interp, const double* x_dev, int64_t n_draws,
                           const double* data_dev, int n_cols, double* out_dev, int extrapolate,
                           int32_t* flag_dev, void* stream);
+
+/* Peer-visible result slabs for the multi-GPU batch (the one collective of the path is
+ * the collection of the [B_r, 1 + R] result rows on one rank).  tc_peer_alloc allocates `bytes` of
+ * device memory on `device` and returns its 64-byte CUDA IPC handle; another process of the node
+ * maps it with tc_peer_open (peer access over NVLink is enabled lazily) and passes row ranges of
+ * the mapping as ngal_dev / xi_dev of tc_predict_batch: finalize_kernel then stores every rank's
+ * results straight into the destination GPU's memory -- the gather is fused into the kernel's
+ * epilogue and only a barrier remains.  tc_peer_close unmaps, tc_peer_free releases. */
+int tc_peer_alloc(int device, size_t bytes, void** ptr_out, unsigned char* handle_out);
+int tc_peer_open(int device, const unsigned char* handle, void** ptr_out);
+int tc_peer_close(int device, void* ptr);
+int tc_peer_free(int device, void* ptr);
 
 /* Live FP64 tensor (DMMA) peak of the device in TFLOP/s, the roofline denominator bench.py
  * reports (MEASURED_PEAKS.json carries no FP64 figure). */

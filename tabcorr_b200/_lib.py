@@ -36,7 +36,8 @@ SYMBOLS = (
     'tc_last_error', 'tc_version', 'tc_model_n_theta', 'tc_table_create', 'tc_table_destroy', 'tc_table_n_rows',
     'tc_table_n_r', 'tc_table_n_tables', 'tc_table_plan', 'tc_occupation_batch',
     'tc_predict_workspace_bytes', 'tc_predict_workspace_bytes_for', 'tc_predict_batch', 'tc_predict_one', 'tc_interp_create', 'tc_interp_destroy',
-    'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_measure_dfma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math')
+    'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_measure_dfma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math',
+    'tc_peer_alloc', 'tc_peer_open', 'tc_peer_close', 'tc_peer_free')
 
 
 class TabCorrB200Error(RuntimeError):
@@ -117,6 +118,15 @@ def load():
     lib.tc_profile_enable.argtypes = [ctypes.c_int]
     lib.tc_profile_read.restype = ctypes.c_int
     lib.tc_profile_read.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    c_ubyte_p = ctypes.POINTER(ctypes.c_ubyte)
+    lib.tc_peer_alloc.restype = ctypes.c_int
+    lib.tc_peer_alloc.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(vp), c_ubyte_p]
+    lib.tc_peer_open.restype = ctypes.c_int
+    lib.tc_peer_open.argtypes = [ctypes.c_int, c_ubyte_p, ctypes.POINTER(vp)]
+    lib.tc_peer_close.restype = ctypes.c_int
+    lib.tc_peer_close.argtypes = [ctypes.c_int, vp]
+    lib.tc_peer_free.restype = ctypes.c_int
+    lib.tc_peer_free.argtypes = [ctypes.c_int, vp]
     lib.tc_debug_math.restype = ctypes.c_int
     lib.tc_debug_math.argtypes = [ctypes.c_int, vp, vp, vp, ctypes.c_int64, vp]
     _lib = lib

@@ -682,6 +682,22 @@ int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t
   return TC_OK;
 }
 
+// Output blocks (gridDim.y) and dynamic shared memory of finalize_kernel: the staging tile of a
+// block (bm draws x outputs of the block) stays below 40 KB; more blocks when few tiles would
+// leave SMs idle.
+void finalize_grid(int n_out, int bm, long long n_tiles, int n_sm, int* fy_out, int* smem_out) {
+  const int max_o = std::max(1, 40000 / (8 * bm) - 1);
+  int fy = (n_out + max_o - 1) / max_o;
+  if (n_tiles <= 4LL * n_sm) {
+    const int outs_per_pass = std::max(1, 256 / bm);
+    fy = std::max(fy, std::min(64, (n_out + outs_per_pass - 1) / outs_per_pass));
+  }
+  fy = std::max(1, std::min(fy, n_out));
+  const int o_per_block = (n_out + fy - 1) / fy;
+  *fy_out = fy;
+  *smem_out = bm * (o_per_block | 1) * (int)sizeof(double);
+}
+
 // optional per-kernel timing for bench.py (tc_profile_enable / tc_profile_read)
 struct Profile {
   bool enabled = false;

@@ -442,34 +442,50 @@ struct FinalizeArgs {
   long long xi_stride;
 };
 
+// Block (tile, y) handles the draws of one tile and the outputs [o_lo, o_hi) of output block y.
+// The sums are staged in shared memory and written out row by row, so that a warp stores
+// consecutive outputs of a draw: coalesced also when the destination is the result slab of
+// another GPU (peer memory over NVLink, distributed.PeerSlab), where scattered 8-byte stores
+// would cost a 32-byte packet each.
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs args) {
+  extern __shared__ double fin_tile[];
   const int bm = args.bm;
   const long long tile = blockIdx.x;
+  const int n_out = args.lay.n_out;
+  const int o_per_block = (n_out + gridDim.y - 1) / gridDim.y;
+  const int o_lo = blockIdx.y * o_per_block, o_hi = min(o_lo + o_per_block, n_out);
+  const int row_len = o_per_block | 1;                     // odd: conflict-free column access
   const int b = threadIdx.x % bm;
   const long long draw = tile * bm + b;
-  if (draw >= args.n_draws) return;
-  const double nc = args.ngal_tile[(tile * 2 + 0) * bm + b];
-  const double ns = args.ngal_tile[(tile * 2 + 1) * bm + b];
-  const double ngal = nc + ns;
-  const double norm = args.mode == TC_MODE_AUTO ? ngal * ngal : ngal;
-  const int o_step = (blockDim.x / bm) * gridDim.y;
-  const int o_first = threadIdx.x / bm + (blockDim.x / bm) * blockIdx.y;
-  if (o_first == 0) {
-    for (int t = 0; t < args.n_tables; t++) {
-      if (args.separate) {
-        args.ngal_out[draw * args.ngal_stride + 2 * t + 0] = nc;
-        args.ngal_out[draw * args.ngal_stride + 2 * t + 1] = ns;
-      } else {
-        args.ngal_out[draw * args.ngal_stride + t] = ngal;
+  const int n_live = (int)min((long long)bm, args.n_draws - tile * bm);
+  if (threadIdx.x < (blockDim.x / bm) * bm && b < n_live) {
+    const double nc = args.ngal_tile[(tile * 2 + 0) * bm + b];
+    const double ns = args.ngal_tile[(tile * 2 + 1) * bm + b];
+    const double ngal = nc + ns;
+    const double norm = args.mode == TC_MODE_AUTO ? ngal * ngal : ngal;
+    if (blockIdx.y == 0 && threadIdx.x < bm) {
+      for (int t = 0; t < args.n_tables; t++) {
+        if (args.separate) {
+          args.ngal_out[draw * args.ngal_stride + 2 * t + 0] = nc;
+          args.ngal_out[draw * args.ngal_stride + 2 * t + 1] = ns;
+        } else {
+          args.ngal_out[draw * args.ngal_stride + t] = ngal;
+        }
       }
     }
+    const double* parts = args.parts + (size_t)tile * args.lay.n_parts * bm + b;
+    for (int o = o_lo + threadIdx.x / bm; o < o_hi; o += blockDim.x / bm) {
+      double s = 0.0;
+      for (int j = args.lay.out_ptr[o]; j < args.lay.out_ptr[o + 1]; j++)
+        s += parts[(size_t)args.lay.out_parts[j] * bm];
+      fin_tile[b * row_len + (o - o_lo)] = s / norm;
+    }
   }
-  const double* parts = args.parts + (size_t)tile * args.lay.n_parts * bm + b;
-  for (int o = o_first; o < args.lay.n_out; o += o_step) {
-    double s = 0.0;
-    for (int j = args.lay.out_ptr[o]; j < args.lay.out_ptr[o + 1]; j++)
-      s += parts[(size_t)args.lay.out_parts[j] * bm];
-    args.xi_out[draw * args.xi_stride + o] = s / norm;
+  __syncthreads();
+  const int n_o = o_hi - o_lo;
+  for (int idx = threadIdx.x; idx < n_live * n_o; idx += blockDim.x) {
+    const int bb = idx / n_o, ol = idx - bb * n_o;
+    args.xi_out[(tile * bm + bb) * args.xi_stride + o_lo + ol] = fin_tile[bb * row_len + ol];
   }
 }
 

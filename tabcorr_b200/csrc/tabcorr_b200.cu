@@ -309,10 +309,9 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
   fa.xi_out = xi;
   fa.xi_stride = xi_stride;
   const int n_out = L.dev.n_out;
-  const int outs_per_block = 256 / kTcM;
-  int fy = std::max(1, std::min(64, (n_out + outs_per_block - 1) / outs_per_block));
-  if (ws.n_tiles > 4LL * n_sm) fy = 1;
-  finalize_kernel<<<dim3((unsigned)ws.n_tiles, fy), 256, 0, stream>>>(fa);
+  int fy, fsmem;
+  finalize_grid(n_out, kTcM, ws.n_tiles, n_sm, &fy, &fsmem);
+  finalize_kernel<<<dim3((unsigned)ws.n_tiles, fy), 256, fsmem, stream>>>(fa);
   TC_CUDA(cudaGetLastError());
   tcgen_poison_kernel<<<64, 256, 0, stream>>>(error_flag, xi, n_draws, xi_stride, n_out);
   TC_CUDA(cudaGetLastError());
@@ -464,11 +463,10 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   fa.ngal_stride = ngal_stride;
   fa.xi_out = xi;
   fa.xi_stride = xi_stride;
-  const int outs_per_block = 256 / bm;
-  int fy = std::max(1, std::min(64, (n_out + outs_per_block - 1) / outs_per_block));
-  if (ws.n_tiles > 4LL * n_sm) fy = 1;
+  int fy, fsmem;
+  finalize_grid(n_out, bm, ws.n_tiles, n_sm, &fy, &fsmem);
   dim3 fgrid((unsigned)ws.n_tiles, fy);
-  finalize_kernel<<<fgrid, 256, 0, stream>>>(fa);
+  finalize_kernel<<<fgrid, 256, fsmem, stream>>>(fa);
   TC_CUDA(cudaGetLastError());
   if (g_profile.enabled) {
     TC_CUDA(cudaEventRecord(g_profile.ev[2], stream));
@@ -676,6 +674,56 @@ int tc_measure_dfma_peak(int device, double* tflops) {
   (void)cudaEventDestroy(e1);
   (void)cudaFree(scratch);
   *tflops = best;
+  return TC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-visible result slabs (multi-GPU path): CUDA IPC around plain cudaMalloc memory
+// ------------------------------------------------------------------------------------------
+int tc_peer_alloc(int device, size_t bytes, void** ptr_out, unsigned char* handle_out) {
+  if (!ptr_out || !handle_out || bytes == 0) return fail(TC_EINVAL, "tc_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_peer_alloc: cannot select CUDA device");
+  void* p = nullptr;
+  TC_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t err = cudaIpcGetMemHandle(&h, p);
+  if (err != cudaSuccess) {
+    (void)cudaFree(p);
+    (void)cudaGetLastError();
+    return fail(TC_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(err));
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return TC_OK;
+}
+
+int tc_peer_open(int device, const unsigned char* handle, void** ptr_out) {
+  if (!ptr_out || !handle) return fail(TC_EINVAL, "tc_peer_open: bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_peer_open: cannot select CUDA device");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  TC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return TC_OK;
+}
+
+int tc_peer_close(int device, void* ptr) {
+  if (!ptr) return TC_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_peer_close: cannot select CUDA device");
+  TC_CUDA(cudaIpcCloseMemHandle(ptr));
+  return TC_OK;
+}
+
+int tc_peer_free(int device, void* ptr) {
+  if (!ptr) return TC_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_peer_free: cannot select CUDA device");
+  TC_CUDA(cudaFree(ptr));
   return TC_OK;
 }
 

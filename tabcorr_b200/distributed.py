@@ -102,6 +102,77 @@ def gather_slab_chunks(compute_chunk, slab, full, n_chunks=3, dst=0, group=None)
         work.wait()
 
 
+class SlabRows:
+    """Rows ``[lo, hi)`` of a :class:`PeerSlab` as seen from this process: a raw device pointer
+    (possibly into another GPU's memory), the row count and the row width in doubles."""
+
+    def __init__(self, ptr, n_rows, width):
+        self.ptr, self.n_rows, self.width = int(ptr), int(n_rows), int(width)
+
+
+class PeerSlab:
+    """The ``[n_total, width]`` float64 result slab of a sharded batch in the HBM of rank
+    ``dst``, mapped into every rank of the node (CUDA IPC; peer access over NVLink / NVSwitch).
+
+    The path's only collective is the collection of the per-rank result rows on one rank
+    (SURVEY.md section 8(e)).  With a peer slab there is no separate gather: every rank hands
+    ``rows(lo, hi)`` to ``TabCorr.predict_into_slab`` and the epilogue kernel of the prediction
+    (``finalize_kernel``, coalesced row stores) writes the rank's results straight into rank
+    ``dst``'s memory while the other SMs still compute; what is left is one barrier.  ``tensor``
+    (on ``dst``) is the assembled result."""
+
+    def __init__(self, n_total, width, dst=0, group=None, device=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.lib = _lib.load()
+        self.n_total, self.width, self.dst, self.group = int(n_total), int(width), dst, group
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        n_bytes = max(8, 8 * self.n_total * self.width)
+        self.base = ctypes.c_void_p()
+        self.owner = self.rank == dst
+        handle = [None]
+        if self.owner:
+            raw = (ctypes.c_ubyte * 64)()
+            _lib.check(self.lib.tc_peer_alloc(self.device, n_bytes, ctypes.byref(self.base), raw))
+            handle[0] = bytes(raw)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast_object_list(handle, src=dist.get_global_rank(group, dst) if group else dst,
+                                       group=group)
+            if not self.owner:
+                raw = (ctypes.c_ubyte * 64).from_buffer_copy(handle[0])
+                _lib.check(self.lib.tc_peer_open(self.device, raw, ctypes.byref(self.base)))
+            dist.barrier(group=group)
+        self.tensor = None
+        if self.owner:
+            class _Holder:   # torch tensor over the raw allocation (dst only)
+                pass
+            holder = _Holder()
+            holder.__cuda_array_interface__ = {
+                'shape': (self.n_total, self.width), 'typestr': '<f8',
+                'data': (int(self.base.value), False), 'version': 2}
+            self._holder = holder
+            self.tensor = torch.as_tensor(holder, device=torch.device('cuda', self.device))
+
+    def rows(self, lo, hi):
+        return SlabRows(int(self.base.value) + 8 * int(lo) * self.width, hi - lo, self.width)
+
+    def close(self):
+        if self.base is None or not self.base.value:
+            return
+        import torch.distributed as dist
+        self.tensor = None
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.barrier(group=self.group)   # nobody writes any more
+        if self.owner:
+            self.lib.tc_peer_free(self.device, self.base)
+        else:
+            self.lib.tc_peer_close(self.device, self.base)
+        self.base = None
+
+
 class SharedHostArray:
     """A float64 host buffer all ranks of one node map (``multiprocessing.shared_memory``), page
     locked for CUDA in every process (``cudaHostRegister``) so that device-to-host copies into it

@@ -286,6 +286,30 @@ class DeviceTableGroup:
             xi = buf.xi_np[:n_draws * xi_cols].reshape(n_draws, xi_cols).copy()
         return ngal, xi
 
+    def predict_into_raw(self, spec, n_gauss, theta, ngal_ptr, ngal_stride, xi_ptr, xi_stride,
+                         precision=_lib.TC_PRECISION_FP64):
+        """Total prediction of the draws ``theta`` (CUDA ``[B, n_theta]``) with the outputs given
+        as raw device pointers and strides in doubles (``tc_predict_batch`` semantics) -- rows of a
+        result slab, possibly in the memory of another GPU of the node."""
+        torch = _torch()
+        if spec.family != 0:
+            occ = self.occupation(spec, n_gauss, theta)
+            theta = None
+        else:
+            occ = None
+            self.plan(n_gauss)
+        n_draws = theta.shape[0] if theta is not None else occ.shape[0]
+        with self._lock:
+            workspace = self._workspace_for(n_draws, False, precision)
+            model = self._model_struct(spec)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.tc_predict_batch(
+                self.handle, ctypes.byref(model), int(n_gauss),
+                theta.data_ptr() if theta is not None else None, 0,
+                occ.data_ptr() if occ is not None else None, n_draws, 0, int(precision),
+                int(ngal_ptr), int(ngal_stride), int(xi_ptr), int(xi_stride),
+                workspace.data_ptr(), workspace.numel(), stream))
+
     def predict_into(self, spec, n_gauss, theta, occ, separate, ngal, ngal_offset, xi, xi_offset,
                      theta_columns=False, precision=_lib.TC_PRECISION_FP64):
         """Fused launch writing this group's tables into the ``[B, T_total, ...]`` buffers ``ngal``
@@ -656,12 +680,18 @@ class TabCorr:
         group = self._ensure_device()
         spec = resolve_model(model) if model is not None else ModelSpec()
         n_draws = theta.shape[0]
+        code = _lib.precision_code(precision) if group.mode == 'auto' else _lib.TC_PRECISION_FP64
+        if hasattr(slab, 'ptr'):   # distributed.SlabRows: rows of a peer slab (maybe another GPU's)
+            if (slab.n_rows, slab.width) != (n_draws, 1 + group.n_r):
+                raise ValueError('slab rows must be [{}, {}]'.format(n_draws, 1 + group.n_r))
+            group.predict_into_raw(spec, int(n_gauss_prim), theta, slab.ptr, slab.width,
+                                   slab.ptr + 8, slab.width, precision=code)
+            return
         if tuple(slab.shape) != (n_draws, 1 + group.n_r) or slab.stride(1) != 1:
             raise ValueError('slab must be a [{}, {}] tensor with unit column stride'.format(
                 n_draws, 1 + group.n_r))
-        code = _lib.precision_code(precision) if group.mode == 'auto' else _lib.TC_PRECISION_FP64
-        group.predict_into(spec, int(n_gauss_prim), theta, None, False, slab[:, :1], 0,
-                           slab[:, 1:], 0, precision=code)
+        group.predict_into_raw(spec, int(n_gauss_prim), theta, slab.data_ptr(), slab.stride(0),
+                               slab.data_ptr() + 8, slab.stride(0), precision=code)
 
     def _predict_batch_small(self, params, model, separate, n_gauss, precision):
         """The zero-copy path for host batches of at most ``SMALL_BATCH`` draws of a family the
