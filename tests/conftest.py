@@ -14,6 +14,8 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
     config.addinivalue_line('markers', 'reference: needs the reference checkout at /root/reference')
+    config.addinivalue_line('markers', 'halotools: parity with a real halotools install (skipped '
+                            'where it is not importable)')
 
 
 @pytest.fixture(scope='session')
