@@ -71,6 +71,13 @@ struct OccPlan {       // device pointers, one per (layout, n_gauss)
   const double* row_c;      // [n_pad, G] normalised quadrature weights
   const double* row_nh;     // [n_pad]
   const double* row_pct;    // [n_pad] secondary-property percentile of the row
+  // series evaluation of the bin averages (occupation.cuh, occupation_item_series)
+  const double4* grp_ser;   // [n_groups] centrals {log10 M centre, half range d of the nodes, 0, 0};
+                            //            satellites {m_ref, u_max, lowest, highest node mass}
+  const double2* grp_mom;   // [kSerMom, n_groups] {row 0, row 1}: k-th scaled node moment / k!
+  const unsigned char* cen_terms;  // [kSerBuckets] Hermite-series terms per bucket of h; 255: nodes
+  const unsigned char* sat_terms;  // [kSerBuckets] binomial-series terms per bucket of y; 255: nodes
+  double cen_d_max;         // largest half range of a centrals group (log10 M)
 };
 
 struct LayoutDev {

@@ -59,8 +59,10 @@ __device__ __forceinline__ double half_erfc_neg(double x, const double* __restri
 #pragma unroll
   for (int k = kErfDeg - 1; k >= 0; k--) p = fma(p, t, c[k * kErfStride]);
   const int hx = __double2hiint(x);
-  const bool huge = (hx & 0x7fffffff) >= 0x40300000;        // |x| >= 16, infinity, NaN
-  const int step_hi = hx < 0 ? 0 : 0x3ff00000;              // 0.0 or 1.0
+  const unsigned ax = hx & 0x7fffffff;
+  const bool huge = ax >= 0x40300000u;                      // |x| >= 16, infinity, NaN
+  const bool nan = ax > 0x7ff00000u || (ax == 0x7ff00000u && __double2loint(x) != 0);
+  const int step_hi = nan ? 0x7ff80000 : hx < 0 ? 0 : 0x3ff00000;   // NaN, 0.0 or 1.0
   return huge ? __hiloint2double(step_hi, 0) : p;
 }
 

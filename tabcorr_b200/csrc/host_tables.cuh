@@ -487,9 +487,104 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
         row_c[(size_t)p * GP + k] = wq[k] * std::pow(node_m[(size_t)q * GP + k], n) / norm;
     }
   }
+  // ---- series evaluation (occupation_item_series): group centres, scaled node moments / k!,
+  // number of terms per bucket of h (centrals) and y (satellites), all in long double ---------
+  std::vector<double4> grp_ser(n_groups);
+  std::vector<double2> grp_mom((size_t)kSerMom * n_groups, make_double2(0.0, 0.0));
+  std::vector<long double> cen_mom_max(kSerMom, 0.0L), sat_mom_max(kSerMom, 0.0L);
+  std::vector<long double> inv_fact(kSerMom + 64, 1.0L);
+  for (size_t k = 1; k < inv_fact.size(); k++) inv_fact[k] = inv_fact[k - 1] / (long double)k;
+  double cen_d_max = 0.0;
+  for (int q = 0; q < n_groups; q++) {
+    const Group& gq = groups[q];
+    const double* nodes = (gq.sat ? node_m.data() : node_logm.data()) + (size_t)q * GP;
+    double lo = nodes[0], hi = nodes[0];
+    for (int k = 1; k < G; k++) { lo = std::min(lo, nodes[k]); hi = std::max(hi, nodes[k]); }
+    const double centre = 0.5 * (lo + hi);
+    // scaled offsets s_j in [-1, 1]: centrals (log10 M - centre) / d, satellites (M / m_ref - 1) / u_max
+    std::vector<long double> sj(G);
+    long double scale = 0.0L;
+    for (int k = 0; k < G; k++) {
+      sj[k] = gq.sat ? (long double)nodes[k] / (long double)centre - 1.0L
+                     : (long double)nodes[k] - (long double)centre;
+      scale = std::max(scale, fabsl(sj[k]));
+    }
+    const double scale_d = (double)scale;             // the kernel multiplies by this double
+    for (int k = 0; k < G; k++) sj[k] = scale_d > 0.0 ? sj[k] / (long double)scale_d : 0.0L;
+    if (gq.sat) {
+      grp_ser[q] = make_double4(centre, scale_d, lo, hi);
+    } else {
+      grp_ser[q] = make_double4(centre, scale_d, 0.0, 0.0);
+      cen_d_max = std::max(cen_d_max, scale_d);
+    }
+    for (size_t s = 0; s < gq.rows.size(); s++) {
+      const int p = L.row_to_pad[gq.rows[s]];
+      for (int k = 0; k < kSerMom; k++) {
+        long double mk = 0.0L;
+        for (int j = 0; j < G; j++) mk += (long double)row_c[(size_t)p * GP + j] * powl(sj[j], k);
+        auto& mx = gq.sat ? sat_mom_max : cen_mom_max;
+        mx[k] = std::max(mx[k], fabsl(mk));
+        double2& dst = grp_mom[(size_t)k * n_groups + q];
+        (s == 0 ? dst.x : dst.y) = (double)(mk * inv_fact[k]);
+      }
+    }
+  }
+  // Terms per bucket: the smallest K whose tail bound is below 1e-14.
+  //   centrals: |term k| <= 1.0865 / sqrt(pi) sqrt(2^(k-1) (k-1)!) h^k / k! max_rows |mu_k|
+  //             (Cramer: |H_n(x)| exp(-x^2 / 2) <= 1.0865 sqrt(2^n n!)), h at the bucket's upper edge;
+  //   satellites: |term k| <= max_{0 <= alpha <= 4} |binom(alpha, k)| y^k max_rows |nu_k|.
+  // Moments beyond the table (k > kSerMaxTerms) are bounded by 1.
+  std::vector<unsigned char> cen_terms(kSerBuckets, 255), sat_terms(kSerBuckets, 255);
+  {
+    const int n_tail = kSerMom + 60;
+    const long double eps = 1e-14L;
+    std::vector<long double> binom_max(n_tail, 0.0L);
+    for (int ia = 0; ia <= 4000; ia++) {
+      const long double alpha = kSerAlphaMax * ia / 4000.0L;
+      long double c = 1.0L;
+      for (int k = 1; k < n_tail; k++) {
+        c *= (alpha - (k - 1)) / k;
+        binom_max[k] = std::max(binom_max[k], fabsl(c) * 1.001L);   // grid spacing margin
+      }
+    }
+    for (int i = 0; i < kSerBuckets; i++) {
+      const long double h = (i + 1) / (long double)kSerCenBucket;
+      const long double y = (i + 1) / (long double)kSerSatBucket;
+      std::vector<long double> tc(n_tail, 0.0L), ts(n_tail, 0.0L);
+      long double herm = 1.0865L / sqrtl(3.14159265358979323846264338327950288L);  // k = 1: sqrt(2^0 0!)
+      for (int k = 1; k < n_tail; k++) {
+        if (k > 1) herm *= sqrtl(2.0L * (k - 1));
+        tc[k] = herm * powl(h, k) * inv_fact[k] * (k < kSerMom ? cen_mom_max[k] : 1.0L);
+        ts[k] = binom_max[k] * powl(y, k) * (k < kSerMom ? sat_mom_max[k] : 1.0L);
+      }
+      long double tail_c = 0.0L, tail_s = 0.0L;
+      int kc = -1, ks = -1;
+      for (int k = n_tail - 1; k >= 2; k--) {   // tail = sum of the terms beyond k
+        if (tail_c <= eps) kc = k;
+        if (tail_s <= eps) ks = k;
+        tail_c += tc[k];
+        tail_s += ts[k];
+      }
+      if (tune("SERIES", 1) == 0) continue;   // experiments: every pair through the node path
+      if (kc >= 0 && kc <= kSerMaxTerms) cen_terms[i] = (unsigned char)std::max(kc, 2);
+      if (ks >= 0 && ks <= kSerMaxTerms) sat_terms[i] = (unsigned char)std::max(ks, 1);
+    }
+  }
   PlanHost ph;
   double *d_logm, *d_m, *d_c, *d_nh, *d_pct; int *d_rows, *d_sat;
   int rc;
+  {
+    double4* d_ser; double2* d_mom; unsigned char *d_ct, *d_st;
+    if ((rc = upload(grp_ser, &d_ser))) return rc; ph.allocations.push_back(d_ser);
+    if ((rc = upload(grp_mom, &d_mom))) return rc; ph.allocations.push_back(d_mom);
+    if ((rc = upload(cen_terms, &d_ct))) return rc; ph.allocations.push_back(d_ct);
+    if ((rc = upload(sat_terms, &d_st))) return rc; ph.allocations.push_back(d_st);
+    ph.dev.grp_ser = d_ser;
+    ph.dev.grp_mom = d_mom;
+    ph.dev.cen_terms = d_ct;
+    ph.dev.sat_terms = d_st;
+    ph.dev.cen_d_max = cen_d_max;
+  }
   if ((rc = upload(node_logm, &d_logm))) return rc; ph.allocations.push_back(d_logm);
   if ((rc = upload(node_m, &d_m))) return rc; ph.allocations.push_back(d_m);
   {
@@ -595,6 +690,33 @@ void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat,
   };
   *n_cen = share(cen);
   *n_sat = share(sat);
+  if (*n_cen + *n_sat == 0) *n_cen = 1;  // table without rows cannot happen; keep n_occ > 0
+}
+
+// Items of an 8-draw block in series mode (series_item): per galaxy type `pieces` draw pieces
+// (a power of two <= 8) times group ranges.  A batch cuts the draws (a warp iteration is one draw
+// x 32 groups, so the per-draw constants are amortised over all groups of the type); a one-draw
+// call cuts the groups into ranges of 32 so that the warps of the block share the draw.
+void pick_series_ranges(const OccPlan& plan, int nt, long long n_draws, int items, int* n_cen,
+                        int* n_sat, int* pieces_cen, int* pieces_sat) {
+  const int cen = plan.n_cen_groups, sat = plan.n_groups - plan.n_cen_groups;
+  const int want = std::max(2, (tune("OCC_ITEMS", items) + nt - 1) / nt);
+  auto share = [&](int count, int* ranges, int* pieces) {
+    *ranges = 0;
+    *pieces = 1;
+    if (count == 0) return;
+    if (n_draws == 1) {
+      *ranges = std::min(8, (count + 31) / 32);
+      return;
+    }
+    const int s = std::max(1, (int)std::lround((double)want * count / (cen + sat)));
+    int p = 1;
+    while (2 * p <= std::min(8, s)) p *= 2;
+    *pieces = p;
+    *ranges = p;
+  };
+  share(cen, n_cen, pieces_cen);
+  share(sat, n_sat, pieces_sat);
   if (*n_cen + *n_sat == 0) *n_cen = 1;  // table without rows cannot happen; keep n_occ > 0
 }
 

@@ -192,6 +192,359 @@ __device__ __forceinline__ void occupation_range(const OccPlan& plan, int n_rang
 }
 
 // ------------------------------------------------------------------------------------------
+// Series evaluation of the Gauss-Legendre averages (zheng07 family).
+//
+// The average of a mass bin is the finite sum  occ_i = sum_j c_ij f(node_j)  (tabcorr.py:568-578).
+// Evaluating f at every node costs G table-driven erf / pow per group and draw; both functions are
+// analytic over the (narrow) bin, so the same finite sum is rewritten -- exactly, up to a
+// truncation bounded below 1e-14 -- as a short series in per-row MOMENTS of the nodes that the
+// plan precomputes in long double (build_plan):
+//
+//   centrals   f = Phi(x), x_j = x_c + h tau_j (tau_j in [-1, 1], h = half bin width / sigma):
+//              sum_j c_ij Phi(x_j) = mu_0 Phi(x_c)
+//                                    + exp(-x_c^2) / sqrt(pi) sum_k H_{k-1}(x_c) (-h)^k... (below)
+//              with Phi^(k)(x) = (-1)^(k-1) H_{k-1}(x) exp(-x^2) / sqrt(pi) (H: physicists'
+//              Hermite polynomials) and mu_k = sum_j c_ij tau_j^k.  The terms
+//              v_k = (-1)^(k-1) H_{k-1}(x_c) h^k obey v_{k+1} = -2 x_c h v_k - 2 (k - 1) h^2 v_{k-1};
+//              the plan stores mu_k / k!.  One erf and one exp per GROUP instead of G erf.
+//   satellites f = ((M - M0) / M1)^alpha, M_j = m_ref (1 + u_max s_j), all M_j > M0:
+//              sum_j c_ij f(M_j) = f(m_ref) sum_k binom(alpha, k) y^k nu_k,  y = u_max m_ref /
+//              (m_ref - M0), nu_k = sum_j c_ij s_j^k; the plan stores nu_k / k!.  One pow per group.
+//
+// The number of terms comes from rigorous tail bounds tabulated per plan (cen_terms: Cramer's
+// bound on the Hermite functions, in buckets of h; sat_terms: the binomial coefficients for
+// 0 <= alpha <= 4, in buckets of y).  The cost no longer depends on n_gauss_prim.
+// Where the series does not apply -- sigma so small that h leaves the table, a bin that
+// straddles M0 or lies just above it, the one bin where the Heaviside perturbation changes its
+// branch, alpha outside [0, 4], modulate_with_cenocc -- the (draw, group) pair is queued in shared
+// memory and the queue is worked off 32 pairs at a time by the node-by-node code above, so the
+// hard pairs of the 8 draws of an item share dense warp iterations instead of stalling the others.
+//
+// Lane mapping: a warp iteration is ONE draw x 32 consecutive groups (sigma, hence the number of
+// terms, is warp-uniform; plan arrays are read coalesced).
+// ------------------------------------------------------------------------------------------
+constexpr int kSerMaxTerms = 24;               // moments 0..24 per row
+constexpr int kSerMom = kSerMaxTerms + 1;
+constexpr int kSerQueue = 64;                  // queued (draw, group) pairs per warp
+#ifndef TC_SER_DRAWS
+#define TC_SER_DRAWS 2
+#endif
+constexpr int kSerDraws = TC_SER_DRAWS;        // draws in flight per warp iteration
+constexpr int kSerBuckets = 64;
+constexpr double kSerCenBucket = 64.0;         // h buckets of width 1/64 up to h = 1
+constexpr double kSerSatBucket = 128.0;        // y buckets of width 1/128 up to y = 0.5
+constexpr double kSerAlphaMax = 4.0;
+constexpr double kInvSqrtPi = 0.56418958354775628695;
+
+// 1 / x to full double precision for a normal positive x: hardware seed + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// Node-by-node evaluation of one (draw, group) pair: the reference arithmetic, used for the pairs
+// the series does not cover.  One copy per translation unit (not inlined into the 24 kernel
+// instantiations).
+__device__ __noinline__ void occupation_pair_nodes(const OccPlan& plan, int grp, bool sat,
+                                                   bool decorated, bool modulate, DrawParams p,
+                                                   double split, const double* __restrict__ tab,
+                                                   double* occ) {
+  double occ0, occ1;
+#define TC_PAIR(SAT_, DEC_, MOD_, U_) \
+  occupation_group<SAT_, DEC_, MOD_, U_>(plan, grp, p, split, tab, occ0, occ1)
+  const bool wide = plan.unroll == kOccUnroll;
+  if (sat) {
+    if (modulate) TC_PAIR(true, true, true, 2);
+    else if (decorated) { if (wide) TC_PAIR(true, true, false, kOccUnroll); else TC_PAIR(true, true, false, 2); }
+    else { if (wide) TC_PAIR(true, false, false, kOccUnroll); else TC_PAIR(true, false, false, 2); }
+  } else {
+    if (decorated) { if (wide) TC_PAIR(false, true, false, kOccUnroll); else TC_PAIR(false, true, false, 2); }
+    else { if (wide) TC_PAIR(false, false, false, kOccUnroll); else TC_PAIR(false, false, false, 2); }
+  }
+#undef TC_PAIR
+  occ[0] = occ0;
+  occ[1] = occ1;
+}
+
+// The parameters one galaxy type needs (exp10 and the divisions are ~50 FP64 instructions each)
+template <bool SAT>
+__device__ __forceinline__ DrawParams load_draw_typed(const double* __restrict__ theta,
+                                                      long long ps, bool everything) {
+  DrawParams p{};
+  if (!SAT || everything) {
+    p.logMmin = theta[0];
+    p.inv_sigma = 1.0 / theta[ps];
+    p.a_cen = fmin(fmax(theta[5 * ps], -1.0), 1.0);
+  }
+  if (SAT || everything) {
+    p.m0 = exp10(theta[2 * ps]);
+    p.inv_m1 = 1.0 / exp10(theta[3 * ps]);
+    p.alpha = theta[4 * ps];
+    p.a_sat = fmin(fmax(theta[6 * ps], -1.0), 1.0);
+  }
+  return p;
+}
+
+// Occupation item of one warp in series mode: draws [0, n_b) of an 8-draw block (parameters of
+// draw b at theta0 + b * theta_ds) times the groups [g_begin, g_end) of ONE galaxy type.
+// `queue` points at kSerQueue ints of shared memory owned by this warp.
+// store(b, padded_row, occ, n_h) receives the Gauss-Legendre averaged occupation of each row.
+template <bool SAT, typename Store>
+__device__ __forceinline__ void occupation_item_series(const OccPlan& plan, const tc_model& model,
+                                                       const double* __restrict__ theta0,
+                                                       long long theta_ds, long long theta_ps,
+                                                       int n_b, int g_begin, int g_end,
+                                                       const double* __restrict__ tab, int* queue,
+                                                       Store store) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool modulate = SAT && model.modulate_with_cenocc != 0;
+  const bool decorated = model.decorated != 0;
+  // lane l holds the parameters of draw l & 7 (clamped to the item's draws)
+  DrawParams mine = load_draw_typed<SAT>(theta0 + (long long)min(lane & 7, n_b - 1) * theta_ds,
+                                         theta_ps, modulate);
+  if (!decorated) mine.a_cen = mine.a_sat = 0.0;   // strengths are ignored unless decorated
+  const double split = model.split;
+  const bool split_ok = decorated && split > 0.0 && split < 1.0;
+  const double ratio = split_ok ? split / (1.0 - split) : 0.0;
+  const double k_down = split_ok ? -(1.0 - split) / split : 0.0;
+  const int ng = plan.n_groups;
+  int head = 0, count = 0;   // ring buffer of queued pairs (warp-uniform)
+
+  auto drain = [&](int n) {  // node-by-node evaluation of the first n queued pairs
+    __syncwarp();
+    const int entry = queue[(head + min(lane, n - 1)) & (kSerQueue - 1)];
+    const int b = entry >> 24, grp = entry & 0xffffff;
+    DrawParams p;
+    p.logMmin = __shfl_sync(full, mine.logMmin, b);
+    p.inv_sigma = __shfl_sync(full, mine.inv_sigma, b);
+    p.m0 = __shfl_sync(full, mine.m0, b);
+    p.inv_m1 = __shfl_sync(full, mine.inv_m1, b);
+    p.alpha = __shfl_sync(full, mine.alpha, b);
+    p.a_cen = __shfl_sync(full, mine.a_cen, b);
+    p.a_sat = __shfl_sync(full, mine.a_sat, b);
+    if (lane < n) {
+      double occ[2];
+      occupation_pair_nodes(plan, grp, SAT, decorated, modulate, p, split, tab, occ);
+      const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
+      store(b, row0, occ[0], plan.row_nh[row0]);
+      if (row1 >= 0) store(b, row1, occ[1], plan.row_nh[row1]);
+    }
+    __syncwarp();
+    head = (head + n) & (kSerQueue - 1);
+    count -= n;
+  };
+
+  // kSerDraws draws in flight per warp iteration: the series of one (draw, group) pair is a chain
+  // of ~100 dependent FP64 operations, and beside DMMA warps a dependent DFMA gets an issue turn
+  // only every ~24-32 cycles (tools/fp64_mix.cu), so independent chains are what hides it
+  for (int b0 = 0; b0 < n_b; b0 += kSerDraws) {
+    // ---- per-draw constants (warp-uniform) -------------------------------------------------
+    double strength[kSerDraws], logMmin[kSerDraws], inv_sigma[kSerDraws], m0[kSerDraws],
+        inv_m1[kSerDraws], alpha[kSerDraws];
+    bool all_queued[kSerDraws];
+    int terms_of[kSerDraws];   // a draw only adds its own terms: results do not depend on which
+    int n_terms = 2;           // draws share the iteration (bitwise batch invariance)
+#pragma unroll
+    for (int u = 0; u < kSerDraws; u++) {
+      const int b = min(b0 + u, n_b - 1);
+      strength[u] = __shfl_sync(full, SAT ? mine.a_sat : mine.a_cen, b);
+      all_queued[u] = modulate;
+      if (!SAT) {
+        logMmin[u] = __shfl_sync(full, mine.logMmin, b);
+        inv_sigma[u] = __shfl_sync(full, mine.inv_sigma, b);
+        const double hb =
+            fmin(fabs(plan.cen_d_max * inv_sigma[u]) * kSerCenBucket, kSerBuckets - 1.0);
+        const int terms = plan.cen_terms[(int)hb];   // a NaN lands in the last bucket (fmin)
+        terms_of[u] = 2;
+        if (!(hb < kSerBuckets - 1.0) || terms == 255) all_queued[u] = true;
+        else terms_of[u] = terms;
+        n_terms = max(n_terms, terms_of[u]);
+      } else {
+        m0[u] = __shfl_sync(full, mine.m0, b);
+        inv_m1[u] = __shfl_sync(full, mine.inv_m1, b);
+        alpha[u] = __shfl_sync(full, mine.alpha, b);
+        if (!(alpha[u] >= 0.0 && alpha[u] <= kSerAlphaMax)) all_queued[u] = true;
+      }
+    }
+    for (int g0 = g_begin; g0 < g_end; g0 += 32) {
+      const int grp = g0 + lane;
+      const bool valid = grp < g_end;
+      const int gsafe = valid ? grp : g_end - 1;
+      const double4 gs = plan.grp_ser[gsafe];
+      const double2* mom = plan.grp_mom + gsafe;
+      const double2 mom0 = mom[0];
+      const int row0 = plan.grp_rows[gsafe * kGroupRows], row1 = plan.grp_rows[gsafe * kGroupRows + 1];
+      double k0 = 0.0, k1 = 0.0;
+      if (split_ok) {
+        k0 = plan.row_pct[row0] > split ? 1.0 : k_down;
+        k1 = (row1 >= 0 && plan.row_pct[max(row1, 0)] > split) ? 1.0 : k_down;
+      }
+      double f0[kSerDraws], f1[kSerDraws];
+      bool queued[kSerDraws];
+      if (!SAT) {
+        // Hermite series around the centre of the group's nodes
+        double phi[kSerDraws], e[kSerDraws], h[kSerDraws], a[kSerDraws], b2[kSerDraws],
+            v_prev[kSerDraws], v[kSerDraws], acc0[kSerDraws], acc1[kSerDraws];
+        double2 m = mom[ng], m2 = mom[2 * ng];
+#pragma unroll
+        for (int u = 0; u < kSerDraws; u++) {
+          const double xc = (gs.x - logMmin[u]) * inv_sigma[u];
+          h[u] = gs.y * inv_sigma[u];
+          phi[u] = half_erfc_neg(xc, tab);
+          e[u] = exp_scaled(fmax(-xc * xc, -1400.0), tab) * kInvSqrtPi;
+          a[u] = -2.0 * xc * h[u];
+          b2[u] = -2.0 * h[u] * h[u];
+          v_prev[u] = h[u];
+          v[u] = a[u] * h[u];
+          acc0[u] = fma(v[u], m2.x, v_prev[u] * m.x);
+          acc1[u] = fma(v[u], m2.y, v_prev[u] * m.y);
+        }
+        double2 m_next = mom[3 * ng];
+        for (int k = 2; k < n_terms; k++) {   // term k + 1
+          m = m_next;
+          m_next = mom[min(k + 2, kSerMaxTerms) * ng];
+          const double km1 = (double)(k - 1);
+#pragma unroll
+          for (int u = 0; u < kSerDraws; u++) {
+            const double vn = fma(a[u], v[u], (b2[u] * km1) * v_prev[u]);
+            if (k < terms_of[u]) {
+              acc0[u] = fma(vn, m.x, acc0[u]);
+              acc1[u] = fma(vn, m.y, acc1[u]);
+            }
+            v_prev[u] = v[u];
+            v[u] = vn;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kSerDraws; u++) {
+          queued[u] = all_queued[u];
+          f0[u] = fma(e[u], acc0[u], mom0.x * phi[u]);
+          f1[u] = fma(e[u], acc1[u], mom0.y * phi[u]);
+          if (split_ok && strength[u] != 0.0) {
+            // Heaviside perturbation (assembias_delta): strength * min(p, q) is linear in f as
+            // long as every node of the group is on the same side of the branch point thr; f is
+            // within h / sqrt(pi) of phi at every node (|Phi'| <= 1 / sqrt(pi))
+            const bool positive = strength[u] > 0.0;
+            const double thr = positive ? 1.0 - split : split;
+            if (fabs(phi[u] - thr) <= h[u] * kInvSqrtPi * (1.0 + 1e-9) + 1e-13) queued[u] = true;
+            const bool above = phi[u] > thr;
+            const double d0 = positive ? (above ? mom0.x - f0[u] : ratio * f0[u])
+                                       : (above ? ratio * (mom0.x - f0[u]) : f0[u]);
+            const double d1 = positive ? (above ? mom0.y - f1[u] : ratio * f1[u])
+                                       : (above ? ratio * (mom0.y - f1[u]) : f1[u]);
+            f0[u] = fma(k0 * strength[u], d0, f0[u]);
+            f1[u] = fma(k1 * strength[u], d1, f1[u]);
+          }
+        }
+      } else {
+        // binomial series around m_ref; gs = {m_ref, u_max, lowest node mass, highest node mass}
+        double y[kSerDraws], ya[kSerDraws], fref[kSerDraws], p[kSerDraws], acc0[kSerDraws],
+            acc1[kSerDraws];
+        bool none[kSerDraws];
+        int kt_of[kSerDraws];
+        int kt = 0;
+        double2 m = mom[ng];
+#pragma unroll
+        for (int u = 0; u < kSerDraws; u++) {
+          none[u] = !(gs.w > m0[u]);              // no node above M0: the occupation is 0
+          const bool all_above = gs.z > m0[u];
+          const double base = all_above ? gs.x - m0[u] : 1.0;
+          y[u] = gs.y * gs.x * fast_rcp(base);
+          const double yb = fmin(y[u] * kSerSatBucket, kSerBuckets - 1.0);
+          const int terms = plan.sat_terms[(int)yb];
+          queued[u] = all_queued[u] || !all_above || !(yb < kSerBuckets - 1.0) || terms == 255;
+          if (none[u]) queued[u] = false;
+          kt_of[u] = valid && !queued[u] && !none[u] ? terms : 0;
+          kt = max(kt, kt_of[u]);
+          fref[u] = pow_pos(base * inv_m1[u], alpha[u], tab);
+          ya[u] = y[u] * alpha[u];
+          p[u] = ya[u];
+          acc0[u] = p[u] * m.x;
+          acc1[u] = p[u] * m.y;
+        }
+        const int kw = __reduce_max_sync(full, kt);
+        double2 m_next = mom[2 * ng];
+        for (int k = 2; k <= kw; k++) {
+          m = m_next;
+          m_next = mom[min(k + 1, kSerMaxTerms) * ng];
+          const double mkm1 = -(double)(k - 1);
+#pragma unroll
+          for (int u = 0; u < kSerDraws; u++) {
+            p[u] *= fma(mkm1, y[u], ya[u]);   // y (alpha - k + 1); the plan divides by k!
+            if (k <= kt_of[u]) {
+              acc0[u] = fma(p[u], m.x, acc0[u]);
+              acc1[u] = fma(p[u], m.y, acc1[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kSerDraws; u++) {
+          f0[u] = none[u] ? 0.0 : fref[u] * (mom0.x + acc0[u]);
+          f1[u] = none[u] ? 0.0 : fref[u] * (mom0.y + acc1[u]);
+          if (split_ok) {
+            // satellites have no upper bound: min(p, q) is ratio * f (strength > 0) or f
+            const double sr = strength[u] > 0.0 ? strength[u] * ratio : strength[u];
+            f0[u] = fma(k0 * sr, f0[u], f0[u]);
+            f1[u] = fma(k1 * sr, f1[u], f1[u]);
+          }
+        }
+      }
+      const double nh0 = plan.row_nh[row0], nh1 = plan.row_nh[max(row1, 0)];
+#pragma unroll
+      for (int u = 0; u < kSerDraws; u++) {
+        const int b = b0 + u;
+        if (b >= n_b) break;                 // warp-uniform
+        const bool q = queued[u] && valid;
+        if (valid && !q) {
+          store(b, row0, f0[u], nh0);
+          if (row1 >= 0) store(b, row1, f1[u], nh1);
+        }
+        const unsigned qm = __ballot_sync(full, q);
+        if (qm) {
+          if (q)
+            queue[(head + count + __popc(qm & ((1u << lane) - 1u))) & (kSerQueue - 1)] =
+                (b << 24) | grp;
+          count += __popc(qm);
+          if (count >= 32) drain(32);
+        }
+      }
+    }
+  }
+  if (count > 0) drain(count);
+}
+
+// Items of an 8-draw block in series mode: item q < n_ranges_cen works on centrals, the others on
+// satellites; a type's items are `pieces` draw pieces x (n_ranges / pieces) group ranges cut in
+// units of 32 groups (one warp iteration).
+struct SeriesItem {
+  bool sat;
+  int b_begin, n_b, g_begin, g_end;
+};
+__device__ __forceinline__ SeriesItem series_item(const OccPlan& plan, int n_ranges_cen,
+                                                  int n_ranges_sat, int pieces_cen,
+                                                  int pieces_sat, int q) {
+  SeriesItem it;
+  it.sat = q >= n_ranges_cen;
+  const int first = it.sat ? plan.n_cen_groups : 0;
+  const int count = it.sat ? plan.n_groups - plan.n_cen_groups : plan.n_cen_groups;
+  const int pieces = it.sat ? pieces_sat : pieces_cen;
+  const int ranges = (it.sat ? n_ranges_sat : n_ranges_cen) / pieces;
+  const int local = it.sat ? q - n_ranges_cen : q;
+  const int piece = local % pieces, range = local / pieces;
+  it.b_begin = 8 * piece / pieces;
+  it.n_b = 8 * (piece + 1) / pieces - it.b_begin;
+  const int units = (count + 31) >> 5;
+  it.g_begin = first + min(count, 32 * (int)((long long)units * range / ranges));
+  it.g_end = first + min(count, 32 * (int)((long long)units * (range + 1) / ranges));
+  return it;
+}
+
+// ------------------------------------------------------------------------------------------
 // standalone occupation kernel (TabCorr.mean_occupation)
 // ------------------------------------------------------------------------------------------
 struct OccArgs {
@@ -201,17 +554,18 @@ struct OccArgs {
   long long theta_ds, theta_ps;
   long long n_draws;
   int n_rows;
-  int n_ranges_cen, n_ranges_sat;
+  int n_ranges_cen, n_ranges_sat;   // items per 8-draw block and galaxy type
+  int pieces_cen, pieces_sat;       // series mode: draw pieces per type (series_item)
   const int* pad_to_row;
   double* occ_out;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs args) {
   __shared__ double tab[kTabDoubles];
+  __shared__ int queue[kWarps][kSerQueue];
   load_math_tables(tab);
   __syncthreads();
-  // one warp per item = 8 draws x one group range; four groups in flight per warp
-  const int lane = threadIdx.x & 31;
+  // one warp per item = a piece of an 8-draw block x a range of groups of one galaxy type
   const int n_ranges = args.n_ranges_cen + args.n_ranges_sat;
   const long long n_blocks = (args.n_draws + 7) / 8;
   const long long n_items = n_blocks * n_ranges;
@@ -219,18 +573,23 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
   for (long long item = warp0; item < n_items; item += (long long)gridDim.x * kWarps) {
     const long long block = item / n_ranges;
     const int q = (int)(item - block * n_ranges);
-    const long long draw = block * 8 + (lane & 7);
-    const bool live = draw < args.n_draws;
-    int g_begin, g_end;
-    occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
-    occupation_item(args.plan, args.model,
-                    args.theta + (live ? draw : args.n_draws - 1) * args.theta_ds, args.theta_ps,
-                    g_begin, g_end, tab,
-                    [&](int row, double occ, double) {
-                      const int dst = args.pad_to_row[row];
-                      if (live && dst >= 0) args.occ_out[draw * args.n_rows + dst] = occ;
-                    },
-                    threadIdx.x >> 3 & 3, 4);
+    const SeriesItem it = series_item(args.plan, args.n_ranges_cen, args.n_ranges_sat,
+                                      args.pieces_cen, args.pieces_sat, q);
+    const long long draw0 = block * 8 + it.b_begin;
+    const int n_b = (int)min((long long)it.n_b, args.n_draws - draw0);
+    if (n_b <= 0 || it.g_end <= it.g_begin) continue;
+    auto store = [&](int b, int row, double occ, double) {
+      const int dst = args.pad_to_row[row];
+      if (dst >= 0) args.occ_out[(draw0 + b) * args.n_rows + dst] = occ;
+    };
+    if (it.sat)
+      occupation_item_series<true>(args.plan, args.model, args.theta + draw0 * args.theta_ds,
+                                   args.theta_ds, args.theta_ps, n_b, it.g_begin, it.g_end, tab,
+                                   queue[threadIdx.x >> 5], store);
+    else
+      occupation_item_series<false>(args.plan, args.model, args.theta + draw0 * args.theta_ds,
+                                    args.theta_ds, args.theta_ps, n_b, it.g_begin, it.g_end, tab,
+                                    queue[threadIdx.x >> 5], store);
   }
 }
 

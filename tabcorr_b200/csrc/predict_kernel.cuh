@@ -48,6 +48,7 @@ struct PredictArgs {
   int n_buf;             // W tiles in shared memory: 2 = occupation of tile t + 1 overlaps tile t
   int n_ranges_cen;      // occupation items per n-tile: group ranges of centrals ...
   int n_ranges_sat;      // ... and of satellites
+  int pieces_cen, pieces_sat;   // draw pieces per type (series_item)
   int occ_stride;        // every occ_stride-th slot of a tile's work list is an occupation item
   int tf32_segment;      // 3xTF32 mode: k8-steps per FP32 accumulation chain
 };
@@ -60,6 +61,7 @@ struct PredictCtrl {
   int n_local;                  // tiles this CTA works on
   long long tile_first;
   double theta_inline[TC_N_THETA];   // shared-memory copy of the inline parameters
+  int ser_queue[kWarps][kSerQueue];  // per warp: (draw, group) pairs waiting for the node path
 };
 
 // One contraction chunk by one warp.  W is the draw tile in B-fragment order.
@@ -363,22 +365,33 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       if (j >= n_buf) flag_wait(&ctrl->empty[buf], (j / n_buf) * kWarps);
       double* Ws = smem + buf * tile_doubles;
       const int nt = idx % NT, q = idx / NT;
-      // a one-draw call spreads all 32 lanes over the groups of the range (column 0 of the tile)
-      const bool one_draw = args.n_draws == 1;
-      const int b = one_draw ? 0 : 8 * nt + (lane & 7);
-      long long draw = (tile_first + j) * BM + b;
-      if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: recompute the last draw
       if (theta_base != nullptr) {
-        int g_begin, g_end;
-        occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
-        occupation_item(args.plan, args.model, theta_base + draw * args.theta_ds, args.theta_ps,
-                        g_begin, g_end, tab,
-                        [&](int row, double occ, double nh) {
-                          store_weight<NT, MODE>(Ws, row, b, occ * nh);
-                        },
-                        one_draw ? lane : (lane >> 3), one_draw ? 32 : 4);
+        const SeriesItem it = series_item(args.plan, args.n_ranges_cen, args.n_ranges_sat,
+                                          args.pieces_cen, args.pieces_sat, q);
+        const int col0 = 8 * nt + it.b_begin;
+        const long long draw0 = (tile_first + j) * BM + col0;
+        // draws beyond the batch are skipped: their columns keep weights of an earlier tile (or the
+        // initial zeros), every column is contracted on its own and finalize ignores them
+        const int n_b = (int)min((long long)it.n_b, args.n_draws - draw0);
+        if (n_b > 0 && it.g_end > it.g_begin) {
+          auto store = [&](int b, int row, double occ, double nh) {
+            store_weight<NT, MODE>(Ws, row, col0 + b, occ * nh);
+          };
+          const double* theta0 = theta_base + draw0 * args.theta_ds;
+          if (it.sat)
+            occupation_item_series<true>(args.plan, args.model, theta0, args.theta_ds,
+                                         args.theta_ps, n_b, it.g_begin, it.g_end, tab,
+                                         ctrl->ser_queue[tid >> 5], store);
+          else
+            occupation_item_series<false>(args.plan, args.model, theta0, args.theta_ds,
+                                          args.theta_ps, n_b, it.g_begin, it.g_end, tab,
+                                          ctrl->ser_queue[tid >> 5], store);
+        }
       } else {
         const int n_q = args.n_ranges_cen + args.n_ranges_sat;
+        const int b = 8 * nt + (lane & 7);
+        long long draw = (tile_first + j) * BM + b;
+        if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: repeat the last draw
         const int r_begin = (int)((long long)lay.n_pad * q / n_q);
         const int r_end = (int)((long long)lay.n_pad * (q + 1) / n_q);
         for (int row = r_begin + (lane >> 3); row < r_end; row += 4) {

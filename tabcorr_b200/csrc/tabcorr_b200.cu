@@ -147,6 +147,12 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   args.pad_to_row = t->layouts[0].dev.pad_to_row;
   args.occ_out = occ;
   pick_ranges(args.plan, 1, &args.n_ranges_cen, &args.n_ranges_sat);
+  if (model->family == TC_FAMILY_ZHENG07)
+    // enough items for every warp of the device, at most 8 draw pieces per type
+    pick_series_ranges(args.plan, 1, n_draws,
+                       (int)std::min<long long>(16, std::max<long long>(
+                           2, (long long)n_sm * kWarps / ((n_draws + 7) / 8))),
+                       &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
   if (model->family == TC_FAMILY_LEAUTHAUD11) {
     const size_t smem = kTabDoubles * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
     static std::mutex m;
@@ -412,8 +418,9 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   args.ngal_tile = reinterpret_cast<double*>(static_cast<char*>(workspace) + ws.parts_bytes);
 
   args.n_buf = ws.n_buf;
-  pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat,
-              t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile);
+  pick_series_ranges(args.plan, ws.nt, n_draws,
+                     t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile,
+                     &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
   {
     // occupation items take every occ_stride-th slot of the first 70 % of a tile's work list (an
     // item runs for tens of microseconds beside DMMA warps that starve its scalar FP64, so the
