@@ -192,6 +192,22 @@ int tc_measure_dmma_peak(int device, double* tflops_out);
  * tabcorr.py:465-578), where bench.py reports node evaluations/s. */
 int tc_measure_dfma_peak(int device, double* tflops_out);
 
+/* Halo-bin reductions of the tabulation side (tabcorr/tabcorr.py:194-227, the n_h histogram and
+ * the per-cell mean primary property behind prim_haloprop_dist_index; sort_into_bins :676-737).
+ * Inputs are device arrays of n_halos doubles: log_prim (what np.histogram2d / np.digitize bin,
+ * computed by the caller exactly as the reference does, np.log10), sec_pct, prim (what is averaged);
+ * prim_edges [n_prim + 1] and sec_edges [n_sec + 1] are HOST arrays of ascending bin edges.
+ * Outputs (HOST arrays of n_sec * n_prim doubles, cell index = sec * n_prim + prim, i.e. the
+ * reference's ravel(order='F')): n_h_out = counts with np.histogram2d semantics (values on the
+ * last edge fall into the last bin), n_members_out and mean_out = number and mean of prim over the
+ * members of np.digitize(right=False) (last edge excluded), mean_out = NaN for empty cells.
+ * Counts are exact; the mean is accumulated in fixed point (52 fractional bits of the position
+ * inside the cell) and is bit-reproducible.  Synchronises the stream. */
+int tc_halo_bins(int device, const double* log_prim_dev, const double* sec_pct_dev,
+                 const double* prim_dev, int64_t n_halos, const double* prim_edges, int n_prim,
+                 const double* sec_edges, int n_sec, double* n_h_out, double* n_members_out,
+                 double* mean_out, void* stream);
+
 /* Element-wise evaluation of the occupation kernel's table-driven math on the current device, for
  * accuracy tests: kind 0: out = 0.5 (1 + erf(x)); kind 1: out = x^y for x > 0. */
 int tc_debug_math(int kind, const double* x_dev, const double* y_dev, double* out_dev, int64_t n,

@@ -432,3 +432,73 @@ class OracleInterpolator:
                 output.append(spline_interpolate(x_model, self.xp, self.a, data,
                                                  extrapolate=extrapolate))
         return tuple(output)
+
+
+# ---------------------------------------------------------------------------------------------
+# tabulation side, the halo-bin table: restated from
+# tabcorr/tabcorr.py:192-234 (n_h histogram, bin columns, prim_haloprop_dist_index),
+# sort_into_bins :676-737 and distribution_index :740-767.  Pinned by tests/golden/halo_bins.npz,
+# which oracle/make_golden_halo_bins.py recorded from the reference's own functions.
+# ---------------------------------------------------------------------------------------------
+def sort_into_bins(log_prim_haloprop, log_prim_haloprop_bins, sec_haloprop_percentile,
+                   sec_haloprop_percentile_bins, x):
+    """Values of ``x`` per (secondary bin, primary bin) cell (tabcorr.py:676-737, no gal_type)."""
+    n_p = len(log_prim_haloprop_bins) - 1
+    n_s = len(sec_haloprop_percentile_bins) - 1
+    i_prim = np.digitize(log_prim_haloprop, bins=log_prim_haloprop_bins, right=False) - 1  # :715
+    i_sec = np.digitize(sec_haloprop_percentile, bins=sec_haloprop_percentile_bins,
+                        right=False) - 1
+    inside = ~((i_prim < 0) | (i_prim >= n_p) | (i_sec < 0) | (i_sec >= n_s))  # :721
+    # (the reference filters x but not the indices, so it only works when every halo is inside;
+    # filtering both is the same thing there and well defined elsewhere)
+    cell = (i_prim + i_sec * n_p)[inside]  # :730
+    values = np.asarray(x)[inside]
+    order = np.argsort(cell, kind='stable')
+    counts = np.insert(np.cumsum(np.bincount(cell, minlength=n_p * n_s)), 0, 0)  # :732-735
+    values = values[order]
+    return [values[counts[i]:counts[i + 1]] for i in range(len(counts) - 1)]
+
+
+def distribution_index(x_min, x_max, x_mean):
+    """tabcorr.py:740-767, with the very scipy call the reference makes."""
+    from scipy.interpolate import interp1d
+    x_max = x_max / x_min
+    x_mean = x_mean / x_min
+    n_interp = np.linspace(-10, +10, 100)
+    x_interp = ((n_interp + 1) / (n_interp + 2) * (x_max**(n_interp + 2) - 1) /
+                (x_max**(n_interp + 1) - 1))
+    return interp1d(x_interp, n_interp, kind='cubic', fill_value=(-10, +10),
+                    bounds_error=False)(x_mean)
+
+
+def halo_bin_table(prim_haloprop, sec_haloprop_percentile, log_prim_haloprop_bins,
+                   sec_haloprop_percentile_bins):
+    """Columns of ``gal_type`` before the centrals/satellites stacking (tabcorr.py:194-227):
+    dict with ``n_h``, the four bin-edge columns, ``prim_haloprop``, ``sec_haloprop_percentile``,
+    ``prim_haloprop_dist_index``, plus ``mean_prim`` (NaN where empty) for the tests."""
+    prim_haloprop = np.asarray(prim_haloprop, dtype=np.float64)
+    n_h, pe, se = np.histogram2d(np.log10(prim_haloprop), sec_haloprop_percentile,
+                                 bins=[log_prim_haloprop_bins, sec_haloprop_percentile_bins])  # :194
+    out = {'n_h': n_h.ravel(order='F')}  # :199
+    grid = np.meshgrid(pe, se)  # :201
+    out['log_prim_haloprop_min'] = grid[0][:-1, :-1].ravel()
+    out['log_prim_haloprop_max'] = grid[0][:-1, 1:].ravel()
+    out['sec_haloprop_percentile_min'] = grid[1][:-1, :-1].ravel()
+    out['sec_haloprop_percentile_max'] = grid[1][1:, :-1].ravel()
+    out['prim_haloprop'] = 10**(0.5 * (out['log_prim_haloprop_min'] +
+                                       out['log_prim_haloprop_max']))  # :208
+    out['sec_haloprop_percentile'] = 0.5 * (out['sec_haloprop_percentile_min'] +
+                                            out['sec_haloprop_percentile_max'])
+    members = sort_into_bins(np.log10(prim_haloprop), pe, sec_haloprop_percentile, se,
+                             prim_haloprop)  # :214
+    dist = np.zeros(len(out['n_h']))
+    mean = np.full(len(out['n_h']), np.nan)
+    for i in range(len(dist)):  # :219-226
+        if len(members[i]) > 0:
+            x_min = 10**out['log_prim_haloprop_min'][i]
+            x_max = 10**out['log_prim_haloprop_max'][i]
+            mean[i] = np.mean(members[i])
+            dist[i] = distribution_index(x_min, x_max, mean[i])
+    out['prim_haloprop_dist_index'] = dist
+    out['mean_prim'] = mean
+    return out

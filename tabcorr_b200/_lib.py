@@ -37,7 +37,7 @@ SYMBOLS = (
     'tc_table_n_r', 'tc_table_n_tables', 'tc_table_plan', 'tc_occupation_batch',
     'tc_predict_workspace_bytes', 'tc_predict_workspace_bytes_for', 'tc_predict_batch', 'tc_predict_one', 'tc_interp_create', 'tc_interp_destroy',
     'tc_interp_apply_batch', 'tc_measure_dmma_peak', 'tc_measure_dfma_peak', 'tc_profile_enable', 'tc_profile_read', 'tc_debug_math',
-    'tc_peer_alloc', 'tc_peer_open', 'tc_peer_close', 'tc_peer_free')
+    'tc_peer_alloc', 'tc_peer_open', 'tc_peer_close', 'tc_peer_free', 'tc_halo_bins')
 
 
 class TabCorrB200Error(RuntimeError):
@@ -114,6 +114,9 @@ def load():
     lib.tc_measure_dmma_peak.argtypes = [ctypes.c_int, c_double_p]
     lib.tc_measure_dfma_peak.restype = ctypes.c_int
     lib.tc_measure_dfma_peak.argtypes = [ctypes.c_int, c_double_p]
+    lib.tc_halo_bins.restype = ctypes.c_int
+    lib.tc_halo_bins.argtypes = [ctypes.c_int, vp, vp, vp, ctypes.c_int64, c_double_p, ctypes.c_int,
+                                 c_double_p, ctypes.c_int, c_double_p, c_double_p, c_double_p, vp]
     lib.tc_profile_enable.restype = ctypes.c_int
     lib.tc_profile_enable.argtypes = [ctypes.c_int]
     lib.tc_profile_read.restype = ctypes.c_int

@@ -11,6 +11,7 @@
 #include "leauthaud11.cuh"
 #include "aux_kernels.cuh"
 #include "tcgen05_contract.cuh"
+#include "halo_bins.cuh"
 
 namespace {
 
@@ -785,8 +786,8 @@ int device_sms(int device, int* n_sm) {
   return TC_OK;
 }
 
-template <int NT, int MODE>
-int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
+template <int NT, int MODE, bool SERIES>
+int launch_predict_as(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
   static std::mutex m;
   static std::map<int, bool> configured;
   int dev = 0;
@@ -794,14 +795,21 @@ int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t
   {
     std::lock_guard<std::mutex> lock(m);
     if (!configured[dev]) {
-      TC_CUDA(cudaFuncSetAttribute(predict_kernel<NT, MODE>,
+      TC_CUDA(cudaFuncSetAttribute(predict_kernel<NT, MODE, SERIES>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
       configured[dev] = true;
     }
   }
-  predict_kernel<NT, MODE><<<grid, kThreads, smem, stream>>>(args);
+  predict_kernel<NT, MODE, SERIES><<<grid, kThreads, smem, stream>>>(args);
   TC_CUDA(cudaGetLastError());
   return TC_OK;
+}
+
+// args.pieces_cen != 0: series items (pick_series_ranges), else node-by-node items (pick_ranges)
+template <int NT, int MODE>
+int launch_predict(const PredictArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
+  return args.pieces_cen != 0 ? launch_predict_as<NT, MODE, true>(args, grid, smem, stream)
+                              : launch_predict_as<NT, MODE, false>(args, grid, smem, stream);
 }
 
 // Output blocks (gridDim.y) and dynamic shared memory of finalize_kernel: the staging tile of a

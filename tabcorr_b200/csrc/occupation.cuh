@@ -226,10 +226,14 @@ __device__ __forceinline__ void occupation_range(const OccPlan& plan, int n_rang
 constexpr int kSerMaxTerms = 24;               // moments 0..24 per row
 constexpr int kSerMom = kSerMaxTerms + 1;
 constexpr int kSerQueue = 64;                  // queued (draw, group) pairs per warp
+#ifndef TC_SER_UNROLL
+#define TC_SER_UNROLL 4
+#endif
 #ifndef TC_SER_DRAWS
 #define TC_SER_DRAWS 2
 #endif
 constexpr int kSerDraws = TC_SER_DRAWS;        // draws in flight per warp iteration
+constexpr int kSerUnroll = TC_SER_UNROLL;      // unrolling of the term loops
 constexpr int kSerBuckets = 64;
 constexpr double kSerCenBucket = 64.0;         // h buckets of width 1/64 up to h = 1
 constexpr double kSerSatBucket = 128.0;        // y buckets of width 1/128 up to y = 0.5
@@ -405,6 +409,7 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
           acc1[u] = fma(v[u], m2.y, v_prev[u] * m.y);
         }
         double2 m_next = mom[3 * ng];
+#pragma unroll kSerUnroll
         for (int k = 2; k < n_terms; k++) {   // term k + 1
           m = m_next;
           m_next = mom[min(k + 2, kSerMaxTerms) * ng];
@@ -469,6 +474,7 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
         }
         const int kw = __reduce_max_sync(full, kt);
         double2 m_next = mom[2 * ng];
+#pragma unroll kSerUnroll
         for (int k = 2; k <= kw; k++) {
           m = m_next;
           m_next = mom[min(k + 1, kSerMaxTerms) * ng];

@@ -48,7 +48,7 @@ struct PredictArgs {
   int n_buf;             // W tiles in shared memory: 2 = occupation of tile t + 1 overlaps tile t
   int n_ranges_cen;      // occupation items per n-tile: group ranges of centrals ...
   int n_ranges_sat;      // ... and of satellites
-  int pieces_cen, pieces_sat;   // draw pieces per type (series_item)
+  int pieces_cen, pieces_sat;   // draw pieces per type (series_item); 0: node-by-node items
   int occ_stride;        // every occ_stride-th slot of a tile's work list is an occupation item
   int tf32_segment;      // 3xTF32 mode: k8-steps per FP32 accumulation chain
 };
@@ -268,7 +268,10 @@ __device__ __forceinline__ void run_chunk_tf32(const LayoutDev& lay, const Chunk
 // Dependencies always point backwards in that sequence, so taking slots in order cannot deadlock:
 // a chunk waits until full[buf] counts all occupation items of its tile, an occupation item until
 // empty[buf] counts every warp having left the list of the tile that used its buffer before.
-template <int NT, int MODE>
+// SERIES selects the occupation items at compile time (series items / node-by-node items), so that
+// a kernel only carries the code of the items it runs: the hot code of the 12 warps (DMMA loops +
+// occupation + slot dispatch) has to stay inside the 32 KB instruction cache.
+template <int NT, int MODE, bool SERIES>
 __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs args) {
   constexpr int BM = 8 * NT;
   extern __shared__ __align__(16) double smem[];
@@ -365,7 +368,23 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       if (j >= n_buf) flag_wait(&ctrl->empty[buf], (j / n_buf) * kWarps);
       double* Ws = smem + buf * tile_doubles;
       const int nt = idx % NT, q = idx / NT;
-      if (theta_base != nullptr) {
+      if (!SERIES && theta_base != nullptr) {
+        // node-by-node items (small tables: the series items' code would push the working set of
+        // the 12 warps out of the instruction cache); a one-draw call spreads all 32 lanes over
+        // the groups of the range (column 0 of the tile)
+        const bool one_draw = args.n_draws == 1;
+        const int b = one_draw ? 0 : 8 * nt + (lane & 7);
+        long long draw = (tile_first + j) * BM + b;
+        if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: recompute the last draw
+        int g_begin, g_end;
+        occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
+        occupation_item(args.plan, args.model, theta_base + draw * args.theta_ds, args.theta_ps,
+                        g_begin, g_end, tab,
+                        [&](int row, double occ, double nh) {
+                          store_weight<NT, MODE>(Ws, row, b, occ * nh);
+                        },
+                        one_draw ? lane : (lane >> 3), one_draw ? 32 : 4);
+      } else if (SERIES && theta_base != nullptr) {
         const SeriesItem it = series_item(args.plan, args.n_ranges_cen, args.n_ranges_sat,
                                           args.pieces_cen, args.pieces_sat, q);
         const int col0 = 8 * nt + it.b_begin;

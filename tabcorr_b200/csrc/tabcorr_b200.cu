@@ -418,9 +418,19 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   args.ngal_tile = reinterpret_cast<double*>(static_cast<char*>(workspace) + ws.parts_bytes);
 
   args.n_buf = ws.n_buf;
-  pick_series_ranges(args.plan, ws.nt, n_draws,
-                     t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile,
-                     &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
+  // Occupation items: series items (occupation_item_series) where they pay -- cross tables
+  // (bound by the occupation arithmetic), many quadrature nodes, tables of 200+ rows -- else the
+  // node-by-node items whose code is smaller (instruction-cache footprint of the fused kernel)
+  const int series_auto = t->mode == TC_MODE_CROSS || plan_g > 16 || L.dev.n_pad >= 200;
+  if (theta != nullptr || theta_inline != nullptr ? tune("SERIES_FUSED", series_auto) != 0 : false) {
+    pick_series_ranges(args.plan, ws.nt, n_draws,
+                       t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile,
+                       &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
+  } else {
+    pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat,
+                t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile);
+    args.pieces_cen = args.pieces_sat = 0;
+  }
   {
     // occupation items take every occ_stride-th slot of the first 70 % of a tile's work list (an
     // item runs for tens of microseconds beside DMMA warps that starve its scalar FP64, so the
@@ -606,6 +616,115 @@ int tc_interp_apply_batch(tc_interp* it, const double* x, int64_t n_draws, const
   unsigned grid = (unsigned)((n_draws + 3) / 4);
   interp_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(args);
   TC_CUDA(cudaGetLastError());
+  return TC_OK;
+}
+
+int tc_halo_bins(int device, const double* log_prim, const double* sec_pct, const double* prim,
+                 int64_t n_halos, const double* prim_edges, int n_prim, const double* sec_edges,
+                 int n_sec, double* n_h_out, double* n_members_out, double* mean_out,
+                 void* stream_) {
+  if (!prim_edges || !sec_edges || !n_h_out || !n_members_out || !mean_out || n_prim <= 0 ||
+      n_sec <= 0 || n_halos < 0 || (n_halos > 0 && (!log_prim || !sec_pct || !prim)))
+    return fail(TC_EINVAL, "tc_halo_bins: bad argument");
+  for (int i = 0; i < n_prim; i++)
+    if (!(prim_edges[i] < prim_edges[i + 1]))
+      return fail(TC_EINVAL, "tc_halo_bins: prim_edges must increase strictly");
+  for (int i = 0; i < n_sec; i++)
+    if (!(sec_edges[i] < sec_edges[i + 1]))
+      return fail(TC_EINVAL, "tc_halo_bins: sec_edges must increase strictly");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TC_ECUDA, "tc_halo_bins: cannot select CUDA device " +
+                                           std::to_string(device) + " (no CUDA device available?)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int n_cells = n_prim * n_sec;
+  const size_t smem = (size_t)4 * n_cells * sizeof(unsigned long long) +
+                      (size_t)(n_prim + n_sec + 2) * sizeof(double);
+  if (smem > (size_t)kSmemLimit)
+    return fail(TC_EUNSUPPORTED, "tc_halo_bins: " + std::to_string(n_cells) +
+                                     " cells do not fit the per-block table in shared memory");
+  // 10**edge like the reference (x_min, x_max of distribution_index, tabcorr.py:219-220)
+  std::vector<double> host((size_t)2 * n_cells + n_prim + n_sec + 2);
+  double* cell_min = host.data();
+  double* cell_inv = cell_min + n_cells;
+  for (int s = 0; s < n_sec; s++) {
+    for (int p = 0; p < n_prim; p++) {
+      const double lo = std::pow(10.0, prim_edges[p]), hi = std::pow(10.0, prim_edges[p + 1]);
+      cell_min[s * n_prim + p] = lo;
+      cell_inv[s * n_prim + p] = 1.0 / (hi - lo);
+    }
+  }
+  std::copy(prim_edges, prim_edges + n_prim + 1, cell_inv + n_cells);
+  std::copy(sec_edges, sec_edges + n_sec + 1, cell_inv + n_cells + n_prim + 1);
+  double* d_in = nullptr;
+  unsigned long long* d_out = nullptr;
+  TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_in), host.size() * sizeof(double)));
+  if (cudaMalloc(reinterpret_cast<void**>(&d_out), (size_t)4 * n_cells * sizeof(unsigned long long)) !=
+      cudaSuccess) {
+    (void)cudaFree(d_in);
+    (void)cudaGetLastError();
+    return fail(TC_ENOMEM, "tc_halo_bins: out of device memory");
+  }
+  auto cleanup = [&]() { (void)cudaFree(d_in); (void)cudaFree(d_out); };
+#define TC_HB(expr)                                                                        \
+  do {                                                                                     \
+    cudaError_t err__ = (expr);                                                            \
+    if (err__ != cudaSuccess) {                                                            \
+      (void)cudaGetLastError();                                                            \
+      cleanup();                                                                           \
+      return fail(TC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));        \
+    }                                                                                      \
+  } while (0)
+  TC_HB(cudaMemcpyAsync(d_in, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
+                        stream));
+  TC_HB(cudaMemsetAsync(d_out, 0, (size_t)4 * n_cells * sizeof(unsigned long long), stream));
+  HaloBinArgs args{};
+  args.log_prim = log_prim;
+  args.sec_pct = sec_pct;
+  args.prim = prim;
+  args.n_halos = n_halos;
+  args.cell_min = d_in;
+  args.cell_inv_width = d_in + n_cells;
+  args.prim_edges = d_in + 2 * n_cells;
+  args.sec_edges = d_in + 2 * n_cells + n_prim + 1;
+  args.n_prim = n_prim;
+  args.n_sec = n_sec;
+  args.counts = d_out;
+  args.counts_open = d_out + n_cells;
+  args.sum_hi = d_out + 2 * n_cells;
+  args.sum_lo = d_out + 3 * n_cells;
+  int n_sm = 0;
+  int rc = device_sms(device, &n_sm);
+  if (rc) { cleanup(); return rc; }
+  if (n_halos > 0) {
+    TC_HB(cudaFuncSetAttribute(halo_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+    // one wave of blocks: 8 per SM while the shared table allows, each striding over the haloes
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)kSmemLimit / (smem + 1024)));
+    const long long want = (n_halos + 255) / 256;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)n_sm * per_sm));
+    halo_bins_kernel<<<grid, 256, smem, stream>>>(args);
+    TC_HB(cudaGetLastError());
+  }
+  std::vector<unsigned long long> res((size_t)4 * n_cells);
+  TC_HB(cudaMemcpyAsync(res.data(), d_out, res.size() * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToHost, stream));
+  TC_HB(cudaStreamSynchronize(stream));
+#undef TC_HB
+  cleanup();
+  for (int c = 0; c < n_cells; c++) {
+    n_h_out[c] = (double)res[c];
+    const unsigned long long members = res[n_cells + c];
+    n_members_out[c] = (double)members;
+    if (members == 0) {
+      mean_out[c] = std::nan("");
+    } else {
+      // mean offset = (sum_hi 2^26 + sum_lo) / 2^52 / members, in long double (64-bit mantissa)
+      const long double total = (long double)res[2 * n_cells + c] * 67108864.0L +
+                                (long double)res[3 * n_cells + c];
+      const long double frac = total / 4503599627370496.0L / (long double)members;
+      mean_out[c] = (double)((long double)cell_min[c] + frac / (long double)cell_inv[c]);
+    }
+  }
   return TC_OK;
 }
 
