@@ -679,6 +679,9 @@ Workspace plan_workspace(const Layout& L, long long n_draws, int n_sm) {
 // balance: 48 smaller ones (measured: N = 240 0.84 -> 0.71 ms per 1e5 draws, N = 1104 3.12 -> 3.04).
 constexpr int kOccItemsPerTile = 14;
 constexpr int kOccItemsPerTileCross = 48;
+// series items of cross tables: 28 (measured: N = 1104 2.68 -> 1.94 ms per 1e5 draws against 48,
+// whose draw pieces shrink to one draw per item; N = 240 0.60 -> 0.57 ms)
+constexpr int kOccSeriesItemsPerTileCross = 28;
 
 void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat,
                  int items = kOccItemsPerTile) {

@@ -424,7 +424,7 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   const int series_auto = t->mode == TC_MODE_CROSS || plan_g > 16 || L.dev.n_pad >= 200;
   if (theta != nullptr || theta_inline != nullptr ? tune("SERIES_FUSED", series_auto) != 0 : false) {
     pick_series_ranges(args.plan, ws.nt, n_draws,
-                       t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile,
+                       t->mode == TC_MODE_CROSS ? kOccSeriesItemsPerTileCross : kOccItemsPerTile,
                        &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
   } else {
     pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat,

@@ -102,6 +102,77 @@ def gather_slab_chunks(compute_chunk, slab, full, n_chunks=3, dst=0, group=None)
         work.wait()
 
 
+class OverlappedGather:
+    """Steps of a data-parallel job whose one collective runs behind the NEXT step's kernels.
+
+    A step's result rows leave for rank ``dst`` with an asynchronous ``gather`` the moment its
+    kernels are queued; the following step's kernels (written into the other of ``depth`` slabs)
+    run while NVLink moves them, so in steady state a step costs ``max(kernels, gather)`` instead
+    of their sum.  ``dst`` assembles every step in place in one of ``depth`` ``[world * n_local,
+    width]`` buffers (rank-major rows like ``shard_bounds``).  Use::
+
+        pipe = OverlappedGather(n_local, width, device)
+        for step in steps:
+            slab = pipe.begin()          # this step's [n_local, width] slab, free to overwrite
+            halotab.predict_into_slab(theta, slab)
+            full = pipe.submit()         # dst: the buffer the step lands in (valid after wait)
+        pipe.finish()                    # every gather has completed on the current stream
+
+    ``begin`` makes the current stream wait for the gather that last read the slab (``depth``
+    steps ago); a consumer on ``dst`` calls ``wait(step)`` before reading that step's buffer.
+    Without an initialised process group the slab is its own result."""
+
+    def __init__(self, n_local, width, device, dst=0, group=None, depth=2, dtype=None):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.group, self.dst, self.depth = group, dst, max(2, int(depth))
+        self.active = dist.is_available() and dist.is_initialized() and \
+            dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.n_local = int(n_local)
+        dtype = dtype or torch.float64
+        self.slabs = [torch.empty((n_local, width), dtype=dtype, device=device)
+                      for _ in range(self.depth)]
+        self.full = None
+        if self.active and self.rank == dst:
+            self.full = [torch.empty((self.world * n_local, width), dtype=dtype, device=device)
+                         for _ in range(self.depth)]
+        self.works = {}
+        self.step = 0
+
+    def begin(self):
+        """The slab of the step about to be computed (its previous gather is waited for)."""
+        self.wait(self.step - self.depth)
+        return self.slabs[self.step % self.depth]
+
+    def submit(self):
+        """Queue the gather of the slab ``begin`` handed out; returns ``dst``'s landing buffer."""
+        k = self.step
+        self.step += 1
+        slab = self.slabs[k % self.depth]
+        if not self.active:
+            return slab
+        receive, full = None, None
+        if self.rank == self.dst:
+            full = self.full[k % self.depth]
+            n = self.n_local
+            receive = [full[r * n:(r + 1) * n] for r in range(self.world)]
+        self.works[k] = self.dist.gather(slab, receive, dst=self.dst, group=self.group,
+                                         async_op=True)
+        return full
+
+    def wait(self, step):
+        work = self.works.pop(step, None)
+        if work is not None:
+            work.wait()
+
+    def finish(self):
+        for k in sorted(self.works):
+            self.wait(k)
+
+
 class SlabRows:
     """Rows ``[lo, hi)`` of a :class:`PeerSlab` as seen from this process: a raw device pointer
     (possibly into another GPU's memory), the row count and the row width in doubles."""

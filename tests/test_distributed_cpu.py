@@ -221,3 +221,50 @@ def test_sweep_world_size_2_equals_single_process(tmp_path, n_draws, chunk):
     assert torch.equal(again, prior.sample(1, again.shape[0], 'cpu'))
     lo, hi = sweep.ZHENG07_PRIOR['logMmin']
     assert float(again[:, 0].min()) >= lo and float(again[:, 0].max()) <= hi
+
+
+# ---------------------------------------------------------------------------------------------
+# OverlappedGather: the gather of step k behind the kernels of step k + 1 (double-buffered slabs)
+# ---------------------------------------------------------------------------------------------
+def _overlap_worker(rank, world, port, n_local, n_steps):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        pipe = tcd.OverlappedGather(n_local, 3, 'cpu', dst=0, depth=2)
+        landed = []
+        for step in range(n_steps):
+            slab = pipe.begin()
+            # every step overwrites the slab it was handed: values encode (step, rank, row)
+            slab.copy_(torch.arange(n_local * 3, dtype=torch.float64).reshape(n_local, 3) +
+                       1000.0 * step + 100.0 * rank)
+            full = pipe.submit()
+            if rank == 0:
+                pipe.wait(step)   # a consumer reads a step's buffer after waiting for its gather
+                landed.append(full.clone())
+            else:
+                assert full is None
+        pipe.finish()
+        assert pipe.works == {}
+        if rank == 0:
+            for step, full in enumerate(landed):
+                for r in range(world):
+                    expect = (torch.arange(n_local * 3, dtype=torch.float64).reshape(n_local, 3) +
+                              1000.0 * step + 100.0 * r)
+                    assert torch.equal(full[r * n_local:(r + 1) * n_local], expect)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_gather_world_size_2():
+    mp.spawn(_overlap_worker, args=(2, _free_port(), 5, 5), nprocs=2, join=True)
+
+
+def test_overlapped_gather_single_process_passthrough():
+    pipe = tcd.OverlappedGather(4, 2, 'cpu')
+    slab = pipe.begin()
+    slab.fill_(7.0)
+    assert pipe.submit() is slab
+    assert pipe.begin() is not slab     # the other buffer
+    pipe.finish()
