@@ -419,8 +419,8 @@ def run_gpu_arm(args):
     import tabcorr_b200
     from tabcorr_b200 import _lib, synthetic
     from tabcorr_b200.models import ModelSpec, theta_from_params
-    from tabcorr_b200.distributed import (OverlappedGather, PeerSlab, gather_slab_chunks,
-                                          predict_batch_sharded)
+    from tabcorr_b200.distributed import (OverlappedGather, PeerCopyGather, PeerSlab,
+                                          gather_slab_chunks, predict_batch_sharded)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -454,9 +454,11 @@ def run_gpu_arm(args):
         peer = PeerSlab(n_draws * world, 1 + N_R, dst=0, device=local_rank)
         full = peer.tensor
         my_rows = peer.rows(rank * n_draws, (rank + 1) * n_draws)
-    elif world > 1 and args.gather == 'overlap':
-        # double-buffered slabs: the gather of step k runs behind the kernels of step k + 1
-        pipe = OverlappedGather(n_draws, 1 + N_R, device, dst=0)
+    elif world > 1 and args.gather in ('overlap', 'overlap-nccl'):
+        # double-buffered slabs: the collection of step k runs behind the kernels of step k + 1,
+        # moved by the copy engines into rank 0's peer-mapped slab ('overlap') or by NCCL
+        pipe = (PeerCopyGather if args.gather == 'overlap' else OverlappedGather)(
+            n_draws, 1 + N_R, device, dst=0)
     elif world > 1 and rank == 0:
         full = torch.empty((n_draws * world, 1 + N_R), dtype=torch.float64, device=device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
@@ -633,9 +635,12 @@ def run_gpu_arm(args):
                 {'collection': ("results stored by the epilogue kernel straight into rank 0's "
                                 'memory (CUDA IPC peer slab over NVLink) + one barrier per step'
                                 if peer is not None else
-                                'asynchronous NCCL gather to rank 0 per step, overlapping the next '
-                                "step's kernels (double-buffered slabs); one timed region over all "
-                                'steps incl. the L2 flushes, closed after the last gather'
+                                ('copy-engine transfer of every rank\'s rows into rank 0\'s peer-'
+                                 'mapped slab (CUDA IPC, NVLink)' if args.gather == 'overlap' else
+                                 'asynchronous NCCL gather to rank 0') +
+                                " per step, overlapping the next step's kernels (double-buffered "
+                                'slabs); one timed region over all steps incl. the L2 flushes, '
+                                'closed after the last transfer and a barrier'
                                 if pipe is not None else
                                 'NCCL gather to rank 0 in {} chunk(s) per step'.format(n_chunks))}
                 if world > 1 else {})),
@@ -691,9 +696,12 @@ def main():
     parser.add_argument('--cpu-sample', type=int, default=8000,
                         help='draws of the workload timed for cpu_baseline')
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    parser.add_argument('--gather', default='overlap', choices=['overlap', 'peer', 'nccl'],
-                        help="N > 1: 'overlap' = asynchronous NCCL gather of step k behind the "
-                             "kernels of step k + 1, 'peer' = results stored straight into rank "
+    parser.add_argument('--gather', default='overlap',
+                        choices=['overlap', 'overlap-nccl', 'peer', 'nccl'],
+                        help="N > 1: 'overlap' = copy-engine transfer of step k's rows into rank "
+                             "0's peer-mapped slab behind the kernels of step k + 1, "
+                             "'overlap-nccl' = the same with an asynchronous NCCL gather, "
+                             "'peer' = results stored straight into rank "
                              "0's memory by the epilogue kernel (CUDA IPC / NVLink), 'nccl' = "
                              "blocking (optionally chunked) NCCL gather inside every step")
     parser.add_argument('--gather-chunks', type=int, default=1,
