@@ -38,8 +38,8 @@ DRAWS_PER_GPU = 100000
 # dram__bytes_read.sum + dram__bytes_write.sum of predict_kernel for this workload (one launch =
 # 1e5 draws).  NOT measured by this run: the constant is copied from the committed ncu --set full
 # capture named in NCU_TRAFFIC_SOURCE; only reported for the default batch size
-NCU_DRAM_BYTES_PER_LAUNCH = 31631104 + 13955840
-NCU_TRAFFIC_SOURCE = 'profiles/r01_predict_kernel_N240_R20.md'
+NCU_DRAM_BYTES_PER_LAUNCH = 10839040 + 16406784
+NCU_TRAFFIC_SOURCE = 'profiles/r02_predict_kernel_N240_R20.md'
 # algorithmic HBM bytes per launch: 7 parameters in, 1 + R results out per draw, the table once
 ALGORITHMIC_BYTES_PER_DRAW = 8 * 7 + 8 * (1 + N_R)
 METRIC = 'HOD predictions/sec (ngal+wp)'

@@ -107,9 +107,24 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ double2 ld_stream(const double2* p) {
+// The table stream: read-only, not worth an L1 line (each warp reads its fragment once per chunk),
+// but it is THE data to keep in L2 -- every draw tile of every CTA re-reads all of it, while the
+// scratch rows and results written beside it are touched once.  Without a hint the no-allocate
+// loads are evict-first in L2 and the streamed writes push table lines out (ncu: 7.6 M of the
+// 282 M evict-first sector reads missed, 150 MB of DRAM reads per launch for a 4.9 MB table).
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p, unsigned long long policy) {
   double2 v;
+#ifdef TC_A_NO_HINT
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+               : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
+#endif
   return v;
 }
 

@@ -253,7 +253,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Node-by-node evaluation of one (draw, group) pair: the reference arithmetic, used for the pairs
 // the series does not cover.  One copy per translation unit (not inlined into the 24 kernel
 // instantiations).
-__device__ __noinline__ void occupation_pair_nodes(const OccPlan& plan, int grp, bool sat,
+__device__ __noinline__ void occupation_pair_nodes(const OccPlan plan, int grp, bool sat,
                                                    bool decorated, bool modulate, DrawParams p,
                                                    double split, const double* __restrict__ tab,
                                                    double* occ) {

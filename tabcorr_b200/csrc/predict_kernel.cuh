@@ -71,6 +71,7 @@ __device__ __forceinline__ void run_chunk(const LayoutDev& lay, const Chunk& ch,
                                           double* __restrict__ parts, int lane) {
   constexpr int BM = 8 * NT;
   const int g = lane >> 2, tig = lane & 3;
+  const unsigned long long keep = l2_keep_policy();
   if (MODE == TC_MODE_AUTO) {
     double sums[NT][2];
 #pragma unroll
@@ -87,12 +88,12 @@ __device__ __forceinline__ void run_chunk(const LayoutDev& lay, const Chunk& ch,
 #pragma unroll
       for (int nt = 0; nt < NT; nt++)
         acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
-      double2 a_next = ld_stream(ap);
+      double2 a_next = ld_stream(ap, keep);
       int ks = ch.k_begin;
       for (; ks < k_both; ks++) {
         const double2 a = a_next;
         ap += 32;
-        a_next = ld_stream(ap);  // the stream is padded by one k-step, always safe
+        a_next = ld_stream(ap, keep);  // the stream is padded by one k-step, always safe
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
           const double b = wk[nt * 32];
@@ -104,7 +105,7 @@ __device__ __forceinline__ void run_chunk(const LayoutDev& lay, const Chunk& ch,
       for (; ks < k_end; ks++) {
         const double2 a = a_next;
         ap += 32;
-        a_next = ld_stream(ap);
+        a_next = ld_stream(ap, keep);
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) dmma884(acc[1][nt], a.y, wk[nt * 32]);
         wk += NT * 32;
@@ -148,11 +149,11 @@ __device__ __forceinline__ void run_chunk(const LayoutDev& lay, const Chunk& ch,
 #pragma unroll
     for (int nt = 0; nt < NT; nt++)
       acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
-    double2 a_next = ld_stream(ap);
+    double2 a_next = ld_stream(ap, keep);
     for (int ks = ch.k_begin; ks < ch.k_cap; ks++) {
       const double2 a = a_next;
       ap += 32;
-      a_next = ld_stream(ap);
+      a_next = ld_stream(ap, keep);
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
         const double b = wk[nt * 32];
@@ -407,17 +408,27 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
                                           ctrl->ser_queue[tid >> 5], store);
         }
       } else {
+        // precomputed occupations occ[draw, row]: a warp reads 32 consecutive rows of one draw
+        // (coalesced; the padded order keeps the table's row order inside a galaxy type), the 8
+        // draws of the n-tile one after the other with all their loads in flight
         const int n_q = args.n_ranges_cen + args.n_ranges_sat;
-        const int b = 8 * nt + (lane & 7);
-        long long draw = (tile_first + j) * BM + b;
-        if (draw >= args.n_draws) draw = args.n_draws - 1;  // tail tile: repeat the last draw
         const int r_begin = (int)((long long)lay.n_pad * q / n_q);
         const int r_end = (int)((long long)lay.n_pad * (q + 1) / n_q);
-        for (int row = r_begin + (lane >> 3); row < r_end; row += 4) {
-          const int src = lay.pad_to_row[row];
-          if (src >= 0)
-            store_weight<NT, MODE>(Ws, row, b,
-                                   args.occ[draw * lay.n_rows + src] * args.plan.row_nh[row]);
+        const long long draw0 = (tile_first + j) * BM + 8 * nt;
+        for (int row0 = r_begin; row0 < r_end; row0 += 32) {
+          const int row = row0 + lane;
+          const int src = row < r_end ? lay.pad_to_row[row] : -1;
+          const double nh = src >= 0 ? args.plan.row_nh[row] : 0.0;
+          double w[8];
+#pragma unroll
+          for (int b = 0; b < 8; b++) {
+            const long long draw = min(draw0 + b, args.n_draws - 1);   // tail tile: repeat the last
+            w[b] = src >= 0 ? args.occ[draw * lay.n_rows + src] : 0.0;
+          }
+          if (src >= 0) {
+#pragma unroll
+            for (int b = 0; b < 8; b++) store_weight<NT, MODE>(Ws, row, 8 * nt + b, w[b] * nh);
+          }
         }
       }
       flag_signal(&ctrl->full[buf], lane);
