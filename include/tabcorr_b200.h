@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 106
+#define TC_VERSION 107
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -56,6 +56,7 @@ extern "C" {
 #define TC_N_THETA 7              /* zheng07 */
 #define TC_N_THETA_LEAUTHAUD11 18
 #define TC_N_THETA_MAX 18
+#define TC_N_THETA_ZHENG07_BASE 5   /* logMmin .. alpha; the strengths follow */
 
 typedef struct tc_table tc_table;   /* device-resident table group (one gal_type, >=1 matrices) */
 typedef struct tc_interp tc_interp; /* tensor-product cubic spline over a table grid */
@@ -63,6 +64,8 @@ typedef struct tc_interp tc_interp; /* tensor-product cubic spline over a table 
 /* Occupation model evaluated by the occupation kernel; replaces the halotools calls at
  * tabcorr/tabcorr.py:556-563 (Zheng07Cens/Zheng07Sats or Leauthaud11Cens/Leauthaud11Sats,
  * optionally decorated with HeavisideAssembias). */
+#define TC_MAX_KNOTS 4   /* control points of a mass-dependent assembly-bias strength / split */
+
 typedef struct tc_model {
   int32_t family;               /* TC_FAMILY_* */
   int32_t decorated;            /* 1 = Heaviside assembly bias on centrals and satellites */
@@ -71,6 +74,22 @@ typedef struct tc_model {
   double split;                 /* percentile split of the decoration (halotools default 0.5) */
   double threshold;             /* leauthaud11: log10 of the stellar-mass threshold */
   double redshift;              /* leauthaud11: redshift of the stellar-to-halo-mass relation */
+  /* Mass-dependent decoration (halotools HeavisideAssembias with assembias_strength_abscissa /
+   * split_abscissa; zheng07 family only).  Index 0: centrals, 1: satellites.
+   * n_strength[t] <= 1: one strength per draw (the layouts above).  n_strength[t] = n in
+   * 2..TC_MAX_KNOTS: the draw carries n strength ordinates for type t (theta: logMmin,
+   * sigma_logM, logM0, logM1, alpha, then the centrals' ordinates, then the satellites'), and
+   * the strength of a halo is the interpolating polynomial of degree n - 1 through
+   * (strength_abscissa[t][k], ordinate k) evaluated at log10(prim_haloprop), clipped to [-1, 1]
+   * (halotools: custom_spline(..., k=3), a spline of degree min(3, n - 1) through n points).
+   * n_split[t] = 0: `split` above; n in 1..TC_MAX_KNOTS: the splitting percentile of type t is
+   * the same kind of polynomial through (split_abscissa[t][k], split_ordinates[t][k]), clipped to
+   * [0, 1] (fixed at model construction, not part of the draw). */
+  int32_t n_strength[2];
+  int32_t n_split[2];
+  double strength_abscissa[2][TC_MAX_KNOTS];
+  double split_abscissa[2][TC_MAX_KNOTS];
+  double split_ordinates[2][TC_MAX_KNOTS];
 } tc_model;
 
 const char* tc_last_error(void);

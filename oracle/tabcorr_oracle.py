@@ -59,7 +59,8 @@ class Zheng07Oracle:
     gal_types = ['centrals', 'satellites']
 
     def __init__(self, param_dict=None, decorated=False, split=0.5, redshift=0.0,
-                 modulate_with_cenocc=False):
+                 modulate_with_cenocc=False, strength_abscissa=((), ()), split_abscissa=((), ()),
+                 split_ordinates=((), ())):
         self.param_dict = dict(logMmin=12.02, sigma_logM=0.26, logM0=11.38, logM1=13.31,
                                alpha=1.06)
         if decorated:
@@ -71,6 +72,46 @@ class Zheng07Oracle:
         self.split = split
         self.redshift = redshift
         self.modulate_with_cenocc = modulate_with_cenocc
+        # mass-dependent decoration, (centrals, satellites): halotools HeavisideAssembias with
+        # assembias_strength_abscissa / split_abscissa (restated from memory of halotools'
+        # heaviside_assembias.py, parity unpinned like the rest of this class)
+        self.strength_abscissa = strength_abscissa
+        self.split_abscissa = split_abscissa
+        self.split_ordinates = split_ordinates
+
+    @staticmethod
+    def _custom_spline(abscissa, ordinates, x):
+        # halotools model_helpers.custom_spline(abscissa, ordinates, k=3): a constant for one
+        # point, else scipy's InterpolatedUnivariateSpline of degree min(3, n - 1)
+        from scipy.interpolate import InterpolatedUnivariateSpline
+        if len(abscissa) == 1:
+            return np.zeros_like(x) + ordinates[0]
+        return InterpolatedUnivariateSpline(abscissa, ordinates,
+                                            k=min(3, len(abscissa) - 1))(x)
+
+    def _strength(self, gal_type, prim_haloprop):
+        # HeavisideAssembias.assembias_strength: spline of the param_dict ordinates over
+        # log10(prim_haloprop), clipped to [-1, 1]
+        t = 0 if gal_type == 'centrals' else 1
+        abscissa = self.strength_abscissa[t]
+        n = max(1, len(abscissa))
+        ordinates = [self.param_dict['mean_occupation_{}_assembias_param{}'.format(gal_type, k + 1)]
+                     for k in range(n)]
+        if n == 1:
+            result = np.zeros_like(prim_haloprop) + ordinates[0]
+        else:
+            result = self._custom_spline(abscissa, ordinates, np.log10(prim_haloprop))
+        return np.clip(result, -1.0, 1.0)
+
+    def _split(self, gal_type, prim_haloprop):
+        # HeavisideAssembias.percentile_splitting_function: spline of the fixed ordinates over
+        # log10(prim_haloprop), clipped to [0, 1]
+        t = 0 if gal_type == 'centrals' else 1
+        if len(self.split_abscissa[t]) == 0:
+            return np.zeros_like(prim_haloprop) + self.split
+        result = self._custom_spline(self.split_abscissa[t], self.split_ordinates[t],
+                                     np.log10(prim_haloprop))
+        return np.clip(result, 0.0, 1.0)
 
     # -- baseline zheng07 ---------------------------------------------------------------
     def _baseline_centrals(self, prim_haloprop):
@@ -93,45 +134,44 @@ class Zheng07Oracle:
         return out
 
     # -- Heaviside assembly bias ----------------------------------------------------------
-    def _decorate(self, baseline, percentile, strength, lower, upper):
+    def _decorate(self, baseline, percentile, strength, lower, upper, split=None):
         # halotools HeavisideAssembias.assembias_decorator: haloes above the split percentile
         # (type 1, fraction 1 - split) get +delta, the rest -delta * (1 - split) / split, which
         # preserves the mean at fixed mass.  delta = strength * (largest perturbation keeping both
-        # sub-populations inside [lower, upper]); strength is clipped to [-1, 1].
-        split = self.split
-        strength = min(max(strength, -1.0), 1.0)
+        # sub-populations inside [lower, upper]); strength is clipped to [-1, 1].  strength and
+        # split are per-halo arrays (functions of the primary halo property) or scalars.
         result = np.array(baseline, dtype=np.float64)
-        if not 0 < split < 1:
-            return result
-        ok = (result > lower) & (result < upper)
+        split = np.broadcast_to(self.split if split is None else split, result.shape)
+        strength = np.clip(np.broadcast_to(strength, result.shape), -1.0, 1.0)
+        ok = (result > lower) & (result < upper) & (split > 0) & (split < 1)
         f = result[ok]
-        frac1 = 1.0 - split
-        frac2 = split
-        if strength > 0:
-            bound = np.minimum(upper - f, frac2 / frac1 * (f - lower))
-            delta = strength * bound
-        else:
-            bound = np.maximum(lower - f, frac2 / frac1 * (f - upper))
-            delta = -strength * bound
-        type1 = percentile[ok] > split
-        f = np.where(type1, f + delta, f - delta * frac1 / frac2)
-        result[ok] = f
+        frac1 = 1.0 - split[ok]
+        frac2 = split[ok]
+        a = strength[ok]
+        with np.errstate(invalid='ignore'):
+            positive = a * np.minimum(upper - f, frac2 / frac1 * (f - lower))
+            negative = -a * np.maximum(lower - f, frac2 / frac1 * (f - upper))
+        delta = np.where(a > 0, positive, negative)
+        type1 = np.asarray(percentile)[ok] > split[ok]
+        result[ok] = np.where(type1, f + delta, f - delta * frac1 / frac2)
         return result
 
     def mean_occupation_centrals(self, prim_haloprop=None, sec_haloprop_percentile=None, **kw):
-        f = self._baseline_centrals(np.asarray(prim_haloprop, dtype=np.float64))
+        prim_haloprop = np.asarray(prim_haloprop, dtype=np.float64)
+        f = self._baseline_centrals(prim_haloprop)
         if self.decorated:
-            f = self._decorate(
-                f, np.asarray(sec_haloprop_percentile),
-                self.param_dict['mean_occupation_centrals_assembias_param1'], 0.0, 1.0)
+            f = self._decorate(f, np.asarray(sec_haloprop_percentile),
+                               self._strength('centrals', prim_haloprop), 0.0, 1.0,
+                               self._split('centrals', prim_haloprop))
         return f
 
     def mean_occupation_satellites(self, prim_haloprop=None, sec_haloprop_percentile=None, **kw):
-        f = self._baseline_satellites(np.asarray(prim_haloprop, dtype=np.float64))
+        prim_haloprop = np.asarray(prim_haloprop, dtype=np.float64)
+        f = self._baseline_satellites(prim_haloprop)
         if self.decorated:
-            f = self._decorate(
-                f, np.asarray(sec_haloprop_percentile),
-                self.param_dict['mean_occupation_satellites_assembias_param1'], 0.0, np.inf)
+            f = self._decorate(f, np.asarray(sec_haloprop_percentile),
+                               self._strength('satellites', prim_haloprop), 0.0, np.inf,
+                               self._split('satellites', prim_haloprop))
         return f
 
 
@@ -164,6 +204,7 @@ class Leauthaud11Oracle(Zheng07Oracle):
         self.redshift = redshift
         self.decorated = decorated
         self.split = split
+        self.strength_abscissa = self.split_abscissa = self.split_ordinates = ((), ())
         self.modulate_with_cenocc = modulate_with_cenocc
 
     def mean_log_halo_mass(self, log_stellar_mass):

@@ -27,6 +27,7 @@ def precision_code(precision):
         raise ValueError("precision must be 'fp64' or '3xtf32'")
     return table[key]
 TC_N_THETA = 7
+TC_MAX_KNOTS = 4
 TC_N_THETA_LEAUTHAUD11 = 18
 TC_FAMILY_ZHENG07 = 0
 TC_FAMILY_LEAUTHAUD11 = 1
@@ -48,7 +49,12 @@ class tc_model(ctypes.Structure):
     _fields_ = [('family', ctypes.c_int32), ('decorated', ctypes.c_int32),
                 ('modulate_with_cenocc', ctypes.c_int32), ('reserved', ctypes.c_int32),
                 ('split', ctypes.c_double), ('threshold', ctypes.c_double),
-                ('redshift', ctypes.c_double)]
+                ('redshift', ctypes.c_double),
+                # mass-dependent decoration, [centrals, satellites] (include/tabcorr_b200.h)
+                ('n_strength', ctypes.c_int32 * 2), ('n_split', ctypes.c_int32 * 2),
+                ('strength_abscissa', (ctypes.c_double * TC_MAX_KNOTS) * 2),
+                ('split_abscissa', (ctypes.c_double * TC_MAX_KNOTS) * 2),
+                ('split_ordinates', (ctypes.c_double * TC_MAX_KNOTS) * 2)]
 
 
 _lib = None

@@ -11,6 +11,7 @@ namespace {
 
 struct DrawParams {
   double logMmin, inv_sigma, m0, inv_m1, alpha, a_cen, a_sat;
+  double s_ord[TC_MAX_KNOTS];   // mass-dependent decoration: the strength ordinates of the item's type
   // node arrays handed to baseline_occupation as (first, second); zheng07 satellites need the
   // mass only, unless they are modulated by the central occupation (log10 mass, mass)
   static __device__ __forceinline__ const double* first_nodes(const OccPlan& plan, bool sat,
@@ -38,6 +39,32 @@ __device__ __forceinline__ DrawParams load_draw(const double* __restrict__ theta
   p.a_cen = fmin(fmax(theta[5 * ps], -1.0), 1.0);
   p.a_sat = fmin(fmax(theta[6 * ps], -1.0), 1.0);
   return p;
+}
+
+// Mass-dependent decoration (tc_model.n_strength / n_split, include/tabcorr_b200.h)
+__device__ __forceinline__ bool model_mass_dependent(const tc_model& m) {
+  return m.decorated && (m.n_strength[0] > 1 || m.n_strength[1] > 1 || m.n_split[0] > 0 ||
+                         m.n_split[1] > 0);
+}
+// doubles per draw of a zheng07-family model and where a type's strength ordinates start
+__device__ __host__ __forceinline__ int zheng07_strength_count(const tc_model& m, int type) {
+  return m.n_strength[type] > 1 ? m.n_strength[type] : 1;
+}
+__device__ __host__ __forceinline__ int zheng07_n_theta(const tc_model& m) {
+  return TC_N_THETA_ZHENG07_BASE + zheng07_strength_count(m, 0) + zheng07_strength_count(m, 1);
+}
+// interpolating polynomial through n <= TC_MAX_KNOTS points (Lagrange form)
+__device__ __forceinline__ double lagrange_eval(int n, const double* x, const double* y, double t) {
+  double sum = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < n; k++) {
+    double w = y[k];
+#pragma unroll 1
+    for (int j = 0; j < n; j++)
+      if (j != k) w *= (t - x[j]) / (x[k] - x[j]);
+    sum += w;
+  }
+  return sum;
 }
 
 // Heaviside assembly bias (halotools HeavisideAssembias, call site tabcorr.py:556-563): haloes above
@@ -125,6 +152,24 @@ __device__ __forceinline__ void occupation_group(const OccPlan& plan, int grp, P
   occ1 = a1;
 }
 
+// The parameters one galaxy type needs (exp10 and the divisions are ~50 FP64 instructions each)
+template <bool SAT>
+__device__ __forceinline__ DrawParams load_draw_typed(const double* __restrict__ theta,
+                                                      long long ps, bool everything) {
+  DrawParams p{};
+  if (!SAT || everything) {
+    p.logMmin = theta[0];
+    p.inv_sigma = 1.0 / theta[ps];
+    p.a_cen = fmin(fmax(theta[5 * ps], -1.0), 1.0);
+  }
+  if (SAT || everything) {
+    p.m0 = exp10(theta[2 * ps]);
+    p.inv_m1 = 1.0 / exp10(theta[3 * ps]);
+    p.alpha = theta[4 * ps];
+    p.a_sat = fmin(fmax(theta[6 * ps], -1.0), 1.0);
+  }
+  return p;
+}
 // Occupation work item of one warp: the 8 draws of one n-tile (lane & 7) times the mass-bin groups
 // [g_begin, g_end), four groups in flight per warp (lane >> 3).  A range never mixes centrals and
 // satellites (groups are ordered centrals first), so the galaxy type is warp-uniform.
@@ -135,9 +180,11 @@ __device__ __forceinline__ void occupation_item_impl(const OccPlan& plan, const 
                                                      long long theta_ps, int g_begin, int g_end,
                                                      const double* __restrict__ tab, Store store,
                                                      int first, int stride) {
-  DrawParams p = load_draw(theta_row, theta_ps);
-  if (!model.decorated) p.a_cen = p.a_sat = 0.0;  // strengths are ignored unless decorated
   const bool sat = g_begin >= plan.n_cen_groups;
+  // only what the item's galaxy type needs: exp10 and the divisions are ~50 FP64 instructions each
+  DrawParams p = sat ? load_draw_typed<true>(theta_row, theta_ps, MODULATE)
+                     : load_draw_typed<false>(theta_row, theta_ps, false);
+  if (!model.decorated) p.a_cen = p.a_sat = 0.0;  // strengths are ignored unless decorated
   for (int grp = g_begin + first; grp < g_end; grp += stride) {
     double occ0, occ1;
     if (sat)
@@ -253,6 +300,52 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Node-by-node evaluation of one (draw, group) pair: the reference arithmetic, used for the pairs
 // the series does not cover.  One copy per translation unit (not inlined into the 24 kernel
 // instantiations).
+// One (draw, group) pair of a model with mass-dependent strength / split: both are evaluated per
+// quadrature node at log10 of the node's mass (halotools evaluates them per halo).
+__device__ __noinline__ void occupation_pair_nodes_massdep(const OccPlan plan, const tc_model model,
+                                                           int grp, bool sat, DrawParams p,
+                                                           const double* __restrict__ tab,
+                                                           double* occ) {
+  const int G = plan.n_gauss, GP = plan.n_gauss_pad, type = sat ? 1 : 0;
+  const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
+  const double* c0 = plan.row_c + (size_t)row0 * GP;
+  const double* c1 = plan.row_c + (size_t)(row1 >= 0 ? row1 : plan.zero_row) * GP;
+  const double* node_m = plan.node_m + (size_t)grp * GP;
+  const double* node_logm = plan.node_logm + (size_t)grp * GP;
+  const double pct0 = plan.row_pct[row0], pct1 = row1 >= 0 ? plan.row_pct[row1] : 0.0;
+  const double hi = sat ? CUDART_INF : 1.0;
+  const bool with_erf = !sat || model.modulate_with_cenocc;
+  const int n_str = model.n_strength[type], n_split = model.n_split[type];
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll 1
+  for (int g = 0; g < G; g++) {
+    const double logm = node_logm[g];
+    double f = 1.0;
+    if (with_erf) f = half_erfc_neg((logm - p.logMmin) * p.inv_sigma, tab);
+    if (sat) {
+      const double d = node_m[g] - p.m0;
+      const bool pos = d > 0.0;
+      const double pw = pow_pos(pos ? d * p.inv_m1 : 1.0, p.alpha, tab);
+      f = pos ? f * pw : 0.0;
+    }
+    double strength = p.s_ord[0];
+    if (n_str > 1) strength = lagrange_eval(n_str, model.strength_abscissa[type], p.s_ord, logm);
+    strength = fmin(fmax(strength, -1.0), 1.0);
+    double split = model.split;
+    if (n_split > 0)
+      split = fmin(fmax(lagrange_eval(n_split, model.split_abscissa[type],
+                                      model.split_ordinates[type], logm), 0.0), 1.0);
+    const bool split_ok = split > 0.0 && split < 1.0;
+    const double ratio = split_ok ? split / (1.0 - split) : 0.0;
+    const double down = split_ok ? -(1.0 - split) / split : 0.0;
+    const double dl = assembias_delta(f, strength, ratio, hi, split_ok);
+    a0 = fma(c0[g], fma(pct0 > split ? 1.0 : down, dl, f), a0);
+    a1 = fma(c1[g], fma((row1 >= 0 && pct1 > split) ? 1.0 : down, dl, f), a1);
+  }
+  occ[0] = a0;
+  occ[1] = a1;
+}
+
 __device__ __noinline__ void occupation_pair_nodes(const OccPlan plan, int grp, bool sat,
                                                    bool decorated, bool modulate, DrawParams p,
                                                    double split, const double* __restrict__ tab,
@@ -274,25 +367,6 @@ __device__ __noinline__ void occupation_pair_nodes(const OccPlan plan, int grp, 
   occ[1] = occ1;
 }
 
-// The parameters one galaxy type needs (exp10 and the divisions are ~50 FP64 instructions each)
-template <bool SAT>
-__device__ __forceinline__ DrawParams load_draw_typed(const double* __restrict__ theta,
-                                                      long long ps, bool everything) {
-  DrawParams p{};
-  if (!SAT || everything) {
-    p.logMmin = theta[0];
-    p.inv_sigma = 1.0 / theta[ps];
-    p.a_cen = fmin(fmax(theta[5 * ps], -1.0), 1.0);
-  }
-  if (SAT || everything) {
-    p.m0 = exp10(theta[2 * ps]);
-    p.inv_m1 = 1.0 / exp10(theta[3 * ps]);
-    p.alpha = theta[4 * ps];
-    p.a_sat = fmin(fmax(theta[6 * ps], -1.0), 1.0);
-  }
-  return p;
-}
-
 // Occupation item of one warp in series mode: draws [0, n_b) of an 8-draw block (parameters of
 // draw b at theta0 + b * theta_ds) times the groups [g_begin, g_end) of ONE galaxy type.
 // `queue` points at kSerQueue ints of shared memory owned by this warp.
@@ -309,6 +383,7 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
   const bool modulate = SAT && model.modulate_with_cenocc != 0;
   const bool decorated = model.decorated != 0;
   // lane l holds the parameters of draw l & 7 (clamped to the item's draws)
+  const bool mass_dep = model_mass_dependent(model);   // strength / split vary from node to node
   DrawParams mine = load_draw_typed<SAT>(theta0 + (long long)min(lane & 7, n_b - 1) * theta_ds,
                                          theta_ps, modulate);
   if (!decorated) mine.a_cen = mine.a_sat = 0.0;   // strengths are ignored unless decorated
@@ -331,9 +406,18 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
     p.alpha = __shfl_sync(full, mine.alpha, b);
     p.a_cen = __shfl_sync(full, mine.a_cen, b);
     p.a_sat = __shfl_sync(full, mine.a_sat, b);
+    if (mass_dep) {   // the strength ordinates of the pair's draw and type, straight from theta
+      const int type = SAT ? 1 : 0;
+      const int first_ord = TC_N_THETA_ZHENG07_BASE + (SAT ? zheng07_strength_count(model, 0) : 0);
+      const int n_ord = zheng07_strength_count(model, type);
+      const double* th = theta0 + (long long)b * theta_ds;
+      for (int k = 0; k < TC_MAX_KNOTS; k++)
+        p.s_ord[k] = k < n_ord ? th[(first_ord + k) * theta_ps] : 0.0;
+    }
     if (lane < n) {
       double occ[2];
-      occupation_pair_nodes(plan, grp, SAT, decorated, modulate, p, split, tab, occ);
+      if (mass_dep) occupation_pair_nodes_massdep(plan, model, grp, SAT, p, tab, occ);
+      else occupation_pair_nodes(plan, grp, SAT, decorated, modulate, p, split, tab, occ);
       const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
       store(b, row0, occ[0], plan.row_nh[row0]);
       if (row1 >= 0) store(b, row1, occ[1], plan.row_nh[row1]);
@@ -357,7 +441,7 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
     for (int u = 0; u < kSerDraws; u++) {
       const int b = min(b0 + u, n_b - 1);
       strength[u] = __shfl_sync(full, SAT ? mine.a_sat : mine.a_cen, b);
-      all_queued[u] = modulate;
+      all_queued[u] = modulate || mass_dep;
       if (!SAT) {
         logMmin[u] = __shfl_sync(full, mine.logMmin, b);
         inv_sigma[u] = __shfl_sync(full, mine.inv_sigma, b);
@@ -375,9 +459,23 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
         if (!(alpha[u] >= 0.0 && alpha[u] <= kSerAlphaMax)) all_queued[u] = true;
       }
     }
+    bool every_draw_queued = true;
+#pragma unroll
+    for (int u = 0; u < kSerDraws; u++) every_draw_queued = every_draw_queued && all_queued[u];
     for (int g0 = g_begin; g0 < g_end; g0 += 32) {
       const int grp = g0 + lane;
       const bool valid = grp < g_end;
+      if (every_draw_queued) {   // nothing for the series to do: straight to the queue
+        for (int b = b0; b < min(b0 + kSerDraws, n_b); b++) {
+          const unsigned qm = __ballot_sync(full, valid);
+          if (valid)
+            queue[(head + count + __popc(qm & ((1u << lane) - 1u))) & (kSerQueue - 1)] =
+                (b << 24) | grp;
+          count += __popc(qm);
+          if (count >= 32) drain(32);
+        }
+        continue;
+      }
       const int gsafe = valid ? grp : g_end - 1;
       const double4 gs = plan.grp_ser[gsafe];
       const double2* mom = plan.grp_mom + gsafe;

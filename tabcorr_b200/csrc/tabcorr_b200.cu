@@ -34,6 +34,35 @@
 
 #include "host_tables.cuh"
 
+namespace {
+
+// the mass-dependent decoration fields of tc_model (include/tabcorr_b200.h)
+int check_model(const tc_model* model) {
+  for (int type = 0; type < 2; type++) {
+    const int ns = model->n_strength[type], np = model->n_split[type];
+    if (ns < 0 || ns > TC_MAX_KNOTS || np < 0 || np > TC_MAX_KNOTS)
+      return fail(TC_EUNSUPPORTED, "tc_model: at most " + std::to_string(TC_MAX_KNOTS) +
+                                       " control points per assembly-bias strength / split");
+    for (int k = 1; k < ns; k++)
+      if (!(model->strength_abscissa[type][k] > model->strength_abscissa[type][k - 1]))
+        return fail(TC_EINVAL, "tc_model: strength_abscissa must increase strictly");
+    for (int k = 1; k < np; k++)
+      if (!(model->split_abscissa[type][k] > model->split_abscissa[type][k - 1]))
+        return fail(TC_EINVAL, "tc_model: split_abscissa must increase strictly");
+    if ((ns > 1 || np > 0) && model->family != TC_FAMILY_ZHENG07)
+      return fail(TC_EUNSUPPORTED, "tc_model: mass-dependent assembly bias is implemented for "
+                                   "TC_FAMILY_ZHENG07 only");
+  }
+  return TC_OK;
+}
+
+bool host_mass_dependent(const tc_model* m) {
+  return m && m->decorated && (m->n_strength[0] > 1 || m->n_strength[1] > 1 || m->n_split[0] > 0 ||
+                               m->n_split[1] > 0);
+}
+
+}  // namespace
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -45,7 +74,10 @@ int tc_version(void) { return TC_VERSION; }
 
 int tc_model_n_theta(const tc_model* model) {
   if (!model) return fail(TC_EINVAL, "tc_model_n_theta: model is NULL");
-  if (model->family == TC_FAMILY_ZHENG07) return TC_N_THETA;
+  if (model->family == TC_FAMILY_ZHENG07) {
+    int rc = check_model(model);
+    return rc != TC_OK ? rc : zheng07_n_theta(*model);
+  }
   if (model->family == TC_FAMILY_LEAUTHAUD11) return TC_N_THETA_LEAUTHAUD11;
   return fail(TC_EUNSUPPORTED, "tc_model_n_theta: unknown model family");
 }
@@ -135,7 +167,9 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   if (rc != TC_OK) return rc;
   int n_sm = 0;
   if ((rc = device_sms(t->device, &n_sm))) return rc;
-  const int n_theta = model->family == TC_FAMILY_LEAUTHAUD11 ? TC_N_THETA_LEAUTHAUD11 : TC_N_THETA;
+  if ((rc = check_model(model))) return rc;
+  const int n_theta = model->family == TC_FAMILY_LEAUTHAUD11 ? TC_N_THETA_LEAUTHAUD11
+                                                              : zheng07_n_theta(*model);
   OccArgs args{};
   args.plan = t->layouts[0].plans[n_gauss].dev;
   args.model = *model;
@@ -349,6 +383,14 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
     return fail(TC_EUNSUPPORTED, "tc_predict_batch: the fused occupation phase implements "
                                  "TC_FAMILY_ZHENG07 only; evaluate tc_occupation_batch and pass "
                                  "its result as occ_dev");
+  if (theta) {
+    int rc_model = check_model(model);
+    if (rc_model != TC_OK) return rc_model;
+  }
+  const bool mass_dep = theta && host_mass_dependent(model);
+  if (mass_dep && theta_inline)
+    return fail(TC_EUNSUPPORTED, "tc_predict_one: models with mass-dependent assembly bias take "
+                                 "the batch entry (their draws have more than TC_N_THETA doubles)");
   if (precision != TC_PRECISION_FP64 && precision != TC_PRECISION_3XTF32)
     return fail(TC_EINVAL, "tc_predict_batch: precision must be TC_PRECISION_FP64 or _3XTF32");
   if (precision == TC_PRECISION_3XTF32 && t->mode != TC_MODE_AUTO)
@@ -362,7 +404,8 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   if (!guard.ok) return fail(TC_ECUDA, "tc_predict_batch: cannot select the table's CUDA device");
   int rc = build_layout(t, separate);
   if (rc != TC_OK) return rc;
-  if (precision == TC_PRECISION_3XTF32 && theta && !theta_inline && tcgen_eligible(t, separate) &&
+  if (precision == TC_PRECISION_3XTF32 && theta && !theta_inline && !mass_dep &&
+      tcgen_eligible(t, separate) &&
       n_draws >= tune("TCGEN_MIN_DRAWS", 1) && workspace &&
       workspace_bytes >= plan_tcgen_workspace(t, n_draws).total) {
     // Blackwell-native contraction (tcgen05 + TMEM + TMA) for every batch size, so that results do
@@ -403,7 +446,7 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   args.plan = L.plans[plan_g].dev;
   if (model) args.model = *model;
   args.theta = theta_inline ? nullptr : theta;
-  args.theta_ds = theta_ld ? 1 : TC_N_THETA;
+  args.theta_ds = theta_ld ? 1 : (model && theta ? zheng07_n_theta(*model) : TC_N_THETA);
   args.theta_ps = theta_ld ? theta_ld : 1;
   if (theta_inline) {
     args.theta_is_inline = 1;
@@ -421,8 +464,10 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   // Occupation items: series items (occupation_item_series) where they pay -- cross tables
   // (bound by the occupation arithmetic), many quadrature nodes, tables of 200+ rows -- else the
   // node-by-node items whose code is smaller (instruction-cache footprint of the fused kernel)
-  const int series_auto = t->mode == TC_MODE_CROSS || plan_g > 16 || L.dev.n_pad >= 200;
-  if (theta != nullptr || theta_inline != nullptr ? tune("SERIES_FUSED", series_auto) != 0 : false) {
+  // (mass-dependent strengths / splits exist in the series items' node path only)
+  const int series_auto = t->mode == TC_MODE_CROSS || plan_g > 16 || L.dev.n_pad >= 200 || mass_dep;
+  if (theta != nullptr || theta_inline != nullptr
+          ? (mass_dep || tune("SERIES_FUSED", series_auto) != 0) : false) {
     pick_series_ranges(args.plan, ws.nt, n_draws,
                        t->mode == TC_MODE_CROSS ? kOccSeriesItemsPerTileCross : kOccItemsPerTile,
                        &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);

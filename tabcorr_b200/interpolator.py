@@ -310,7 +310,7 @@ class Interpolator:
                 raise ValueError('The key {} is not present in the parameter dictionary of the '
                                  'model.'.format(key))
         spec = resolve_model(model) if model is not None else spec_from_params(params)
-        if as_numpy and not defer_range_check and spec.family == 0:
+        if as_numpy and not defer_range_check and spec.latency_paths:
             from .models import theta_columns
             columns = theta_columns(params, spec)
             x_columns = [np.asarray(params[key], dtype=np.float64) for key in self._keys]
@@ -404,7 +404,7 @@ class Interpolator:
             for i in self.unique_gal_type_index:
                 self.tabcorr_list[i]._check_consistency(model)
         spec = resolve_model(model)
-        if spec.family != 0:
+        if not spec.latency_paths:
             # families outside the fused kernel: the batch path with one draw
             params = {k: np.atleast_1d(np.float64(v)) for k, v in model.param_dict.items()
                       if np.ndim(v) == 0}

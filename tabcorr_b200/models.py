@@ -53,11 +53,39 @@ ZHENG07_PUBLISHED = {
 }
 
 
+MAX_KNOTS = 4   # TC_MAX_KNOTS of the C ABI
+
+
+def _knots(values, name):
+    """Control points of a mass-dependent strength / split as a tuple of floats."""
+    if values is None:
+        return ()
+    values = tuple(float(v) for v in np.atleast_1d(np.asarray(values, dtype=np.float64)))
+    if len(values) > MAX_KNOTS:
+        raise NotImplementedError('{}: at most {} control points are implemented (an interpolating '
+                                  'polynomial through them; halotools switches to a cubic spline '
+                                  'from the fifth)'.format(name, MAX_KNOTS))
+    return values
+
+
+def assembias_keys(gal_type, n):
+    """halotools' ``param_dict`` keys of the ``n`` strength ordinates of one galaxy type."""
+    return tuple('mean_occupation_{}_assembias_param{}'.format(gal_type, k + 1) for k in range(n))
+
+
 class ModelSpec:
-    """What the kernel needs to know about a model (mirrors ``tc_model`` in the C ABI)."""
+    """What the kernel needs to know about a model (mirrors ``tc_model`` in the C ABI).
+
+    Mass-dependent decoration (halotools ``HeavisideAssembias`` with ``assembias_strength_abscissa``
+    / ``split_abscissa``; zheng07 family): ``strength_abscissa = (cen, sat)`` are the log10
+    primary-property positions of each type's strength ordinates -- the draw then carries
+    ``mean_occupation_<type>_assembias_param1..n`` -- and ``split_abscissa`` / ``split_ordinates``
+    give each type's splitting percentile as a function of mass.  An empty tuple means the
+    constant of the plain model (one strength per type, ``split``)."""
 
     def __init__(self, family=0, decorated=False, modulate_with_cenocc=False, split=0.5,
-                 threshold=0.0, redshift=0.0):
+                 threshold=0.0, redshift=0.0, strength_abscissa=((), ()),
+                 split_abscissa=((), ()), split_ordinates=((), ())):
         self.family = int(family)
         if self.family not in FAMILY_KEYS:
             raise NotImplementedError('unknown occupation family {}'.format(family))
@@ -66,6 +94,35 @@ class ModelSpec:
         self.split = float(split)
         self.threshold = float(threshold)   # leauthaud11: log10 stellar-mass threshold
         self.redshift = float(redshift)     # leauthaud11: redshift of the SMHM parameters
+        self.strength_abscissa = tuple(_knots(v, 'assembias_strength_abscissa')
+                                       for v in strength_abscissa)
+        self.split_abscissa = tuple(_knots(v, 'split_abscissa') for v in split_abscissa)
+        self.split_ordinates = tuple(_knots(v, 'split') for v in split_ordinates)
+        for absc, ordi in zip(self.split_abscissa, self.split_ordinates):
+            if len(absc) != len(ordi):
+                raise ValueError('split_abscissa and split ordinates differ in length')
+        for absc in self.strength_abscissa + self.split_abscissa:
+            if any(b <= a for a, b in zip(absc[:-1], absc[1:])):
+                raise ValueError('abscissa must increase strictly')
+        if self.mass_dependent and (self.family != FAMILY_ZHENG07 or not self.decorated):
+            raise NotImplementedError('mass-dependent assembly bias is implemented for decorated '
+                                      'zheng07 models')
+
+    @property
+    def mass_dependent(self):
+        return (any(len(a) > 1 for a in self.strength_abscissa) or
+                any(len(a) > 0 for a in self.split_abscissa))
+
+    @property
+    def latency_paths(self):
+        """Whether the zero-copy one-draw / small-batch entries (seven parameters in the launch
+        arguments or pinned columns) apply: fused family, one strength per galaxy type."""
+        return self.family == FAMILY_ZHENG07 and not self.mass_dependent
+
+    @property
+    def n_strength(self):
+        """Strength ordinates per draw (centrals, satellites)."""
+        return tuple(max(1, len(a)) for a in self.strength_abscissa)
 
     @property
     def occupation_keys(self):
@@ -73,17 +130,27 @@ class ModelSpec:
         return FAMILY_KEYS[self.family]
 
     @property
+    def strength_keys(self):
+        return (assembias_keys('centrals', self.n_strength[0]) +
+                assembias_keys('satellites', self.n_strength[1]))
+
+    @property
     def theta_keys(self):
         """param_dict keys of the kernel's parameter vector, in kernel order."""
-        return FAMILY_KEYS[self.family] + ASSEMBIAS_KEYS
+        return FAMILY_KEYS[self.family] + self.strength_keys
 
     @property
     def n_theta(self):
         return len(self.theta_keys)
 
+    @property
+    def n_base(self):
+        return len(FAMILY_KEYS[self.family])
+
     def key(self):
         return (self.family, self.decorated, self.modulate_with_cenocc, self.split,
-                self.threshold, self.redshift)
+                self.threshold, self.redshift, self.strength_abscissa, self.split_abscissa,
+                self.split_ordinates)
 
 
 def spec_from_params(params):
@@ -110,18 +177,43 @@ class Zheng07Model:
 
     def __init__(self, threshold=-20, redshift=0.0, prim_haloprop_key='halo_mvir',
                  sec_haloprop_key='halo_nfw_conc', decorated=False, split=0.5,
-                 modulate_with_cenocc=False, **ignored):
+                 modulate_with_cenocc=False, assembias_strength=0.5,
+                 assembias_strength_abscissa=None, split_abscissa=None, **ignored):
+        """``assembias_strength`` / ``assembias_strength_abscissa`` and ``split`` /
+        ``split_abscissa`` follow halotools' ``HeavisideAssembias`` keywords: lists make the
+        strength (``mean_occupation_*_assembias_param1..n``) or the splitting percentile a
+        function of log10 of the primary halo property, for centrals and satellites alike."""
         try:
             values = ZHENG07_PUBLISHED[float(threshold)]
         except KeyError:
             raise KeyError('no published zheng07 parameters for threshold {}'.format(threshold))
         self.param_dict = dict(zip(ZHENG07_KEYS, values))
         self.decorated = bool(decorated)
-        self.split = float(split)
         self.modulate_with_cenocc = bool(modulate_with_cenocc)
+        strengths = np.atleast_1d(np.asarray(assembias_strength, dtype=np.float64))
+        knots = _knots(assembias_strength_abscissa, 'assembias_strength_abscissa')
+        if len(strengths) > 1 and len(knots) != len(strengths):
+            raise ValueError('assembias_strength_abscissa must match assembias_strength in length')
+        if len(knots) <= 1 or len(strengths) <= 1:
+            knots = ()
+        self.strength_abscissa = (knots, knots)
+        split_values = _knots(split, 'split')
+        split_knots = _knots(split_abscissa, 'split_abscissa')
+        if len(split_values) > 1 or len(split_knots) > 0:
+            if len(split_knots) != len(split_values):
+                raise ValueError('split_abscissa must match split in length')
+            self.split = 0.5
+            self.split_abscissa = (split_knots, split_knots)
+            self.split_ordinates = (split_values, split_values)
+        else:
+            self.split = float(split_values[0])
+            self.split_abscissa = ((), ())
+            self.split_ordinates = ((), ())
         if self.decorated:
-            for key in ASSEMBIAS_KEYS:
-                self.param_dict[key] = 0.5
+            for gal_type in ('centrals', 'satellites'):
+                for key, value in zip(assembias_keys(gal_type, max(1, len(knots))),
+                                      np.broadcast_to(strengths, max(1, len(knots)))):
+                    self.param_dict[key] = float(value)
         self.threshold = threshold
         self.redshift = redshift
         self.gal_types = ['centrals', 'satellites']
@@ -201,8 +293,26 @@ def _constant_split(component):
         return 0.5
     ordinates = np.unique(np.asarray(ordinates, dtype=float))
     if len(ordinates) != 1:
-        raise NotImplementedError('mass-dependent assembly-bias splits are not implemented')
+        raise NotImplementedError('mass-dependent assembly-bias splits are not implemented for '
+                                  'this family')
     return float(ordinates[0])
+
+
+def _decoration_knots(component):
+    """``(strength_abscissa, split_abscissa, split_ordinates)`` of a halotools
+    ``HeavisideAssembias`` component: its ``_assembias_strength_abscissa`` (one entry: a constant
+    strength) and ``_split_abscissa`` / ``_split_ordinates`` (all ordinates equal: a constant)."""
+    strength = _knots(getattr(component, '_assembias_strength_abscissa', None),
+                      'assembias_strength_abscissa')
+    if len(strength) <= 1:
+        strength = ()
+    ordinates = getattr(component, '_split_ordinates', None)
+    if ordinates is None:
+        return strength, (), (0.5,)
+    ordinates = _knots(ordinates, 'split')
+    if len(set(ordinates)) == 1:
+        return strength, (), (ordinates[0],)
+    return strength, _knots(getattr(component, '_split_abscissa', None), 'split_abscissa'), ordinates
 
 
 def resolve_model(model):
@@ -212,7 +322,10 @@ def resolve_model(model):
     if hasattr(model, 'tabcorr_b200_family'):
         return ModelSpec(model.tabcorr_b200_family, model.decorated, model.modulate_with_cenocc,
                          model.split, getattr(model, 'threshold', 0.0),
-                         getattr(model, 'redshift', 0.0))
+                         getattr(model, 'redshift', 0.0),
+                         getattr(model, 'strength_abscissa', ((), ())),
+                         getattr(model, 'split_abscissa', ((), ())),
+                         getattr(model, 'split_ordinates', ((), ())))
     components = getattr(model, '_input_model_dictionary', None)
     if components is not None and 'centrals_occupation' in components:
         cens = components['centrals_occupation']
@@ -221,10 +334,18 @@ def resolve_model(model):
         if names == ('Zheng07Cens', 'Zheng07Sats'):
             return ModelSpec(0, False, getattr(sats, 'modulate_with_cenocc', False), 0.5)
         if names == ('AssembiasZheng07Cens', 'AssembiasZheng07Sats'):
-            split = _constant_split(cens)
-            if _constant_split(sats) != split:
-                raise NotImplementedError('different splits for centrals and satellites')
-            return ModelSpec(0, True, getattr(sats, 'modulate_with_cenocc', False), split)
+            knots = [_decoration_knots(c) for c in (cens, sats)]
+            strength_abscissa = tuple(k[0] for k in knots)
+            if all(len(k[1]) == 0 for k in knots) and knots[0][2] == knots[1][2]:
+                # one constant split for both galaxy types
+                return ModelSpec(0, True, getattr(sats, 'modulate_with_cenocc', False),
+                                 knots[0][2][0], strength_abscissa=strength_abscissa)
+            # per-type and / or mass-dependent splits: a constant is a single control point
+            split_abscissa = tuple(k[1] if len(k[1]) else (0.0,) for k in knots)
+            split_ordinates = tuple(k[2] for k in knots)
+            return ModelSpec(0, True, getattr(sats, 'modulate_with_cenocc', False), 0.5,
+                             strength_abscissa=strength_abscissa, split_abscissa=split_abscissa,
+                             split_ordinates=split_ordinates)
         if names in (('Leauthaud11Cens', 'Leauthaud11Sats'),
                      ('AssembiasLeauthaud11Cens', 'AssembiasLeauthaud11Sats')):
             decorated = names[0].startswith('Assembias')
@@ -246,7 +367,10 @@ def resolve_model(model):
     if param_dict is not None and all(k in param_dict for k in ZHENG07_KEYS):
         return ModelSpec(0, getattr(model, 'decorated', False),
                          getattr(model, 'modulate_with_cenocc', False),
-                         getattr(model, 'split', 0.5))
+                         getattr(model, 'split', 0.5),
+                         strength_abscissa=getattr(model, 'strength_abscissa', ((), ())),
+                         split_abscissa=getattr(model, 'split_abscissa', ((), ())),
+                         split_ordinates=getattr(model, 'split_ordinates', ((), ())))
     if param_dict is not None and all(k in param_dict for k in LEAUTHAUD11_KEYS):
         if not hasattr(model, 'threshold'):
             raise NotImplementedError('a leauthaud11 model needs a `threshold` attribute')
@@ -269,7 +393,7 @@ def theta_columns(params, spec=None):
     if missing:
         raise ValueError('missing occupation parameters: {}'.format(', '.join(missing)))
     if spec.decorated:
-        missing = [k for k in ASSEMBIAS_KEYS if k not in params]
+        missing = [k for k in spec.strength_keys if k not in params]
         if missing:
             raise ValueError('missing assembly-bias parameters: {}'.format(', '.join(missing)))
     return [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in spec.theta_keys]

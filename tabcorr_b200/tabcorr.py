@@ -195,8 +195,18 @@ class DeviceTableGroup:
 
     @staticmethod
     def _model_struct(spec):
-        return _lib.tc_model(spec.family, int(spec.decorated), int(spec.modulate_with_cenocc), 0,
-                             spec.split, spec.threshold, spec.redshift)
+        model = _lib.tc_model(spec.family, int(spec.decorated), int(spec.modulate_with_cenocc), 0,
+                              spec.split, spec.threshold, spec.redshift)
+        for t in range(2):   # mass-dependent decoration (centrals, satellites)
+            absc = spec.strength_abscissa[t]
+            model.n_strength[t] = len(absc) if len(absc) > 1 else 0
+            for k, value in enumerate(absc):
+                model.strength_abscissa[t][k] = value
+            model.n_split[t] = len(spec.split_abscissa[t])
+            for k, (a, o) in enumerate(zip(spec.split_abscissa[t], spec.split_ordinates[t])):
+                model.split_abscissa[t][k] = a
+                model.split_ordinates[t][k] = o
+        return model
 
     def occupation(self, spec, n_gauss, theta, theta_columns=False):
         """theta: CUDA tensor ``[B, n_theta]`` (or ``[n_theta, B]`` with ``theta_columns``) ->
@@ -221,7 +231,7 @@ class DeviceTableGroup:
         ``ngal [T, 1|2]``, ``xi [T, R, C]`` (copies).  Latency path, see ``_SingleDrawBuffers``."""
         torch = _torch()
         self.plan(n_gauss)
-        if spec.family != 0:
+        if not spec.latency_paths:
             # families outside the fused kernel: occupation kernel + contraction (no latency path)
             theta = _to_device_f64(np.asarray(values, dtype=np.float64)[np.newaxis, :], self.device)
             n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
@@ -576,13 +586,14 @@ class TabCorr:
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             theta = _to_device_f64(params, group.device)
-            if theta.ndim != 2 or theta.shape[1] not in (spec.n_theta - 2, spec.n_theta):
+            if theta.ndim != 2 or theta.shape[1] not in (spec.n_base, spec.n_theta):
                 raise ValueError('params must be a dict of arrays or a [B, {}|{}] array ordered as '
-                                 '{}'.format(spec.n_theta - 2, spec.n_theta,
+                                 '{}'.format(spec.n_base, spec.n_theta,
                                              ', '.join(spec.theta_keys)))
-            if theta.shape[1] == spec.n_theta - 2:
-                theta = torch.cat([theta, torch.zeros((theta.shape[0], 2), dtype=torch.float64,
-                                                      device=theta.device)], dim=1)
+            if theta.shape[1] == spec.n_base:
+                theta = torch.cat([theta, torch.zeros((theta.shape[0], spec.n_theta - spec.n_base),
+                                                      dtype=torch.float64, device=theta.device)],
+                                  dim=1)
         return spec, theta
 
     def predict_batch(self, params, separate_gal_type=False, n_gauss_prim=10, model=None,
@@ -698,13 +709,13 @@ class TabCorr:
         fused kernel implements; None when the batch does not qualify."""
         if isinstance(params, dict):
             spec = resolve_model(model) if model is not None else spec_from_params(params)
-            if spec.family != 0:
+            if not spec.latency_paths:
                 return None
             columns = theta_columns(params, spec)
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             array = np.asarray(params, dtype=np.float64)
-            if spec.family != 0 or array.ndim != 2 or array.shape[1] not in (5, 7):
+            if not spec.latency_paths or array.ndim != 2 or array.shape[1] not in (5, 7):
                 return None   # the general path reports shape errors
             columns = [array[:, j] for j in range(array.shape[1])]
             columns += [np.float64(0.0)] * (7 - len(columns))
@@ -745,9 +756,9 @@ class TabCorr:
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             array = np.asarray(params, dtype=np.float64)
-            if array.ndim != 2 or array.shape[1] not in (spec.n_theta - 2, spec.n_theta):
+            if array.ndim != 2 or array.shape[1] not in (spec.n_base, spec.n_theta):
                 raise ValueError('params must be a dict of arrays or a [B, {}|{}] array ordered as '
-                                 '{}'.format(spec.n_theta - 2, spec.n_theta,
+                                 '{}'.format(spec.n_base, spec.n_theta,
                                              ', '.join(spec.theta_keys)))
             columns = [array[:, j] for j in range(array.shape[1])]
             columns += [np.float64(0.0)] * (spec.n_theta - len(columns))

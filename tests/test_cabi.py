@@ -45,7 +45,9 @@ def test_version_and_constants(lib):
     assert int(re.search(r'#define TC_N_THETA (\d+)', text).group(1)) == _lib.TC_N_THETA
     assert int(re.search(r'#define TC_N_THETA_LEAUTHAUD11 (\d+)', text).group(1)) == \
         _lib.TC_N_THETA_LEAUTHAUD11
-    assert ctypes.sizeof(_lib.tc_model) == 40  # 4 x int32 + 3 doubles, as declared in the header
+    # 4 x int32 + 3 doubles + the mass-dependent decoration block (2 x 2 int32 + 3 x 2 x 4 doubles)
+    assert int(re.search(r'#define TC_MAX_KNOTS (\d+)', text).group(1)) == _lib.TC_MAX_KNOTS == 4
+    assert ctypes.sizeof(_lib.tc_model) == 40 + 16 + 3 * 2 * 4 * 8
     from tabcorr_b200 import models
     for family, n_theta in ((_lib.TC_FAMILY_ZHENG07, _lib.TC_N_THETA),
                             (_lib.TC_FAMILY_LEAUTHAUD11, _lib.TC_N_THETA_LEAUTHAUD11)):
@@ -53,6 +55,15 @@ def test_version_and_constants(lib):
         model = _lib.tc_model(family, 0, 0, 0, 0.5, 10.5, 0.0)
         assert lib.tc_model_n_theta(ctypes.byref(model)) == n_theta == spec.n_theta
     assert lib.tc_model_n_theta(ctypes.byref(_lib.tc_model(9, 0, 0, 0, 0.5, 0.0, 0.0))) == -3
+    # mass-dependent strengths: the draw grows by the extra ordinates; bad control points are refused
+    from tabcorr_b200.tabcorr import DeviceTableGroup
+    spec = models.ModelSpec(0, True, strength_abscissa=((11.0, 12.0, 13.0), (11.5, 13.5)))
+    model = DeviceTableGroup._model_struct(spec)
+    assert lib.tc_model_n_theta(ctypes.byref(model)) == spec.n_theta == 5 + 3 + 2
+    model.strength_abscissa[0][1] = 10.0
+    assert lib.tc_model_n_theta(ctypes.byref(model)) == -1 and b'increase' in lib.tc_last_error()
+    model.n_strength[0] = 7
+    assert lib.tc_model_n_theta(ctypes.byref(model)) == -3
 
 
 def test_argument_errors_do_not_need_a_device(lib):

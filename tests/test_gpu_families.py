@@ -204,3 +204,71 @@ def test_full_size_properties(tb):
     ngal_100, xi_100 = halotab.predict(model, n_gauss_prim=100)
     np.testing.assert_allclose(ngal_10, ngal_100, rtol=1e-4)
     np.testing.assert_allclose(xi_10, xi_100, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# mass-dependent assembly bias (halotools HeavisideAssembias with *_abscissa keywords)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('mode', ['auto', 'cross'])
+def test_mass_dependent_assembias_against_oracle(tb, orc, mode):
+    """Strength ordinates per draw (mean_occupation_*_assembias_param1..n) and a splitting
+    percentile that varies with halo mass, centrals and satellites with different control
+    points: occupations, ngal and xi against the oracle's restatement of halotools'
+    assembias_strength / percentile_splitting_function (spline of degree min(3, n - 1) over
+    log10 M, clipped), through the batch, the one-model and the separate_gal_type entries."""
+    from tabcorr_b200.models import ModelSpec, assembias_keys
+    tab = cases.synthetic.make_table(n_mass=24, n_sec=2, n_r=5, seed=12, mode=mode)
+    halotab = tb.TabCorr.from_arrays(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'],
+                                     tab['attrs'])
+    table = orc.OracleTable(tab['gal_type'], tab['tpcf_matrix'], tab['tpcf_shape'], mode)
+    knots = dict(strength_abscissa=((11.0, 12.5, 14.0), (11.5, 12.2, 13.0, 14.5)),
+                 split_abscissa=((11.0, 14.5), (0.0,)), split_ordinates=((0.25, 0.7), (0.4,)))
+    spec = ModelSpec(0, True, **knots)
+    assert spec.n_theta == 5 + 3 + 4
+    n_draws = 40
+    rng = np.random.default_rng(8)
+    draws = cases.synthetic.make_draws(n_draws, seed=6)
+    for key in assembias_keys('centrals', 3) + assembias_keys('satellites', 4):
+        draws[key] = rng.uniform(-1.6, 1.6, n_draws)      # beyond [-1, 1]: clipped per halo
+    for n_gauss in (3, 10):
+        ngal, xi = halotab.predict_batch(draws, model=spec, n_gauss_prim=n_gauss)
+        ngal_sep, xi_sep = halotab.predict_batch(draws, model=spec, n_gauss_prim=n_gauss,
+                                                 separate_gal_type=True)
+        occ = halotab.mean_occupation_batch(draws, model=spec, n_gauss_prim=n_gauss).cpu().numpy()
+        for i in (0, 7, n_draws - 1):
+            model = orc.Zheng07Oracle(cases.draws_row(draws, i), decorated=True, **knots)
+            occ_ref = orc.mean_occupation(table, model, n_gauss)
+            np.testing.assert_allclose(occ[i], occ_ref, rtol=1e-11,
+                                       atol=1e-13 * max(1.0, occ_ref.max()))
+            ngal_ref, xi_ref = orc.predict(table, occ_ref)
+            close(ngal[i], ngal_ref)
+            close(xi[i], xi_ref)
+            ngal_ref_sep, _ = orc.predict(table, occ_ref, separate_gal_type=True)
+            for key in ngal_ref_sep:
+                close(ngal_sep[key][i], ngal_ref_sep[key])
+    # equal ordinates and a flat split are the plain decorated model, to rounding
+    flat = {k: v for k, v in draws.items() if 'assembias' not in k}
+    for key in assembias_keys('centrals', 3) + assembias_keys('satellites', 4):
+        flat[key] = np.full(n_draws, 0.6 if 'centrals' in key else -0.35)
+    flat_spec = ModelSpec(0, True, split=0.4, strength_abscissa=knots['strength_abscissa'],
+                          split_abscissa=((11.0, 14.0), ()), split_ordinates=((0.4, 0.4), ()))
+    plain = dict({k: v for k, v in flat.items() if 'assembias' not in k},
+                 mean_occupation_centrals_assembias_param1=np.full(n_draws, 0.6),
+                 mean_occupation_satellites_assembias_param1=np.full(n_draws, -0.35))
+    a = halotab.predict_batch(flat, model=flat_spec)
+    b = halotab.predict_batch(plain, model=ModelSpec(0, True, split=0.4))
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-10, atol=1e-12 * np.abs(b[1]).max())
+    # the reference's calling convention: predict(model) with a model object
+    model = tb.models.PrebuiltHodModelFactory(
+        'decorated-zheng07', threshold=-20, assembias_strength=[0.9, -0.5, 0.3],
+        assembias_strength_abscissa=[11.0, 12.5, 14.0], split=[0.3, 0.6], split_abscissa=[11.0, 14.0])
+    ngal1, xi1 = halotab.predict(model)
+    resolved = tb.models.resolve_model(model)
+    oracle_model = orc.Zheng07Oracle(dict(model.param_dict), decorated=True,
+                                     strength_abscissa=resolved.strength_abscissa,
+                                     split_abscissa=resolved.split_abscissa,
+                                     split_ordinates=resolved.split_ordinates)
+    ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, oracle_model))
+    close(ngal1, ngal_ref)
+    close(xi1, xi_ref)

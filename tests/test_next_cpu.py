@@ -120,14 +120,14 @@ def test_resolve_model_families():
     model = SimpleNamespace(_input_model_dictionary={'centrals_occupation': cens,
                                                      'satellites_occupation': sats})
     spec = models.resolve_model(model)
-    assert spec.key() == (1, False, True, 0.5, 10.5, 0.1) and spec.n_theta == 18
+    assert spec.key()[:6] == (1, False, True, 0.5, 10.5, 0.1) and spec.n_theta == 18
     assert spec.theta_keys[:16] == models.LEAUTHAUD11_KEYS
     cens.param_dict['scatter_model_param2'] = 0.3
     with pytest.raises(NotImplementedError, match='scatter'):
         models.resolve_model(model)
     model = models.PrebuiltHodModelFactory('hearin15', threshold=11.0, redshift=0.5)
     spec = models.resolve_model(model)
-    assert spec.key() == (1, True, True, 0.5, 11.0, 0.5)
+    assert spec.key()[:6] == (1, True, True, 0.5, 11.0, 0.5) and not spec.mass_dependent
     theta = models.theta_from_params(model.param_dict, 1, spec)
     assert theta.shape == (1, 18) and theta[0, 16] == 1.0 and theta[0, 17] == 0.2
     with pytest.raises(ValueError, match='missing occupation parameters'):
@@ -166,3 +166,69 @@ def test_leauthaud11_oracle_known_answers():
         model.mean_occupation_satellites(prim_haloprop=mass, sec_haloprop_percentile=pct),
         [7.82793499675266e-06, 0.007944292740829723, 0.03765846917308047, 1.1702449732622406],
         rtol=1e-10)
+
+
+def test_mass_dependent_assembias_models():
+    """halotools HeavisideAssembias with assembias_strength_abscissa / split_abscissa: the model
+    objects map to kernel descriptors with per-type control points, the draw grows by the extra
+    strength ordinates, and the oracle's restatement reduces to the constant model when all
+    ordinates are equal (tabcorr/tabcorr.py:556-563 passes whatever model it is given)."""
+    from types import SimpleNamespace
+    from oracle import tabcorr_oracle as orc
+    from tabcorr_b200 import models
+
+    model = models.PrebuiltHodModelFactory(
+        'decorated-zheng07', threshold=-20, assembias_strength=[0.8, -0.3, 0.1],
+        assembias_strength_abscissa=[11.0, 12.5, 14.0], split=[0.3, 0.6], split_abscissa=[11.0, 14.0])
+    spec = models.resolve_model(model)
+    assert spec.mass_dependent and not spec.latency_paths and spec.n_strength == (3, 3)
+    assert spec.theta_keys[5:8] == models.assembias_keys('centrals', 3)
+    assert spec.theta_keys[8:] == models.assembias_keys('satellites', 3) and spec.n_theta == 11
+    theta = models.theta_from_params(model.param_dict, 1, spec)
+    assert list(theta[0, 5:]) == [0.8, -0.3, 0.1, 0.8, -0.3, 0.1]
+    assert spec.split_abscissa == ((11.0, 14.0),) * 2 and spec.split_ordinates == ((0.3, 0.6),) * 2
+
+    # a halotools-shaped model: class names + the attributes HeavisideAssembias keeps
+    def component(name, **attrs):
+        obj = type(name, (), {})()
+        for k, v in attrs.items():
+            setattr(obj, k, v)
+        return obj
+    cens = component('AssembiasZheng07Cens', _assembias_strength_abscissa=[12.0, 13.0],
+                     _split_abscissa=[2], _split_ordinates=[0.5])
+    sats = component('AssembiasZheng07Sats', _assembias_strength_abscissa=[2],
+                     _split_abscissa=[11.0, 12.0, 13.0], _split_ordinates=[0.2, 0.5, 0.7],
+                     modulate_with_cenocc=False)
+    spec = models.resolve_model(SimpleNamespace(
+        _input_model_dictionary={'centrals_occupation': cens, 'satellites_occupation': sats}))
+    assert spec.strength_abscissa == ((12.0, 13.0), ()) and spec.n_strength == (2, 1)
+    assert spec.split_abscissa == ((0.0,), (11.0, 12.0, 13.0))
+    assert spec.split_ordinates == ((0.5,), (0.2, 0.5, 0.7))
+    with pytest.raises(NotImplementedError, match='control points'):
+        models.ModelSpec(0, True, strength_abscissa=((11, 12, 13, 14, 15), ()))
+    with pytest.raises(NotImplementedError, match='decorated zheng07'):
+        models.ModelSpec(1, True, strength_abscissa=((11, 12), ()))
+
+    # oracle: equal ordinates == the constant model; a real mass dependence changes the result
+    mass = 10**np.linspace(11.0, 14.5, 9)
+    pct = np.tile([0.25, 0.75], 5)[:9]
+    params = dict(orc.Zheng07Oracle(decorated=True).param_dict)
+    constant = orc.Zheng07Oracle(params, decorated=True, split=0.4)
+    flat = dict(params)
+    for t in ('centrals', 'satellites'):
+        for k in range(3):
+            flat['mean_occupation_{}_assembias_param{}'.format(t, k + 1)] = 0.5
+    same = orc.Zheng07Oracle(flat, decorated=True, split=0.4,
+                             strength_abscissa=((11.0, 12.5, 14.0),) * 2,
+                             split_abscissa=((11.0, 14.0),) * 2, split_ordinates=((0.4, 0.4),) * 2)
+    for fn in ('mean_occupation_centrals', 'mean_occupation_satellites'):
+        a = getattr(constant, fn)(prim_haloprop=mass, sec_haloprop_percentile=pct)
+        b = getattr(same, fn)(prim_haloprop=mass, sec_haloprop_percentile=pct)
+        np.testing.assert_allclose(b, a, rtol=1e-13)
+    flat['mean_occupation_centrals_assembias_param2'] = -0.9
+    varied = orc.Zheng07Oracle(flat, decorated=True, split=0.4,
+                               strength_abscissa=((11.0, 12.5, 14.0),) * 2)
+    assert not np.allclose(varied.mean_occupation_centrals(prim_haloprop=mass,
+                                                           sec_haloprop_percentile=pct),
+                           constant.mean_occupation_centrals(prim_haloprop=mass,
+                                                             sec_haloprop_percentile=pct))
