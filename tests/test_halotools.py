@@ -127,3 +127,34 @@ def test_kernel_equals_halotools_through_the_reference_quadrature(kind):
         ngal, xi = halotab.predict(model, check_consistency=False)
         np.testing.assert_allclose(ngal, ngal_ref, rtol=1e-10)
         np.testing.assert_allclose(xi, xi_ref, rtol=1e-10, atol=1e-13 * np.abs(xi_ref).max())
+
+
+def test_mass_dependent_assembias_oracle_equals_halotools():
+    """HeavisideAssembias with assembias_strength_abscissa / split_abscissa: the oracle's
+    restatement (spline of degree min(3, n - 1) over log10 M, clipped) and the attribute mapping of
+    ``models.resolve_model`` against the real components."""
+    from halotools.empirical_models import (AssembiasZheng07Cens, AssembiasZheng07Sats,
+                                            HodModelFactory, NFWPhaseSpace, TrivialPhaseSpace)
+    from tabcorr_b200 import models
+    cens = AssembiasZheng07Cens(threshold=-20, assembias_strength=[0.8, -0.3, 0.1],
+                                assembias_strength_abscissa=[11.0, 12.5, 14.0])
+    sats = AssembiasZheng07Sats(threshold=-20, assembias_strength=[0.5, -0.5],
+                                assembias_strength_abscissa=[12.0, 14.0],
+                                split=[0.3, 0.6], split_abscissa=[11.0, 14.0])
+    model = HodModelFactory(centrals_occupation=cens, satellites_occupation=sats,
+                            centrals_profile=TrivialPhaseSpace(),
+                            satellites_profile=NFWPhaseSpace())
+    spec = models.resolve_model(model)
+    assert spec.mass_dependent and spec.n_strength == (3, 2)
+    oracle = orc.Zheng07Oracle(dict(model.param_dict), decorated=True,
+                               strength_abscissa=spec.strength_abscissa,
+                               split_abscissa=spec.split_abscissa,
+                               split_ordinates=spec.split_ordinates)
+    oracle.split = spec.split
+    pct = np.random.default_rng(5).uniform(0, 1, len(MASS))
+    for name in ('centrals', 'satellites'):
+        ours = getattr(oracle, 'mean_occupation_' + name)(prim_haloprop=MASS,
+                                                          sec_haloprop_percentile=pct)
+        theirs = getattr(model, 'mean_occupation_' + name)(prim_haloprop=MASS,
+                                                           sec_haloprop_percentile=pct)
+        np.testing.assert_allclose(ours, theirs, rtol=1e-12, atol=1e-300)
