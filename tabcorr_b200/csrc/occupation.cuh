@@ -302,10 +302,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // instantiations).
 // One (draw, group) pair of a model with mass-dependent strength / split: both are evaluated per
 // quadrature node at log10 of the node's mass (halotools evaluates them per halo).
-__device__ __noinline__ void occupation_pair_nodes_massdep(const OccPlan plan, const tc_model model,
-                                                           int grp, bool sat, DrawParams p,
-                                                           const double* __restrict__ tab,
-                                                           double* occ) {
+__device__ __forceinline__ void occupation_pair_nodes_massdep(const OccPlan& plan,
+                                                              const tc_model& model, int grp,
+                                                              bool sat, const DrawParams& p,
+                                                              const double* __restrict__ tab,
+                                                              double* occ) {
   const int G = plan.n_gauss, GP = plan.n_gauss_pad, type = sat ? 1 : 0;
   const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
   const double* c0 = plan.row_c + (size_t)row0 * GP;
@@ -383,7 +384,6 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
   const bool modulate = SAT && model.modulate_with_cenocc != 0;
   const bool decorated = model.decorated != 0;
   // lane l holds the parameters of draw l & 7 (clamped to the item's draws)
-  const bool mass_dep = model_mass_dependent(model);   // strength / split vary from node to node
   DrawParams mine = load_draw_typed<SAT>(theta0 + (long long)min(lane & 7, n_b - 1) * theta_ds,
                                          theta_ps, modulate);
   if (!decorated) mine.a_cen = mine.a_sat = 0.0;   // strengths are ignored unless decorated
@@ -406,18 +406,9 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
     p.alpha = __shfl_sync(full, mine.alpha, b);
     p.a_cen = __shfl_sync(full, mine.a_cen, b);
     p.a_sat = __shfl_sync(full, mine.a_sat, b);
-    if (mass_dep) {   // the strength ordinates of the pair's draw and type, straight from theta
-      const int type = SAT ? 1 : 0;
-      const int first_ord = TC_N_THETA_ZHENG07_BASE + (SAT ? zheng07_strength_count(model, 0) : 0);
-      const int n_ord = zheng07_strength_count(model, type);
-      const double* th = theta0 + (long long)b * theta_ds;
-      for (int k = 0; k < TC_MAX_KNOTS; k++)
-        p.s_ord[k] = k < n_ord ? th[(first_ord + k) * theta_ps] : 0.0;
-    }
     if (lane < n) {
       double occ[2];
-      if (mass_dep) occupation_pair_nodes_massdep(plan, model, grp, SAT, p, tab, occ);
-      else occupation_pair_nodes(plan, grp, SAT, decorated, modulate, p, split, tab, occ);
+      occupation_pair_nodes(plan, grp, SAT, decorated, modulate, p, split, tab, occ);
       const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
       store(b, row0, occ[0], plan.row_nh[row0]);
       if (row1 >= 0) store(b, row1, occ[1], plan.row_nh[row1]);
@@ -441,7 +432,7 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
     for (int u = 0; u < kSerDraws; u++) {
       const int b = min(b0 + u, n_b - 1);
       strength[u] = __shfl_sync(full, SAT ? mine.a_sat : mine.a_cen, b);
-      all_queued[u] = modulate || mass_dep;
+      all_queued[u] = modulate;
       if (!SAT) {
         logMmin[u] = __shfl_sync(full, mine.logMmin, b);
         inv_sigma[u] = __shfl_sync(full, mine.inv_sigma, b);
@@ -459,23 +450,9 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
         if (!(alpha[u] >= 0.0 && alpha[u] <= kSerAlphaMax)) all_queued[u] = true;
       }
     }
-    bool every_draw_queued = true;
-#pragma unroll
-    for (int u = 0; u < kSerDraws; u++) every_draw_queued = every_draw_queued && all_queued[u];
     for (int g0 = g_begin; g0 < g_end; g0 += 32) {
       const int grp = g0 + lane;
       const bool valid = grp < g_end;
-      if (every_draw_queued) {   // nothing for the series to do: straight to the queue
-        for (int b = b0; b < min(b0 + kSerDraws, n_b); b++) {
-          const unsigned qm = __ballot_sync(full, valid);
-          if (valid)
-            queue[(head + count + __popc(qm & ((1u << lane) - 1u))) & (kSerQueue - 1)] =
-                (b << 24) | grp;
-          count += __popc(qm);
-          if (count >= 32) drain(32);
-        }
-        continue;
-      }
       const int gsafe = valid ? grp : g_end - 1;
       const double4 gs = plan.grp_ser[gsafe];
       const double2* mom = plan.grp_mom + gsafe;
@@ -694,6 +671,43 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
       occupation_item_series<false>(args.plan, args.model, args.theta + draw0 * args.theta_ds,
                                     args.theta_ds, args.theta_ps, n_b, it.g_begin, it.g_end, tab,
                                     queue[threadIdx.x >> 5], store);
+  }
+}
+
+// Models with mass-dependent assembly-bias strength / split (tc_model.n_strength / n_split): one
+// thread per (draw, group) pair, node by node (the series of occupation_item_series needs a
+// strength and a split that are constant over the bin).
+__global__ void __launch_bounds__(256) occupation_massdep_kernel(const OccArgs args) {
+  __shared__ double tab[kTabDoubles];
+  load_math_tables(tab);
+  __syncthreads();
+  const OccPlan& plan = args.plan;
+  const long long n_pairs = args.n_draws * plan.n_groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_pairs;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long draw = idx / plan.n_groups;
+    const int grp = (int)(idx - draw * plan.n_groups);
+    const bool sat = grp >= plan.n_cen_groups;
+    const double* th = args.theta + draw * args.theta_ds;
+    const long long ps = args.theta_ps;
+    DrawParams p{};
+    p.logMmin = th[0];
+    p.inv_sigma = 1.0 / th[ps];
+    p.m0 = exp10(th[2 * ps]);
+    p.inv_m1 = 1.0 / exp10(th[3 * ps]);
+    p.alpha = th[4 * ps];
+    const int first = TC_N_THETA_ZHENG07_BASE + (sat ? zheng07_strength_count(args.model, 0) : 0);
+    const int n_ord = zheng07_strength_count(args.model, sat ? 1 : 0);
+    for (int k = 0; k < TC_MAX_KNOTS; k++) p.s_ord[k] = k < n_ord ? th[(first + k) * ps] : 0.0;
+    double occ[2];
+    occupation_pair_nodes_massdep(plan, args.model, grp, sat, p, tab, occ);
+    const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
+    const int dst0 = args.pad_to_row[row0];
+    if (dst0 >= 0) args.occ_out[draw * args.n_rows + dst0] = occ[0];
+    if (row1 >= 0) {
+      const int dst1 = args.pad_to_row[row1];
+      if (dst1 >= 0) args.occ_out[draw * args.n_rows + dst1] = occ[1];
+    }
   }
 }
 

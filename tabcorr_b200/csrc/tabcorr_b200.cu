@@ -205,6 +205,14 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
     TC_CUDA(cudaGetLastError());
     return TC_OK;
   }
+  if (host_mass_dependent(model)) {
+    const long long n_pairs = n_draws * args.plan.n_groups;
+    const int grid_md = (int)std::max<long long>(
+        1, std::min<long long>((n_pairs + 255) / 256, (long long)n_sm * 8));
+    occupation_massdep_kernel<<<grid_md, 256, 0, static_cast<cudaStream_t>(stream)>>>(args);
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+  }
   const long long n_items = (n_draws + 7) / 8 * (args.n_ranges_cen + args.n_ranges_sat);
   int grid = (int)std::max<long long>(1, std::min<long long>((n_items + kWarps - 1) / kWarps,
                                                              (long long)n_sm));
@@ -387,10 +395,10 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
     int rc_model = check_model(model);
     if (rc_model != TC_OK) return rc_model;
   }
-  const bool mass_dep = theta && host_mass_dependent(model);
-  if (mass_dep && theta_inline)
-    return fail(TC_EUNSUPPORTED, "tc_predict_one: models with mass-dependent assembly bias take "
-                                 "the batch entry (their draws have more than TC_N_THETA doubles)");
+  if (theta && host_mass_dependent(model))
+    return fail(TC_EUNSUPPORTED, "tc_predict_batch: models with mass-dependent assembly bias are "
+                                 "evaluated by tc_occupation_batch (strength and split vary from "
+                                 "quadrature node to node); pass its result as occ_dev");
   if (precision != TC_PRECISION_FP64 && precision != TC_PRECISION_3XTF32)
     return fail(TC_EINVAL, "tc_predict_batch: precision must be TC_PRECISION_FP64 or _3XTF32");
   if (precision == TC_PRECISION_3XTF32 && t->mode != TC_MODE_AUTO)
@@ -404,7 +412,7 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   if (!guard.ok) return fail(TC_ECUDA, "tc_predict_batch: cannot select the table's CUDA device");
   int rc = build_layout(t, separate);
   if (rc != TC_OK) return rc;
-  if (precision == TC_PRECISION_3XTF32 && theta && !theta_inline && !mass_dep &&
+  if (precision == TC_PRECISION_3XTF32 && theta && !theta_inline &&
       tcgen_eligible(t, separate) &&
       n_draws >= tune("TCGEN_MIN_DRAWS", 1) && workspace &&
       workspace_bytes >= plan_tcgen_workspace(t, n_draws).total) {
@@ -446,7 +454,7 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   args.plan = L.plans[plan_g].dev;
   if (model) args.model = *model;
   args.theta = theta_inline ? nullptr : theta;
-  args.theta_ds = theta_ld ? 1 : (model && theta ? zheng07_n_theta(*model) : TC_N_THETA);
+  args.theta_ds = theta_ld ? 1 : TC_N_THETA;
   args.theta_ps = theta_ld ? theta_ld : 1;
   if (theta_inline) {
     args.theta_is_inline = 1;
@@ -464,10 +472,8 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   // Occupation items: series items (occupation_item_series) where they pay -- cross tables
   // (bound by the occupation arithmetic), many quadrature nodes, tables of 200+ rows -- else the
   // node-by-node items whose code is smaller (instruction-cache footprint of the fused kernel)
-  // (mass-dependent strengths / splits exist in the series items' node path only)
-  const int series_auto = t->mode == TC_MODE_CROSS || plan_g > 16 || L.dev.n_pad >= 200 || mass_dep;
-  if (theta != nullptr || theta_inline != nullptr
-          ? (mass_dep || tune("SERIES_FUSED", series_auto) != 0) : false) {
+  const int series_auto = t->mode == TC_MODE_CROSS || plan_g > 16 || L.dev.n_pad >= 200;
+  if (theta != nullptr || theta_inline != nullptr ? tune("SERIES_FUSED", series_auto) != 0 : false) {
     pick_series_ranges(args.plan, ws.nt, n_draws,
                        t->mode == TC_MODE_CROSS ? kOccSeriesItemsPerTileCross : kOccItemsPerTile,
                        &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);

@@ -302,7 +302,7 @@ class DeviceTableGroup:
         as raw device pointers and strides in doubles (``tc_predict_batch`` semantics) -- rows of a
         result slab, possibly in the memory of another GPU of the node."""
         torch = _torch()
-        if spec.family != 0:
+        if spec.family != 0 or spec.mass_dependent:
             occ = self.occupation(spec, n_gauss, theta)
             theta = None
         else:
@@ -328,7 +328,7 @@ class DeviceTableGroup:
         ``theta_columns``.  Families the fused kernel does not implement (leauthaud11) run the
         occupation kernel first and contract its output."""
         torch = _torch()
-        if theta is not None and spec is not None and spec.family != 0:
+        if theta is not None and spec is not None and (spec.family != 0 or spec.mass_dependent):
             occ = self.occupation(spec, n_gauss, theta, theta_columns=theta_columns)
             theta, theta_columns = None, False
         n_draws = (theta.shape[1] if theta_columns else theta.shape[0]) if theta is not None \
@@ -553,10 +553,23 @@ class TabCorr:
 
     @staticmethod
     def _no_occ_kwargs(occ_kwargs):
-        if occ_kwargs:
+        """``**occ_kwargs`` of ``mean_occupation`` / ``predict`` (``tabcorr/tabcorr.py:556-563``:
+        passed on to ``model.mean_occupation_<gal_type>`` together with ``prim_haloprop`` and
+        ``sec_haloprop_percentile``).  The occupation components of the implemented families
+        (halotools Zheng07Cens/Sats, Leauthaud11Cens/Sats, their HeavisideAssembias decorations)
+        read exactly four keywords: the two the reference supplies itself -- repeating them is the
+        reference's ``TypeError`` -- and ``table`` / ``sec_haloprop``, which halotools ignores once
+        those two are present.  Anything else can only belong to a user-defined component the
+        kernel does not implement."""
+        for key in occ_kwargs:
+            if key in ('prim_haloprop', 'sec_haloprop_percentile'):
+                raise TypeError("mean_occupation() got multiple values for keyword argument "
+                                "'{}'".format(key))
+        unknown = [k for k in occ_kwargs if k not in ('table', 'sec_haloprop')]
+        if unknown:
             raise NotImplementedError(
                 'keyword arguments for the occupation functions ({}) are not supported by the '
-                'CUDA occupation kernel'.format(', '.join(occ_kwargs)))
+                'CUDA occupation kernel'.format(', '.join(unknown)))
 
     # ------------------------------------------------------------------ reference API
     def mean_occupation(self, model, n_gauss_prim=10, check_consistency=True, **occ_kwargs):

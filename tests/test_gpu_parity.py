@@ -106,6 +106,16 @@ def test_consistency_errors(tb, golden_dir):
         halotab.predict(model)
     halotab.predict(tb.PrebuiltHodModelFactory('zheng07', threshold=-18, redshift=0.5),
                     check_consistency=False)
+    # **occ_kwargs (tabcorr.py:556-563): the keywords halotools' components read are either the
+    # reference's own (a TypeError there too) or ignored next to them; others cannot be honoured
+    model = tb.PrebuiltHodModelFactory('zheng07', threshold=-18)
+    ngal, xi = halotab.predict(model)
+    ngal2, xi2 = halotab.predict(model, table=None, sec_haloprop=np.ones(3))
+    assert ngal == ngal2 and np.array_equal(xi, xi2)
+    with pytest.raises(TypeError, match='multiple values'):
+        halotab.predict(model, prim_haloprop=np.ones(3))
+    with pytest.raises(NotImplementedError, match='custom_knob'):
+        halotab.mean_occupation(model, custom_knob=1.0)
 
 
 def test_ds_efficient_interpolator(tb, golden, golden_dir):
