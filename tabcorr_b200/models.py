@@ -94,6 +94,15 @@ class ModelSpec:
         self.split = float(split)
         self.threshold = float(threshold)   # leauthaud11: log10 stellar-mass threshold
         self.redshift = float(redshift)     # leauthaud11: redshift of the SMHM parameters
+        self._theta_keys = FAMILY_KEYS[self.family] + ASSEMBIAS_KEYS
+        self.mass_dependent = False
+        self.n_strength = (1, 1)    # strength ordinates per draw (centrals, satellites)
+        if not (any(len(v) for v in strength_abscissa) or any(len(v) for v in split_abscissa) or
+                any(len(v) for v in split_ordinates)):
+            # the plain model: one strength per type, one split (the latency paths construct a
+            # ModelSpec per call, so nothing is validated or formatted here)
+            self.strength_abscissa = self.split_abscissa = self.split_ordinates = ((), ())
+            return
         self.strength_abscissa = tuple(_knots(v, 'assembias_strength_abscissa')
                                        for v in strength_abscissa)
         self.split_abscissa = tuple(_knots(v, 'split_abscissa') for v in split_abscissa)
@@ -104,14 +113,15 @@ class ModelSpec:
         for absc in self.strength_abscissa + self.split_abscissa:
             if any(b <= a for a, b in zip(absc[:-1], absc[1:])):
                 raise ValueError('abscissa must increase strictly')
+        self.mass_dependent = (any(len(a) > 1 for a in self.strength_abscissa) or
+                               any(len(a) > 0 for a in self.split_abscissa))
         if self.mass_dependent and (self.family != FAMILY_ZHENG07 or not self.decorated):
             raise NotImplementedError('mass-dependent assembly bias is implemented for decorated '
                                       'zheng07 models')
-
-    @property
-    def mass_dependent(self):
-        return (any(len(a) > 1 for a in self.strength_abscissa) or
-                any(len(a) > 0 for a in self.split_abscissa))
+        self.n_strength = tuple(max(1, len(a)) for a in self.strength_abscissa)
+        self._theta_keys = (FAMILY_KEYS[self.family] +
+                            assembias_keys('centrals', self.n_strength[0]) +
+                            assembias_keys('satellites', self.n_strength[1]))
 
     @property
     def latency_paths(self):
@@ -120,24 +130,18 @@ class ModelSpec:
         return self.family == FAMILY_ZHENG07 and not self.mass_dependent
 
     @property
-    def n_strength(self):
-        """Strength ordinates per draw (centrals, satellites)."""
-        return tuple(max(1, len(a)) for a in self.strength_abscissa)
-
-    @property
     def occupation_keys(self):
         """The family's occupation parameters (without the assembly-bias strengths)."""
         return FAMILY_KEYS[self.family]
 
     @property
     def strength_keys(self):
-        return (assembias_keys('centrals', self.n_strength[0]) +
-                assembias_keys('satellites', self.n_strength[1]))
+        return self._theta_keys[len(FAMILY_KEYS[self.family]):]
 
     @property
     def theta_keys(self):
         """param_dict keys of the kernel's parameter vector, in kernel order."""
-        return FAMILY_KEYS[self.family] + self.strength_keys
+        return self._theta_keys
 
     @property
     def n_theta(self):

@@ -197,6 +197,8 @@ class DeviceTableGroup:
     def _model_struct(spec):
         model = _lib.tc_model(spec.family, int(spec.decorated), int(spec.modulate_with_cenocc), 0,
                               spec.split, spec.threshold, spec.redshift)
+        if not spec.mass_dependent and not any(len(a) for a in spec.split_abscissa):
+            return model
         for t in range(2):   # mass-dependent decoration (centrals, satellites)
             absc = spec.strength_abscissa[t]
             model.n_strength[t] = len(absc) if len(absc) > 1 else 0
