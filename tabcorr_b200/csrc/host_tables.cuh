@@ -702,7 +702,7 @@ void pick_ranges(const OccPlan& plan, int nt, int* n_cen, int* n_sat,
 // x 32 groups, so the per-draw constants are amortised over all groups of the type); a one-draw
 // call cuts the groups into ranges of 32 so that the warps of the block share the draw.
 void pick_series_ranges(const OccPlan& plan, int nt, long long n_draws, int items, int* n_cen,
-                        int* n_sat, int* pieces_cen, int* pieces_sat) {
+                        int* n_sat, int* pieces_cen, int* pieces_sat, bool latency = false) {
   const int cen = plan.n_cen_groups, sat = plan.n_groups - plan.n_cen_groups;
   const int want = std::max(2, (tune("OCC_ITEMS", items) + nt - 1) / nt);
   auto share = [&](int count, int* ranges, int* pieces) {
@@ -711,6 +711,15 @@ void pick_series_ranges(const OccPlan& plan, int nt, long long n_draws, int item
     if (count == 0) return;
     if (n_draws == 1) {
       *ranges = std::min(8, (count + 31) / 32);
+      return;
+    }
+    if (latency) {
+      // a few dozen draws are a latency problem: one draw and 32 groups per item, so that an
+      // item is a single chain of ~150 dependent operations and the 12 warps of a block share
+      // the tile (measured at N = 240: 8 / 32 draws per call 88 / 84 us with 8-draw items, 76 /
+      // 78 us so -- the node items of round 1: 75 / 74 us; from 128 draws on the larger items win)
+      *pieces = 8;
+      *ranges = 8 * std::min(8, (count + 31) / 32);
       return;
     }
     const int s = std::max(1, (int)std::lround((double)want * count / (cen + sat)));

@@ -476,7 +476,8 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
   if (theta != nullptr || theta_inline != nullptr ? tune("SERIES_FUSED", series_auto) != 0 : false) {
     pick_series_ranges(args.plan, ws.nt, n_draws,
                        t->mode == TC_MODE_CROSS ? kOccSeriesItemsPerTileCross : kOccItemsPerTile,
-                       &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
+                       &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat,
+                       n_draws <= 64);   // measured: 8 / 32 draws 88 / 84 -> 76 / 78 us, 128+ slower
   } else {
     pick_ranges(args.plan, ws.nt, &args.n_ranges_cen, &args.n_ranges_sat,
                 t->mode == TC_MODE_CROSS ? kOccItemsPerTileCross : kOccItemsPerTile);
