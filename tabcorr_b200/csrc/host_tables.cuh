@@ -640,7 +640,7 @@ void pick_tile(int n_pad, long long n_draws, int n_sm, int* nt_out, int* n_buf_o
     return 0;
   };
   int n_buf = widest(2) >= 5 ? 2 : 1;
-  if (forced == 1 || forced == 2) n_buf = forced;
+  if (forced >= 1 && forced <= kMaxWBuffers && widest(forced) > 0) n_buf = forced;
   if (widest(n_buf) == 0) n_buf = 1;
   int best = 0;
   for (int nt = 8; nt >= 1; nt--) {

@@ -53,9 +53,11 @@ struct PredictArgs {
   int tf32_segment;      // 3xTF32 mode: k8-steps per FP32 accumulation chain
 };
 
+constexpr int kMaxWBuffers = 4;
+
 struct PredictCtrl {
-  int full[2];                  // occupation items finished, per W buffer (n_occ per tile)
-  int empty[2];                 // warps that left a tile's work list, per W buffer (kWarps per tile)
+  int full[kMaxWBuffers];       // occupation items finished, per W buffer (n_occ per tile)
+  int empty[kMaxWBuffers];      // warps that left a tile's work list, per W buffer (kWarps per tile)
   int next;                     // work-list cursor
   int first_lo, last_hi;        // chunk range of the CTA's first / last tile
   int n_local;                  // tiles this CTA works on
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       ctrl->first_lo = first_lo;
       ctrl->last_hi = last_hi;
       ctrl->next = 0;
-      ctrl->full[0] = ctrl->full[1] = ctrl->empty[0] = ctrl->empty[1] = 0;
+      for (int b = 0; b < kMaxWBuffers; b++) ctrl->full[b] = ctrl->empty[b] = 0;
     }
     if (args.theta_is_inline && tid < TC_N_THETA) ctrl->theta_inline[tid] = args.theta_inline[tid];
   }
