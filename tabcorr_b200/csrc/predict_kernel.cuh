@@ -51,6 +51,9 @@ struct PredictArgs {
   int pieces_cen, pieces_sat;   // draw pieces per type (series_item); 0: node-by-node items
   int occ_stride;        // every occ_stride-th slot of a tile's work list is an occupation item
   int tf32_segment;      // 3xTF32 mode: k8-steps per FP32 accumulation chain
+  int stress_ns;         // test hook (TC_TUNE_STRESS): pseudo-random delays of up to this many
+                         // nanoseconds before every occupation item and contraction chunk, to
+                         // perturb the schedule the full / empty counters have to order
 };
 
 constexpr int kMaxWBuffers = 4;
@@ -363,6 +366,10 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       else { kind = 2; idx = u - min(n_occ, q); }
     }
 
+    if (args.stress_ns > 0 && kind != 0) {   // warp-uniform pseudo-random delay (test hook)
+      const unsigned h = ((unsigned)i * 2654435761u) ^ ((unsigned)blockIdx.x * 40503u);
+      __nanosleep((h >> 8) % (unsigned)args.stress_ns);
+    }
     if (kind == 1) {
       // ---- occupation item idx of tile list + occ_ahead -> W[(list + occ_ahead) % n_buf] ------
       const int j = list + occ_ahead;

@@ -495,6 +495,7 @@ int predict_impl(tc_table* t, const tc_model* model, int n_gauss, const double* 
     args.occ_stride = ws.n_buf == 1 ? 1 : std::max(1, (int)((long long)spread * slots / (100LL * n_occ)));
   }
   args.tf32_segment = std::max(1, tune("TF32_SEG", kTf32Segment));
+  args.stress_ns = std::max(0, tune("STRESS", 0));
   const int bm = 8 * ws.nt;
   const size_t smem = predict_smem_bytes(L.dev.n_pad, ws.nt, ws.n_buf);
   const int gx = (int)std::min<long long>(ws.n_tiles * L.dev.n_chunks, n_sm);

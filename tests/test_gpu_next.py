@@ -141,6 +141,33 @@ def test_pipeline_chunk_schedules_agree_bitwise(tb, chunk):
     np.testing.assert_allclose(sep[0]['centrals'] + sep[0]['satellites'], ref[0], rtol=1e-13)
 
 
+@pytest.mark.parametrize('shape', [(60, 2, 6, 'auto'), (20, 1, 6, 'auto'), (40, 2, 19, 'cross')])
+def test_schedule_perturbation_leaves_results_bitwise_equal(tb, shape, monkeypatch):
+    """The W tiles of the fused kernel are handed from occupation items to contraction chunks
+    (and back, when a buffer is reused) through the `full` / `empty` counters, not through block
+    barriers -- something compute-sanitizer's racecheck cannot follow (it reports every such
+    hand-over as a hazard, profiles/r02_sanitizer.md).  This test perturbs the schedule instead:
+    TC_TUNE_STRESS makes every occupation item and every chunk start after a pseudo-random delay
+    of up to 50 us, so writers routinely finish long after readers are ready and the other way
+    round; a missing or misplaced wait would read stale weights.  Several tiles per CTA, series
+    items (N = 240, cross) and node items (N = 40), batch and precomputed-occupation input."""
+    n_mass, n_sec, n_r, mode = shape
+    tab = cases.synthetic.make_table(n_mass=n_mass, n_sec=n_sec, n_r=n_r, seed=33, mode=mode)
+    halotab = table_from_dict(tb, tab)
+    n_draws = 30000
+    draws = cases.synthetic.make_draws(n_draws, seed=17, decorated=True)
+    ref = halotab.predict_batch(draws, pipeline_chunk=0)
+    occ = halotab.mean_occupation_batch(draws).cpu().numpy()
+    ref_occ = halotab.predict_batch(None, occupation=occ, pipeline_chunk=0)
+    for stress in ('50000', '3000'):
+        monkeypatch.setenv('TC_TUNE_STRESS', stress)
+        out = halotab.predict_batch(draws, pipeline_chunk=0)
+        out_occ = halotab.predict_batch(None, occupation=occ, pipeline_chunk=0)
+        monkeypatch.delenv('TC_TUNE_STRESS')
+        assert np.array_equal(ref[0], out[0]) and np.array_equal(ref[1], out[1])
+        assert np.array_equal(ref_occ[0], out_occ[0]) and np.array_equal(ref_occ[1], out_occ[1])
+
+
 def test_cfg3_decorated_multipoles_against_oracle(tb):
     """BASELINE configs[2]: xi_0,2,4 (R = 3 x 14), decorated zheng07, n_gauss_prim = 10, at batch
     size 2e4; a sample of draws against the oracle plus the G-convergence property."""
