@@ -491,7 +491,8 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   // ---- series evaluation (occupation_item_series): group centres, scaled node moments / k!,
   // number of terms per bucket of h (centrals) and y (satellites), all in long double ---------
   std::vector<double4> grp_ser(n_groups);
-  std::vector<double2> grp_mom((size_t)kSerMom * n_groups, make_double2(0.0, 0.0));
+  // (two zero rows behind the last moment: the term loops prefetch one row ahead)
+  std::vector<double2> grp_mom((size_t)(kSerMom + 2) * n_groups, make_double2(0.0, 0.0));
   std::vector<long double> cen_mom_max(kSerMom, 0.0L), sat_mom_max(kSerMom, 0.0L);
   std::vector<long double> inv_fact(kSerMom + 64, 1.0L);
   for (size_t k = 1; k < inv_fact.size(); k++) inv_fact[k] = inv_fact[k - 1] / (long double)k;

@@ -483,19 +483,31 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
           acc0[u] = fma(v[u], m2.x, v_prev[u] * m.x);
           acc1[u] = fma(v[u], m2.y, v_prev[u] * m.y);
         }
-        double2 m_next = mom[3 * ng];
+        // Terms 3 .. n_terms.  A draw adds only its own terms (results must not depend on which
+        // draws share the iteration): when the smaller count is reached the finished chain's
+        // recurrence is zeroed (0 * moment adds exactly nothing) and the other runs on.
+        static_assert(kSerDraws <= 2, "the two-phase term loop handles at most two chains");
+        const double2* mp = mom + 3 * ng;      // the plan pads the moment table by two rows
+        double2 m_next = *mp;
+        int k_first = n_terms;
+#pragma unroll
+        for (int u = 0; u < kSerDraws; u++) k_first = min(k_first, terms_of[u]);
 #pragma unroll kSerUnroll
         for (int k = 2; k < n_terms; k++) {   // term k + 1
+          if (k == k_first) {                 // (warp-uniform, taken at most once)
+#pragma unroll
+            for (int u = 0; u < kSerDraws; u++)
+              if (terms_of[u] == k_first) v[u] = v_prev[u] = 0.0;
+          }
           m = m_next;
-          m_next = mom[min(k + 2, kSerMaxTerms) * ng];
+          mp += ng;
+          m_next = *mp;
           const double km1 = (double)(k - 1);
 #pragma unroll
           for (int u = 0; u < kSerDraws; u++) {
             const double vn = fma(a[u], v[u], (b2[u] * km1) * v_prev[u]);
-            if (k < terms_of[u]) {
-              acc0[u] = fma(vn, m.x, acc0[u]);
-              acc1[u] = fma(vn, m.y, acc1[u]);
-            }
+            acc0[u] = fma(vn, m.x, acc0[u]);
+            acc1[u] = fma(vn, m.y, acc1[u]);
             v_prev[u] = v[u];
             v[u] = vn;
           }
@@ -527,7 +539,6 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
             acc1[kSerDraws];
         bool none[kSerDraws];
         int kt_of[kSerDraws];
-        int kt = 0;
         double2 m = mom[ng];
 #pragma unroll
         for (int u = 0; u < kSerDraws; u++) {
@@ -540,27 +551,40 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
           queued[u] = all_queued[u] || !all_above || !(yb < kSerBuckets - 1.0) || terms == 255;
           if (none[u]) queued[u] = false;
           kt_of[u] = valid && !queued[u] && !none[u] ? terms : 0;
-          kt = max(kt, kt_of[u]);
           fref[u] = pow_pos(base * inv_m1[u], alpha[u], tab);
           ya[u] = y[u] * alpha[u];
           p[u] = ya[u];
           acc0[u] = p[u] * m.x;
           acc1[u] = p[u] * m.y;
         }
-        const int kw = __reduce_max_sync(full, kt);
-        double2 m_next = mom[2 * ng];
+        // Terms 2 .. kw[u], kw[u] = the largest count of draw u's lanes in this window of 32
+        // groups (a property of the draw and the window, not of the batch; lanes needing fewer
+        // terms add further valid ones).  Two chains as for the centrals.
+        int kw[kSerDraws], k_last = 0, k_first = kSerMaxTerms;
+#pragma unroll
+        for (int u = 0; u < kSerDraws; u++) {
+          kw[u] = __reduce_max_sync(full, kt_of[u]);
+          k_last = max(k_last, kw[u]);
+          k_first = min(k_first, kw[u]);
+        }
+        const double2* mp = mom + 2 * ng;
+        double2 m_next = *mp;
 #pragma unroll kSerUnroll
-        for (int k = 2; k <= kw; k++) {
+        for (int k = 2; k <= k_last; k++) {
+          if (k == k_first + 1) {             // (warp-uniform, taken at most once)
+#pragma unroll
+            for (int u = 0; u < kSerDraws; u++)
+              if (kw[u] == k_first) p[u] = 0.0;
+          }
           m = m_next;
-          m_next = mom[min(k + 1, kSerMaxTerms) * ng];
+          mp += ng;
+          m_next = *mp;
           const double mkm1 = -(double)(k - 1);
 #pragma unroll
           for (int u = 0; u < kSerDraws; u++) {
             p[u] *= fma(mkm1, y[u], ya[u]);   // y (alpha - k + 1); the plan divides by k!
-            if (k <= kt_of[u]) {
-              acc0[u] = fma(p[u], m.x, acc0[u]);
-              acc1[u] = fma(p[u], m.y, acc1[u]);
-            }
+            acc0[u] = fma(p[u], m.x, acc0[u]);
+            acc1[u] = fma(p[u], m.y, acc1[u]);
           }
         }
 #pragma unroll
