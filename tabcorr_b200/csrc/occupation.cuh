@@ -371,7 +371,7 @@ __device__ __noinline__ void occupation_pair_nodes(const OccPlan plan, int grp, 
 // Occupation item of one warp in series mode: draws [0, n_b) of an 8-draw block (parameters of
 // draw b at theta0 + b * theta_ds) times the groups [g_begin, g_end) of ONE galaxy type.
 // `queue` points at kSerQueue ints of shared memory owned by this warp.
-// store(b, padded_row, occ, n_h) receives the Gauss-Legendre averaged occupation of each row.
+// store(b, group, padded_row, occ, n_h) receives the Gauss-Legendre averaged occupation of each row.
 template <bool SAT, typename Store>
 __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, const tc_model& model,
                                                        const double* __restrict__ theta0,
@@ -410,8 +410,8 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
       double occ[2];
       occupation_pair_nodes(plan, grp, SAT, decorated, modulate, p, split, tab, occ);
       const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
-      store(b, row0, occ[0], plan.row_nh[row0]);
-      if (row1 >= 0) store(b, row1, occ[1], plan.row_nh[row1]);
+      store(b, grp, row0, occ[0], plan.row_nh[row0]);
+      if (row1 >= 0) store(b, grp, row1, occ[1], plan.row_nh[row1]);
     }
     __syncwarp();
     head = (head + n) & (kSerQueue - 1);
@@ -606,8 +606,8 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
         if (b >= n_b) break;                 // warp-uniform
         const bool q = queued[u] && valid;
         if (valid && !q) {
-          store(b, row0, f0[u], nh0);
-          if (row1 >= 0) store(b, row1, f1[u], nh1);
+          store(b, grp, row0, f0[u], nh0);
+          if (row1 >= 0) store(b, grp, row1, f1[u], nh1);
         }
         const unsigned qm = __ballot_sync(full, q);
         if (qm) {
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) occupation_kernel(const OccArgs a
     const long long draw0 = block * 8 + it.b_begin;
     const int n_b = (int)min((long long)it.n_b, args.n_draws - draw0);
     if (n_b <= 0 || it.g_end <= it.g_begin) continue;
-    auto store = [&](int b, int row, double occ, double) {
+    auto store = [&](int b, int, int row, double occ, double) {
       const int dst = args.pad_to_row[row];
       if (dst >= 0) args.occ_out[(draw0 + b) * args.n_rows + dst] = occ;
     };

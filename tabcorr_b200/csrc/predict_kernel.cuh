@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
         // initial zeros), every column is contracted on its own and finalize ignores them
         const int n_b = (int)min((long long)it.n_b, args.n_draws - draw0);
         if (n_b > 0 && it.g_end > it.g_begin) {
-          auto store = [&](int b, int row, double occ, double nh) {
+          auto store = [&](int b, int, int row, double occ, double nh) {
             store_weight<NT, MODE>(Ws, row, col0 + b, occ * nh);
           };
           const double* theta0 = theta_base + draw0 * args.theta_ds;

@@ -277,7 +277,13 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
   wa.theta_ds = theta_ld ? 1 : TC_N_THETA;
   wa.theta_ps = theta_ld ? theta_ld : 1;
   wa.n_draws = n_draws;
-  pick_ranges(wa.plan, 1, &wa.n_ranges_cen, &wa.n_ranges_sat);
+  // (never the one-draw item shape: the order in which a draw's weights are summed into its
+  // number density follows the items, and results must not depend on the batch size)
+  pick_series_ranges(wa.plan, 1, std::max<int64_t>(n_draws, 2),
+                     (int)std::min<long long>(16, std::max<long long>(
+                         2, (long long)n_sm * kWarps / ((n_draws + 7) / 8))),
+                     &wa.n_ranges_cen, &wa.n_ranges_sat, &wa.pieces_cen, &wa.pieces_sat);
+  wa.max_groups = std::max(wa.plan.n_cen_groups, wa.plan.n_groups - wa.plan.n_cen_groups);
   if (wa.n_ranges_cen + wa.n_ranges_sat > ws.n_ranges_max)
     return fail(TC_EUNSUPPORTED, "tcgen05 path: too many occupation ranges");
   wa.kp = L.tcgen.kp;
@@ -291,7 +297,12 @@ int predict_tcgen(tc_table* t, const tc_model* model, int n_gauss, const double*
     const long long n_items = (n_draws + 7) / 8 * (wa.n_ranges_cen + wa.n_ranges_sat);
     const int grid = (int)std::max<long long>(
         1, std::min<long long>((n_items + kWarps - 1) / kWarps, (long long)n_sm));
-    weights_image_kernel<<<grid, kThreads, 0, stream>>>(wa);
+    const size_t wsmem = (size_t)kWarps * 8 * wa.max_groups * sizeof(double);
+    if (wsmem + 16 * 1024 > (size_t)kSmemLimit)
+      return fail(TC_EUNSUPPORTED, "tcgen05 path: too many mass-bin groups per galaxy type");
+    TC_CUDA(cudaFuncSetAttribute(weights_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)wsmem));
+    weights_image_kernel<<<grid, kThreads, wsmem, stream>>>(wa);
     TC_CUDA(cudaGetLastError());
   }
 

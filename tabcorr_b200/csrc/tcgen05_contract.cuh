@@ -590,6 +590,8 @@ struct WeightsImageArgs {
   long long theta_ds, theta_ps;
   long long n_draws;
   int n_ranges_cen, n_ranges_sat;
+  int pieces_cen, pieces_sat;       // draw pieces per type (series_item)
+  int max_groups;                   // groups of the larger galaxy type
   int kp, n_pad, n_rows;
   float* h_img;
   float* c_img;
@@ -599,49 +601,83 @@ struct WeightsImageArgs {
 
 __global__ void __launch_bounds__(kThreads, 1) weights_image_kernel(const WeightsImageArgs args) {
   __shared__ double tab[kTabDoubles];
+  __shared__ int queue[kWarps][kSerQueue];
+  // per warp: the weight sum of every (draw, group) pair of the item, [8][max_groups] -- summed
+  // afterwards in group order, so that a draw's number density does not depend on which lane
+  // happened to evaluate which pair (bitwise independence of the batch composition)
+  extern __shared__ double pair_sums_all[];
   load_math_tables(tab);
+  for (int i = threadIdx.x; i < kWarps * 8 * args.max_groups; i += kThreads) pair_sums_all[i] = 0.0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  // one warp per item = a piece of an 8-draw block x a range of groups of one galaxy type
+  // (series items, occupation.cuh); h image: [tile][row / 32][draw][row % 32], so that the thread
+  // owning a TMEM lane reads 128 contiguous bytes per 32-column store
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* pair_sums = pair_sums_all + (size_t)warp * 8 * args.max_groups;
   const int n_ranges = args.n_ranges_cen + args.n_ranges_sat;
   const long long n_blocks = (args.n_draws + 7) / 8;
   const long long n_items = n_blocks * n_ranges;
-  const long long warp0 = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const long long warp0 = (long long)blockIdx.x * kWarps + warp;
   const int n_chunks = args.kp / 32;
   for (long long item = warp0; item < n_items; item += (long long)gridDim.x * kWarps) {
     const long long block = item / n_ranges;
     const int q = (int)(item - block * n_ranges);
-    const long long draw = block * 8 + (lane & 7);
-    const bool live = draw < args.n_draws;
-    const long long tile = draw / kTcM;
-    const int m = (int)(draw - tile * kTcM);
-    // h image: [tile][row / 32][draw][row % 32], so that the thread owning a TMEM lane reads 128
-    // contiguous bytes per 32-column store
-    float* h_tile = args.h_img + ((size_t)tile * n_chunks * kTcM + m) * 32;
-    float* c_tile = args.c_img + (size_t)tile * args.n_pad * kTcM + m;
-    int g_begin, g_end;
-    occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
-    if (q == 0 && live) {   // K padding of the draw's image row (the table stream is zero there too)
-      for (int row = args.n_rows + (lane >> 3); row < args.kp; row += 4)
-        h_tile[(size_t)(row >> 5) * kTcM * 32 + (row & 31)] = 0.0f;
+    const SeriesItem it = series_item(args.plan, args.n_ranges_cen, args.n_ranges_sat,
+                                      args.pieces_cen, args.pieces_sat, q);
+    const long long draw0 = block * 8 + it.b_begin;
+    const int n_b = (int)max(0LL, min((long long)it.n_b, args.n_draws - draw0));
+    if (q == 0) {   // K padding of the block's image rows (the table stream is zero there too)
+      const long long draw = block * 8 + (lane & 7);
+      if (draw < args.n_draws) {
+        const long long tile = draw / kTcM;
+        float* h_tile = args.h_img + ((size_t)tile * n_chunks * kTcM + (draw - tile * kTcM)) * 32;
+        for (int row = args.n_rows + (lane >> 3); row < args.kp; row += 4)
+          h_tile[(size_t)(row >> 5) * kTcM * 32 + (row & 31)] = 0.0f;
+      }
     }
-    double total = 0.0;
-    occupation_item(args.plan, args.model,
-                    args.theta + (live ? draw : args.n_draws - 1) * args.theta_ds, args.theta_ps,
-                    g_begin, g_end, tab,
-                    [&](int row, double occ, double nh) {
-                      const double w = occ * nh;
-                      const float h = to_tf32((float)w);
-                      total += w;
-                      if (live) {
-                        h_tile[(size_t)(row >> 5) * kTcM * 32 + (row & 31)] = h;
-                        c_tile[(size_t)row * kTcM] = (float)(2.0 * w - (double)h);
-                      }
-                    },
-                    threadIdx.x >> 3 & 3, 4);
-    // number density of the range: the four lanes of a draw hold disjoint groups (fixed order)
-    total += __shfl_xor_sync(0xffffffffu, total, 8);
-    total += __shfl_xor_sync(0xffffffffu, total, 16);
-    if (lane < 8 && live) args.ngal_parts[(size_t)q * args.ngal_ld + draw] = total;
+    if (n_b > 0 && it.g_end > it.g_begin) {
+      auto store = [&](int b, int grp, int row, double occ, double nh) {
+        const double w = occ * nh;
+        const float h = to_tf32((float)w);
+        const long long draw = draw0 + b;
+        const long long tile = draw / kTcM;
+        const int m = (int)(draw - tile * kTcM);
+        args.h_img[((size_t)tile * n_chunks * kTcM + m) * 32 + (size_t)(row >> 5) * kTcM * 32 +
+                   (row & 31)] = h;
+        args.c_img[(size_t)tile * args.n_pad * kTcM + (size_t)row * kTcM + m] =
+            (float)(2.0 * w - (double)h);
+        pair_sums[b * args.max_groups + grp - it.g_begin] += w;   // rows of a pair: one lane
+      };
+      const double* theta0 = args.theta + draw0 * args.theta_ds;
+      if (it.sat)
+        occupation_item_series<true>(args.plan, args.model, theta0, args.theta_ds, args.theta_ps,
+                                     n_b, it.g_begin, it.g_end, tab, queue[warp], store);
+      else
+        occupation_item_series<false>(args.plan, args.model, theta0, args.theta_ds, args.theta_ps,
+                                      n_b, it.g_begin, it.g_end, tab, queue[warp], store);
+    }
+    __syncwarp();
+    // number density of the item per draw: the lanes' sums in a fixed order; draws of the block
+    // outside the item's piece get an explicit zero
+    const int n_grp = it.g_end - it.g_begin;
+    for (int b = 0; b < it.n_b; b++) {
+      double v = 0.0;
+      for (int g = lane; g < n_grp; g += 32) {   // ascending groups per lane, then a fixed tree
+        v += pair_sums[b * args.max_groups + g];
+        pair_sums[b * args.max_groups + g] = 0.0;
+      }
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      const long long draw = block * 8 + it.b_begin + b;
+      if (lane == 0 && draw < args.n_draws) args.ngal_parts[(size_t)q * args.ngal_ld + draw] = v;
+    }
+    if (lane < 8 && (lane < it.b_begin || lane >= it.b_begin + it.n_b) &&
+        block * 8 + lane < args.n_draws)
+      args.ngal_parts[(size_t)q * args.ngal_ld + block * 8 + lane] = 0.0;
+    __syncwarp();
   }
 }
 
