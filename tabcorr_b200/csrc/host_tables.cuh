@@ -132,7 +132,12 @@ int build_layout(tc_table* t, int separate) {
     const int n_comp = separate ? 3 : 1;
     out_lists.assign((size_t)Reff * n_comp, {});
     const int c16 = nc_pad / 16;  // first satellite tile (split layout)
-    int pieces = std::max(1, std::min(T16, (tune("CHUNKS", 6 * kWarps) + Reff - 1) / Reff));
+    // chunks per draw tile: enough to balance 12 warps, few enough that slot dispatch, accumulator
+    // set-up and the 96-shuffle reduction at the end of a chunk stay small beside its DMMAs
+    // (measured per 1e5 draws, 72 -> this: N = 60 0.613 -> 0.600 ms, N = 120 1.58 -> 1.55,
+    // N = 240 3.86 -> 3.84; N = 500 prefers 72: 16.25 vs 16.47)
+    const int chunk_target = T16 > 16 ? 72 : T16 > 8 ? 48 : 40;
+    int pieces = std::max(1, std::min(T16, (tune("CHUNKS", chunk_target) + Reff - 1) / Reff));
     auto add_range = [&](int r, int mt_lo, int mt_hi, int k_begin, int k_cap, int comp, int np) {
       // cost of tile mt ~ number of k-steps
       auto cost = [&](int mt) { return std::max(0, std::min(4 * (mt + 1), k_cap) - k_begin); };
