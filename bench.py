@@ -38,7 +38,7 @@ DRAWS_PER_GPU = 100000
 # dram__bytes_read.sum + dram__bytes_write.sum of predict_kernel for this workload (one launch =
 # 1e5 draws).  NOT measured by this run: the constant is copied from the committed ncu --set full
 # capture named in NCU_TRAFFIC_SOURCE; only reported for the default batch size
-NCU_DRAM_BYTES_PER_LAUNCH = 10839040 + 16406784
+NCU_DRAM_BYTES_PER_LAUNCH = 10725632 + 4377344
 NCU_TRAFFIC_SOURCE = 'profiles/r02_predict_kernel_N240_R20.md'
 # algorithmic HBM bytes per launch: 7 parameters in, 1 + R results out per draw, the table once
 ALGORITHMIC_BYTES_PER_DRAW = 8 * 7 + 8 * (1 + N_R)
@@ -617,7 +617,9 @@ def run_gpu_arm(args):
                                      'same time; exceeds the peak because only half of the '
                                      'symmetric product is executed -- not a roofline fraction',
             'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
-            'traffic_unit': 'bytes of DRAM read + write per launch',
+            'traffic_unit': 'bytes of DRAM read + write per predict_kernel launch (its reads are '
+                            'the draws + the table; the results, 16.8 MB of the algorithmic bytes, '
+                            'are written by finalize_kernel)',
             'traffic_source': 'constant copied from the ncu --set full capture summarised in ' +
                               NCU_TRAFFIC_SOURCE + ' (not measured by this run)',
             'algorithmic_bytes_per_launch': ALGORITHMIC_BYTES_PER_DRAW * draws_per_launch + table_bytes,
