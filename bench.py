@@ -457,8 +457,15 @@ def run_gpu_arm(args):
     elif world > 1 and args.gather in ('overlap', 'overlap-nccl'):
         # double-buffered slabs: the collection of step k runs behind the kernels of step k + 1,
         # moved by the copy engines into rank 0's peer-mapped slab ('overlap') or by NCCL
-        pipe = (PeerCopyGather if args.gather == 'overlap' else OverlappedGather)(
-            n_draws, 1 + N_R, device, dst=0)
+        try:
+            pipe = (PeerCopyGather if args.gather == 'overlap' else OverlappedGather)(
+                n_draws, 1 + N_R, device, dst=0)
+        except RuntimeError as err:   # no CUDA IPC / peer access on this node: all ranks agree
+            if rank == 0:
+                print('bench.py: {}; falling back to --gather overlap-nccl'.format(err),
+                      file=sys.stderr)
+            args.gather = 'overlap-nccl'
+            pipe = OverlappedGather(n_draws, 1 + N_R, device, dst=0)
     elif world > 1 and rank == 0:
         full = torch.empty((n_draws * world, 1 + N_R), dtype=torch.float64, device=device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)

@@ -287,17 +287,38 @@ class PeerSlab:
         self.base = ctypes.c_void_p()
         self.owner = self.rank == dst
         handle = [None]
+        error = None
         if self.owner:
             raw = (ctypes.c_ubyte * 64)()
-            _lib.check(self.lib.tc_peer_alloc(self.device, n_bytes, ctypes.byref(self.base), raw))
-            handle[0] = bytes(raw)
+            try:
+                _lib.check(self.lib.tc_peer_alloc(self.device, n_bytes, ctypes.byref(self.base),
+                                                  raw))
+                handle[0] = bytes(raw)
+            except _lib.TabCorrB200Error as err:   # the other ranks learn it from the None handle
+                error = err
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.broadcast_object_list(handle, src=dist.get_global_rank(group, dst) if group else dst,
                                        group=group)
-            if not self.owner:
+            if not self.owner and handle[0] is not None:
                 raw = (ctypes.c_ubyte * 64).from_buffer_copy(handle[0])
-                _lib.check(self.lib.tc_peer_open(self.device, raw, ctypes.byref(self.base)))
-            dist.barrier(group=group)
+                try:
+                    _lib.check(self.lib.tc_peer_open(self.device, raw, ctypes.byref(self.base)))
+                except _lib.TabCorrB200Error as err:
+                    error = err
+            # every rank takes the same decision (a rank that raised alone would leave the
+            # others waiting in the next collective)
+            ok = torch.tensor([0 if (error is not None or handle[0] is None) else 1],
+                              dtype=torch.int32, device=torch.device('cuda', self.device))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if self.base.value:
+                    (self.lib.tc_peer_free if self.owner else self.lib.tc_peer_close)(
+                        self.device, self.base)
+                self.base = None
+                raise RuntimeError('peer-mapped result slab unavailable on this node (CUDA IPC / '
+                                   'peer access): {}'.format(error or 'failed on another rank'))
+        elif error is not None:
+            raise error
         self.tensor = None
         if self.owner:
             class _Holder:   # torch tensor over the raw allocation (dst only)
