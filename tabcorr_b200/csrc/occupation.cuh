@@ -492,25 +492,30 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
         int k_first = n_terms;
 #pragma unroll
         for (int u = 0; u < kSerDraws; u++) k_first = min(k_first, terms_of[u]);
+        // (two passes over ONE copy of the loop: the compiler turns a test inside the loop into
+        // selects on every term)
+        int k = 2;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          const int k_end = pass == 0 ? k_first : n_terms;
 #pragma unroll kSerUnroll
-        for (int k = 2; k < n_terms; k++) {   // term k + 1
-          if (k == k_first) {                 // (warp-uniform, taken at most once)
+          for (; k < k_end; k++) {   // term k + 1
+            m = m_next;
+            mp += ng;
+            m_next = *mp;
+            const double km1 = (double)(k - 1);
 #pragma unroll
-            for (int u = 0; u < kSerDraws; u++)
-              if (terms_of[u] == k_first) v[u] = v_prev[u] = 0.0;
+            for (int u = 0; u < kSerDraws; u++) {
+              const double vn = fma(a[u], v[u], (b2[u] * km1) * v_prev[u]);
+              acc0[u] = fma(vn, m.x, acc0[u]);
+              acc1[u] = fma(vn, m.y, acc1[u]);
+              v_prev[u] = v[u];
+              v[u] = vn;
+            }
           }
-          m = m_next;
-          mp += ng;
-          m_next = *mp;
-          const double km1 = (double)(k - 1);
 #pragma unroll
-          for (int u = 0; u < kSerDraws; u++) {
-            const double vn = fma(a[u], v[u], (b2[u] * km1) * v_prev[u]);
-            acc0[u] = fma(vn, m.x, acc0[u]);
-            acc1[u] = fma(vn, m.y, acc1[u]);
-            v_prev[u] = v[u];
-            v[u] = vn;
-          }
+          for (int u = 0; u < kSerDraws; u++)
+            if (terms_of[u] == k_first) v[u] = v_prev[u] = 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kSerDraws; u++) {
@@ -569,23 +574,26 @@ __device__ __forceinline__ void occupation_item_series(const OccPlan& plan, cons
         }
         const double2* mp = mom + 2 * ng;
         double2 m_next = *mp;
+        int k = 2;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          const int k_end = pass == 0 ? k_first : k_last;
 #pragma unroll kSerUnroll
-        for (int k = 2; k <= k_last; k++) {
-          if (k == k_first + 1) {             // (warp-uniform, taken at most once)
+          for (; k <= k_end; k++) {
+            m = m_next;
+            mp += ng;
+            m_next = *mp;
+            const double mkm1 = -(double)(k - 1);
 #pragma unroll
-            for (int u = 0; u < kSerDraws; u++)
-              if (kw[u] == k_first) p[u] = 0.0;
+            for (int u = 0; u < kSerDraws; u++) {
+              p[u] *= fma(mkm1, y[u], ya[u]);   // y (alpha - k + 1); the plan divides by k!
+              acc0[u] = fma(p[u], m.x, acc0[u]);
+              acc1[u] = fma(p[u], m.y, acc1[u]);
+            }
           }
-          m = m_next;
-          mp += ng;
-          m_next = *mp;
-          const double mkm1 = -(double)(k - 1);
 #pragma unroll
-          for (int u = 0; u < kSerDraws; u++) {
-            p[u] *= fma(mkm1, y[u], ya[u]);   // y (alpha - k + 1); the plan divides by k!
-            acc0[u] = fma(p[u], m.x, acc0[u]);
-            acc1[u] = fma(p[u], m.y, acc1[u]);
-          }
+          for (int u = 0; u < kSerDraws; u++)
+            if (kw[u] == k_first) p[u] = 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kSerDraws; u++) {
