@@ -33,9 +33,23 @@ struct HaloBinArgs {
   unsigned long long* sum_lo;
 };
 
-// number of edges <= x (np.searchsorted(edges, x, side='right')); NaN sorts behind everything
-__device__ __forceinline__ int edges_at_or_below(const double* edges, int n_edges, double x) {
+// number of edges <= x (np.searchsorted(edges, x, side='right')); NaN sorts behind everything.
+// The reference's bins are np.linspace edges, so the position is guessed from the first and the
+// last edge and then corrected against the actual edges (exact for any ascending edges: up to
+// three steps either way, else a binary search).
+__device__ __forceinline__ int edges_at_or_below(const double* edges, int n_edges, double x,
+                                                 double inv_step) {
   if (!(x == x)) return n_edges;
+  if (x < edges[0]) return 0;
+  if (x >= edges[n_edges - 1]) return n_edges;
+  int k = min(max((int)((x - edges[0]) * inv_step) + 1, 1), n_edges - 1);   // edges[k-1] <= x < edges[k]?
+#pragma unroll 1
+  for (int step = 0; step < 3; step++) {
+    if (edges[k - 1] > x) k--;
+    else if (edges[k] <= x) k++;
+    else return k;
+  }
+  if (edges[k - 1] <= x && x < edges[k]) return k;
   int lo = 0, hi = n_edges;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -44,47 +58,62 @@ __device__ __forceinline__ int edges_at_or_below(const double* edges, int n_edge
   return lo;
 }
 
+// Haloes per block at most: the per-block tables are 32-bit (native shared-memory atomics; 64-bit
+// ones are compare-and-swap loops that collapse under the contention of the low-mass cells), and
+// the fixed-point position is accumulated in four 13-bit slices: 2^13 * 2^18 < 2^32.
+constexpr long long kHaloBinsPerBlock = 1LL << 18;
+
 __global__ void __launch_bounds__(256) halo_bins_kernel(const HaloBinArgs args) {
-  extern __shared__ unsigned long long hb_smem[];
+  extern __shared__ __align__(16) unsigned hb_smem[];
   const int n_cells = args.n_prim * args.n_sec;
-  unsigned long long* s_count = hb_smem;
-  unsigned long long* s_open = s_count + n_cells;
-  unsigned long long* s_hi = s_open + n_cells;
-  unsigned long long* s_lo = s_hi + n_cells;
-  double* s_pe = reinterpret_cast<double*>(s_lo + n_cells);
+  unsigned* s_count = hb_smem;                 // [n_cells] histogram2d semantics
+  unsigned* s_open = s_count + n_cells;        // [n_cells] digitize semantics
+  unsigned* s_q = s_open + n_cells;            // [4][n_cells] 13-bit slices of the positions
+  double* s_pe = reinterpret_cast<double*>(s_q + 4 * n_cells + ((6 * n_cells) & 1));
   double* s_se = s_pe + args.n_prim + 1;
-  for (int i = threadIdx.x; i < 4 * n_cells; i += blockDim.x) hb_smem[i] = 0ull;
+  for (int i = threadIdx.x; i < 6 * n_cells; i += blockDim.x) hb_smem[i] = 0u;
   for (int i = threadIdx.x; i <= args.n_prim; i += blockDim.x) s_pe[i] = args.prim_edges[i];
   for (int i = threadIdx.x; i <= args.n_sec; i += blockDim.x) s_se[i] = args.sec_edges[i];
   __syncthreads();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < args.n_halos;
-       i += (long long)gridDim.x * blockDim.x) {
+  // a contiguous range of at most kHaloBinsPerBlock haloes per block
+  const double inv_step_p = args.n_prim / (s_pe[args.n_prim] - s_pe[0]);
+  const double inv_step_s = args.n_sec / (s_se[args.n_sec] - s_se[0]);
+  const long long per_block = (args.n_halos + gridDim.x - 1) / gridDim.x;
+  const long long lo = blockIdx.x * per_block, hi = min(lo + per_block, args.n_halos);
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const double lp = args.log_prim[i], sp = args.sec_pct[i];
     // np.histogramdd: searchsorted(side='right'), values on the last edge belong to the last bin
-    int ip = edges_at_or_below(s_pe, args.n_prim + 1, lp);
-    int is = edges_at_or_below(s_se, args.n_sec + 1, sp);
+    const int ip = edges_at_or_below(s_pe, args.n_prim + 1, lp, inv_step_p);
+    const int is = edges_at_or_below(s_se, args.n_sec + 1, sp, inv_step_s);
     const bool p_edge = lp == s_pe[args.n_prim], s_edge = sp == s_se[args.n_sec];
     const int ip_closed = ip - (p_edge ? 1 : 0), is_closed = is - (s_edge ? 1 : 0);
     if (ip_closed >= 1 && ip_closed <= args.n_prim && is_closed >= 1 && is_closed <= args.n_sec)
-      atomicAdd(&s_count[(is_closed - 1) * args.n_prim + ip_closed - 1], 1ull);
+      atomicAdd(&s_count[(is_closed - 1) * args.n_prim + ip_closed - 1], 1u);
     // np.digitize(right=False) of sort_into_bins: the last edge is outside
     if (ip >= 1 && ip <= args.n_prim && is >= 1 && is <= args.n_sec) {
       const int cell = (is - 1) * args.n_prim + ip - 1;
       double v = (args.prim[i] - args.cell_min[cell]) * args.cell_inv_width[cell];
       v = fmin(fmax(v, 0.0), 1.0);     // log10 rounding can leave a member a hair outside
       const unsigned long long q = (unsigned long long)(v * 4503599627370496.0);   // 2^52
-      atomicAdd(&s_open[cell], 1ull);
-      atomicAdd(&s_hi[cell], q >> 26);
-      atomicAdd(&s_lo[cell], q & 0x3ffffffull);
+      atomicAdd(&s_open[cell], 1u);
+      atomicAdd(&s_q[cell], (unsigned)(q & 0x1fffu));
+      atomicAdd(&s_q[n_cells + cell], (unsigned)((q >> 13) & 0x1fffu));
+      atomicAdd(&s_q[2 * n_cells + cell], (unsigned)((q >> 26) & 0x1fffu));
+      atomicAdd(&s_q[3 * n_cells + cell], (unsigned)(q >> 39));   // 14 bits: v = 1 gives 2^13
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
-    if (s_count[c]) atomicAdd(&args.counts[c], s_count[c]);
+    if (s_count[c]) atomicAdd(&args.counts[c], (unsigned long long)s_count[c]);
     if (s_open[c]) {
-      atomicAdd(&args.counts_open[c], s_open[c]);
-      atomicAdd(&args.sum_hi[c], s_hi[c]);
-      atomicAdd(&args.sum_lo[c], s_lo[c]);
+      atomicAdd(&args.counts_open[c], (unsigned long long)s_open[c]);
+      // sum of q = slices recombined; kept as the two 26-bit halves the host expects
+      const unsigned long long low = (unsigned long long)s_q[c] +
+                                     ((unsigned long long)s_q[n_cells + c] << 13);
+      const unsigned long long high = (unsigned long long)s_q[2 * n_cells + c] +
+                                      ((unsigned long long)s_q[3 * n_cells + c] << 13);
+      atomicAdd(&args.sum_lo[c], low);
+      atomicAdd(&args.sum_hi[c], high);
     }
   }
 }

@@ -701,7 +701,7 @@ int tc_halo_bins(int device, const double* log_prim, const double* sec_pct, cons
                                            std::to_string(device) + " (no CUDA device available?)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int n_cells = n_prim * n_sec;
-  const size_t smem = (size_t)4 * n_cells * sizeof(unsigned long long) +
+  const size_t smem = (size_t)(6 * n_cells + 2) * sizeof(unsigned) +
                       (size_t)(n_prim + n_sec + 2) * sizeof(double);
   if (smem > (size_t)kSmemLimit)
     return fail(TC_EUNSUPPORTED, "tc_halo_bins: " + std::to_string(n_cells) +
@@ -721,14 +721,15 @@ int tc_halo_bins(int device, const double* log_prim, const double* sec_pct, cons
   std::copy(sec_edges, sec_edges + n_sec + 1, cell_inv + n_cells + n_prim + 1);
   double* d_in = nullptr;
   unsigned long long* d_out = nullptr;
-  TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_in), host.size() * sizeof(double)));
-  if (cudaMalloc(reinterpret_cast<void**>(&d_out), (size_t)4 * n_cells * sizeof(unsigned long long)) !=
-      cudaSuccess) {
-    (void)cudaFree(d_in);
+  // stream-ordered allocations: served from the driver's pool after the first call
+  TC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_in), host.size() * sizeof(double), stream));
+  if (cudaMallocAsync(reinterpret_cast<void**>(&d_out),
+                      (size_t)4 * n_cells * sizeof(unsigned long long), stream) != cudaSuccess) {
+    (void)cudaFreeAsync(d_in, stream);
     (void)cudaGetLastError();
     return fail(TC_ENOMEM, "tc_halo_bins: out of device memory");
   }
-  auto cleanup = [&]() { (void)cudaFree(d_in); (void)cudaFree(d_out); };
+  auto cleanup = [&]() { (void)cudaFreeAsync(d_in, stream); (void)cudaFreeAsync(d_out, stream); };
 #define TC_HB(expr)                                                                        \
   do {                                                                                     \
     cudaError_t err__ = (expr);                                                            \
@@ -762,10 +763,12 @@ int tc_halo_bins(int device, const double* log_prim, const double* sec_pct, cons
   if (n_halos > 0) {
     TC_HB(cudaFuncSetAttribute(halo_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-    // one wave of blocks: 8 per SM while the shared table allows, each striding over the haloes
+    // blocks of contiguous halo ranges: a few waves for balance, and never more haloes per
+    // block than the 32-bit per-block tables hold
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)kSmemLimit / (smem + 1024)));
-    const long long want = (n_halos + 255) / 256;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)n_sm * per_sm));
+    const long long for_balance = std::min<long long>((n_halos + 8191) / 8192, 4LL * n_sm * per_sm);
+    const long long for_range = (n_halos + kHaloBinsPerBlock - 1) / kHaloBinsPerBlock;
+    const int grid = (int)std::max<long long>(1, std::max(for_balance, for_range));
     halo_bins_kernel<<<grid, 256, smem, stream>>>(args);
     TC_HB(cudaGetLastError());
   }
