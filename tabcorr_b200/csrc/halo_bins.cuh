@@ -9,8 +9,9 @@
 // CTA keeps a private copy of the cell table in shared memory (the mass function puts most haloes
 // into a handful of low-mass cells: global atomics on those would serialise in L2) and flushes it
 // once.  Counts are integers; the per-cell sums are accumulated in FIXED POINT (52 fractional bits
-// of (x - x_min) / (x_max - x_min), split into two 26-bit halves summed in 64-bit integers), so
-// the result does not depend on the order of the atomics: bit-reproducible for any grid.
+// of (x - x_min) / (x_max - x_min), in 13-bit slices summed in 32-bit words per block and in 64-bit
+// words across blocks), so the result does not depend on the order of the atomics:
+// bit-reproducible for any grid.  Measured: 3.0 TB/s = 46 % of the HBM copy rate.
 #pragma once
 
 #include "common.cuh"
