@@ -78,6 +78,10 @@ struct OccPlan {       // device pointers, one per (layout, n_gauss)
   const unsigned char* cen_terms;  // [kSerBuckets] Hermite-series terms per bucket of h; 255: nodes
   const unsigned char* sat_terms;  // [kSerBuckets] binomial-series terms per bucket of y; 255: nodes
   double cen_d_max;         // largest half range of a centrals group (log10 M)
+  // leauthaud11 kernel: mass bins = {centrals group, satellites group} over identical node masses
+  // (-1: no such group), evaluated together (leauthaud11.cuh)
+  const int2* l11_bins;     // [n_l11_bins]
+  int n_l11_bins;
 };
 
 struct LayoutDev {

@@ -602,6 +602,28 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
     ph.allocations.push_back(d_inv);
     ph.dev.node_inv_m = d_inv;
   }
+  {
+    // mass bins of the leauthaud11 kernel: every centrals group with the (first unused) satellites
+    // group over the same mass range -- the same nodes -- then the unpaired satellites groups
+    std::vector<int2> l11_bins;
+    std::vector<char> used(n_groups, 0);
+    for (int q = 0; q < n_groups; q++) {
+      if (groups[q].sat) continue;
+      int mate = -1;
+      for (int s = 0; s < n_groups && mate < 0; s++)
+        if (groups[s].sat && !used[s] && groups[s].lo == groups[q].lo && groups[s].hi == groups[q].hi)
+          mate = s;
+      if (mate >= 0) used[mate] = 1;
+      l11_bins.push_back(make_int2(q, mate));
+    }
+    for (int s = 0; s < n_groups; s++)
+      if (groups[s].sat && !used[s]) l11_bins.push_back(make_int2(-1, s));
+    int2* d_bins;
+    if ((rc = upload(l11_bins, &d_bins))) return rc;
+    ph.allocations.push_back(d_bins);
+    ph.dev.l11_bins = d_bins;
+    ph.dev.n_l11_bins = (int)l11_bins.size();
+  }
   if ((rc = upload(grp_rows, &d_rows))) return rc; ph.allocations.push_back(d_rows);
   if ((rc = upload(grp_is_sat, &d_sat))) return rc; ph.allocations.push_back(d_sat);
   if ((rc = upload(row_c, &d_c))) return rc; ph.allocations.push_back(d_c);

@@ -32,7 +32,20 @@ namespace {
 // input of predict_kernel.  Restated from memory of halotools -- parity unpinned, see DESIGN.md.
 // ------------------------------------------------------------------------------------------
 constexpr int kL11Knots = 100;
-constexpr int kL11DrawsPerBlock = 64;     // 64 x 3.2 KB of spline tables + math tables < 227 KB
+#ifndef TC_L11_THREADS
+#define TC_L11_THREADS 192
+#endif
+#ifndef TC_L11_DRAWS
+#define TC_L11_DRAWS 32
+#endif
+#ifndef TC_L11_MIN_BLOCKS
+#define TC_L11_MIN_BLOCKS 2
+#endif
+// Two CTAs of 6 warps and 32 draws share an SM (2 x 109 KB of shared memory, <= 170 registers per
+// thread): while one CTA is in the latency-bound tridiagonal solves the other evaluates nodes.
+constexpr int kL11Threads = TC_L11_THREADS;
+constexpr int kL11DrawsPerBlock = TC_L11_DRAWS;
+constexpr int kL11MinBlocks = TC_L11_MIN_BLOCKS;
 constexpr double kL11LittleH = 0.7;        // Behroozi10SmHm.littleh
 constexpr double kL11LittleHSats = 0.72;   // Leauthaud11Sats.littleh
 constexpr double kL11LogMsLo = 8.5, kL11LogMsHi = 12.5;
@@ -52,34 +65,9 @@ struct L11Draw {
                           // falls into 8 different 16-byte bank groups
 };
 static_assert(sizeof(L11Draw) % 128 == 80, "L11Draw stride chosen against bank conflicts");
-
-struct L11Params {
-  const L11Draw* d;
-  double threshold;
-  double a_cen, a_sat;
-  int hint;   // knot interval of the group's first node: the nodes of a mass bin ascend from it
-  double next_x[3];   // abscissae of the next three knots (+inf past the last interval)
-  // baseline_occupation receives (log10 mass, 1 / mass)
-  static __device__ __forceinline__ const double* first_nodes(const OccPlan& plan, bool, bool) {
-    return plan.node_logm;
-  }
-  static __device__ __forceinline__ const double* second_nodes(const OccPlan& plan) {
-    return plan.node_inv_m;
-  }
-  static __device__ __forceinline__ bool needs_second(bool sat, bool) { return sat; }
-  __device__ __forceinline__ void begin_group(double logm) {
-    int i = 0;   // largest knot index in [0, kL11Knots - 2] with x_i <= logm (0 if none)
-#pragma unroll
-    for (int step = 64; step >= 1; step >>= 1) {
-      const int j = i + step;
-      if (j <= kL11Knots - 2 && d->knot[j].x <= logm) i = j;
-    }
-    hint = i;
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-      next_x[j] = i + 1 + j <= kL11Knots - 2 ? d->knot[i + 1 + j].x : CUDART_INF;
-  }
-};
+constexpr size_t kL11SmemBytes =
+    (kTabDoubles + kL11Knots) * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
+static_assert(kL11MinBlocks * (kL11SmemBytes + 1024) <= 228 * 1024, "CTAs per SM vs shared memory");
 
 __device__ __forceinline__ double l11_knot_logms(int k) {
   // numpy.linspace(8.5, 12.5, 100): arange(100) * step + start, last element set to stop
@@ -89,221 +77,288 @@ __device__ __forceinline__ double l11_knot_logms(int k) {
 
 // Behroozi10SmHm.mean_log_halo_mass: log10 M_h [h = 1 units] of log10 M* [h = 1 units].  halotools
 // converts M* -> M* / h^2 and M_h -> M_h h through 10** and log10; here the conversions are added
-// in log space (differences at the 1e-16 level).
+// in log space (differences at the 1e-16 level).  FAST: 10^z through the exp table (relative
+// error ~1e-16 like the library's, a fifth of its instructions) -- the 100 knots of every draw.
+template <bool FAST>
 __device__ __forceinline__ double l11_log_halo_mass(double log_ms, double logm0, double logm1,
-                                                    double beta, double delta, double gamma) {
+                                                    double beta, double delta, double gamma,
+                                                    const double* __restrict__ tab) {
   const double log_h = -0.15490195998574316929;   // log10(0.7)
   const double lr = log_ms - 2.0 * log_h - logm0;  // log10(M* / M0) in h = 0.7 units
-  return logm1 + beta * lr + exp10(delta * lr) / (1.0 + exp10(-gamma * lr)) - 0.5 + log_h;
+  const double up = FAST ? exp_scaled(delta * lr * kLn10, tab) : exp10(delta * lr);
+  const double dn = FAST ? exp_scaled(-gamma * lr * kLn10, tab) : exp10(-gamma * lr);
+  return logm1 + beta * lr + up / (1.0 + dn) - 0.5 + log_h;
 }
 
-__device__ __forceinline__ double l11_log_mstar(double logm, const L11Params& p) {
-  // the nodes of a group ascend from the hinted interval and a mass bin spans few knots: three
-  // branch-free steps against the cached abscissae, then (rarely) a linear walk
-  int i = p.hint + (p.next_x[0] <= logm ? 1 : 0) + (p.next_x[1] <= logm ? 1 : 0) +
-          (p.next_x[2] <= logm ? 1 : 0);
-  if (p.next_x[2] <= logm)
-    while (i < kL11Knots - 2 && p.d->knot[i + 1].x <= logm) i++;
-  const double4 c = p.d->knot[i];
-  const double t = logm - c.x;
-  return fma(t, fma(t, fma(t, c.z, c.w), c.y), l11_knot_logms(i));
-}
-
-template <bool SAT, bool MODULATE>
-__device__ __forceinline__ double baseline_occupation(double logm, double inv_mass,
-                                                      const L11Params& p,
-                                                      const double* __restrict__ tab) {
-  if (!SAT) {
-    const double x = (l11_log_mstar(logm, p) - p.threshold) * p.d->inv_scatter;
-    return half_erfc_neg(x, tab) + p.d->bad;
-  }
-  // exp(-M_cut / (M h)) (M h / M_sat)^alphasat = exp(alphasat (ln M + ln(h / M_sat)) - M_cut / (M h))
-  double y = fma(p.d->alphasat, fma(logm, kLn10, p.d->ln_h_over_msat), p.d->neg_mcut_h * inv_mass);
-  y = fmin(fmax(y, -800.0), 800.0);
-  double f = exp_scaled(y, tab);
-  if (MODULATE) {
-    const double x = (l11_log_mstar(logm, p) - p.threshold) * p.d->inv_scatter;
-    f *= half_erfc_neg(x, tab);
-  }
-  return f + p.d->bad;
-}
-
-// Spline tables and per-draw constants of one block of draws, by the whole CTA.
-__device__ void l11_prepare_block(L11Draw* draws, int n_block, long long draw0,
+// Spline tables and per-draw constants of one block of draws, by the whole CTA.  `sk`: the knot
+// ordinates log10 M* (shared by all draws), `tab`: the math tables.
+__device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
+                                  const double* __restrict__ tab, int n_block, long long draw0,
                                   long long n_draws, const double* __restrict__ theta,
                                   long long theta_ds, long long theta_ps, const tc_model& model) {
-  const double a1 = 1.0 / (1.0 + model.redshift) - 1.0;   // a - 1
-  // (1) knot abscissae and per-draw constants
-  for (int idx = threadIdx.x; idx < n_block * (kL11Knots + 1); idx += blockDim.x) {
-    const int b = idx / (kL11Knots + 1), k = idx - b * (kL11Knots + 1);
-    const long long draw = min(draw0 + b, n_draws - 1);
-    const double* th = theta + draw * theta_ds;
+  constexpr int n = kL11Knots;
+  // (0) one thread per draw: relation parameters at the model redshift (parked in the y, z, w
+  // slots of knots 0 and 1, free until (2)) and the constants of the occupation functions
+  for (int b = threadIdx.x; b < n_block; b += blockDim.x) {
+    const double a1 = 1.0 / (1.0 + model.redshift) - 1.0;   // a - 1
+    const double* th = theta + min(draw0 + b, n_draws - 1) * theta_ds;
     const double logm0 = fma(th[1 * theta_ps], a1, th[0]);
     const double logm1 = fma(th[3 * theta_ps], a1, th[2 * theta_ps]);
     const double beta = fma(th[5 * theta_ps], a1, th[4 * theta_ps]);
     const double delta = fma(th[7 * theta_ps], a1, th[6 * theta_ps]);
     const double gamma = fma(th[9 * theta_ps], a1, th[8 * theta_ps]);
-    if (k < kL11Knots) {
-      draws[b].knot[k].x = l11_log_halo_mass(l11_knot_logms(k), logm0, logm1, beta, delta, gamma);
-    } else {
-      // Leauthaud11Sats._update_satellite_params: knee = h M_h(threshold) / 1e12
-      const double log_knee = l11_log_halo_mass(model.threshold, logm0, logm1, beta, delta, gamma) +
-                              log10(kL11LittleHSats) - 12.0;
-      const double msat = 1e12 * th[12 * theta_ps] * exp10(th[15 * theta_ps] * log_knee);
-      const double mcut = 1e12 * th[13 * theta_ps] * exp10(th[14 * theta_ps] * log_knee);
-      draws[b].inv_scatter = 1.0 / (1.4142135623730951 * th[10 * theta_ps]);
-      draws[b].neg_mcut_h = -mcut / kL11LittleHSats;
-      draws[b].ln_h_over_msat = log(kL11LittleHSats / msat);
-      draws[b].alphasat = th[11 * theta_ps];
-      draws[b].a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
-      draws[b].a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;
-    }
+    L11Draw& D = draws[b];
+    D.knot[0].y = logm0;
+    D.knot[0].z = logm1;
+    D.knot[0].w = beta;
+    D.knot[1].y = delta;
+    D.knot[1].z = gamma;
+    // Leauthaud11Sats._update_satellite_params: knee = h M_h(threshold) / 1e12
+    const double log_knee =
+        l11_log_halo_mass<false>(model.threshold, logm0, logm1, beta, delta, gamma, tab) +
+        log10(kL11LittleHSats) - 12.0;
+    const double msat = 1e12 * th[12 * theta_ps] * exp10(th[15 * theta_ps] * log_knee);
+    const double mcut = 1e12 * th[13 * theta_ps] * exp10(th[14 * theta_ps] * log_knee);
+    D.inv_scatter = 1.0 / (1.4142135623730951 * th[10 * theta_ps]);
+    D.neg_mcut_h = -mcut / kL11LittleHSats;
+    D.ln_h_over_msat = log(kL11LittleHSats / msat);
+    D.alphasat = th[11 * theta_ps];
+    D.a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
+    D.a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;
+    D.bad = 0.0;
   }
   __syncthreads();
-  // (2) second derivatives m_k of the not-a-knot spline s(x): one thread per draw (Thomas).
-  // interior equations h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 (d_i - d_{i-1}),
-  // d_i = (s_{i+1} - s_i) / h_i, with m_0 and m_{n-1} eliminated through the continuity of the
-  // third derivative at knots 1 and n - 2.  Scratch: knot[i].y = modified upper diagonal,
-  // knot[i].z = modified right-hand side, knot[i].w = m_i.  The draws are spread over the warps
-  // (one lane group per SM sub-partition) because the recurrences are latency bound.
+  // (1) knot abscissae
+  for (int idx = threadIdx.x; idx < n_block * n; idx += blockDim.x) {
+    const int b = idx / n, k = idx - b * n;
+    const L11Draw& D = draws[b];
+    draws[b].knot[k].x = l11_log_halo_mass<true>(sk[k], D.knot[0].y, D.knot[0].z, D.knot[0].w,
+                                                 D.knot[1].y, D.knot[1].z, tab);
+  }
+  __syncthreads();
+  // (2) reciprocal interval widths (y slot), monotonicity
+  for (int idx = threadIdx.x; idx < n_block * (n - 1); idx += blockDim.x) {
+    const int b = idx / (n - 1), k = idx - b * (n - 1);
+    const double h = draws[b].knot[k + 1].x - draws[b].knot[k].x;
+    draws[b].knot[k].y = 1.0 / h;
+    if (!(h > 0.0)) draws[b].bad = CUDART_NAN;
+  }
+  __syncthreads();
+  // (3) HALVED second derivatives c2_k = m_k / 2 of the not-a-knot spline s(x): one lane per draw
+  // (Thomas).  Interior equations h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} =
+  // 6 (d_i - d_{i-1}), d_i = (s_{i+1} - s_i) / h_i, with m_0 and m_{n-1} eliminated through the
+  // continuity of the third derivative at knots 1 and n - 2; the right-hand side is halved, so
+  // the solution is exactly m / 2.  Scratch: knot[i].z = modified upper diagonal, knot[i].w =
+  // modified right-hand side, then c2_i.  The recurrences are latency bound (one reciprocal per
+  // step on the critical path); the other CTA of the SM works meanwhile.
+  for (int b = threadIdx.x; b < n_block; b += blockDim.x) {
+    L11Draw& D = draws[b];
+    double x_cur = D.knot[1].x;
+    double h_prev = x_cur - D.knot[0].x;                    // h_0
+    double ih_prev = D.knot[0].y;
+    double d_prev = (sk[1] - sk[0]) * ih_prev;
+    double cp = 0.0, rp = 0.0;                              // c'_{i-1}, r'_{i-1}
+    for (int i = 1; i <= n - 2; i++) {
+      const double x_next = D.knot[i + 1].x;
+      const double h = x_next - x_cur, ih = D.knot[i].y;    // h_i, 1 / h_i
+      const double d = (sk[i + 1] - sk[i]) * ih;
+      double lower = h_prev, diag = 2.0 * (h_prev + h), upper = h;
+      if (i == 1) {
+        const double e = h_prev * h_prev * ih;
+        lower = 0.0;
+        diag = 3.0 * h_prev + 2.0 * h + e;
+        upper = h - e;
+      }
+      if (i == n - 2) {
+        const double e = h * h * ih_prev;
+        lower = h_prev - e;
+        diag = 2.0 * h_prev + 3.0 * h + e;
+        upper = 0.0;
+      }
+      const double rhs = 3.0 * (d - d_prev);
+      const double inv = 1.0 / (diag - lower * cp);
+      cp = upper * inv;
+      rp = (rhs - lower * rp) * inv;
+      D.knot[i].z = cp;
+      D.knot[i].w = rp;
+      x_cur = x_next;
+      h_prev = h;
+      ih_prev = ih;
+      d_prev = d;
+    }
+    double m_next = 0.0;
+    for (int i = n - 2; i >= 1; i--) {
+      const double m = D.knot[i].w - D.knot[i].z * m_next;
+      D.knot[i].w = m;
+      m_next = m;
+    }
+    const double h0 = D.knot[1].x - D.knot[0].x;
+    D.knot[0].w = D.knot[1].w - h0 * D.knot[1].y * (D.knot[2].w - D.knot[1].w);
+    const double ha = D.knot[n - 1].x - D.knot[n - 2].x;
+    D.knot[n - 1].w =
+        D.knot[n - 2].w + ha * D.knot[n - 3].y * (D.knot[n - 2].w - D.knot[n - 3].w);
+  }
+  __syncthreads();
+  // (4) cubic coefficients per interval: c1 and c3 replace 1 / h (y) and the scratch (z); w = c2
+  // of knots k, k + 1 is only read
+  for (int idx = threadIdx.x; idx < n_block * (n - 1); idx += blockDim.x) {
+    const int b = idx / (n - 1), k = idx - b * (n - 1);
+    const double4 k0 = draws[b].knot[k];
+    const double x1 = draws[b].knot[k + 1].x, m1 = draws[b].knot[k + 1].w;
+    const double h = x1 - k0.x, ih = k0.y;
+    const double d = (sk[k + 1] - sk[k]) * ih;
+    draws[b].knot[k].y = d - h * (2.0 * k0.w + m1) * (1.0 / 3.0);
+    draws[b].knot[k].z = (m1 - k0.w) * ih * (1.0 / 3.0);
+  }
+  __syncthreads();
+}
+
+// One lane: one draw x one mass bin = the centrals group `cen` and / or the satellites group
+// `sat` over the same node masses (-1: absent).  The spline and the erf of a node serve both
+// galaxy types (Leauthaud11Sats is modulated by <N_cen> by default); the Gauss-Legendre weights
+// and the Heaviside decoration are those of occupation_group (occupation.cuh).
+template <int U, bool DECORATED>
+__device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __restrict__ d,
+                                        const double* __restrict__ sk,
+                                        const double* __restrict__ tab, int cen, int sat,
+                                        double* __restrict__ out) {
+  const OccPlan& plan = args.plan;
+  const int G = plan.n_gauss_pad;
+  const int lead = cen >= 0 ? cen : sat;
+  const double* __restrict__ node = plan.node_logm + (size_t)lead * G;
+  const double* __restrict__ node_inv = plan.node_inv_m + (size_t)lead * G;
+  const bool has_cen = cen >= 0, has_sat = sat >= 0;
+  const bool modulate = args.model.modulate_with_cenocc != 0;
+  int rows[4] = {-1, -1, -1, -1};
+  if (has_cen) { rows[0] = plan.grp_rows[cen * kGroupRows]; rows[1] = plan.grp_rows[cen * kGroupRows + 1]; }
+  if (has_sat) { rows[2] = plan.grp_rows[sat * kGroupRows]; rows[3] = plan.grp_rows[sat * kGroupRows + 1]; }
+  const double* __restrict__ w0 = plan.row_c + (size_t)(rows[0] >= 0 ? rows[0] : plan.zero_row) * G;
+  const double* __restrict__ w1 = plan.row_c + (size_t)(rows[1] >= 0 ? rows[1] : plan.zero_row) * G;
+  const double* __restrict__ w2 = plan.row_c + (size_t)(rows[2] >= 0 ? rows[2] : plan.zero_row) * G;
+  const double* __restrict__ w3 = plan.row_c + (size_t)(rows[3] >= 0 ? rows[3] : plan.zero_row) * G;
+  double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0, ratio = 0.0;
+  bool split_ok = false;
+  if (DECORATED) {
+    const double split = args.model.split;
+    split_ok = split > 0.0 && split < 1.0;
+    ratio = split / (1.0 - split);
+    const double down = -(1.0 - split) / split;
+    k0 = (rows[0] >= 0 && plan.row_pct[rows[0]] > split) ? 1.0 : down;
+    k1 = (rows[1] >= 0 && plan.row_pct[rows[1]] > split) ? 1.0 : down;
+    k2 = (rows[2] >= 0 && plan.row_pct[rows[2]] > split) ? 1.0 : down;
+    k3 = (rows[3] >= 0 && plan.row_pct[rows[3]] > split) ? 1.0 : down;
+  }
+  // knot interval of the first node (7-step binary search); the nodes of a bin ascend from it and
+  // a bin spans few knots: per node three branch-free steps against the cached abscissae, then
+  // (rarely) a linear walk
+  int hint = 0;   // largest knot index in [0, kL11Knots - 2] with x_i <= node[0] (0 if none)
   {
-    const int lanes = (n_block + kWarps - 1) / kWarps;              // draws per warp
-    const int b = (threadIdx.x >> 5) * lanes + (threadIdx.x & 31);
-    if ((threadIdx.x & 31) < lanes && b < n_block) {
-      L11Draw& D = draws[b];
-      constexpr int n = kL11Knots;
-      double h_prev = D.knot[1].x - D.knot[0].x;            // h_0
-      bool increasing = h_prev > 0.0;
-      double d_prev = (l11_knot_logms(1) - l11_knot_logms(0)) / h_prev;
-      double cp = 0.0, rp = 0.0;                            // c'_{i-1}, r'_{i-1}
-      for (int i = 1; i <= n - 2; i++) {
-        const double h = D.knot[i + 1].x - D.knot[i].x;     // h_i
-        increasing = increasing && h > 0.0;
-        const double d = (l11_knot_logms(i + 1) - l11_knot_logms(i)) / h;
-        double lower = h_prev, diag = 2.0 * (h_prev + h), upper = h;
-        if (i == 1) {
-          lower = 0.0;
-          diag = 3.0 * h_prev + 2.0 * h + h_prev * h_prev / h;
-          upper = h - h_prev * h_prev / h;
-        }
-        if (i == n - 2) {
-          lower = h_prev - h * h / h_prev;
-          diag = 2.0 * h_prev + 3.0 * h + h * h / h_prev;
-          upper = 0.0;
-        }
-        const double rhs = 6.0 * (d - d_prev);
-        const double inv = 1.0 / (diag - lower * cp);
-        cp = upper * inv;
-        rp = (rhs - lower * rp) * inv;
-        D.knot[i].y = cp;
-        D.knot[i].z = rp;
-        h_prev = h;
-        d_prev = d;
-      }
-      double m_next = 0.0;
-      for (int i = n - 2; i >= 1; i--) {
-        const double m = D.knot[i].z - D.knot[i].y * m_next;
-        D.knot[i].w = m;
-        m_next = m;
-      }
-      const double h0 = D.knot[1].x - D.knot[0].x, h1 = D.knot[2].x - D.knot[1].x;
-      D.knot[0].w = D.knot[1].w - h0 / h1 * (D.knot[2].w - D.knot[1].w);
-      const double ha = D.knot[n - 1].x - D.knot[n - 2].x, hb = D.knot[n - 2].x - D.knot[n - 3].x;
-      D.knot[n - 1].w = D.knot[n - 2].w + ha / hb * (D.knot[n - 2].w - D.knot[n - 3].w);
-      D.bad = increasing ? 0.0 : CUDART_NAN;
+    const double first = node[0];
+#pragma unroll
+    for (int step = 64; step >= 1; step >>= 1) {
+      const int j = hint + step;
+      if (j <= kL11Knots - 2 && d->knot[j].x <= first) hint = j;
     }
   }
-  __syncthreads();
-  // (3) cubic coefficients per interval: c1 and c3 go to the (now dead) y and z slots -- only x
-  // and w (= m) of knots k, k + 1 are read in this pass -- then w becomes c2 = m / 2
-  for (int idx = threadIdx.x; idx < n_block * (kL11Knots - 1); idx += blockDim.x) {
-    const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
-    const double x0 = draws[b].knot[k].x, x1 = draws[b].knot[k + 1].x;
-    const double m0 = draws[b].knot[k].w, m1 = draws[b].knot[k + 1].w;
-    const double h = x1 - x0;
-    const double d = (l11_knot_logms(k + 1) - l11_knot_logms(k)) / h;
-    draws[b].knot[k].y = d - h * (2.0 * m0 + m1) * (1.0 / 6.0);
-    draws[b].knot[k].z = (m1 - m0) / (6.0 * h);
+  double next_x[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    next_x[j] = hint + 1 + j <= kL11Knots - 2 ? d->knot[hint + 1 + j].x : CUDART_INF;
+  const double threshold = args.model.threshold, inv_scatter = d->inv_scatter;
+  const double alphasat = d->alphasat, ln_h_over_msat = d->ln_h_over_msat;
+  const double neg_mcut_h = d->neg_mcut_h;
+  const double a_cen = d->a_cen, a_sat = d->a_sat;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  for (int g = 0; g < G; g += U) {
+    double e[U], logm[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      logm[u] = node[g + u];
+      int i = hint + (next_x[0] <= logm[u] ? 1 : 0) + (next_x[1] <= logm[u] ? 1 : 0) +
+              (next_x[2] <= logm[u] ? 1 : 0);
+      if (next_x[2] <= logm[u])
+        while (i < kL11Knots - 2 && d->knot[i + 1].x <= logm[u]) i++;
+      const double4 c = d->knot[i];
+      const double t = logm[u] - c.x;
+      const double s = fma(t, fma(t, fma(t, c.z, c.w), c.y), sk[i]);
+      e[u] = half_erfc_neg((s - threshold) * inv_scatter, tab);
+    }
+    if (has_cen) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (DECORATED) {
+          const double dl = assembias_delta(e[u], a_cen, ratio, 1.0, split_ok);
+          acc0 = fma(w0[g + u], fma(k0, dl, e[u]), acc0);
+          acc1 = fma(w1[g + u], fma(k1, dl, e[u]), acc1);
+        } else {
+          acc0 = fma(w0[g + u], e[u], acc0);
+          acc1 = fma(w1[g + u], e[u], acc1);
+        }
+      }
+    }
+    if (has_sat) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        // exp(-M_cut / (M h)) (M h / M_sat)^alphasat = exp(alphasat (ln M + ln(h / M_sat)) - M_cut / (M h))
+        double y = fma(alphasat, fma(logm[u], kLn10, ln_h_over_msat), neg_mcut_h * node_inv[g + u]);
+        y = fmin(fmax(y, -800.0), 800.0);
+        double f = exp_scaled(y, tab);
+        if (modulate) f *= e[u];
+        if (DECORATED) {
+          const double dl = assembias_delta(f, a_sat, ratio, CUDART_INF, split_ok);
+          acc2 = fma(w2[g + u], fma(k2, dl, f), acc2);
+          acc3 = fma(w3[g + u], fma(k3, dl, f), acc3);
+        } else {
+          acc2 = fma(w2[g + u], f, acc2);
+          acc3 = fma(w3[g + u], f, acc3);
+        }
+      }
+    }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < n_block * (kL11Knots - 1); idx += blockDim.x) {
-    const int b = idx / (kL11Knots - 1), k = idx - b * (kL11Knots - 1);
-    draws[b].knot[k].w *= 0.5;
+  const double bad = d->bad;
+  if (out) {
+    if (rows[0] >= 0 && args.pad_to_row[rows[0]] >= 0) out[args.pad_to_row[rows[0]]] = acc0 + bad;
+    if (rows[1] >= 0 && args.pad_to_row[rows[1]] >= 0) out[args.pad_to_row[rows[1]]] = acc1 + bad;
+    if (rows[2] >= 0 && args.pad_to_row[rows[2]] >= 0) out[args.pad_to_row[rows[2]]] = acc2 + bad;
+    if (rows[3] >= 0 && args.pad_to_row[rows[3]] >= 0) out[args.pad_to_row[rows[3]]] = acc3 + bad;
   }
-  __syncthreads();
 }
 
-template <bool DECORATED, bool MODULATE, int U, typename Store>
-__device__ __forceinline__ void occupation_item_l11(const OccPlan& plan, const tc_model& model,
-                                                    const L11Draw* d, int g_begin, int g_end,
-                                                    const double* __restrict__ tab, Store store) {
-  L11Params p;
-  p.d = d;
-  p.threshold = model.threshold;
-  p.a_cen = d->a_cen;
-  p.a_sat = d->a_sat;
-  p.hint = 0;
-  const bool sat = g_begin >= plan.n_cen_groups;
-  for (int grp = g_begin + (threadIdx.x >> 3 & 3); grp < g_end; grp += 4) {
-    double occ0, occ1;
-    if (sat)
-      occupation_group<true, DECORATED, MODULATE, U>(plan, grp, p, model.split, tab, occ0, occ1);
-    else
-      occupation_group<false, DECORATED, false, U>(plan, grp, p, model.split, tab, occ0, occ1);
-    const int row0 = plan.grp_rows[grp * kGroupRows], row1 = plan.grp_rows[grp * kGroupRows + 1];
-    store(row0, occ0, plan.row_nh[row0]);
-    if (row1 >= 0) store(row1, occ1, plan.row_nh[row1]);
-  }
-}
-
-// quadrature nodes in flight per lane: kOccUnroll when it divides n_gauss, else 2 (see build_plan)
-template <bool DECORATED, bool MODULATE, typename Store>
-__device__ __forceinline__ void occupation_item_l11_any(const OccArgs& args, const L11Draw* d,
-                                                        int g_begin, int g_end,
-                                                        const double* __restrict__ tab,
-                                                        Store store) {
-  if (args.plan.unroll == kOccUnroll)
-    occupation_item_l11<DECORATED, MODULATE, kOccUnroll>(args.plan, args.model, d, g_begin, g_end,
-                                                         tab, store);
-  else
-    occupation_item_l11<DECORATED, MODULATE, 2>(args.plan, args.model, d, g_begin, g_end, tab,
-                                                store);
-}
-
-__global__ void __launch_bounds__(kThreads, 1) occupation_l11_kernel(const OccArgs args) {
+__global__ void __launch_bounds__(kL11Threads, kL11MinBlocks)
+occupation_l11_kernel(const OccArgs args) {
   extern __shared__ __align__(16) double l11_smem[];
   double* tab = l11_smem;
-  L11Draw* draws = reinterpret_cast<L11Draw*>(l11_smem + kTabDoubles);
+  double* sk = l11_smem + kTabDoubles;
+  L11Draw* draws = reinterpret_cast<L11Draw*>(sk + kL11Knots);
   load_math_tables(tab);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_ranges = args.n_ranges_cen + args.n_ranges_sat;
+  for (int k = threadIdx.x; k < kL11Knots; k += blockDim.x) sk[k] = l11_knot_logms(k);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long n_blocks = (args.n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;
+  const int n_bins = args.plan.n_l11_bins, n_quads = (n_bins + 3) >> 2;
   for (long long block = blockIdx.x; block < n_blocks; block += gridDim.x) {
     const long long draw0 = block * kL11DrawsPerBlock;
     const int n_block = (int)min((long long)kL11DrawsPerBlock, args.n_draws - draw0);
-    __syncthreads();   // the previous block's tables are no longer read
-    l11_prepare_block(draws, n_block, draw0, args.n_draws, args.theta, args.theta_ds,
+    __syncthreads();   // the previous block's tables are no longer read; tab and sk are filled
+    l11_prepare_block(draws, sk, tab, n_block, draw0, args.n_draws, args.theta, args.theta_ds,
                       args.theta_ps, args.model);
-    // one warp per item = 8 draws x one group range; four groups in flight per warp
-    const int n_items = (kL11DrawsPerBlock / 8) * n_ranges;
-    for (int item = warp; item < n_items; item += kWarps) {
-      const int sub = item / n_ranges, q = item - sub * n_ranges;
-      const int b = min(sub * 8 + (lane & 7), n_block - 1);
-      const long long draw = draw0 + sub * 8 + (lane & 7);
-      const bool live = draw < args.n_draws;
-      int g_begin, g_end;
-      occupation_range(args.plan, args.n_ranges_cen, args.n_ranges_sat, q, g_begin, g_end);
-      auto store = [&](int row, double occ, double) {
-        const int dst = args.pad_to_row[row];
-        if (live && dst >= 0) args.occ_out[draw * args.n_rows + dst] = occ;
-      };
-      const bool mod = args.model.modulate_with_cenocc != 0;
+    // one warp per unit = 8 draws (lane & 7) x 4 mass bins (lane >> 3)
+    const int n_units = ((n_block + 7) >> 3) * n_quads;
+    for (int unit = warp; unit < n_units; unit += n_warps) {
+      const int sub = unit / n_quads, quad = unit - sub * n_quads;
+      const int b = sub * 8 + (lane & 7), bin = quad * 4 + (lane >> 3);
+      if (b >= n_block || bin >= n_bins) continue;
+      const int2 pair = args.plan.l11_bins[bin];
+      double* out = args.occ_out + (draw0 + b) * args.n_rows;
       if (args.model.decorated) {
-        if (mod) occupation_item_l11_any<true, true>(args, draws + b, g_begin, g_end, tab, store);
-        else occupation_item_l11_any<true, false>(args, draws + b, g_begin, g_end, tab, store);
+        if (args.plan.unroll == kOccUnroll)
+          l11_bin<kOccUnroll, true>(args, draws + b, sk, tab, pair.x, pair.y, out);
+        else
+          l11_bin<2, true>(args, draws + b, sk, tab, pair.x, pair.y, out);
       } else {
-        if (mod) occupation_item_l11_any<false, true>(args, draws + b, g_begin, g_end, tab, store);
-        else occupation_item_l11_any<false, false>(args, draws + b, g_begin, g_end, tab, store);
+        if (args.plan.unroll == kOccUnroll)
+          l11_bin<kOccUnroll, false>(args, draws + b, sk, tab, pair.x, pair.y, out);
+        else
+          l11_bin<2, false>(args, draws + b, sk, tab, pair.x, pair.y, out);
       }
     }
   }

@@ -188,7 +188,7 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
                            2, (long long)n_sm * kWarps / ((n_draws + 7) / 8))),
                        &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
   if (model->family == TC_FAMILY_LEAUTHAUD11) {
-    const size_t smem = kTabDoubles * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
+    const size_t smem = kL11SmemBytes;
     static std::mutex m;
     static std::map<int, bool> configured;
     {
@@ -196,12 +196,16 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
       if (!configured[t->device]) {
         TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         configured[t->device] = true;
       }
     }
     const long long n_blocks = (n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(n_blocks, n_sm));
-    occupation_l11_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(args);
+    const int grid = (int)std::max<long long>(
+        1, std::min<long long>(n_blocks, (long long)n_sm * kL11MinBlocks));
+    occupation_l11_kernel<<<grid, kL11Threads, smem, static_cast<cudaStream_t>(stream)>>>(args);
     TC_CUDA(cudaGetLastError());
     return TC_OK;
   }
