@@ -228,7 +228,9 @@ int tc_halo_bins(int device, const double* log_prim_dev, const double* sec_pct_d
                  double* mean_out, void* stream);
 
 /* Element-wise evaluation of the occupation kernel's table-driven math on the current device, for
- * accuracy tests: kind 0: out = 0.5 (1 + erf(x)); kind 1: out = x^y for x > 0. */
+ * accuracy tests: kind 0: out = 0.5 (1 + erf(x)); kind 1: out = x^y for x > 0; kinds 2 / 3: the
+ * leauthaud11 kernel's grouped erf (one coefficient column for nodes that lie close together)
+ * of the pair (x, y), out = 0.5 (1 + erf(x)) / 0.5 (1 + erf(y)). */
 int tc_debug_math(int kind, const double* x_dev, const double* y_dev, double* out_dev, int64_t n,
                   void* stream);
 

@@ -41,6 +41,20 @@ constexpr double kRoundMagic = 6755399441055744.0;              // 2^52 + 2^51: 
 
 __device__ double g_math_tables[kTabDoubles];
 
+// Wide erf table of the leauthaud11 kernel (leauthaud11.cuh): the same intervals of width 0.5
+// (29 of them, centred at -7, -6.5, ..., 7, and two saturated columns), but every polynomial is a
+// degree-19 fit over centre +- 0.75, so that the quadrature nodes a lane evaluates together -- a
+// few hundredths apart in x -- share ONE column of coefficients: 20 coefficient loads per group
+// of nodes instead of 14 per node (the kernel is bound by shared-memory wavefronts).  Absolute
+// error < 2e-16 (rounding level).  Followed by a copy of the 2^(j/32) table.
+constexpr int kErfWDeg = 19;
+constexpr int kErfWPoly = 29;                                   // polynomial columns
+constexpr int kErfWStride = 32;
+constexpr double kErfWHalf = 0.75;                              // validity |x - centre| <= 0.75
+constexpr int kErfWDoubles = (kErfWDeg + 1) * kErfWStride;      // 640
+constexpr int kL11TabDoubles = kErfWDoubles + kExpEntries;      // 672 doubles = 5376 bytes
+__device__ double g_l11_tables[kL11TabDoubles];
+
 __device__ __forceinline__ void load_math_tables(double* tab) {
   for (int i = threadIdx.x; i < kTabDoubles; i += blockDim.x) tab[i] = g_math_tables[i];
 }
@@ -85,7 +99,7 @@ __device__ __forceinline__ double log_pos(double t, const double* __restrict__ t
 
 // e^y for |y| < 2^26: 32-entry 2^(j/32) table + degree-6 polynomial; |y| beyond ~690 saturates
 // instead of overflowing
-__device__ __forceinline__ double exp_scaled(double y, const double* __restrict__ tab) {
+__device__ __forceinline__ double exp_scaled_with(double y, const double* __restrict__ exp_tab) {
   const double v = fma(y, 46.16624130844682903551 /* 32 / ln 2 */, kRoundMagic);
   const double kf = v - kRoundMagic;
   double q = fma(-kf, 0.0216608493924982895 /* hi(ln2 / 32) */, y);
@@ -97,9 +111,59 @@ __device__ __forceinline__ double exp_scaled(double y, const double* __restrict_
   w = fma(w, q, 1.0);
   w = fma(w, q, 1.0);
   const int k = __double2loint(v);
-  const double res = tab[kTabExp + (k & (kExpEntries - 1))] * w;   // in [1, 2) * (1 +- 0.011)
+  const double res = exp_tab[k & (kExpEntries - 1)] * w;   // in [1, 2) * (1 +- 0.011)
   const int scale = min(max(k >> 5, -1000), 1000);
   return __hiloint2double(__double2hiint(res) + (scale << 20), __double2loint(res));
+}
+__device__ __forceinline__ double exp_scaled(double y, const double* __restrict__ tab) {
+  return exp_scaled_with(y, tab + kTabExp);
+}
+
+// 0.5 (1 + erf(x)) of U arguments that lie close together, through ONE column of the wide table
+// (`wt`, kErfWDoubles doubles): the column is chosen by the midpoint of the first and the last
+// argument; an argument further than kErfWHalf from the column's centre sends the lane through
+// the one-column-per-argument path.  Arguments are clamped to [-16, 16] (the saturated columns
+// give the exact 0 / 1 erf gives beyond; NaN arguments are the caller's business).
+template <int U>
+__device__ __forceinline__ void half_erfc_neg_group(double (&x)[U], const double* __restrict__ wt) {
+  constexpr double kOffset = 14.0;   // column i is centred at -7 + i / 2
+#pragma unroll
+  for (int u = 0; u < U; u++) x[u] = fmin(fmax(x[u], -16.0), 16.0);
+  const double xm = 0.5 * (x[0] + x[U - 1]);
+  const double v = fma(xm, 2.0, kOffset + kRoundMagic);
+  const double xc = fma(v - kRoundMagic, 0.5, -0.5 * kOffset);
+  const double* c = wt + (min(max(__double2loint(v), -1), kErfWPoly) + 1);
+  double t[U], p[U];
+  bool near = true;
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    t[u] = x[u] - xc;
+    near = near && fabs(t[u]) <= kErfWHalf;
+  }
+  if (near) {
+    const double top = c[kErfWDeg * kErfWStride];
+#pragma unroll
+    for (int u = 0; u < U; u++) p[u] = top;
+#pragma unroll
+    for (int k = kErfWDeg - 1; k >= 0; k--) {
+      const double ck = c[k * kErfWStride];
+#pragma unroll
+      for (int u = 0; u < U; u++) p[u] = fma(p[u], t[u], ck);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) x[u] = p[u];
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const double vu = fma(x[u], 2.0, kOffset + kRoundMagic);
+      const double tu = x[u] - fma(vu - kRoundMagic, 0.5, -0.5 * kOffset);   // in [-0.25, 0.25]
+      const double* cu = wt + (min(max(__double2loint(vu), -1), kErfWPoly) + 1);
+      double q = cu[kErfWDeg * kErfWStride];
+#pragma unroll
+      for (int k = kErfWDeg - 1; k >= 0; k--) q = fma(q, tu, cu[k * kErfWStride]);
+      x[u] = q;
+    }
+  }
 }
 
 // t^alpha for t > 0 (normal double); |alpha ln t| beyond ~690 saturates instead of overflowing
@@ -108,14 +172,25 @@ __device__ __forceinline__ double pow_pos(double t, double alpha, const double* 
 }
 
 // element-wise evaluation of the table-driven math, for the accuracy tests (tc_debug_math)
+// kind 2: the wide-table erf of the leauthaud11 kernel on the pair (x[i], y[i]); out[i] = value at
+// x[i], and if out has room (kind 3) the value at y[i]
 __global__ void debug_math_kernel(int kind, const double* x, const double* y, double* out,
                                   long long n) {
   __shared__ double tab[kTabDoubles];
+  __shared__ double wide[kL11TabDoubles];
   load_math_tables(tab);
+  for (int i = threadIdx.x; i < kL11TabDoubles; i += blockDim.x) wide[i] = g_l11_tables[i];
   __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    out[i] = kind == 0 ? half_erfc_neg(x[i], tab) : pow_pos(x[i], y[i], tab);
+       i += (long long)gridDim.x * blockDim.x) {
+    if (kind >= 2) {
+      double pair[2] = {x[i], y[i]};
+      half_erfc_neg_group<2>(pair, wide);
+      out[i] = pair[kind - 2];
+    } else {
+      out[i] = kind == 0 ? half_erfc_neg(x[i], tab) : pow_pos(x[i], y[i], tab);
+    }
+  }
 }
 
 }  // namespace

@@ -808,6 +808,40 @@ int ensure_math_tables(int device) {
   }
   for (int j = 0; j < kExpEntries; j++) tab[kTabExp + j] = (double)exp2l((long double)j / kExpEntries);
   TC_CUDA(cudaMemcpyToSymbol(g_math_tables, tab.data(), sizeof(double) * kTabDoubles));
+  {
+    // wide erf table (half_erfc_neg_group): degree-19 fits over centre +- 0.75, monomials in
+    // t = x - centre
+    std::vector<double> wide(kL11TabDoubles, 0.0);
+    const int nw = kErfWDeg + 1;
+    wide[kErfWPoly + 1] = 1.0;   // saturated columns: 0 below the first, 1 above the last interval
+    for (int i = 0; i < kErfWPoly; i++) {
+      const long double xc = -7.0L + 0.5L * i, half = (long double)kErfWHalf;
+      std::vector<long double> fs(nw), a(nw, 0.0L);
+      for (int j = 0; j < nw; j++) fs[j] = 0.5L * erfcl(-(xc + half * cosl(pi * (j + 0.5L) / nw)));
+      for (int k = 0; k < nw; k++) {
+        long double sum = 0.0L;
+        for (int j = 0; j < nw; j++) sum += fs[j] * cosl(k * pi * (j + 0.5L) / nw);
+        a[k] = (k == 0 ? 1.0L : 2.0L) * sum / nw;
+      }
+      std::vector<long double> mono(nw, 0.0L), t0(nw, 0.0L), t1(nw, 0.0L), t2(nw, 0.0L);
+      t0[0] = 1.0L;
+      t1[1] = 1.0L;
+      for (int d = 0; d < nw; d++) mono[d] += a[0] * t0[d] + a[1] * t1[d];
+      for (int k = 2; k < nw; k++) {  // T_k = 2 s T_{k-1} - T_{k-2}
+        for (int d = 0; d < nw; d++) t2[d] = (d > 0 ? 2.0L * t1[d - 1] : 0.0L) - t0[d];
+        for (int d = 0; d < nw; d++) mono[d] += a[k] * t2[d];
+        t0 = t1;
+        t1 = t2;
+      }
+      long double scale = 1.0L;    // s = t / half
+      for (int d = 0; d < nw; d++) {
+        wide[(size_t)d * kErfWStride + i + 1] = (double)(mono[d] * scale);
+        scale /= half;
+      }
+    }
+    for (int j = 0; j < kExpEntries; j++) wide[kErfWDoubles + j] = tab[kTabExp + j];
+    TC_CUDA(cudaMemcpyToSymbol(g_l11_tables, wide.data(), sizeof(double) * kL11TabDoubles));
+  }
   done[device] = true;
   return TC_OK;
 }

@@ -66,13 +66,17 @@ struct L11Draw {
 };
 static_assert(sizeof(L11Draw) % 128 == 80, "L11Draw stride chosen against bank conflicts");
 constexpr size_t kL11SmemBytes =
-    (kTabDoubles + kL11Knots) * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
+    (kL11TabDoubles + kL11Knots) * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
 static_assert(kL11MinBlocks * (kL11SmemBytes + 1024) <= 228 * 1024, "CTAs per SM vs shared memory");
 
 __device__ __forceinline__ double l11_knot_logms(int k) {
   // numpy.linspace(8.5, 12.5, 100): arange(100) * step + start, last element set to stop
   return k == kL11Knots - 1 ? kL11LogMsHi
                             : (double)k * ((kL11LogMsHi - kL11LogMsLo) / (kL11Knots - 1)) + kL11LogMsLo;
+}
+
+__device__ __forceinline__ double l11_knot_logms_inner(int k) {   // the same for k < kL11Knots - 1
+  return (double)k * ((kL11LogMsHi - kL11LogMsLo) / (kL11Knots - 1)) + kL11LogMsLo;
 }
 
 // Behroozi10SmHm.mean_log_halo_mass: log10 M_h [h = 1 units] of log10 M* [h = 1 units].  halotools
@@ -85,8 +89,8 @@ __device__ __forceinline__ double l11_log_halo_mass(double log_ms, double logm0,
                                                     const double* __restrict__ tab) {
   const double log_h = -0.15490195998574316929;   // log10(0.7)
   const double lr = log_ms - 2.0 * log_h - logm0;  // log10(M* / M0) in h = 0.7 units
-  const double up = FAST ? exp_scaled(delta * lr * kLn10, tab) : exp10(delta * lr);
-  const double dn = FAST ? exp_scaled(-gamma * lr * kLn10, tab) : exp10(-gamma * lr);
+  const double up = FAST ? exp_scaled_with(delta * lr * kLn10, tab + kErfWDoubles) : exp10(delta * lr);
+  const double dn = FAST ? exp_scaled_with(-gamma * lr * kLn10, tab + kErfWDoubles) : exp10(-gamma * lr);
   return logm1 + beta * lr + up / (1.0 + dn) - 0.5 + log_h;
 }
 
@@ -125,7 +129,11 @@ __device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
     D.alphasat = th[11 * theta_ps];
     D.a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
     D.a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;
-    D.bad = 0.0;
+    // the erf argument is clamped below (NaN would be lost): a parameter that is not finite makes
+    // every occupation of the draw NaN through `bad`
+    double sum = 0.0;
+    for (int k = 0; k < (model.decorated ? 18 : 16); k++) sum += th[k * theta_ps];
+    D.bad = sum - sum;
   }
   __syncthreads();
   // (1) knot abscissae
@@ -260,29 +268,42 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
       if (j <= kL11Knots - 2 && d->knot[j].x <= first) hint = j;
     }
   }
-  double next_x[3];
-#pragma unroll
-  for (int j = 0; j < 3; j++)
-    next_x[j] = hint + 1 + j <= kL11Knots - 2 ? d->knot[hint + 1 + j].x : CUDART_INF;
   const double threshold = args.model.threshold, inv_scatter = d->inv_scatter;
   const double alphasat = d->alphasat, ln_h_over_msat = d->ln_h_over_msat;
   const double neg_mcut_h = d->neg_mcut_h;
   const double a_cen = d->a_cen, a_sat = d->a_sat;
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
   for (int g = 0; g < G; g += U) {
+    // The U nodes of an iteration advance through every stage together (straight-line code, U
+    // independent dependency chains): interval, cubic, erf, then the two galaxy types.
+    double next_x[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      next_x[j] = hint + 1 + j <= kL11Knots - 2 ? d->knot[hint + 1 + j].x : CUDART_INF;
     double e[U], logm[U];
+    int idx[U];
+    bool far = false;
 #pragma unroll
     for (int u = 0; u < U; u++) {
       logm[u] = node[g + u];
-      int i = hint + (next_x[0] <= logm[u] ? 1 : 0) + (next_x[1] <= logm[u] ? 1 : 0) +
-              (next_x[2] <= logm[u] ? 1 : 0);
-      if (next_x[2] <= logm[u])
-        while (i < kL11Knots - 2 && d->knot[i + 1].x <= logm[u]) i++;
-      const double4 c = d->knot[i];
-      const double t = logm[u] - c.x;
-      const double s = fma(t, fma(t, fma(t, c.z, c.w), c.y), sk[i]);
-      e[u] = half_erfc_neg((s - threshold) * inv_scatter, tab);
+      idx[u] = hint + (next_x[0] <= logm[u] ? 1 : 0) + (next_x[1] <= logm[u] ? 1 : 0) +
+               (next_x[2] <= logm[u] ? 1 : 0);
+      far = far || next_x[2] <= logm[u];
     }
+    if (far) {   // rare: a node more than three knots beyond the hint
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        while (idx[u] < kL11Knots - 2 && d->knot[idx[u] + 1].x <= logm[u]) idx[u]++;
+    }
+    hint = idx[U - 1];   // the nodes ascend (zero-weight padding nodes repeat the first one)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const double4 c = d->knot[idx[u]];
+      const double t = logm[u] - c.x;
+      const double s = fma(t, fma(t, fma(t, c.z, c.w), c.y), l11_knot_logms_inner(idx[u]));
+      e[u] = (s - threshold) * inv_scatter;
+    }
+    half_erfc_neg_group<U>(e, tab);
     if (has_cen) {
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -297,30 +318,33 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
       }
     }
     if (has_sat) {
+      double f[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         // exp(-M_cut / (M h)) (M h / M_sat)^alphasat = exp(alphasat (ln M + ln(h / M_sat)) - M_cut / (M h))
-        double y = fma(alphasat, fma(logm[u], kLn10, ln_h_over_msat), neg_mcut_h * node_inv[g + u]);
-        y = fmin(fmax(y, -800.0), 800.0);
-        double f = exp_scaled(y, tab);
-        if (modulate) f *= e[u];
+        const double y = fma(alphasat, fma(logm[u], kLn10, ln_h_over_msat), neg_mcut_h * node_inv[g + u]);
+        f[u] = exp_scaled_with(fmin(fmax(y, -800.0), 800.0), tab + kErfWDoubles) * (modulate ? e[u] : 1.0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
         if (DECORATED) {
-          const double dl = assembias_delta(f, a_sat, ratio, CUDART_INF, split_ok);
-          acc2 = fma(w2[g + u], fma(k2, dl, f), acc2);
-          acc3 = fma(w3[g + u], fma(k3, dl, f), acc3);
+          const double dl = assembias_delta(f[u], a_sat, ratio, CUDART_INF, split_ok);
+          acc2 = fma(w2[g + u], fma(k2, dl, f[u]), acc2);
+          acc3 = fma(w3[g + u], fma(k3, dl, f[u]), acc3);
         } else {
-          acc2 = fma(w2[g + u], f, acc2);
-          acc3 = fma(w3[g + u], f, acc3);
+          acc2 = fma(w2[g + u], f[u], acc2);
+          acc3 = fma(w3[g + u], f[u], acc3);
         }
       }
     }
   }
-  const double bad = d->bad;
-  if (out) {
-    if (rows[0] >= 0 && args.pad_to_row[rows[0]] >= 0) out[args.pad_to_row[rows[0]]] = acc0 + bad;
-    if (rows[1] >= 0 && args.pad_to_row[rows[1]] >= 0) out[args.pad_to_row[rows[1]]] = acc1 + bad;
-    if (rows[2] >= 0 && args.pad_to_row[rows[2]] >= 0) out[args.pad_to_row[rows[2]]] = acc2 + bad;
-    if (rows[3] >= 0 && args.pad_to_row[rows[3]] >= 0) out[args.pad_to_row[rows[3]]] = acc3 + bad;
+  const double bad = d->bad;   // NaN: table not increasing, or a parameter that is not finite
+  const double acc[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    if (rows[r] < 0) continue;
+    const int dst = args.pad_to_row[rows[r]];
+    if (dst >= 0) out[dst] = acc[r] + bad;
   }
 }
 
@@ -328,9 +352,9 @@ __global__ void __launch_bounds__(kL11Threads, kL11MinBlocks)
 occupation_l11_kernel(const OccArgs args) {
   extern __shared__ __align__(16) double l11_smem[];
   double* tab = l11_smem;
-  double* sk = l11_smem + kTabDoubles;
+  double* sk = l11_smem + kL11TabDoubles;
   L11Draw* draws = reinterpret_cast<L11Draw*>(sk + kL11Knots);
-  load_math_tables(tab);
+  for (int i = threadIdx.x; i < kL11TabDoubles; i += blockDim.x) tab[i] = g_l11_tables[i];
   for (int k = threadIdx.x; k < kL11Knots; k += blockDim.x) sk[k] = l11_knot_logms(k);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long n_blocks = (args.n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;

@@ -801,7 +801,8 @@ int tc_halo_bins(int device, const double* log_prim, const double* sec_pct, cons
 
 int tc_debug_math(int kind, const double* x, const double* y, double* out, int64_t n,
                   void* stream) {
-  if (!x || !out || (kind != 0 && !y) || n < 0) return fail(TC_EINVAL, "tc_debug_math: bad argument");
+  if (!x || !out || (kind != 0 && !y) || n < 0 || kind < 0 || kind > 3)
+    return fail(TC_EINVAL, "tc_debug_math: bad argument");
   if (n == 0) return TC_OK;
   int device = 0;
   TC_CUDA(cudaGetDevice(&device));

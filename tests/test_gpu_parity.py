@@ -393,6 +393,20 @@ def test_device_math_accuracy(tb):
     _lib.check(lib.tc_debug_math(1, td.data_ptr(), ad.data_ptr(), out.data_ptr(), len(t), None))
     got = out.cpu().numpy()
     assert np.max(np.abs(got / t**alpha - 1)) < 1e-13
+    # grouped erf of the leauthaud11 kernel: pairs close together share one coefficient column
+    # (|x - y| <= 1 keeps most pairs on that path), pairs far apart take the per-argument path
+    x = np.concatenate([rng.uniform(-8.5, 8.5, 200000), rng.uniform(-8.5, 8.5, 50000),
+                        [-100.0, 100.0, 7.24, 7.26, -7.26, 16.0, 1e300, -1e300, np.inf]])
+    y = np.concatenate([x[:200000] + rng.uniform(-1.0, 1.0, 200000), rng.uniform(-20, 20, 50000),
+                        [-99.0, 7.0, 7.26, 6.3, -6.3, -16.0, 1.0, -1.0, -np.inf]])
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    for kind, arg in ((2, x), (3, y)):
+        out = torch.empty_like(xd)
+        _lib.check(lib.tc_debug_math(kind, xd.data_ptr(), yd.data_ptr(), out.data_ptr(), len(x),
+                                     None))
+        got = out.cpu().numpy()
+        assert np.all(np.isfinite(got))
+        assert np.max(np.abs(got - 0.5 * (1 + erf(arg)))) < 3e-15, (kind, np.max(np.abs(got - 0.5 * (1 + erf(arg)))))
 
 
 @pytest.mark.parametrize('seed', range(12))
