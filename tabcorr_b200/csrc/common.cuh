@@ -56,6 +56,20 @@ struct Chunk {
   int r, mt0, mt1, k_begin, k_cap, part_row, pad0, pad1;
 };
 
+// One mass bin of the leauthaud11 kernel (leauthaud11.cuh): the centrals group and / or the
+// satellites group over the same quadrature nodes, with everything the kernel needs about their
+// rows in one record (no chains of dependent loads at the start and the end of a bin).
+struct alignas(16) L11Bin {
+  int cen, sat;          // group indices, -1: absent
+  int same_w;            // 1: the satellites rows carry the same normalised weights as the centrals rows
+  int pad0;
+  int row[4];            // padded rows {centrals 0, centrals 1, satellites 0, satellites 1}, -1: absent
+  int dst[4];            // their reference row index (column of the occupation output), -1: none
+  double first_logm;     // log10 mass of the first node
+  double pad1;
+  double pct[4];         // secondary-property percentile of the rows
+};
+
 struct OccPlan {       // device pointers, one per (layout, n_gauss)
   int n_groups;
   int n_cen_groups;         // groups are ordered centrals first
@@ -80,7 +94,7 @@ struct OccPlan {       // device pointers, one per (layout, n_gauss)
   double cen_d_max;         // largest half range of a centrals group (log10 M)
   // leauthaud11 kernel: mass bins = {centrals group, satellites group} over identical node masses
   // (-1: no such group), evaluated together (leauthaud11.cuh)
-  const int2* l11_bins;     // [n_l11_bins]
+  const L11Bin* l11_bins;   // [n_l11_bins]
   int n_l11_bins;
 };
 

@@ -127,9 +127,9 @@ __device__ __forceinline__ double exp_scaled(double y, const double* __restrict_
 template <int U>
 __device__ __forceinline__ void half_erfc_neg_group(double (&x)[U], const double* __restrict__ wt) {
   constexpr double kOffset = 14.0;   // column i is centred at -7 + i / 2
-#pragma unroll
-  for (int u = 0; u < U; u++) x[u] = fmin(fmax(x[u], -16.0), 16.0);
-  const double xm = 0.5 * (x[0] + x[U - 1]);
+  // only the midpoint is clamped here: arguments near a clamped midpoint pass the distance test
+  // below, all others (and NaN) take the per-argument path, which clamps each of them
+  const double xm = fmin(fmax(0.5 * (x[0] + x[U - 1]), -16.0), 16.0);
   const double v = fma(xm, 2.0, kOffset + kRoundMagic);
   const double xc = fma(v - kRoundMagic, 0.5, -0.5 * kOffset);
   const double* c = wt + (min(max(__double2loint(v), -1), kErfWPoly) + 1);
@@ -155,8 +155,9 @@ __device__ __forceinline__ void half_erfc_neg_group(double (&x)[U], const double
   } else {
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const double vu = fma(x[u], 2.0, kOffset + kRoundMagic);
-      const double tu = x[u] - fma(vu - kRoundMagic, 0.5, -0.5 * kOffset);   // in [-0.25, 0.25]
+      const double xu = fmin(fmax(x[u], -16.0), 16.0);
+      const double vu = fma(xu, 2.0, kOffset + kRoundMagic);
+      const double tu = xu - fma(vu - kRoundMagic, 0.5, -0.5 * kOffset);   // in [-0.25, 0.25]
       const double* cu = wt + (min(max(__double2loint(vu), -1), kErfWPoly) + 1);
       double q = cu[kErfWDeg * kErfWStride];
 #pragma unroll

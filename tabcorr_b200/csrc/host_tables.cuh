@@ -605,7 +605,33 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
   {
     // mass bins of the leauthaud11 kernel: every centrals group with the (first unused) satellites
     // group over the same mass range -- the same nodes -- then the unpaired satellites groups
-    std::vector<int2> l11_bins;
+    std::vector<L11Bin> l11_bins;
+    std::vector<int> pad_to_ref(n_pad, -1);
+    for (int i = 0; i < N; i++) pad_to_ref[L.row_to_pad[i]] = i;
+    auto same_weights = [&](int q, int s) {   // row by row the same normalised weights
+      for (int k = 0; k < kGroupRows; k++) {
+        const int a = grp_rows[(size_t)q * kGroupRows + k], b = grp_rows[(size_t)s * kGroupRows + k];
+        if ((a < 0) != (b < 0)) return false;
+        if (a >= 0 && std::memcmp(&row_c[(size_t)a * GP], &row_c[(size_t)b * GP], sizeof(double) * GP))
+          return false;
+      }
+      return true;
+    };
+    auto make_bin = [&](int q, int s) {
+      L11Bin bin{};
+      bin.cen = q;
+      bin.sat = s;
+      bin.same_w = q >= 0 && s >= 0 && same_weights(q, s) ? 1 : 0;
+      for (int k = 0; k < 4; k++) {
+        const int grp = k < 2 ? q : s;
+        const int row = grp >= 0 ? grp_rows[(size_t)grp * kGroupRows + (k & 1)] : -1;
+        bin.row[k] = row;
+        bin.dst[k] = row >= 0 ? pad_to_ref[row] : -1;
+        bin.pct[k] = row >= 0 ? row_pct[row] : 0.0;
+      }
+      bin.first_logm = node_logm[(size_t)(q >= 0 ? q : s) * GP];
+      return bin;
+    };
     std::vector<char> used(n_groups, 0);
     for (int q = 0; q < n_groups; q++) {
       if (groups[q].sat) continue;
@@ -614,11 +640,11 @@ int build_plan(tc_table* t, int separate, int n_gauss) {
         if (groups[s].sat && !used[s] && groups[s].lo == groups[q].lo && groups[s].hi == groups[q].hi)
           mate = s;
       if (mate >= 0) used[mate] = 1;
-      l11_bins.push_back(make_int2(q, mate));
+      l11_bins.push_back(make_bin(q, mate));
     }
     for (int s = 0; s < n_groups; s++)
-      if (groups[s].sat && !used[s]) l11_bins.push_back(make_int2(-1, s));
-    int2* d_bins;
+      if (groups[s].sat && !used[s]) l11_bins.push_back(make_bin(-1, s));
+    L11Bin* d_bins;
     if ((rc = upload(l11_bins, &d_bins))) return rc;
     ph.allocations.push_back(d_bins);
     ph.dev.l11_bins = d_bins;

@@ -227,23 +227,22 @@ __device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
 // and the Heaviside decoration are those of occupation_group (occupation.cuh).
 template <int U, bool DECORATED>
 __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __restrict__ d,
-                                        const double* __restrict__ sk,
-                                        const double* __restrict__ tab, int cen, int sat,
+                                        const double* __restrict__ tab,
+                                        const L11Bin* __restrict__ bin_ptr,
                                         double* __restrict__ out) {
   const OccPlan& plan = args.plan;
   const int G = plan.n_gauss_pad;
+  const L11Bin bin = *bin_ptr;
+  const int cen = bin.cen, sat = bin.sat;
   const int lead = cen >= 0 ? cen : sat;
   const double* __restrict__ node = plan.node_logm + (size_t)lead * G;
   const double* __restrict__ node_inv = plan.node_inv_m + (size_t)lead * G;
-  const bool has_cen = cen >= 0, has_sat = sat >= 0;
+  const bool has_cen = cen >= 0, has_sat = sat >= 0, same_w = bin.same_w != 0;
   const bool modulate = args.model.modulate_with_cenocc != 0;
-  int rows[4] = {-1, -1, -1, -1};
-  if (has_cen) { rows[0] = plan.grp_rows[cen * kGroupRows]; rows[1] = plan.grp_rows[cen * kGroupRows + 1]; }
-  if (has_sat) { rows[2] = plan.grp_rows[sat * kGroupRows]; rows[3] = plan.grp_rows[sat * kGroupRows + 1]; }
-  const double* __restrict__ w0 = plan.row_c + (size_t)(rows[0] >= 0 ? rows[0] : plan.zero_row) * G;
-  const double* __restrict__ w1 = plan.row_c + (size_t)(rows[1] >= 0 ? rows[1] : plan.zero_row) * G;
-  const double* __restrict__ w2 = plan.row_c + (size_t)(rows[2] >= 0 ? rows[2] : plan.zero_row) * G;
-  const double* __restrict__ w3 = plan.row_c + (size_t)(rows[3] >= 0 ? rows[3] : plan.zero_row) * G;
+  const double* __restrict__ w0 = plan.row_c + (size_t)(bin.row[0] >= 0 ? bin.row[0] : plan.zero_row) * G;
+  const double* __restrict__ w1 = plan.row_c + (size_t)(bin.row[1] >= 0 ? bin.row[1] : plan.zero_row) * G;
+  const double* __restrict__ w2 = plan.row_c + (size_t)(bin.row[2] >= 0 ? bin.row[2] : plan.zero_row) * G;
+  const double* __restrict__ w3 = plan.row_c + (size_t)(bin.row[3] >= 0 ? bin.row[3] : plan.zero_row) * G;
   double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0, ratio = 0.0;
   bool split_ok = false;
   if (DECORATED) {
@@ -251,17 +250,17 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
     split_ok = split > 0.0 && split < 1.0;
     ratio = split / (1.0 - split);
     const double down = -(1.0 - split) / split;
-    k0 = (rows[0] >= 0 && plan.row_pct[rows[0]] > split) ? 1.0 : down;
-    k1 = (rows[1] >= 0 && plan.row_pct[rows[1]] > split) ? 1.0 : down;
-    k2 = (rows[2] >= 0 && plan.row_pct[rows[2]] > split) ? 1.0 : down;
-    k3 = (rows[3] >= 0 && plan.row_pct[rows[3]] > split) ? 1.0 : down;
+    k0 = (bin.row[0] >= 0 && bin.pct[0] > split) ? 1.0 : down;
+    k1 = (bin.row[1] >= 0 && bin.pct[1] > split) ? 1.0 : down;
+    k2 = (bin.row[2] >= 0 && bin.pct[2] > split) ? 1.0 : down;
+    k3 = (bin.row[3] >= 0 && bin.pct[3] > split) ? 1.0 : down;
   }
   // knot interval of the first node (7-step binary search); the nodes of a bin ascend from it and
   // a bin spans few knots: per node three branch-free steps against the cached abscissae, then
   // (rarely) a linear walk
   int hint = 0;   // largest knot index in [0, kL11Knots - 2] with x_i <= node[0] (0 if none)
   {
-    const double first = node[0];
+    const double first = bin.first_logm;
 #pragma unroll
     for (int step = 64; step >= 1; step >>= 1) {
       const int j = hint + step;
@@ -304,16 +303,19 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
       e[u] = (s - threshold) * inv_scatter;
     }
     half_erfc_neg_group<U>(e, tab);
+    double wa[U], wb[U];   // weights of the centrals rows (the satellites rows' too if same_w)
     if (has_cen) {
 #pragma unroll
       for (int u = 0; u < U; u++) {
+        wa[u] = w0[g + u];
+        wb[u] = w1[g + u];
         if (DECORATED) {
           const double dl = assembias_delta(e[u], a_cen, ratio, 1.0, split_ok);
-          acc0 = fma(w0[g + u], fma(k0, dl, e[u]), acc0);
-          acc1 = fma(w1[g + u], fma(k1, dl, e[u]), acc1);
+          acc0 = fma(wa[u], fma(k0, dl, e[u]), acc0);
+          acc1 = fma(wb[u], fma(k1, dl, e[u]), acc1);
         } else {
-          acc0 = fma(w0[g + u], e[u], acc0);
-          acc1 = fma(w1[g + u], e[u], acc1);
+          acc0 = fma(wa[u], e[u], acc0);
+          acc1 = fma(wb[u], e[u], acc1);
         }
       }
     }
@@ -322,18 +324,21 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
 #pragma unroll
       for (int u = 0; u < U; u++) {
         // exp(-M_cut / (M h)) (M h / M_sat)^alphasat = exp(alphasat (ln M + ln(h / M_sat)) - M_cut / (M h))
-        const double y = fma(alphasat, fma(logm[u], kLn10, ln_h_over_msat), neg_mcut_h * node_inv[g + u]);
-        f[u] = exp_scaled_with(fmin(fmax(y, -800.0), 800.0), tab + kErfWDoubles) * (modulate ? e[u] : 1.0);
+        double y = fma(alphasat, fma(logm[u], kLn10, ln_h_over_msat), neg_mcut_h * node_inv[g + u]);
+        y = y < -800.0 ? -800.0 : y;   // (plain selects: NaN parameters are reported through `bad`)
+        y = y > 800.0 ? 800.0 : y;
+        f[u] = exp_scaled_with(y, tab + kErfWDoubles) * (modulate ? e[u] : 1.0);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
+        const double wc = same_w ? wa[u] : w2[g + u], wd = same_w ? wb[u] : w3[g + u];
         if (DECORATED) {
           const double dl = assembias_delta(f[u], a_sat, ratio, CUDART_INF, split_ok);
-          acc2 = fma(w2[g + u], fma(k2, dl, f[u]), acc2);
-          acc3 = fma(w3[g + u], fma(k3, dl, f[u]), acc3);
+          acc2 = fma(wc, fma(k2, dl, f[u]), acc2);
+          acc3 = fma(wd, fma(k3, dl, f[u]), acc3);
         } else {
-          acc2 = fma(w2[g + u], f[u], acc2);
-          acc3 = fma(w3[g + u], f[u], acc3);
+          acc2 = fma(wc, f[u], acc2);
+          acc3 = fma(wd, f[u], acc3);
         }
       }
     }
@@ -341,11 +346,8 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
   const double bad = d->bad;   // NaN: table not increasing, or a parameter that is not finite
   const double acc[4] = {acc0, acc1, acc2, acc3};
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    if (rows[r] < 0) continue;
-    const int dst = args.pad_to_row[rows[r]];
-    if (dst >= 0) out[dst] = acc[r] + bad;
-  }
+  for (int r = 0; r < 4; r++)
+    if (bin.dst[r] >= 0) out[bin.dst[r]] = acc[r] + bad;
 }
 
 __global__ void __launch_bounds__(kL11Threads, kL11MinBlocks)
@@ -371,18 +373,18 @@ occupation_l11_kernel(const OccArgs args) {
       const int sub = unit / n_quads, quad = unit - sub * n_quads;
       const int b = sub * 8 + (lane & 7), bin = quad * 4 + (lane >> 3);
       if (b >= n_block || bin >= n_bins) continue;
-      const int2 pair = args.plan.l11_bins[bin];
+      const L11Bin* bin_ptr = args.plan.l11_bins + bin;
       double* out = args.occ_out + (draw0 + b) * args.n_rows;
       if (args.model.decorated) {
         if (args.plan.unroll == kOccUnroll)
-          l11_bin<kOccUnroll, true>(args, draws + b, sk, tab, pair.x, pair.y, out);
+          l11_bin<kOccUnroll, true>(args, draws + b, tab, bin_ptr, out);
         else
-          l11_bin<2, true>(args, draws + b, sk, tab, pair.x, pair.y, out);
+          l11_bin<2, true>(args, draws + b, tab, bin_ptr, out);
       } else {
         if (args.plan.unroll == kOccUnroll)
-          l11_bin<kOccUnroll, false>(args, draws + b, sk, tab, pair.x, pair.y, out);
+          l11_bin<kOccUnroll, false>(args, draws + b, tab, bin_ptr, out);
         else
-          l11_bin<2, false>(args, draws + b, sk, tab, pair.x, pair.y, out);
+          l11_bin<2, false>(args, draws + b, tab, bin_ptr, out);
       }
     }
   }

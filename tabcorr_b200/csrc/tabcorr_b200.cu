@@ -196,9 +196,11 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
       if (!configured[t->device]) {
         TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // just enough shared memory for the resident CTAs: what is left is L1 for the plan arrays
+        const int carveout = (int)std::min<size_t>(
+            100, (kL11MinBlocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
         TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
-                                     cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
         configured[t->device] = true;
       }
     }

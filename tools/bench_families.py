@@ -21,6 +21,7 @@ def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--draws', type=int, default=100000)
     parser.add_argument('--reps', type=int, default=10)
+    parser.add_argument('--only', default=None, help='substring of the family name')
     args = parser.parse_args()
     import torch
     import tabcorr_b200
@@ -59,6 +60,8 @@ def main():
          synthetic.make_draws_leauthaud11(args.draws, seed=1, decorated=True)),
     ]
     for name, spec, draws in cases:
+        if args.only and args.only not in name:
+            continue
         theta = torch.from_numpy(theta_from_params(draws, None, spec)).cuda()
         t_predict = timed(lambda: group.predict_into(spec, 10, theta, None, False, ngal, 0, xi, 0))
         t_occ = timed(lambda: group.occupation(spec, 10, theta))
