@@ -245,6 +245,24 @@ def run_configs(args, world, rank, local_rank, lib, peak_dmma):
         out.append({'config': 'cfg3 N=240 R=3x14 multipoles, decorated zheng07, G=10',
                     'n_draws': n_draws, 'ms': ms, 'preds_per_s': n_draws / ms * 1e3,
                     'executed_frac': frac(240, 42, 'auto', ms, n_draws)})
+        # ---- the other occupation family on the headline table -----------------
+        from tabcorr_b200 import models
+        tab2 = synthetic.make_table(n_mass=N_MASS, n_sec=N_SEC, n_r=N_R)
+        halotab2 = table_of(tab2)
+        for name, dec in (('leauthaud11', False), ('hearin15', True)):
+            spec = ModelSpec(models.FAMILY_LEAUTHAUD11, dec, True, 0.5, 10.5, 0.0)
+            theta = torch.from_numpy(theta_from_params(
+                synthetic.make_draws_leauthaud11(n_draws, seed=1, decorated=dec), None,
+                spec)).cuda()
+            ms = timed(lambda: halotab2.predict_batch(theta, model=spec, as_numpy=False,
+                                                      n_gauss_prim=N_GAUSS))
+            ms_occ = timed(lambda: halotab2.mean_occupation_batch(theta, n_gauss_prim=N_GAUSS,
+                                                                  model=spec))
+            out.append({'config': 'cfg2 table (N=240, R=20, G=10), {}: occupation kernel -> '
+                                  'contraction'.format(name),
+                        'n_draws': n_draws, 'ms': ms, 'preds_per_s': n_draws / ms * 1e3,
+                        'occupation_kernel_ms': ms_occ,
+                        'executed_frac': frac(2 * N_MASS * N_SEC, N_R, 'auto', ms, n_draws)})
         # ---- cfg4: database-style Interpolator, per-draw cosmology ----------------------------
         axes = {'alpha_s': np.linspace(0.8, 1.2, 4), 'log_eta': np.log10(np.geomspace(1 / 3, 3, 4))}
         interps = []
