@@ -272,3 +272,59 @@ def test_mass_dependent_assembias_against_oracle(tb, orc, mode):
     ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, oracle_model))
     close(ngal1, ngal_ref)
     close(xi1, xi_ref)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_ragged_shuffled_tables(tb, orc, seed):
+    """The mass bins of the leauthaud11 kernel pair the centrals group and the satellites group
+    over the same node masses: tables with (mass, secondary) cells dropped at random and rows in
+    random order leave bins with one galaxy type only, groups with a single row and pairs whose
+    rows carry different weights.  Random n_gauss_prim (incl. values the five-node unrolling does
+    not divide), batch sizes around the 32-draw blocks, legacy tables, all model variants."""
+    rng = np.random.default_rng(500 + seed)
+    n_mass, n_sec = int(rng.integers(3, 40)), int(rng.integers(1, 4))
+    tab = tb.synthetic.make_table(n_mass=n_mass, n_sec=n_sec, n_r=3, mode='cross', seed=seed)
+    gal_type = tab['gal_type']
+    keep = np.flatnonzero(rng.random(len(gal_type)) > 0.25)
+    if len(keep) < 2:
+        keep = np.arange(len(gal_type))
+    keep = rng.permutation(keep)
+    gal_type, matrix = gal_type[keep], tab['tpcf_matrix'][:, keep]
+    if rng.random() < 0.3:   # legacy table without the mass-function slope column
+        names = [k for k in gal_type.dtype.names if k != 'prim_haloprop_dist_index']
+        legacy = np.zeros(len(gal_type), dtype=[(k, gal_type.dtype[k]) for k in names])
+        for k in names:
+            legacy[k] = gal_type[k]
+        gal_type = legacy
+    kw = VARIANTS[seed % len(VARIANTS)]
+    n_gauss = int(rng.choice([1, 2, 3, 5, 7, 10, 12]))
+    n_draws = int(rng.choice([1, 7, 31, 32, 33, 65, 100]))
+    draws = tb.synthetic.make_draws_leauthaud11(n_draws, seed=seed, decorated=kw['decorated'])
+    spec = tb.models.ModelSpec(tb.models.FAMILY_LEAUTHAUD11, kw['decorated'],
+                               kw['modulate_with_cenocc'], kw.get('split', 0.5),
+                               kw['threshold'], kw['redshift'])
+    halotab = tb.TabCorr.from_arrays(gal_type, matrix, tab['tpcf_shape'], tab['attrs'])
+    table = orc.OracleTable(gal_type, matrix, tab['tpcf_shape'], 'cross')
+    occ = halotab.mean_occupation_batch(draws, n_gauss_prim=n_gauss, model=spec).cpu().numpy()
+    assert occ.shape == (n_draws, len(gal_type))
+    for i in sorted(set([0, n_draws // 2, n_draws - 1])):
+        model = orc.Leauthaud11Oracle(cases.draws_row(draws, i), **kw)
+        ref = orc.mean_occupation(table, model, n_gauss)
+        np.testing.assert_allclose(occ[i], ref, rtol=5e-11, atol=5e-11 * max(1.0, ref.max()))
+
+
+def test_not_finite_parameters_give_nan(tb, orc):
+    """A parameter that is not finite, or a stellar-to-halo-mass table that is not increasing
+    (halotools raises there), makes every occupation of that draw NaN and leaves the others."""
+    halotab, _ = table_pair(tb, orc, 'syn36x3')
+    draws = tb.synthetic.make_draws_leauthaud11(40, seed=3)
+    spec = tb.models.ModelSpec(tb.models.FAMILY_LEAUTHAUD11, False, True, 0.5, 10.5, 0.0)
+    clean = halotab.mean_occupation_batch(draws, model=spec).cpu().numpy()
+    assert np.all(np.isfinite(clean))
+    bad = {k: np.array(v, dtype=np.float64, copy=True) for k, v in draws.items()}
+    bad['scatter_model_param1'][5] = np.nan
+    bad['smhm_beta_0'][17] = -3.0      # decreasing relation: the spline table is not monotonic
+    occ = halotab.mean_occupation_batch(bad, model=spec).cpu().numpy()
+    assert np.all(np.isnan(occ[5])) and np.all(np.isnan(occ[17]))
+    rest = np.setdiff1d(np.arange(40), [5, 17])
+    assert np.array_equal(occ[rest], clean[rest])
