@@ -46,6 +46,11 @@ constexpr int kL11Knots = 100;
 constexpr int kL11Threads = TC_L11_THREADS;
 constexpr int kL11DrawsPerBlock = TC_L11_DRAWS;
 constexpr int kL11MinBlocks = TC_L11_MIN_BLOCKS;
+#ifndef TC_L11_LANE_BINS
+#define TC_L11_LANE_BINS 4
+#endif
+constexpr int kL11LaneBins = TC_L11_LANE_BINS;        // mass bins per warp iteration (power of two)
+constexpr int kL11LaneDraws = 32 / kL11LaneBins;      // draws per warp iteration
 constexpr double kL11LittleH = 0.7;        // Behroozi10SmHm.littleh
 constexpr double kL11LittleHSats = 0.72;   // Leauthaud11Sats.littleh
 constexpr double kL11LogMsLo = 8.5, kL11LogMsHi = 12.5;
@@ -360,18 +365,21 @@ occupation_l11_kernel(const OccArgs args) {
   for (int k = threadIdx.x; k < kL11Knots; k += blockDim.x) sk[k] = l11_knot_logms(k);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long n_blocks = (args.n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;
-  const int n_bins = args.plan.n_l11_bins, n_quads = (n_bins + 3) >> 2;
+  const int n_bins = args.plan.n_l11_bins, n_quads = (n_bins + kL11LaneBins - 1) / kL11LaneBins;
   for (long long block = blockIdx.x; block < n_blocks; block += gridDim.x) {
     const long long draw0 = block * kL11DrawsPerBlock;
     const int n_block = (int)min((long long)kL11DrawsPerBlock, args.n_draws - draw0);
     __syncthreads();   // the previous block's tables are no longer read; tab and sk are filled
     l11_prepare_block(draws, sk, tab, n_block, draw0, args.n_draws, args.theta, args.theta_ds,
                       args.theta_ps, args.model);
-    // one warp per unit = 8 draws (lane & 7) x 4 mass bins (lane >> 3)
-    const int n_units = ((n_block + 7) >> 3) * n_quads;
+    // one warp per unit = kL11LaneDraws draws x kL11LaneBins consecutive mass bins; the lanes of a
+    // draw are adjacent (neighbouring bins of one draw read the same or neighbouring knots and
+    // erf columns: fewer shared-memory wavefronts than with the draws adjacent)
+    const int n_units = ((n_block + kL11LaneDraws - 1) / kL11LaneDraws) * n_quads;
     for (int unit = warp; unit < n_units; unit += n_warps) {
       const int sub = unit / n_quads, quad = unit - sub * n_quads;
-      const int b = sub * 8 + (lane & 7), bin = quad * 4 + (lane >> 3);
+      const int b = sub * kL11LaneDraws + lane / kL11LaneBins;
+      const int bin = quad * kL11LaneBins + (lane & (kL11LaneBins - 1));
       if (b >= n_block || bin >= n_bins) continue;
       const L11Bin* bin_ptr = args.plan.l11_bins + bin;
       double* out = args.occ_out + (draw0 + b) * args.n_rows;
