@@ -157,41 +157,54 @@ __device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
     if (!(h > 0.0)) draws[b].bad = CUDART_NAN;
   }
   __syncthreads();
-  // (3) HALVED second derivatives c2_k = m_k / 2 of the not-a-knot spline s(x): one lane per draw
-  // (Thomas).  Interior equations h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} =
-  // 6 (d_i - d_{i-1}), d_i = (s_{i+1} - s_i) / h_i, with m_0 and m_{n-1} eliminated through the
-  // continuity of the third derivative at knots 1 and n - 2; the right-hand side is halved, so
-  // the solution is exactly m / 2.  Scratch: knot[i].z = modified upper diagonal, knot[i].w =
-  // modified right-hand side, then c2_i.  The recurrences are latency bound (one reciprocal per
-  // step on the critical path); the other CTA of the SM works meanwhile.
-  for (int b = threadIdx.x; b < n_block; b += blockDim.x) {
-    L11Draw& D = draws[b];
+  // (3) HALVED second derivatives c2_k = m_k / 2 of the not-a-knot spline s(x).  Interior equations
+  // h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 (d_i - d_{i-1}), d_i = (s_{i+1} -
+  // s_i) / h_i, with m_0 and m_{n-1} eliminated through the continuity of the third derivative at
+  // knots 1 and n - 2; the right-hand side is halved, so the solution is exactly m / 2.
+  // The recurrences are latency bound (one lane per draw, one reciprocal per row on the critical
+  // path) and the rest of the CTA waits for them, so the system is eliminated FROM BOTH ENDS
+  // (twisted factorisation): warp 0 runs the Thomas elimination down rows 1 .. kMid, warp 1 its
+  // mirror image up rows n - 2 .. kMid + 1; the two meet in a 2 x 2 system for rows kMid and
+  // kMid + 1 and substitute outwards.  Half the sequential length of a one-sided solve.
+  // Scratch: knot[i].z = modified off-diagonal, knot[i].w = modified right-hand side, then c2_i.
+  constexpr int kMid = (n - 2) / 2;
+  static_assert(kL11DrawsPerBlock <= 32 && kL11Threads >= 64, "one lane per draw, two warps");
+  const int solver_warp = threadIdx.x >> 5, b_lane = threadIdx.x & 31;
+  const bool solving = solver_warp < 2 && b_lane < n_block;
+  auto row = [&](int i, double h_prev, double h, double ih_prev, double ih, double& lower,
+                 double& diag, double& upper) {
+    lower = h_prev;
+    diag = 2.0 * (h_prev + h);
+    upper = h;
+    if (i == 1) {
+      const double e = h_prev * h_prev * ih;
+      lower = 0.0;
+      diag = 3.0 * h_prev + 2.0 * h + e;
+      upper = h - e;
+    }
+    if (i == n - 2) {
+      const double e = h * h * ih_prev;
+      lower = h_prev - e;
+      diag = 2.0 * h_prev + 3.0 * h + e;
+      upper = 0.0;
+    }
+  };
+  if (solving && solver_warp == 0) {
+    L11Draw& D = draws[b_lane];
     double x_cur = D.knot[1].x;
-    double h_prev = x_cur - D.knot[0].x;                    // h_0
-    double ih_prev = D.knot[0].y;
+    double h_prev = x_cur - D.knot[0].x, ih_prev = D.knot[0].y;   // h_0, 1 / h_0
     double d_prev = (sk[1] - sk[0]) * ih_prev;
-    double cp = 0.0, rp = 0.0;                              // c'_{i-1}, r'_{i-1}
-    for (int i = 1; i <= n - 2; i++) {
+    double cp = 0.0, rp = 0.0;                                    // c'_{i-1}, r'_{i-1}
+#pragma unroll 2
+    for (int i = 1; i <= kMid; i++) {
       const double x_next = D.knot[i + 1].x;
-      const double h = x_next - x_cur, ih = D.knot[i].y;    // h_i, 1 / h_i
+      const double h = x_next - x_cur, ih = D.knot[i].y;          // h_i, 1 / h_i
       const double d = (sk[i + 1] - sk[i]) * ih;
-      double lower = h_prev, diag = 2.0 * (h_prev + h), upper = h;
-      if (i == 1) {
-        const double e = h_prev * h_prev * ih;
-        lower = 0.0;
-        diag = 3.0 * h_prev + 2.0 * h + e;
-        upper = h - e;
-      }
-      if (i == n - 2) {
-        const double e = h * h * ih_prev;
-        lower = h_prev - e;
-        diag = 2.0 * h_prev + 3.0 * h + e;
-        upper = 0.0;
-      }
-      const double rhs = 3.0 * (d - d_prev);
+      double lower, diag, upper;
+      row(i, h_prev, h, ih_prev, ih, lower, diag, upper);
       const double inv = 1.0 / (diag - lower * cp);
       cp = upper * inv;
-      rp = (rhs - lower * rp) * inv;
+      rp = (3.0 * (d - d_prev) - lower * rp) * inv;
       D.knot[i].z = cp;
       D.knot[i].w = rp;
       x_cur = x_next;
@@ -199,14 +212,60 @@ __device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
       ih_prev = ih;
       d_prev = d;
     }
-    double m_next = 0.0;
-    for (int i = n - 2; i >= 1; i--) {
+  } else if (solving) {
+    L11Draw& D = draws[b_lane];
+    double x_cur = D.knot[n - 2].x;
+    double h = D.knot[n - 1].x - x_cur, ih = D.knot[n - 2].y;     // h_{n-2}, 1 / h_{n-2}
+    double d = (sk[n - 1] - sk[n - 2]) * ih;
+    double bq = 0.0, br = 0.0;                                    // mirrored c'_{i+1}, r'_{i+1}
+#pragma unroll 2
+    for (int i = n - 2; i >= kMid + 1; i--) {
+      const double x_before = D.knot[i - 1].x;
+      const double h_prev = x_cur - x_before, ih_prev = D.knot[i - 1].y;   // h_{i-1}, 1 / h_{i-1}
+      const double d_prev = (sk[i] - sk[i - 1]) * ih_prev;
+      double lower, diag, upper;
+      row(i, h_prev, h, ih_prev, ih, lower, diag, upper);
+      const double inv = 1.0 / (diag - upper * bq);
+      bq = lower * inv;
+      br = (3.0 * (d - d_prev) - upper * br) * inv;
+      D.knot[i].z = bq;
+      D.knot[i].w = br;
+      x_cur = x_before;
+      h = h_prev;
+      ih = ih_prev;
+      d = d_prev;
+    }
+  }
+  __syncthreads();
+  double c2_mid = 0.0, c2_mid1 = 0.0;   // rows kMid and kMid + 1: x_k + c' x_{k+1} = r', q x_k + x_{k+1} = r
+  if (solving) {
+    const L11Draw& D = draws[b_lane];
+    const double cp = D.knot[kMid].z, rp = D.knot[kMid].w;
+    const double bq = D.knot[kMid + 1].z, br = D.knot[kMid + 1].w;
+    c2_mid1 = (br - bq * rp) / (1.0 - bq * cp);
+    c2_mid = rp - cp * c2_mid1;
+  }
+  __syncthreads();   // both warps have read the four values before either overwrites its own
+  if (solving && solver_warp == 0) {
+    L11Draw& D = draws[b_lane];
+    D.knot[kMid].w = c2_mid;
+    double m_next = c2_mid;
+    for (int i = kMid - 1; i >= 1; i--) {
       const double m = D.knot[i].w - D.knot[i].z * m_next;
       D.knot[i].w = m;
       m_next = m;
     }
     const double h0 = D.knot[1].x - D.knot[0].x;
     D.knot[0].w = D.knot[1].w - h0 * D.knot[1].y * (D.knot[2].w - D.knot[1].w);
+  } else if (solving) {
+    L11Draw& D = draws[b_lane];
+    D.knot[kMid + 1].w = c2_mid1;
+    double m_prev = c2_mid1;
+    for (int i = kMid + 2; i <= n - 2; i++) {
+      const double m = D.knot[i].w - D.knot[i].z * m_prev;
+      D.knot[i].w = m;
+      m_prev = m;
+    }
     const double ha = D.knot[n - 1].x - D.knot[n - 2].x;
     D.knot[n - 1].w =
         D.knot[n - 2].w + ha * D.knot[n - 3].y * (D.knot[n - 2].w - D.knot[n - 3].w);
