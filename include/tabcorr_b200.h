@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 107
+#define TC_VERSION 108
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -50,12 +50,14 @@ extern "C" {
  *       smhm_beta_a, smhm_delta_0, smhm_delta_a, smhm_gamma_0, smhm_gamma_a, scatter_model_param1,
  *       alphasat, bsat, bcut, betacut, betasat, A_cen, A_sat
  * (halotools param_dict names; A_cen / A_sat are the mean_occupation_{centrals,satellites}_
- * assembias_param1 strengths, ignored unless decorated). */
+ * assembias_param1 strengths, ignored unless decorated).  With a mass-dependent strength
+ * (tc_model.n_strength > 1) a family's base parameters (5 / 16) are followed by the n_strength[0]
+ * ordinates of the centrals and the n_strength[1] ordinates of the satellites. */
 #define TC_FAMILY_ZHENG07 0
 #define TC_FAMILY_LEAUTHAUD11 1
 #define TC_N_THETA 7              /* zheng07 */
 #define TC_N_THETA_LEAUTHAUD11 18
-#define TC_N_THETA_MAX 18
+#define TC_N_THETA_MAX 24             /* leauthaud11 with 4 + 4 strength ordinates */
 #define TC_N_THETA_ZHENG07_BASE 5   /* logMmin .. alpha; the strengths follow */
 
 typedef struct tc_table tc_table;   /* device-resident table group (one gal_type, >=1 matrices) */

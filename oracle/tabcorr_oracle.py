@@ -193,18 +193,24 @@ class Leauthaud11Oracle(Zheng07Oracle):
                     alphasat=1.0, bsat=10.62, bcut=1.47, betacut=-0.13, betasat=0.859)
 
     def __init__(self, param_dict=None, threshold=10.5, redshift=0.0, decorated=False, split=0.5,
-                 modulate_with_cenocc=True):
+                 modulate_with_cenocc=True, strength_abscissa=((), ()), split_abscissa=((), ()),
+                 split_ordinates=((), ())):
         self.param_dict = dict(self.DEFAULTS)
         if decorated:
-            self.param_dict['mean_occupation_centrals_assembias_param1'] = 0.5
-            self.param_dict['mean_occupation_satellites_assembias_param1'] = 0.5
+            for t, gal_type in enumerate(('centrals', 'satellites')):
+                for k in range(max(1, len(strength_abscissa[t]))):
+                    self.param_dict['mean_occupation_{}_assembias_param{}'.format(
+                        gal_type, k + 1)] = 0.5
         if param_dict is not None:
             self.param_dict.update(param_dict)
         self.threshold = threshold
         self.redshift = redshift
         self.decorated = decorated
         self.split = split
-        self.strength_abscissa = self.split_abscissa = self.split_ordinates = ((), ())
+        # mass-dependent decoration: HeavisideAssembias keywords, see Zheng07Oracle
+        self.strength_abscissa = strength_abscissa
+        self.split_abscissa = split_abscissa
+        self.split_ordinates = split_ordinates
         self.modulate_with_cenocc = modulate_with_cenocc
 
     def mean_log_halo_mass(self, log_stellar_mass):

@@ -56,6 +56,13 @@ constexpr double kL11LittleHSats = 0.72;   // Leauthaud11Sats.littleh
 constexpr double kL11LogMsLo = 8.5, kL11LogMsHi = 12.5;
 constexpr double kLn10 = 2.302585092994045684;
 
+// doubles per draw: the 16 occupation parameters, then the assembly-bias strength ordinates of the
+// centrals and of the satellites (one each unless the strength depends on mass)
+constexpr int kL11Base = 16;
+__device__ __host__ __forceinline__ int l11_n_theta(const tc_model& m) {
+  return kL11Base + zheng07_strength_count(m, 0) + zheng07_strength_count(m, 1);
+}
+
 struct L11Draw {
   // knot k: x = log10 M_h of the knot; y, z, w = c1, c3, c2 of the cubic on [knot k, knot k + 1):
   // log10 M* = s_k + t (c1 + t (c2 + t c3)), t = log10 M - x
@@ -70,9 +77,15 @@ struct L11Draw {
                           // falls into 8 different 16-byte bank groups
 };
 static_assert(sizeof(L11Draw) % 128 == 80, "L11Draw stride chosen against bank conflicts");
-constexpr size_t kL11SmemBytes =
-    (kL11TabDoubles + kL11Knots) * sizeof(double) + kL11DrawsPerBlock * sizeof(L11Draw);
-static_assert(kL11MinBlocks * (kL11SmemBytes + 1024) <= 228 * 1024, "CTAs per SM vs shared memory");
+// (MASSDEP: + the strength ordinates of a mass-dependent decoration, 2 x TC_MAX_KNOTS doubles per
+// draw)
+constexpr int kL11OrdDoubles = kL11DrawsPerBlock * 2 * TC_MAX_KNOTS;
+constexpr size_t l11_smem_bytes(bool massdep) {
+  return (kL11TabDoubles + kL11Knots + (massdep ? kL11OrdDoubles : 0)) * sizeof(double) +
+         kL11DrawsPerBlock * sizeof(L11Draw);
+}
+static_assert(kL11MinBlocks * (l11_smem_bytes(true) + 1024) <= 228 * 1024,
+              "CTAs per SM vs shared memory");
 
 __device__ __forceinline__ double l11_knot_logms(int k) {
   // numpy.linspace(8.5, 12.5, 100): arange(100) * step + start, last element set to stop
@@ -101,7 +114,9 @@ __device__ __forceinline__ double l11_log_halo_mass(double log_ms, double logm0,
 
 // Spline tables and per-draw constants of one block of draws, by the whole CTA.  `sk`: the knot
 // ordinates log10 M* (shared by all draws), `tab`: the math tables.
-__device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
+template <bool MASSDEP>
+__device__ __forceinline__ void l11_prepare_block(L11Draw* draws, double* __restrict__ ords,
+                                  const double* __restrict__ sk,
                                   const double* __restrict__ tab, int n_block, long long draw0,
                                   long long n_draws, const double* __restrict__ theta,
                                   long long theta_ds, long long theta_ps, const tc_model& model) {
@@ -132,12 +147,23 @@ __device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
     D.neg_mcut_h = -mcut / kL11LittleHSats;
     D.ln_h_over_msat = log(kL11LittleHSats / msat);
     D.alphasat = th[11 * theta_ps];
-    D.a_cen = model.decorated ? fmin(fmax(th[16 * theta_ps], -1.0), 1.0) : 0.0;
-    D.a_sat = model.decorated ? fmin(fmax(th[17 * theta_ps], -1.0), 1.0) : 0.0;
+    // strengths: ordinates [centrals 0..3 | satellites 0..3] (the first of each is the constant
+    // strength of the plain decoration; clipped per node when they depend on mass)
+    const int n_cen_ord = zheng07_strength_count(model, 0), n_sat_ord = zheng07_strength_count(model, 1);
+    if (MASSDEP) {
+      for (int k = 0; k < TC_MAX_KNOTS; k++) {
+        ords[b * 2 * TC_MAX_KNOTS + k] = k < n_cen_ord ? th[(kL11Base + k) * theta_ps] : 0.0;
+        ords[b * 2 * TC_MAX_KNOTS + TC_MAX_KNOTS + k] =
+            k < n_sat_ord ? th[(kL11Base + n_cen_ord + k) * theta_ps] : 0.0;
+      }
+    }
+    D.a_cen = model.decorated ? fmin(fmax(th[kL11Base * theta_ps], -1.0), 1.0) : 0.0;
+    D.a_sat = model.decorated ? fmin(fmax(th[(kL11Base + n_cen_ord) * theta_ps], -1.0), 1.0) : 0.0;
     // the erf argument is clamped below (NaN would be lost): a parameter that is not finite makes
     // every occupation of the draw NaN through `bad`
     double sum = 0.0;
-    for (int k = 0; k < (model.decorated ? 18 : 16); k++) sum += th[k * theta_ps];
+    for (int k = 0; k < (model.decorated ? l11_n_theta(model) : kL11Base); k++)
+      sum += th[k * theta_ps];
     D.bad = sum - sum;
   }
   __syncthreads();
@@ -285,12 +311,46 @@ __device__ void l11_prepare_block(L11Draw* draws, const double* __restrict__ sk,
   __syncthreads();
 }
 
+// Heaviside perturbation of one node when the strength and / or the split of galaxy type `type`
+// depend on mass (tc_model.n_strength / n_split): both are the interpolating polynomial of their
+// control points at log10 of the node mass, clipped to [-1, 1] / [0, 1].  Returns delta and the
+// factors of the two rows (+1 above the split percentile, -(1 - s) / s below).
+__device__ __forceinline__ double l11_massdep_delta(const tc_model& model, int type,
+                                                    const double* __restrict__ ord, double logm,
+                                                    double f, double hi, int row_a, int row_b,
+                                                    double pct_a, double pct_b, double& ka,
+                                                    double& kb) {
+  const int n_str = model.n_strength[type], n_split = model.n_split[type];
+  double strength = ord[0];
+  if (n_str > 1) {
+    double o[TC_MAX_KNOTS];
+#pragma unroll
+    for (int k = 0; k < TC_MAX_KNOTS; k++) o[k] = ord[k];
+    strength = lagrange_eval(n_str, model.strength_abscissa[type], o, logm);
+  }
+  strength = fmin(fmax(strength, -1.0), 1.0);
+  double split = model.split;
+  if (n_split > 0)
+    split = fmin(fmax(lagrange_eval(n_split, model.split_abscissa[type],
+                                    model.split_ordinates[type], logm), 0.0), 1.0);
+  const bool split_ok = split > 0.0 && split < 1.0;
+  const double ratio = split_ok ? split / (1.0 - split) : 0.0;
+  const double down = split_ok ? -(1.0 - split) / split : 0.0;
+  ka = (row_a >= 0 && pct_a > split) ? 1.0 : down;
+  kb = (row_b >= 0 && pct_b > split) ? 1.0 : down;
+  return assembias_delta(f, strength, ratio, hi, split_ok);
+}
+
 // One lane: one draw x one mass bin = the centrals group `cen` and / or the satellites group
 // `sat` over the same node masses (-1: absent).  The spline and the erf of a node serve both
 // galaxy types (Leauthaud11Sats is modulated by <N_cen> by default); the Gauss-Legendre weights
 // and the Heaviside decoration are those of occupation_group (occupation.cuh).
-template <int U, bool DECORATED>
+// DEC: 0 no decoration, 1 constant strength and split, 2 strength and / or split depend on mass
+// (evaluated per node at log10 of the node mass, like occupation_pair_nodes_massdep; `ords`: the
+// draw's strength ordinates).
+template <int U, int DEC>
 __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __restrict__ d,
+                                        const double* __restrict__ ords,
                                         const double* __restrict__ tab,
                                         const L11Bin* __restrict__ bin_ptr,
                                         double* __restrict__ out) {
@@ -307,6 +367,7 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
   const double* __restrict__ w1 = plan.row_c + (size_t)(bin.row[1] >= 0 ? bin.row[1] : plan.zero_row) * G;
   const double* __restrict__ w2 = plan.row_c + (size_t)(bin.row[2] >= 0 ? bin.row[2] : plan.zero_row) * G;
   const double* __restrict__ w3 = plan.row_c + (size_t)(bin.row[3] >= 0 ? bin.row[3] : plan.zero_row) * G;
+  constexpr bool DECORATED = DEC == 1;
   double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0, ratio = 0.0;
   bool split_ok = false;
   if (DECORATED) {
@@ -373,7 +434,13 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
       for (int u = 0; u < U; u++) {
         wa[u] = w0[g + u];
         wb[u] = w1[g + u];
-        if (DECORATED) {
+        if (DEC == 2) {
+          double ka, kb;
+          const double dl = l11_massdep_delta(args.model, 0, ords, logm[u], e[u], 1.0, bin.row[0],
+                                              bin.row[1], bin.pct[0], bin.pct[1], ka, kb);
+          acc0 = fma(wa[u], fma(ka, dl, e[u]), acc0);
+          acc1 = fma(wb[u], fma(kb, dl, e[u]), acc1);
+        } else if (DECORATED) {
           const double dl = assembias_delta(e[u], a_cen, ratio, 1.0, split_ok);
           acc0 = fma(wa[u], fma(k0, dl, e[u]), acc0);
           acc1 = fma(wb[u], fma(k1, dl, e[u]), acc1);
@@ -396,7 +463,14 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const double wc = same_w ? wa[u] : w2[g + u], wd = same_w ? wb[u] : w3[g + u];
-        if (DECORATED) {
+        if (DEC == 2) {
+          double ka, kb;
+          const double dl = l11_massdep_delta(args.model, 1, ords + TC_MAX_KNOTS, logm[u], f[u],
+                                              CUDART_INF, bin.row[2], bin.row[3], bin.pct[2],
+                                              bin.pct[3], ka, kb);
+          acc2 = fma(wc, fma(ka, dl, f[u]), acc2);
+          acc3 = fma(wd, fma(kb, dl, f[u]), acc3);
+        } else if (DECORATED) {
           const double dl = assembias_delta(f[u], a_sat, ratio, CUDART_INF, split_ok);
           acc2 = fma(wc, fma(k2, dl, f[u]), acc2);
           acc3 = fma(wd, fma(k3, dl, f[u]), acc3);
@@ -414,12 +488,16 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
     if (bin.dst[r] >= 0) out[bin.dst[r]] = acc[r] + bad;
 }
 
+// MASSDEP: the kernel of models whose assembly-bias strength / split depend on mass (a kernel of
+// its own, so that the plain models' kernel does not carry its code and shared memory).
+template <bool MASSDEP>
 __global__ void __launch_bounds__(kL11Threads, kL11MinBlocks)
 occupation_l11_kernel(const OccArgs args) {
   extern __shared__ __align__(16) double l11_smem[];
   double* tab = l11_smem;
   double* sk = l11_smem + kL11TabDoubles;
-  L11Draw* draws = reinterpret_cast<L11Draw*>(sk + kL11Knots);
+  double* ords = sk + kL11Knots;   // [draw][centrals ordinates | satellites ordinates]
+  L11Draw* draws = reinterpret_cast<L11Draw*>(ords + (MASSDEP ? kL11OrdDoubles : 0));
   for (int i = threadIdx.x; i < kL11TabDoubles; i += blockDim.x) tab[i] = g_l11_tables[i];
   for (int k = threadIdx.x; k < kL11Knots; k += blockDim.x) sk[k] = l11_knot_logms(k);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -429,7 +507,7 @@ occupation_l11_kernel(const OccArgs args) {
     const long long draw0 = block * kL11DrawsPerBlock;
     const int n_block = (int)min((long long)kL11DrawsPerBlock, args.n_draws - draw0);
     __syncthreads();   // the previous block's tables are no longer read; tab and sk are filled
-    l11_prepare_block(draws, sk, tab, n_block, draw0, args.n_draws, args.theta, args.theta_ds,
+    l11_prepare_block<MASSDEP>(draws, ords, sk, tab, n_block, draw0, args.n_draws, args.theta, args.theta_ds,
                       args.theta_ps, args.model);
     // one warp per unit = kL11LaneDraws draws x kL11LaneBins consecutive mass bins; the lanes of a
     // draw are adjacent (neighbouring bins of one draw read the same or neighbouring knots and
@@ -442,16 +520,19 @@ occupation_l11_kernel(const OccArgs args) {
       if (b >= n_block || bin >= n_bins) continue;
       const L11Bin* bin_ptr = args.plan.l11_bins + bin;
       double* out = args.occ_out + (draw0 + b) * args.n_rows;
-      if (args.model.decorated) {
+      const double* ord = ords + b * 2 * TC_MAX_KNOTS;
+      if (MASSDEP) {   // rare: one instantiation, a node at a time
+        l11_bin<1, 2>(args, draws + b, ord, tab, bin_ptr, out);
+      } else if (args.model.decorated) {
         if (args.plan.unroll == kOccUnroll)
-          l11_bin<kOccUnroll, true>(args, draws + b, tab, bin_ptr, out);
+          l11_bin<kOccUnroll, 1>(args, draws + b, ord, tab, bin_ptr, out);
         else
-          l11_bin<2, true>(args, draws + b, tab, bin_ptr, out);
+          l11_bin<2, 1>(args, draws + b, ord, tab, bin_ptr, out);
       } else {
         if (args.plan.unroll == kOccUnroll)
-          l11_bin<kOccUnroll, false>(args, draws + b, tab, bin_ptr, out);
+          l11_bin<kOccUnroll, 0>(args, draws + b, ord, tab, bin_ptr, out);
         else
-          l11_bin<2, false>(args, draws + b, tab, bin_ptr, out);
+          l11_bin<2, 0>(args, draws + b, ord, tab, bin_ptr, out);
       }
     }
   }

@@ -49,9 +49,6 @@ int check_model(const tc_model* model) {
     for (int k = 1; k < np; k++)
       if (!(model->split_abscissa[type][k] > model->split_abscissa[type][k - 1]))
         return fail(TC_EINVAL, "tc_model: split_abscissa must increase strictly");
-    if ((ns > 1 || np > 0) && model->family != TC_FAMILY_ZHENG07)
-      return fail(TC_EUNSUPPORTED, "tc_model: mass-dependent assembly bias is implemented for "
-                                   "TC_FAMILY_ZHENG07 only");
   }
   return TC_OK;
 }
@@ -78,7 +75,10 @@ int tc_model_n_theta(const tc_model* model) {
     int rc = check_model(model);
     return rc != TC_OK ? rc : zheng07_n_theta(*model);
   }
-  if (model->family == TC_FAMILY_LEAUTHAUD11) return TC_N_THETA_LEAUTHAUD11;
+  if (model->family == TC_FAMILY_LEAUTHAUD11) {
+    int rc = check_model(model);
+    return rc != TC_OK ? rc : l11_n_theta(*model);
+  }
   return fail(TC_EUNSUPPORTED, "tc_model_n_theta: unknown model family");
 }
 
@@ -168,7 +168,7 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
   int n_sm = 0;
   if ((rc = device_sms(t->device, &n_sm))) return rc;
   if ((rc = check_model(model))) return rc;
-  const int n_theta = model->family == TC_FAMILY_LEAUTHAUD11 ? TC_N_THETA_LEAUTHAUD11
+  const int n_theta = model->family == TC_FAMILY_LEAUTHAUD11 ? l11_n_theta(*model)
                                                               : zheng07_n_theta(*model);
   OccArgs args{};
   args.plan = t->layouts[0].plans[n_gauss].dev;
@@ -188,26 +188,32 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
                            2, (long long)n_sm * kWarps / ((n_draws + 7) / 8))),
                        &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
   if (model->family == TC_FAMILY_LEAUTHAUD11) {
-    const size_t smem = kL11SmemBytes;
+    const bool massdep = host_mass_dependent(model);
+    const size_t smem = l11_smem_bytes(massdep);
     static std::mutex m;
-    static std::map<int, bool> configured;
+    static std::map<std::pair<int, bool>, bool> configured;
     {
       std::lock_guard<std::mutex> lock_attr(m);
-      if (!configured[t->device]) {
-        TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (!configured[{t->device, massdep}]) {
         // just enough shared memory for the resident CTAs: what is left is L1 for the plan arrays
         const int carveout = (int)std::min<size_t>(
             100, (kL11MinBlocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-        TC_CUDA(cudaFuncSetAttribute(occupation_l11_kernel,
-                                     cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
-        configured[t->device] = true;
+        const void* kernel = massdep ? (const void*)occupation_l11_kernel<true>
+                                     : (const void*)occupation_l11_kernel<false>;
+        TC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+        TC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     carveout));
+        configured[{t->device, massdep}] = true;
       }
     }
     const long long n_blocks = (n_draws + kL11DrawsPerBlock - 1) / kL11DrawsPerBlock;
     const int grid = (int)std::max<long long>(
         1, std::min<long long>(n_blocks, (long long)n_sm * kL11MinBlocks));
-    occupation_l11_kernel<<<grid, kL11Threads, smem, static_cast<cudaStream_t>(stream)>>>(args);
+    if (massdep)
+      occupation_l11_kernel<true><<<grid, kL11Threads, smem, static_cast<cudaStream_t>(stream)>>>(args);
+    else
+      occupation_l11_kernel<false><<<grid, kL11Threads, smem, static_cast<cudaStream_t>(stream)>>>(args);
     TC_CUDA(cudaGetLastError());
     return TC_OK;
   }

@@ -77,7 +77,7 @@ class ModelSpec:
     """What the kernel needs to know about a model (mirrors ``tc_model`` in the C ABI).
 
     Mass-dependent decoration (halotools ``HeavisideAssembias`` with ``assembias_strength_abscissa``
-    / ``split_abscissa``; zheng07 family): ``strength_abscissa = (cen, sat)`` are the log10
+    / ``split_abscissa``; either family): ``strength_abscissa = (cen, sat)`` are the log10
     primary-property positions of each type's strength ordinates -- the draw then carries
     ``mean_occupation_<type>_assembias_param1..n`` -- and ``split_abscissa`` / ``split_ordinates``
     give each type's splitting percentile as a function of mass.  An empty tuple means the
@@ -115,9 +115,8 @@ class ModelSpec:
                 raise ValueError('abscissa must increase strictly')
         self.mass_dependent = (any(len(a) > 1 for a in self.strength_abscissa) or
                                any(len(a) > 0 for a in self.split_abscissa))
-        if self.mass_dependent and (self.family != FAMILY_ZHENG07 or not self.decorated):
-            raise NotImplementedError('mass-dependent assembly bias is implemented for decorated '
-                                      'zheng07 models')
+        if self.mass_dependent and not self.decorated:
+            raise NotImplementedError('mass-dependent assembly bias needs a decorated model')
         self.n_strength = tuple(max(1, len(a)) for a in self.strength_abscissa)
         self._theta_keys = (FAMILY_KEYS[self.family] +
                             assembias_keys('centrals', self.n_strength[0]) +
@@ -241,14 +240,41 @@ class Leauthaud11Model:
     def __init__(self, threshold=10.5, redshift=0.0, prim_haloprop_key='halo_mvir',
                  sec_haloprop_key='halo_nfw_conc', decorated=False, split=0.5,
                  modulate_with_cenocc=True, central_assembias_strength=1.0,
-                 satellite_assembias_strength=0.2, **ignored):
+                 satellite_assembias_strength=0.2, assembias_strength_abscissa=None,
+                 split_abscissa=None, **ignored):
+        """``central_assembias_strength`` / ``satellite_assembias_strength`` with
+        ``assembias_strength_abscissa`` and ``split`` / ``split_abscissa`` follow halotools'
+        ``HeavisideAssembias`` keywords: lists make a strength
+        (``mean_occupation_*_assembias_param1..n``) or the splitting percentile a function of
+        log10 of the primary halo property (the same abscissa for centrals and satellites)."""
         self.param_dict = dict(zip(LEAUTHAUD11_KEYS, LEAUTHAUD11_DEFAULTS))
         self.decorated = bool(decorated)
-        self.split = float(split)
         self.modulate_with_cenocc = bool(modulate_with_cenocc)
+        strengths = [np.atleast_1d(np.asarray(v, dtype=np.float64))
+                     for v in (central_assembias_strength, satellite_assembias_strength)]
+        knots = _knots(assembias_strength_abscissa, 'assembias_strength_abscissa')
+        if any(len(v) > 1 and len(v) != len(knots) for v in strengths):
+            raise ValueError('assembias_strength_abscissa must match the strengths in length')
+        if len(knots) <= 1 or all(len(v) <= 1 for v in strengths):
+            knots = ()
+        self.strength_abscissa = (knots, knots)
+        split_values = _knots(split, 'split')
+        split_knots = _knots(split_abscissa, 'split_abscissa')
+        if len(split_values) > 1 or len(split_knots) > 0:
+            if len(split_knots) != len(split_values):
+                raise ValueError('split_abscissa must match split in length')
+            self.split = 0.5
+            self.split_abscissa = (split_knots, split_knots)
+            self.split_ordinates = (split_values, split_values)
+        else:
+            self.split = float(split_values[0])
+            self.split_abscissa = ((), ())
+            self.split_ordinates = ((), ())
         if self.decorated:
-            self.param_dict[ASSEMBIAS_KEYS[0]] = float(central_assembias_strength)
-            self.param_dict[ASSEMBIAS_KEYS[1]] = float(satellite_assembias_strength)
+            for gal_type, values in zip(('centrals', 'satellites'), strengths):
+                for key, value in zip(assembias_keys(gal_type, max(1, len(knots))),
+                                      np.broadcast_to(values, max(1, len(knots)))):
+                    self.param_dict[key] = float(value)
         self.threshold = float(threshold)
         self.redshift = float(redshift)
         self.gal_types = ['centrals', 'satellites']
@@ -353,17 +379,23 @@ def resolve_model(model):
         if names in (('Leauthaud11Cens', 'Leauthaud11Sats'),
                      ('AssembiasLeauthaud11Cens', 'AssembiasLeauthaud11Sats')):
             decorated = names[0].startswith('Assembias')
-            split = 0.5
-            if decorated:
-                split = _constant_split(cens)
-                if _constant_split(sats) != split:
-                    raise NotImplementedError('different splits for centrals and satellites')
             _single_scatter(cens)
             if float(sats.threshold) != float(cens.threshold):
                 raise NotImplementedError('different thresholds for centrals and satellites')
-            return ModelSpec(FAMILY_LEAUTHAUD11, decorated,
-                             getattr(sats, 'modulate_with_cenocc', True), split,
-                             float(cens.threshold), float(getattr(cens, 'redshift', 0.0)))
+            common = (FAMILY_LEAUTHAUD11, decorated, getattr(sats, 'modulate_with_cenocc', True))
+            place = (float(cens.threshold), float(getattr(cens, 'redshift', 0.0)))
+            if not decorated:
+                return ModelSpec(*common, 0.5, *place)
+            knots = [_decoration_knots(c) for c in (cens, sats)]
+            strength_abscissa = tuple(k[0] for k in knots)
+            if all(len(k[1]) == 0 for k in knots) and knots[0][2] == knots[1][2]:
+                # one constant split for both galaxy types
+                return ModelSpec(*common, knots[0][2][0], *place,
+                                 strength_abscissa=strength_abscissa)
+            # per-type and / or mass-dependent splits: a constant is a single control point
+            return ModelSpec(*common, 0.5, *place, strength_abscissa=strength_abscissa,
+                             split_abscissa=tuple(k[1] if len(k[1]) else (0.0,) for k in knots),
+                             split_ordinates=tuple(k[2] for k in knots))
         raise NotImplementedError(
             'occupation components {} are not implemented by the CUDA occupation kernel; '
             'pass precomputed occupations as an ndarray instead'.format(names))
@@ -381,7 +413,10 @@ def resolve_model(model):
         return ModelSpec(FAMILY_LEAUTHAUD11, getattr(model, 'decorated', False),
                          getattr(model, 'modulate_with_cenocc', True),
                          getattr(model, 'split', 0.5), float(model.threshold),
-                         float(getattr(model, 'redshift', 0.0)))
+                         float(getattr(model, 'redshift', 0.0)),
+                         strength_abscissa=getattr(model, 'strength_abscissa', ((), ())),
+                         split_abscissa=getattr(model, 'split_abscissa', ((), ())),
+                         split_ordinates=getattr(model, 'split_ordinates', ((), ())))
     raise NotImplementedError(
         'cannot map {!r} to a kernel occupation family (zheng07, leauthaud11 and their '
         'decorated versions)'.format(model))

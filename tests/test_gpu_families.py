@@ -274,6 +274,64 @@ def test_mass_dependent_assembias_against_oracle(tb, orc, mode):
     close(xi1, xi_ref)
 
 
+def test_hearin15_mass_dependent_assembias_against_oracle(tb, orc):
+    """The same keywords for the leauthaud11 family: strength ordinates per draw and a splitting
+    percentile that varies with halo mass, different control points for centrals and satellites,
+    against the oracle (Leauthaud11Oracle shares Zheng07Oracle's restatement of halotools'
+    assembias_strength / percentile_splitting_function)."""
+    from tabcorr_b200.models import ModelSpec, assembias_keys
+    halotab, table = table_pair(tb, orc, 'syn36x3')
+    knots = dict(strength_abscissa=((11.0, 12.5, 14.0), (11.5, 12.2, 13.0, 14.5)),
+                 split_abscissa=((11.0, 14.5), (0.0,)), split_ordinates=((0.25, 0.7), (0.4,)))
+    spec = ModelSpec(tb.models.FAMILY_LEAUTHAUD11, True, True, 0.5, 10.5, 0.0, **knots)
+    assert spec.n_theta == 16 + 3 + 4
+    n_draws = 37
+    rng = np.random.default_rng(18)
+    draws = tb.synthetic.make_draws_leauthaud11(n_draws, seed=16)
+    for key in assembias_keys('centrals', 3) + assembias_keys('satellites', 4):
+        draws[key] = rng.uniform(-1.6, 1.6, n_draws)      # beyond [-1, 1]: clipped per halo
+    for n_gauss in (3, 10):
+        occ = halotab.mean_occupation_batch(draws, model=spec, n_gauss_prim=n_gauss).cpu().numpy()
+        ngal, xi = halotab.predict_batch(draws, model=spec, n_gauss_prim=n_gauss)
+        for i in (0, 7, n_draws - 1):
+            model = orc.Leauthaud11Oracle(cases.draws_row(draws, i), threshold=10.5, redshift=0.0,
+                                          decorated=True, modulate_with_cenocc=True, **knots)
+            occ_ref = orc.mean_occupation(table, model, n_gauss)
+            np.testing.assert_allclose(occ[i], occ_ref, rtol=5e-11,
+                                       atol=5e-11 * max(1.0, occ_ref.max()))
+            ngal_ref, xi_ref = orc.predict(table, occ_ref)
+            close(ngal[i], ngal_ref)
+            close(xi[i].ravel(), np.ravel(xi_ref))
+    # equal ordinates and a flat split are the plain hearin15 model, to rounding
+    flat = {k: v for k, v in draws.items() if 'assembias' not in k}
+    for key in assembias_keys('centrals', 3) + assembias_keys('satellites', 4):
+        flat[key] = np.full(n_draws, 0.6 if 'centrals' in key else -0.35)
+    flat_spec = ModelSpec(tb.models.FAMILY_LEAUTHAUD11, True, True, 0.4, 10.5, 0.0,
+                          strength_abscissa=knots['strength_abscissa'],
+                          split_abscissa=((11.0, 14.0), ()), split_ordinates=((0.4, 0.4), ()))
+    plain = dict({k: v for k, v in flat.items() if 'assembias' not in k},
+                 mean_occupation_centrals_assembias_param1=np.full(n_draws, 0.6),
+                 mean_occupation_satellites_assembias_param1=np.full(n_draws, -0.35))
+    a = halotab.mean_occupation_batch(flat, model=flat_spec).cpu().numpy()
+    b = halotab.mean_occupation_batch(
+        plain, model=ModelSpec(tb.models.FAMILY_LEAUTHAUD11, True, True, 0.4, 10.5, 0.0)).cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-13 * b.max())
+    # the reference's calling convention: predict(model) with a model object
+    model = tb.PrebuiltHodModelFactory(
+        'hearin15', threshold=10.5, central_assembias_strength=[0.9, -0.5, 0.3],
+        satellite_assembias_strength=[0.1, 0.2, 0.3], assembias_strength_abscissa=[11.0, 12.5, 14.0],
+        split=[0.3, 0.6], split_abscissa=[11.0, 14.0])
+    ngal1, xi1 = halotab.predict(model)
+    resolved = tb.models.resolve_model(model)
+    oracle_model = orc.Leauthaud11Oracle(dict(model.param_dict), threshold=10.5, decorated=True,
+                                         strength_abscissa=resolved.strength_abscissa,
+                                         split_abscissa=resolved.split_abscissa,
+                                         split_ordinates=resolved.split_ordinates)
+    ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, oracle_model))
+    close(ngal1, ngal_ref)
+    close(xi1, xi_ref)
+
+
 @pytest.mark.parametrize('seed', range(8))
 def test_ragged_shuffled_tables(tb, orc, seed):
     """The mass bins of the leauthaud11 kernel pair the centrals group and the satellites group

@@ -206,8 +206,30 @@ def test_mass_dependent_assembias_models():
     assert spec.split_ordinates == ((0.5,), (0.2, 0.5, 0.7))
     with pytest.raises(NotImplementedError, match='control points'):
         models.ModelSpec(0, True, strength_abscissa=((11, 12, 13, 14, 15), ()))
-    with pytest.raises(NotImplementedError, match='decorated zheng07'):
-        models.ModelSpec(1, True, strength_abscissa=((11, 12), ()))
+    with pytest.raises(NotImplementedError, match='decorated'):
+        models.ModelSpec(1, False, strength_abscissa=((11, 12), ()))
+    # the leauthaud11 family (hearin15) takes the same keywords
+    spec = models.ModelSpec(1, True, threshold=10.5, strength_abscissa=((11, 12), ()),
+                            split_abscissa=((), (11.0, 13.0)), split_ordinates=((), (0.3, 0.6)))
+    assert spec.mass_dependent and spec.n_strength == (2, 1) and spec.n_theta == 16 + 2 + 1
+    assert spec.theta_keys[16:18] == models.assembias_keys('centrals', 2)
+    model = models.PrebuiltHodModelFactory(
+        'hearin15', threshold=10.8, central_assembias_strength=[0.9, 0.2, -0.4],
+        satellite_assembias_strength=0.3, assembias_strength_abscissa=[11.5, 12.5, 14.0],
+        split=[0.3, 0.6], split_abscissa=[11.0, 14.0])
+    spec = models.resolve_model(model)
+    assert spec.family == 1 and spec.mass_dependent and spec.n_strength == (3, 3)
+    theta = models.theta_from_params(model.param_dict, 1, spec)
+    assert theta.shape == (1, 22) and list(theta[0, 16:]) == [0.9, 0.2, -0.4, 0.3, 0.3, 0.3]
+    cens = component('AssembiasLeauthaud11Cens', _assembias_strength_abscissa=[12.0, 13.0],
+                     _split_abscissa=[2], _split_ordinates=[0.5], threshold=10.5, redshift=0.0)
+    sats = component('AssembiasLeauthaud11Sats', _assembias_strength_abscissa=[2],
+                     _split_abscissa=[11.0, 13.0], _split_ordinates=[0.2, 0.7], threshold=10.5,
+                     modulate_with_cenocc=True)
+    spec = models.resolve_model(SimpleNamespace(
+        _input_model_dictionary={'centrals_occupation': cens, 'satellites_occupation': sats}))
+    assert spec.family == 1 and spec.n_strength == (2, 1)
+    assert spec.split_abscissa == ((0.0,), (11.0, 13.0))
 
     # oracle: equal ordinates == the constant model; a real mass dependence changes the result
     mass = 10**np.linspace(11.0, 14.5, 9)
