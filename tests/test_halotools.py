@@ -158,3 +158,35 @@ def test_mass_dependent_assembias_oracle_equals_halotools():
         theirs = getattr(model, 'mean_occupation_' + name)(prim_haloprop=MASS,
                                                            sec_haloprop_percentile=pct)
         np.testing.assert_allclose(ours, theirs, rtol=1e-12, atol=1e-300)
+
+
+def test_mass_dependent_hearin15_oracle_equals_halotools():
+    """The same keywords on the leauthaud11 family: AssembiasLeauthaud11Cens / Sats with
+    assembias_strength_abscissa / split_abscissa against Leauthaud11Oracle and the attribute
+    mapping of ``models.resolve_model``."""
+    from halotools.empirical_models import (AssembiasLeauthaud11Cens, AssembiasLeauthaud11Sats,
+                                            HodModelFactory, NFWPhaseSpace, TrivialPhaseSpace)
+    from tabcorr_b200 import models
+    cens = AssembiasLeauthaud11Cens(threshold=10.5, assembias_strength=[0.8, -0.3, 0.1],
+                                    assembias_strength_abscissa=[11.0, 12.5, 14.0])
+    sats = AssembiasLeauthaud11Sats(threshold=10.5, assembias_strength=[0.5, -0.5],
+                                    assembias_strength_abscissa=[12.0, 14.0],
+                                    split=[0.3, 0.6], split_abscissa=[11.0, 14.0])
+    model = HodModelFactory(centrals_occupation=cens, satellites_occupation=sats,
+                            centrals_profile=TrivialPhaseSpace(),
+                            satellites_profile=NFWPhaseSpace())
+    spec = models.resolve_model(model)
+    assert spec.family == 1 and spec.mass_dependent and spec.n_strength == (3, 2)
+    oracle = orc.Leauthaud11Oracle(dict(model.param_dict), threshold=10.5, decorated=True,
+                                   modulate_with_cenocc=spec.modulate_with_cenocc,
+                                   strength_abscissa=spec.strength_abscissa,
+                                   split_abscissa=spec.split_abscissa,
+                                   split_ordinates=spec.split_ordinates)
+    oracle.split = spec.split
+    pct = np.random.default_rng(6).uniform(0, 1, len(MASS))
+    for name in ('centrals', 'satellites'):
+        ours = getattr(oracle, 'mean_occupation_' + name)(prim_haloprop=MASS,
+                                                          sec_haloprop_percentile=pct)
+        theirs = getattr(model, 'mean_occupation_' + name)(prim_haloprop=MASS,
+                                                           sec_haloprop_percentile=pct)
+        np.testing.assert_allclose(ours, theirs, rtol=1e-10, atol=1e-300)
