@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TC_VERSION 108
+#define TC_VERSION 109
 
 #define TC_OK 0
 #define TC_EINVAL (-1)      /* bad argument */
@@ -52,12 +52,13 @@ extern "C" {
  * (halotools param_dict names; A_cen / A_sat are the mean_occupation_{centrals,satellites}_
  * assembias_param1 strengths, ignored unless decorated).  With a mass-dependent strength
  * (tc_model.n_strength > 1) a family's base parameters (5 / 16) are followed by the n_strength[0]
- * ordinates of the centrals and the n_strength[1] ordinates of the satellites. */
+ * ordinates of the centrals and the n_strength[1] ordinates of the satellites; leauthaud11 with a
+ * mass-dependent scatter (tc_model.n_scatter = n > 1) appends scatter_model_param2..n. */
 #define TC_FAMILY_ZHENG07 0
 #define TC_FAMILY_LEAUTHAUD11 1
 #define TC_N_THETA 7              /* zheng07 */
 #define TC_N_THETA_LEAUTHAUD11 18
-#define TC_N_THETA_MAX 24             /* leauthaud11 with 4 + 4 strength ordinates */
+#define TC_N_THETA_MAX 27             /* leauthaud11 with 4 + 4 strength and 4 scatter ordinates */
 #define TC_N_THETA_ZHENG07_BASE 5   /* logMmin .. alpha; the strengths follow */
 
 typedef struct tc_table tc_table;   /* device-resident table group (one gal_type, >=1 matrices) */
@@ -72,7 +73,8 @@ typedef struct tc_model {
   int32_t family;               /* TC_FAMILY_* */
   int32_t decorated;            /* 1 = Heaviside assembly bias on centrals and satellites */
   int32_t modulate_with_cenocc; /* 1 = <N_sat> is multiplied by the baseline <N_cen> */
-  int32_t reserved;
+  int32_t n_scatter;            /* leauthaud11: control points of a mass-dependent stellar-mass
+                                 * scatter (0 / 1: the constant scatter_model_param1), see below */
   double split;                 /* percentile split of the decoration (halotools default 0.5) */
   double threshold;             /* leauthaud11: log10 of the stellar-mass threshold */
   double redshift;              /* leauthaud11: redshift of the stellar-to-halo-mass relation */
@@ -92,6 +94,12 @@ typedef struct tc_model {
   double strength_abscissa[2][TC_MAX_KNOTS];
   double split_abscissa[2][TC_MAX_KNOTS];
   double split_ordinates[2][TC_MAX_KNOTS];
+  /* leauthaud11, n_scatter = n in 2..TC_MAX_KNOTS (halotools LogNormalScatterModel with
+   * scatter_abscissa / scatter_ordinates): the log-normal scatter in stellar mass of a halo is the
+   * interpolating polynomial through (scatter_abscissa[k], scatter_model_param<k+1>) at
+   * log10(prim_haloprop); the draw carries scatter_model_param1 in its usual place and
+   * scatter_model_param2..n behind the strength ordinates. */
+  double scatter_abscissa[TC_MAX_KNOTS];
 } tc_model;
 
 const char* tc_last_error(void);

@@ -194,7 +194,7 @@ class Leauthaud11Oracle(Zheng07Oracle):
 
     def __init__(self, param_dict=None, threshold=10.5, redshift=0.0, decorated=False, split=0.5,
                  modulate_with_cenocc=True, strength_abscissa=((), ()), split_abscissa=((), ()),
-                 split_ordinates=((), ())):
+                 split_ordinates=((), ()), scatter_abscissa=()):
         self.param_dict = dict(self.DEFAULTS)
         if decorated:
             for t, gal_type in enumerate(('centrals', 'satellites')):
@@ -211,7 +211,18 @@ class Leauthaud11Oracle(Zheng07Oracle):
         self.strength_abscissa = strength_abscissa
         self.split_abscissa = split_abscissa
         self.split_ordinates = split_ordinates
+        # LogNormalScatterModel with scatter_abscissa / scatter_ordinates: the scatter of a halo is
+        # custom_spline(abscissa, scatter_model_param1..n) at log10(prim_haloprop) (restated from
+        # memory of halotools' smhm_components.py, parity unpinned)
+        self.scatter_abscissa = scatter_abscissa
         self.modulate_with_cenocc = modulate_with_cenocc
+
+    def mean_scatter(self, prim_haloprop):
+        n = len(self.scatter_abscissa)
+        if n <= 1:
+            return np.zeros_like(prim_haloprop) + self.param_dict['scatter_model_param1']
+        ordinates = [self.param_dict['scatter_model_param{}'.format(k + 1)] for k in range(n)]
+        return self._custom_spline(self.scatter_abscissa, ordinates, np.log10(prim_haloprop))
 
     def mean_log_halo_mass(self, log_stellar_mass):
         # Behroozi10SmHm.mean_log_halo_mass: parameters were fit with h = 0.7, inputs/outputs are
@@ -242,7 +253,7 @@ class Leauthaud11Oracle(Zheng07Oracle):
     def _baseline_centrals(self, prim_haloprop):
         # Leauthaud11Cens.mean_occupation
         logmstar = self.mean_log_stellar_mass(prim_haloprop)
-        logscatter = np.sqrt(2.0) * self.param_dict['scatter_model_param1']
+        logscatter = np.sqrt(2.0) * self.mean_scatter(np.asarray(prim_haloprop, dtype=np.float64))
         return 0.5 * (1.0 - erf((self.threshold - logmstar) / logscatter))
 
     def _baseline_satellites(self, prim_haloprop):

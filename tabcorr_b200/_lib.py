@@ -47,14 +47,16 @@ class TabCorrB200Error(RuntimeError):
 
 class tc_model(ctypes.Structure):
     _fields_ = [('family', ctypes.c_int32), ('decorated', ctypes.c_int32),
-                ('modulate_with_cenocc', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('modulate_with_cenocc', ctypes.c_int32), ('n_scatter', ctypes.c_int32),
                 ('split', ctypes.c_double), ('threshold', ctypes.c_double),
                 ('redshift', ctypes.c_double),
                 # mass-dependent decoration, [centrals, satellites] (include/tabcorr_b200.h)
                 ('n_strength', ctypes.c_int32 * 2), ('n_split', ctypes.c_int32 * 2),
                 ('strength_abscissa', (ctypes.c_double * TC_MAX_KNOTS) * 2),
                 ('split_abscissa', (ctypes.c_double * TC_MAX_KNOTS) * 2),
-                ('split_ordinates', (ctypes.c_double * TC_MAX_KNOTS) * 2)]
+                ('split_ordinates', (ctypes.c_double * TC_MAX_KNOTS) * 2),
+                # leauthaud11: control points of a mass-dependent stellar-mass scatter
+                ('scatter_abscissa', ctypes.c_double * TC_MAX_KNOTS)]
 
 
 _lib = None

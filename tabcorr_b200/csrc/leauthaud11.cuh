@@ -60,8 +60,15 @@ constexpr double kLn10 = 2.302585092994045684;
 // centrals and of the satellites (one each unless the strength depends on mass)
 constexpr int kL11Base = 16;
 __device__ __host__ __forceinline__ int l11_n_theta(const tc_model& m) {
-  return kL11Base + zheng07_strength_count(m, 0) + zheng07_strength_count(m, 1);
+  return kL11Base + zheng07_strength_count(m, 0) + zheng07_strength_count(m, 1) +
+         (m.n_scatter > 1 ? m.n_scatter - 1 : 0);
 }
+// models that run in occupation_l11_kernel<true>: strength, split or scatter depend on mass
+__device__ __host__ __forceinline__ bool l11_mass_dependent(const tc_model& m) {
+  return m.n_scatter > 1 || (m.decorated && (m.n_strength[0] > 1 || m.n_strength[1] > 1 ||
+                                             m.n_split[0] > 0 || m.n_split[1] > 0));
+}
+constexpr int kL11OrdPerDraw = 3 * TC_MAX_KNOTS;   // centrals strengths | satellites strengths | scatter
 
 struct L11Draw {
   // knot k: x = log10 M_h of the knot; y, z, w = c1, c3, c2 of the cubic on [knot k, knot k + 1):
@@ -77,9 +84,9 @@ struct L11Draw {
                           // falls into 8 different 16-byte bank groups
 };
 static_assert(sizeof(L11Draw) % 128 == 80, "L11Draw stride chosen against bank conflicts");
-// (MASSDEP: + the strength ordinates of a mass-dependent decoration, 2 x TC_MAX_KNOTS doubles per
+// (MASSDEP: + the ordinates of a mass-dependent decoration / scatter, 3 x TC_MAX_KNOTS doubles per
 // draw)
-constexpr int kL11OrdDoubles = kL11DrawsPerBlock * 2 * TC_MAX_KNOTS;
+constexpr int kL11OrdDoubles = kL11DrawsPerBlock * kL11OrdPerDraw;
 constexpr size_t l11_smem_bytes(bool massdep) {
   return (kL11TabDoubles + kL11Knots + (massdep ? kL11OrdDoubles : 0)) * sizeof(double) +
          kL11DrawsPerBlock * sizeof(L11Draw);
@@ -151,10 +158,15 @@ __device__ __forceinline__ void l11_prepare_block(L11Draw* draws, double* __rest
     // strength of the plain decoration; clipped per node when they depend on mass)
     const int n_cen_ord = zheng07_strength_count(model, 0), n_sat_ord = zheng07_strength_count(model, 1);
     if (MASSDEP) {
+      double* o = ords + b * kL11OrdPerDraw;
       for (int k = 0; k < TC_MAX_KNOTS; k++) {
-        ords[b * 2 * TC_MAX_KNOTS + k] = k < n_cen_ord ? th[(kL11Base + k) * theta_ps] : 0.0;
-        ords[b * 2 * TC_MAX_KNOTS + TC_MAX_KNOTS + k] =
-            k < n_sat_ord ? th[(kL11Base + n_cen_ord + k) * theta_ps] : 0.0;
+        o[k] = model.decorated && k < n_cen_ord ? th[(kL11Base + k) * theta_ps] : 0.0;
+        o[TC_MAX_KNOTS + k] =
+            model.decorated && k < n_sat_ord ? th[(kL11Base + n_cen_ord + k) * theta_ps] : 0.0;
+        o[2 * TC_MAX_KNOTS + k] =
+            k == 0 ? th[10 * theta_ps]
+                   : k < model.n_scatter ? th[(kL11Base + n_cen_ord + n_sat_ord + k - 1) * theta_ps]
+                                         : 0.0;
       }
     }
     D.a_cen = model.decorated ? fmin(fmax(th[kL11Base * theta_ps], -1.0), 1.0) : 0.0;
@@ -162,8 +174,9 @@ __device__ __forceinline__ void l11_prepare_block(L11Draw* draws, double* __rest
     // the erf argument is clamped below (NaN would be lost): a parameter that is not finite makes
     // every occupation of the draw NaN through `bad`
     double sum = 0.0;
-    for (int k = 0; k < (model.decorated ? l11_n_theta(model) : kL11Base); k++)
-      sum += th[k * theta_ps];
+    for (int k = 0; k < l11_n_theta(model); k++)   // (the strengths only if they are used)
+      if (model.decorated || k < kL11Base || k >= kL11Base + n_cen_ord + n_sat_ord)
+        sum += th[k * theta_ps];
     D.bad = sum - sum;
   }
   __syncthreads();
@@ -345,9 +358,10 @@ __device__ __forceinline__ double l11_massdep_delta(const tc_model& model, int t
 // `sat` over the same node masses (-1: absent).  The spline and the erf of a node serve both
 // galaxy types (Leauthaud11Sats is modulated by <N_cen> by default); the Gauss-Legendre weights
 // and the Heaviside decoration are those of occupation_group (occupation.cuh).
-// DEC: 0 no decoration, 1 constant strength and split, 2 strength and / or split depend on mass
-// (evaluated per node at log10 of the node mass, like occupation_pair_nodes_massdep; `ords`: the
-// draw's strength ordinates).
+// DEC: 0 no decoration, 1 constant strength and split, 2 the general model: strength, split and / or
+// the stellar-mass scatter depend on mass (evaluated per node at log10 of the node mass, like
+// occupation_pair_nodes_massdep; `ords`: the draw's strength and scatter ordinates; an undecorated
+// model has zero strengths).
 template <int U, int DEC>
 __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __restrict__ d,
                                         const double* __restrict__ ords,
@@ -426,6 +440,13 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
       const double t = logm[u] - c.x;
       const double s = fma(t, fma(t, fma(t, c.z, c.w), c.y), l11_knot_logms_inner(idx[u]));
       e[u] = (s - threshold) * inv_scatter;
+      if (DEC == 2 && args.model.n_scatter > 1) {   // sigma(log10 M): polynomial through the control points
+        double o[TC_MAX_KNOTS];
+#pragma unroll
+        for (int k = 0; k < TC_MAX_KNOTS; k++) o[k] = ords[2 * TC_MAX_KNOTS + k];
+        const double sigma = lagrange_eval(args.model.n_scatter, args.model.scatter_abscissa, o, logm[u]);
+        e[u] = (s - threshold) / (1.4142135623730951 * sigma);
+      }
     }
     half_erfc_neg_group<U>(e, tab);
     double wa[U], wb[U];   // weights of the centrals rows (the satellites rows' too if same_w)
@@ -520,7 +541,7 @@ occupation_l11_kernel(const OccArgs args) {
       if (b >= n_block || bin >= n_bins) continue;
       const L11Bin* bin_ptr = args.plan.l11_bins + bin;
       double* out = args.occ_out + (draw0 + b) * args.n_rows;
-      const double* ord = ords + b * 2 * TC_MAX_KNOTS;
+      const double* ord = ords + b * kL11OrdPerDraw;
       if (MASSDEP) {   // rare: one instantiation, a node at a time
         l11_bin<1, 2>(args, draws + b, ord, tab, bin_ptr, out);
       } else if (args.model.decorated) {

@@ -50,6 +50,14 @@ int check_model(const tc_model* model) {
       if (!(model->split_abscissa[type][k] > model->split_abscissa[type][k - 1]))
         return fail(TC_EINVAL, "tc_model: split_abscissa must increase strictly");
   }
+  if (model->n_scatter < 0 || model->n_scatter > TC_MAX_KNOTS)
+    return fail(TC_EUNSUPPORTED, "tc_model: at most " + std::to_string(TC_MAX_KNOTS) +
+                                     " control points of the stellar-mass scatter");
+  if (model->n_scatter > 1 && model->family != TC_FAMILY_LEAUTHAUD11)
+    return fail(TC_EINVAL, "tc_model: n_scatter belongs to TC_FAMILY_LEAUTHAUD11");
+  for (int k = 1; k < model->n_scatter; k++)
+    if (!(model->scatter_abscissa[k] > model->scatter_abscissa[k - 1]))
+      return fail(TC_EINVAL, "tc_model: scatter_abscissa must increase strictly");
   return TC_OK;
 }
 
@@ -188,7 +196,7 @@ int tc_occupation_batch(tc_table* t, const tc_model* model, int n_gauss, const d
                            2, (long long)n_sm * kWarps / ((n_draws + 7) / 8))),
                        &args.n_ranges_cen, &args.n_ranges_sat, &args.pieces_cen, &args.pieces_sat);
   if (model->family == TC_FAMILY_LEAUTHAUD11) {
-    const bool massdep = host_mass_dependent(model);
+    const bool massdep = l11_mass_dependent(*model);
     const size_t smem = l11_smem_bytes(massdep);
     static std::mutex m;
     static std::map<std::pair<int, bool>, bool> configured;

@@ -85,7 +85,7 @@ class ModelSpec:
 
     def __init__(self, family=0, decorated=False, modulate_with_cenocc=False, split=0.5,
                  threshold=0.0, redshift=0.0, strength_abscissa=((), ()),
-                 split_abscissa=((), ()), split_ordinates=((), ())):
+                 split_abscissa=((), ()), split_ordinates=((), ()), scatter_abscissa=()):
         self.family = int(family)
         if self.family not in FAMILY_KEYS:
             raise NotImplementedError('unknown occupation family {}'.format(family))
@@ -97,12 +97,21 @@ class ModelSpec:
         self._theta_keys = FAMILY_KEYS[self.family] + ASSEMBIAS_KEYS
         self.mass_dependent = False
         self.n_strength = (1, 1)    # strength ordinates per draw (centrals, satellites)
+        # leauthaud11: log10 primary-property positions of the scatter_model_param1..n ordinates
+        # (halotools LogNormalScatterModel scatter_abscissa); one or none: the constant scatter
+        self.scatter_abscissa = ()
+        if len(scatter_abscissa) > 1:
+            return self._init_general(strength_abscissa, split_abscissa, split_ordinates,
+                                      scatter_abscissa)
         if not (any(len(v) for v in strength_abscissa) or any(len(v) for v in split_abscissa) or
                 any(len(v) for v in split_ordinates)):
             # the plain model: one strength per type, one split (the latency paths construct a
             # ModelSpec per call, so nothing is validated or formatted here)
             self.strength_abscissa = self.split_abscissa = self.split_ordinates = ((), ())
             return
+        self._init_general(strength_abscissa, split_abscissa, split_ordinates, ())
+
+    def _init_general(self, strength_abscissa, split_abscissa, split_ordinates, scatter_abscissa):
         self.strength_abscissa = tuple(_knots(v, 'assembias_strength_abscissa')
                                        for v in strength_abscissa)
         self.split_abscissa = tuple(_knots(v, 'split_abscissa') for v in split_abscissa)
@@ -118,9 +127,18 @@ class ModelSpec:
         if self.mass_dependent and not self.decorated:
             raise NotImplementedError('mass-dependent assembly bias needs a decorated model')
         self.n_strength = tuple(max(1, len(a)) for a in self.strength_abscissa)
+        scatter = _knots(scatter_abscissa, 'scatter_abscissa')
+        if len(scatter) > 1:
+            if self.family != FAMILY_LEAUTHAUD11:
+                raise NotImplementedError('a stellar-mass scatter belongs to the leauthaud11 family')
+            if any(b <= a for a, b in zip(scatter[:-1], scatter[1:])):
+                raise ValueError('abscissa must increase strictly')
+            self.scatter_abscissa = scatter
         self._theta_keys = (FAMILY_KEYS[self.family] +
                             assembias_keys('centrals', self.n_strength[0]) +
-                            assembias_keys('satellites', self.n_strength[1]))
+                            assembias_keys('satellites', self.n_strength[1]) +
+                            tuple('scatter_model_param{}'.format(k + 1)
+                                  for k in range(1, len(self.scatter_abscissa))))
 
     @property
     def latency_paths(self):
@@ -135,7 +153,13 @@ class ModelSpec:
 
     @property
     def strength_keys(self):
-        return self._theta_keys[len(FAMILY_KEYS[self.family]):]
+        n = len(FAMILY_KEYS[self.family])
+        return self._theta_keys[n:n + self.n_strength[0] + self.n_strength[1]]
+
+    @property
+    def scatter_keys(self):
+        """``scatter_model_param2..n`` of a mass-dependent stellar-mass scatter (leauthaud11)."""
+        return self._theta_keys[len(FAMILY_KEYS[self.family]) + sum(self.n_strength):]
 
     @property
     def theta_keys(self):
@@ -153,7 +177,7 @@ class ModelSpec:
     def key(self):
         return (self.family, self.decorated, self.modulate_with_cenocc, self.split,
                 self.threshold, self.redshift, self.strength_abscissa, self.split_abscissa,
-                self.split_ordinates)
+                self.split_ordinates, self.scatter_abscissa)
 
 
 def spec_from_params(params):
@@ -241,13 +265,22 @@ class Leauthaud11Model:
                  sec_haloprop_key='halo_nfw_conc', decorated=False, split=0.5,
                  modulate_with_cenocc=True, central_assembias_strength=1.0,
                  satellite_assembias_strength=0.2, assembias_strength_abscissa=None,
-                 split_abscissa=None, **ignored):
+                 split_abscissa=None, scatter_abscissa=None, scatter_ordinates=None, **ignored):
         """``central_assembias_strength`` / ``satellite_assembias_strength`` with
         ``assembias_strength_abscissa`` and ``split`` / ``split_abscissa`` follow halotools'
         ``HeavisideAssembias`` keywords: lists make a strength
         (``mean_occupation_*_assembias_param1..n``) or the splitting percentile a function of
         log10 of the primary halo property (the same abscissa for centrals and satellites)."""
         self.param_dict = dict(zip(LEAUTHAUD11_KEYS, LEAUTHAUD11_DEFAULTS))
+        # halotools LogNormalScatterModel: scatter_abscissa / scatter_ordinates make the stellar-mass
+        # scatter a function of log10 of the primary halo property (scatter_model_param1..n)
+        scatter_knots = _knots(scatter_abscissa, 'scatter_abscissa')
+        scatter_values = _knots(scatter_ordinates, 'scatter_ordinates')
+        if len(scatter_knots) != len(scatter_values):
+            raise ValueError('scatter_abscissa must match scatter_ordinates in length')
+        self.scatter_abscissa = scatter_knots if len(scatter_knots) > 1 else ()
+        for k, value in enumerate(scatter_values):
+            self.param_dict['scatter_model_param{}'.format(k + 1)] = float(value)
         self.decorated = bool(decorated)
         self.modulate_with_cenocc = bool(modulate_with_cenocc)
         strengths = [np.atleast_1d(np.asarray(v, dtype=np.float64))
@@ -307,13 +340,21 @@ def PrebuiltHodModelFactory(model_nickname, **kwargs):
         "'decorated-zheng07', 'leauthaud11', 'hearin15')".format(model_nickname))
 
 
-def _single_scatter(component):
-    """halotools' LogNormalScatterModel has one ``scatter_model_param<i>`` per abscissa; the
-    kernel implements the (default) constant scatter."""
+def _scatter_knots(component):
+    """``scatter_abscissa`` of a halotools ``Leauthaud11Cens``: its stellar-to-halo-mass model
+    (``smhm_model``, a ``Behroozi10SmHm``) keeps a ``LogNormalScatterModel`` (``scatter_model``)
+    whose ``abscissa`` are the log10 primary-property positions of ``scatter_model_param1..n``.
+    One ordinate is the (default) constant scatter."""
     extra = [k for k in getattr(component, 'param_dict', {})
              if k.startswith('scatter_model_param') and k != 'scatter_model_param1']
-    if extra:
-        raise NotImplementedError('mass-dependent stellar-mass scatter is not implemented')
+    if not extra:
+        return ()
+    scatter_model = getattr(getattr(component, 'smhm_model', None), 'scatter_model', None)
+    abscissa = getattr(scatter_model, 'abscissa', None)
+    if abscissa is None or len(np.atleast_1d(abscissa)) != len(extra) + 1:
+        raise NotImplementedError('mass-dependent stellar-mass scatter: cannot find the '
+                                  'scatter_abscissa of the model (smhm_model.scatter_model.abscissa)')
+    return _knots(abscissa, 'scatter_abscissa')
 
 
 def _constant_split(component):
@@ -355,7 +396,8 @@ def resolve_model(model):
                          getattr(model, 'redshift', 0.0),
                          getattr(model, 'strength_abscissa', ((), ())),
                          getattr(model, 'split_abscissa', ((), ())),
-                         getattr(model, 'split_ordinates', ((), ())))
+                         getattr(model, 'split_ordinates', ((), ())),
+                         getattr(model, 'scatter_abscissa', ()))
     components = getattr(model, '_input_model_dictionary', None)
     if components is not None and 'centrals_occupation' in components:
         cens = components['centrals_occupation']
@@ -379,23 +421,23 @@ def resolve_model(model):
         if names in (('Leauthaud11Cens', 'Leauthaud11Sats'),
                      ('AssembiasLeauthaud11Cens', 'AssembiasLeauthaud11Sats')):
             decorated = names[0].startswith('Assembias')
-            _single_scatter(cens)
+            scatter = _scatter_knots(cens)
             if float(sats.threshold) != float(cens.threshold):
                 raise NotImplementedError('different thresholds for centrals and satellites')
             common = (FAMILY_LEAUTHAUD11, decorated, getattr(sats, 'modulate_with_cenocc', True))
             place = (float(cens.threshold), float(getattr(cens, 'redshift', 0.0)))
             if not decorated:
-                return ModelSpec(*common, 0.5, *place)
+                return ModelSpec(*common, 0.5, *place, scatter_abscissa=scatter)
             knots = [_decoration_knots(c) for c in (cens, sats)]
             strength_abscissa = tuple(k[0] for k in knots)
             if all(len(k[1]) == 0 for k in knots) and knots[0][2] == knots[1][2]:
                 # one constant split for both galaxy types
                 return ModelSpec(*common, knots[0][2][0], *place,
-                                 strength_abscissa=strength_abscissa)
+                                 strength_abscissa=strength_abscissa, scatter_abscissa=scatter)
             # per-type and / or mass-dependent splits: a constant is a single control point
             return ModelSpec(*common, 0.5, *place, strength_abscissa=strength_abscissa,
                              split_abscissa=tuple(k[1] if len(k[1]) else (0.0,) for k in knots),
-                             split_ordinates=tuple(k[2] for k in knots))
+                             split_ordinates=tuple(k[2] for k in knots), scatter_abscissa=scatter)
         raise NotImplementedError(
             'occupation components {} are not implemented by the CUDA occupation kernel; '
             'pass precomputed occupations as an ndarray instead'.format(names))
@@ -416,7 +458,8 @@ def resolve_model(model):
                          float(getattr(model, 'redshift', 0.0)),
                          strength_abscissa=getattr(model, 'strength_abscissa', ((), ())),
                          split_abscissa=getattr(model, 'split_abscissa', ((), ())),
-                         split_ordinates=getattr(model, 'split_ordinates', ((), ())))
+                         split_ordinates=getattr(model, 'split_ordinates', ((), ())),
+                         scatter_abscissa=getattr(model, 'scatter_abscissa', ()))
     raise NotImplementedError(
         'cannot map {!r} to a kernel occupation family (zheng07, leauthaud11 and their '
         'decorated versions)'.format(model))
@@ -435,6 +478,9 @@ def theta_columns(params, spec=None):
         missing = [k for k in spec.strength_keys if k not in params]
         if missing:
             raise ValueError('missing assembly-bias parameters: {}'.format(', '.join(missing)))
+    missing = [k for k in spec.scatter_keys if k not in params]
+    if missing:
+        raise ValueError('missing scatter parameters: {}'.format(', '.join(missing)))
     return [np.asarray(params.get(k, 0.0), dtype=np.float64) for k in spec.theta_keys]
 
 

@@ -197,6 +197,10 @@ class DeviceTableGroup:
     def _model_struct(spec):
         model = _lib.tc_model(spec.family, int(spec.decorated), int(spec.modulate_with_cenocc), 0,
                               spec.split, spec.threshold, spec.redshift)
+        if len(spec.scatter_abscissa) > 1:   # leauthaud11: mass-dependent stellar-mass scatter
+            model.n_scatter = len(spec.scatter_abscissa)
+            for k, value in enumerate(spec.scatter_abscissa):
+                model.scatter_abscissa[k] = value
         if not spec.mass_dependent and not any(len(a) for a in spec.split_abscissa):
             return model
         for t in range(2):   # mass-dependent decoration (centrals, satellites)

@@ -47,7 +47,7 @@ def test_version_and_constants(lib):
         _lib.TC_N_THETA_LEAUTHAUD11
     # 4 x int32 + 3 doubles + the mass-dependent decoration block (2 x 2 int32 + 3 x 2 x 4 doubles)
     assert int(re.search(r'#define TC_MAX_KNOTS (\d+)', text).group(1)) == _lib.TC_MAX_KNOTS == 4
-    assert ctypes.sizeof(_lib.tc_model) == 40 + 16 + 3 * 2 * 4 * 8
+    assert ctypes.sizeof(_lib.tc_model) == 40 + 16 + 3 * 2 * 4 * 8 + 4 * 8
     from tabcorr_b200 import models
     for family, n_theta in ((_lib.TC_FAMILY_ZHENG07, _lib.TC_N_THETA),
                             (_lib.TC_FAMILY_LEAUTHAUD11, _lib.TC_N_THETA_LEAUTHAUD11)):

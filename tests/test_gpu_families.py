@@ -332,6 +332,60 @@ def test_hearin15_mass_dependent_assembias_against_oracle(tb, orc):
     close(xi1, xi_ref)
 
 
+@pytest.mark.parametrize('decorated', [False, True])
+def test_mass_dependent_scatter_against_oracle(tb, orc, decorated):
+    """halotools' LogNormalScatterModel with scatter_abscissa / scatter_ordinates: the stellar-mass
+    scatter of a halo is the spline of scatter_model_param1..n over log10 M; alone and together
+    with a mass-dependent decoration."""
+    from tabcorr_b200.models import ModelSpec, assembias_keys
+    halotab, table = table_pair(tb, orc, 'syn36x3')
+    knots = dict(scatter_abscissa=(11.0, 13.0, 15.0))
+    if decorated:
+        knots.update(strength_abscissa=((11.0, 14.0), ()), split_abscissa=((), (11.0, 14.5)),
+                     split_ordinates=((), (0.3, 0.6)))
+    spec = ModelSpec(tb.models.FAMILY_LEAUTHAUD11, decorated, True, 0.5, 10.5, 0.0, **knots)
+    assert spec.n_theta == 18 + (1 if decorated else 0) + 2
+    n_draws = 35
+    rng = np.random.default_rng(28)
+    draws = tb.synthetic.make_draws_leauthaud11(n_draws, seed=26, decorated=decorated)
+    draws['scatter_model_param2'] = rng.uniform(0.1, 0.35, n_draws)
+    draws['scatter_model_param3'] = rng.uniform(0.1, 0.35, n_draws)
+    if decorated:
+        for key in assembias_keys('centrals', 2):
+            draws[key] = rng.uniform(-1.2, 1.2, n_draws)
+    for n_gauss in (3, 10):
+        occ = halotab.mean_occupation_batch(draws, model=spec, n_gauss_prim=n_gauss).cpu().numpy()
+        ngal, xi = halotab.predict_batch(draws, model=spec, n_gauss_prim=n_gauss)
+        for i in (0, 11, n_draws - 1):
+            model = orc.Leauthaud11Oracle(cases.draws_row(draws, i), threshold=10.5, redshift=0.0,
+                                          decorated=decorated, modulate_with_cenocc=True, **knots)
+            occ_ref = orc.mean_occupation(table, model, n_gauss)
+            np.testing.assert_allclose(occ[i], occ_ref, rtol=5e-11,
+                                       atol=5e-11 * max(1.0, occ_ref.max()))
+            ngal_ref, xi_ref = orc.predict(table, occ_ref)
+            close(ngal[i], ngal_ref)
+            close(xi[i].ravel(), np.ravel(xi_ref))
+    # equal ordinates are the constant scatter, to rounding
+    if not decorated:
+        flat = dict(draws, scatter_model_param2=draws['scatter_model_param1'],
+                    scatter_model_param3=draws['scatter_model_param1'])
+        a = halotab.mean_occupation_batch(flat, model=spec).cpu().numpy()
+        b = halotab.mean_occupation_batch(
+            draws, model=ModelSpec(tb.models.FAMILY_LEAUTHAUD11, False, True, 0.5, 10.5,
+                                   0.0)).cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * b.max())
+        # the reference's calling convention
+        model = tb.PrebuiltHodModelFactory('leauthaud11', threshold=10.5,
+                                           scatter_abscissa=[12.0, 15.0],
+                                           scatter_ordinates=[0.3, 0.12])
+        ngal1, xi1 = halotab.predict(model)
+        oracle_model = orc.Leauthaud11Oracle(dict(model.param_dict), threshold=10.5,
+                                             scatter_abscissa=(12.0, 15.0))
+        ngal_ref, xi_ref = orc.predict(table, orc.mean_occupation(table, oracle_model))
+        close(ngal1, ngal_ref)
+        close(xi1, xi_ref)
+
+
 @pytest.mark.parametrize('seed', range(8))
 def test_ragged_shuffled_tables(tb, orc, seed):
     """The mass bins of the leauthaud11 kernel pair the centrals group and the satellites group

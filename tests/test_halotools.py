@@ -190,3 +190,27 @@ def test_mass_dependent_hearin15_oracle_equals_halotools():
         theirs = getattr(model, 'mean_occupation_' + name)(prim_haloprop=MASS,
                                                            sec_haloprop_percentile=pct)
         np.testing.assert_allclose(ours, theirs, rtol=1e-10, atol=1e-300)
+
+
+def test_mass_dependent_scatter_oracle_equals_halotools():
+    """Leauthaud11Cens with scatter_abscissa / scatter_ordinates (LogNormalScatterModel): the
+    oracle's per-halo scatter and the attribute path ``models.resolve_model`` reads
+    (``smhm_model.scatter_model.abscissa``) against the real components."""
+    from halotools.empirical_models import (HodModelFactory, Leauthaud11Cens, Leauthaud11Sats,
+                                            NFWPhaseSpace, TrivialPhaseSpace)
+    from tabcorr_b200 import models
+    kw = dict(threshold=10.5, scatter_abscissa=[12.0, 15.0], scatter_ordinates=[0.3, 0.12])
+    cens = Leauthaud11Cens(**kw)
+    sats = Leauthaud11Sats(**kw)
+    model = HodModelFactory(centrals_occupation=cens, satellites_occupation=sats,
+                            centrals_profile=TrivialPhaseSpace(),
+                            satellites_profile=NFWPhaseSpace())
+    spec = models.resolve_model(model)
+    assert spec.family == 1 and spec.scatter_abscissa == (12.0, 15.0) and spec.n_theta == 19
+    oracle = orc.Leauthaud11Oracle(dict(model.param_dict), threshold=10.5,
+                                   modulate_with_cenocc=spec.modulate_with_cenocc,
+                                   scatter_abscissa=spec.scatter_abscissa)
+    for name in ('centrals', 'satellites'):
+        ours = getattr(oracle, 'mean_occupation_' + name)(prim_haloprop=MASS)
+        theirs = getattr(model, 'mean_occupation_' + name)(prim_haloprop=MASS)
+        np.testing.assert_allclose(ours, theirs, rtol=1e-10, atol=1e-300)

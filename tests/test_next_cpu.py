@@ -221,6 +221,29 @@ def test_mass_dependent_assembias_models():
     assert spec.family == 1 and spec.mass_dependent and spec.n_strength == (3, 3)
     theta = models.theta_from_params(model.param_dict, 1, spec)
     assert theta.shape == (1, 22) and list(theta[0, 16:]) == [0.9, 0.2, -0.4, 0.3, 0.3, 0.3]
+    # mass-dependent stellar-mass scatter (halotools LogNormalScatterModel keywords)
+    spec = models.ModelSpec(1, False, True, 0.5, 10.5, 0.0, scatter_abscissa=(11.0, 13.0, 15.0))
+    assert spec.n_theta == 18 + 2 and spec.theta_keys[18:] == ('scatter_model_param2',
+                                                               'scatter_model_param3')
+    assert not spec.mass_dependent and spec.scatter_keys == spec.theta_keys[18:]
+    model = models.PrebuiltHodModelFactory('leauthaud11', scatter_abscissa=[12, 15],
+                                           scatter_ordinates=[0.3, 0.1])
+    spec = models.resolve_model(model)
+    theta = models.theta_from_params(model.param_dict, 1, spec)
+    assert spec.scatter_abscissa == (12.0, 15.0) and theta.shape == (1, 19)
+    assert theta[0, 10] == 0.3 and theta[0, 18] == 0.1
+    with pytest.raises(ValueError, match='scatter'):
+        models.theta_from_params({k: v for k, v in model.param_dict.items()
+                                  if k != 'scatter_model_param2'}, 1, spec)
+    with pytest.raises(NotImplementedError, match='leauthaud11'):
+        models.ModelSpec(0, False, scatter_abscissa=(11.0, 13.0))
+    smhm = SimpleNamespace(scatter_model=SimpleNamespace(abscissa=[12.0, 15.0]))
+    cens = component('Leauthaud11Cens', threshold=10.5, redshift=0.0, smhm_model=smhm,
+                     param_dict={'scatter_model_param1': 0.3, 'scatter_model_param2': 0.1})
+    sats = component('Leauthaud11Sats', threshold=10.5, modulate_with_cenocc=True)
+    spec = models.resolve_model(SimpleNamespace(
+        _input_model_dictionary={'centrals_occupation': cens, 'satellites_occupation': sats}))
+    assert spec.scatter_abscissa == (12.0, 15.0) and spec.n_theta == 19
     cens = component('AssembiasLeauthaud11Cens', _assembias_strength_abscissa=[12.0, 13.0],
                      _split_abscissa=[2], _split_ordinates=[0.5], threshold=10.5, redshift=0.0)
     sats = component('AssembiasLeauthaud11Sats', _assembias_strength_abscissa=[2],
