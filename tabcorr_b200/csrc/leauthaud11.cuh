@@ -491,16 +491,20 @@ __device__ __forceinline__ void l11_bin(const OccArgs& args, const L11Draw* __re
                                               bin.pct[3], ka, kb);
           acc2 = fma(wc, fma(ka, dl, f[u]), acc2);
           acc3 = fma(wd, fma(kb, dl, f[u]), acc3);
-        } else if (DECORATED) {
-          const double dl = assembias_delta(f[u], a_sat, ratio, CUDART_INF, split_ok);
-          acc2 = fma(wc, fma(k2, dl, f[u]), acc2);
-          acc3 = fma(wd, fma(k3, dl, f[u]), acc3);
-        } else {
+        } else {   // (DEC == 1: the satellites' perturbation is applied to the sums below)
           acc2 = fma(wc, f[u], acc2);
           acc3 = fma(wd, f[u], acc3);
         }
       }
     }
+  }
+  if (DECORATED) {
+    // Unbounded above, the satellites' Heaviside perturbation is linear in the baseline
+    // (assembias_delta with hi = inf: A > 0: delta = A s / (1 - s) f, A <= 0: delta = A f), so it
+    // scales the Gauss-Legendre sums instead of every node
+    const double c = split_ok ? a_sat * (a_sat > 0.0 ? ratio : 1.0) : 0.0;
+    acc2 = fma(k2 * c, acc2, acc2);
+    acc3 = fma(k3 * c, acc3, acc3);
   }
   const double bad = d->bad;   // NaN: table not increasing, or a parameter that is not finite
   const double acc[4] = {acc0, acc1, acc2, acc3};
