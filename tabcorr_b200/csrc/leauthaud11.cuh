@@ -116,7 +116,8 @@ __device__ __forceinline__ double l11_log_halo_mass(double log_ms, double logm0,
   const double lr = log_ms - 2.0 * log_h - logm0;  // log10(M* / M0) in h = 0.7 units
   const double up = FAST ? exp_scaled_with(delta * lr * kLn10, tab + kErfWDoubles) : exp10(delta * lr);
   const double dn = FAST ? exp_scaled_with(-gamma * lr * kLn10, tab + kErfWDoubles) : exp10(-gamma * lr);
-  return logm1 + beta * lr + up / (1.0 + dn) - 0.5 + log_h;
+  // (the fast reciprocal: two Newton steps on the hardware seed, full precision for normal x)
+  return logm1 + beta * lr + (FAST ? up * fast_rcp(1.0 + dn) : up / (1.0 + dn)) - 0.5 + log_h;
 }
 
 // Spline tables and per-draw constants of one block of draws, by the whole CTA.  `sk`: the knot
@@ -192,7 +193,7 @@ __device__ __forceinline__ void l11_prepare_block(L11Draw* draws, double* __rest
   for (int idx = threadIdx.x; idx < n_block * (n - 1); idx += blockDim.x) {
     const int b = idx / (n - 1), k = idx - b * (n - 1);
     const double h = draws[b].knot[k + 1].x - draws[b].knot[k].x;
-    draws[b].knot[k].y = 1.0 / h;
+    draws[b].knot[k].y = fast_rcp(h);   // (h <= 0 or NaN: the draw is flagged below)
     if (!(h > 0.0)) draws[b].bad = CUDART_NAN;
   }
   __syncthreads();
@@ -241,7 +242,7 @@ __device__ __forceinline__ void l11_prepare_block(L11Draw* draws, double* __rest
       const double d = (sk[i + 1] - sk[i]) * ih;
       double lower, diag, upper;
       row(i, h_prev, h, ih_prev, ih, lower, diag, upper);
-      const double inv = 1.0 / (diag - lower * cp);
+      const double inv = fast_rcp(diag - lower * cp);
       cp = upper * inv;
       rp = (3.0 * (d - d_prev) - lower * rp) * inv;
       D.knot[i].z = cp;
@@ -264,7 +265,7 @@ __device__ __forceinline__ void l11_prepare_block(L11Draw* draws, double* __rest
       const double d_prev = (sk[i] - sk[i - 1]) * ih_prev;
       double lower, diag, upper;
       row(i, h_prev, h, ih_prev, ih, lower, diag, upper);
-      const double inv = 1.0 / (diag - upper * bq);
+      const double inv = fast_rcp(diag - upper * bq);
       bq = lower * inv;
       br = (3.0 * (d - d_prev) - upper * br) * inv;
       D.knot[i].z = bq;
