@@ -23,9 +23,13 @@ namespace {
 // log10 M* = linspace(8.5, 12.5, 100) and evaluates the interpolating cubic spline (scipy
 // InterpolatedUnivariateSpline, k = 3: not-a-knot end conditions, cubic extrapolation) of log10 M*
 // over log10 M_h.  Parity means reproducing that spline, not the exact inverse, so every draw
-// builds the same table and solves the same not-a-knot system (Thomas algorithm) in shared
-// memory; a mass bin is then one 7-step binary search, and a node a short walk and one cubic.
+// builds the same table and solves the same not-a-knot system (eliminated from both ends by two
+// warps) in shared memory; a mass bin -- the centrals group and the satellites group over the same
+// node masses, evaluated together -- is then one 7-step binary search, and a node a short walk,
+// one cubic, one erf (five nodes share a column of a wide-interval table) and one exponential.
 // A draw whose table is not strictly increasing (halotools raises there) gets NaN occupations.
+// Strength / split of the Heaviside decoration and the stellar-mass scatter may depend on mass
+// (tc_model.n_strength / n_split / n_scatter): occupation_l11_kernel<true>.
 //
 // This family does not run inside the fused kernel (its per-draw spline does not fit beside the W
 // tiles): occupation_l11_kernel writes occ[B, N] and the contraction runs on the occupation
