@@ -238,15 +238,36 @@ class DeviceTableGroup:
         torch = _torch()
         self.plan(n_gauss)
         if not spec.latency_paths:
-            # families outside the fused kernel: occupation kernel + contraction (no latency path)
-            theta = _to_device_f64(np.asarray(values, dtype=np.float64)[np.newaxis, :], self.device)
-            n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
-            ngal = torch.empty((1, self.n_tables, n_ng), dtype=torch.float64, device=self.device)
-            xi = torch.empty((1, self.n_tables, self.n_r * n_comp), dtype=torch.float64,
-                             device=self.device)
-            self.predict_into(spec, n_gauss, theta, None, separate, ngal, 0, xi, 0)
-            return (ngal[0].cpu().numpy(),
-                    xi[0].cpu().numpy().reshape(self.n_tables, self.n_r, n_comp))
+            # families outside the fused kernel: occupation kernel -> contraction on its output,
+            # with the same persistent buffers (parameters and results in pinned host memory the
+            # kernels access directly, the occupations in a device buffer): two ctypes calls and
+            # one stream synchronisation, no allocations, no copy launches
+            values = np.asarray(values, dtype=np.float64)
+            if values.shape != (spec.n_theta,):
+                raise ValueError('the parameter array has {} entries, the model family needs {} '
+                                 '({})'.format(values.size, spec.n_theta,
+                                               ', '.join(spec.theta_keys)))
+            with self._lock:
+                if self._single is None:
+                    self._single = _SingleDrawBuffers(self)
+                buf = self._single
+                buf.theta_any_np[:spec.n_theta] = values
+                n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
+                model = self._model_struct(spec)
+                stream = torch.cuda.current_stream(self.device)
+                _lib.check(self.lib.tc_occupation_batch(
+                    self.handle, ctypes.byref(model), int(n_gauss), buf.theta_any.data_ptr(), 0, 1,
+                    buf.occ.data_ptr(), stream.cuda_stream))
+                _lib.check(self.lib.tc_predict_batch(
+                    self.handle, ctypes.byref(model), int(n_gauss), None, 0, buf.occ.data_ptr(), 1,
+                    int(separate), _lib.TC_PRECISION_FP64, buf.ngal.data_ptr(),
+                    self.n_tables * n_ng, buf.xi.data_ptr(), self.n_tables * self.n_r * n_comp,
+                    buf.workspace.data_ptr(), buf.workspace.numel(), stream.cuda_stream))
+                stream.synchronize()
+                ngal = buf.ngal_np[:self.n_tables * n_ng].reshape(self.n_tables, n_ng).copy()
+                xi = buf.xi_np[:self.n_tables * self.n_r * n_comp].reshape(
+                    self.n_tables, self.n_r, n_comp).copy()
+            return ngal, xi
         with self._lock:
             if self._single is None:
                 self._single = _SingleDrawBuffers(self)
@@ -367,6 +388,10 @@ class _SingleDrawBuffers:
         torch = _torch()
         f64 = torch.float64
         self.theta = torch.zeros(len(THETA_KEYS), dtype=f64, pin_memory=True)
+        # families that run as occupation kernel -> contraction: any parameter vector, occupations
+        self.theta_any = torch.zeros(32, dtype=f64, pin_memory=True)   # >= TC_N_THETA_MAX
+        self.theta_any_np = self.theta_any.numpy()
+        self.occ = torch.zeros((1, group.n_rows), dtype=f64, device=group.device)
         self.ngal = torch.zeros(2 * group.n_tables, dtype=f64, pin_memory=True)
         self.xi = torch.zeros(group.n_tables * group.n_r * 3, dtype=f64, pin_memory=True)
         self.theta_np, self.ngal_np, self.xi_np = (self.theta.numpy(), self.ngal.numpy(),
