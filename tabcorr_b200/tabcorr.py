@@ -139,6 +139,7 @@ class DeviceTableGroup:
         self._copy_streams = None
         self._single = None
         self._small = None
+        self._small_occ = None
         self._lock = threading.Lock()
 
     def __del__(self):
@@ -323,6 +324,35 @@ class DeviceTableGroup:
             xi = buf.xi_np[:n_draws * xi_cols].reshape(n_draws, xi_cols).copy()
         return ngal, xi
 
+    def predict_small_occupation(self, spec, n_gauss, columns, n_draws, separate):
+        """:meth:`predict_small` for the families that run as occupation kernel -> contraction
+        (leauthaud11 / hearin15, mass-dependent decoration): the same persistent pinned buffers,
+        the occupations of the batch in a persistent device buffer between the two library calls."""
+        torch = _torch()
+        self.plan(n_gauss)
+        with self._lock:
+            if self._small_occ is None:
+                self._small_occ = _SmallBatchBuffers(self, SMALL_BATCH, occupation=True)
+            buf = self._small_occ
+            for j, column in enumerate(columns):
+                buf.theta_np[j, :n_draws] = column
+            n_ng, n_comp = (2 if separate else 1), self.n_comp(separate)
+            ngal_cols, xi_cols = self.n_tables * n_ng, self.n_tables * self.n_r * n_comp
+            model = self._model_struct(spec)
+            stream = torch.cuda.current_stream(self.device)
+            _lib.check(self.lib.tc_occupation_batch(
+                self.handle, ctypes.byref(model), int(n_gauss), buf.theta.data_ptr(), buf.capacity,
+                int(n_draws), buf.occ.data_ptr(), stream.cuda_stream))
+            _lib.check(self.lib.tc_predict_batch(
+                self.handle, ctypes.byref(model), int(n_gauss), None, 0, buf.occ.data_ptr(),
+                int(n_draws), int(separate), _lib.TC_PRECISION_FP64, buf.ngal.data_ptr(), ngal_cols,
+                buf.xi.data_ptr(), xi_cols, buf.workspace.data_ptr(), buf.workspace.numel(),
+                stream.cuda_stream))
+            stream.synchronize()
+            ngal = buf.ngal_np[:n_draws * ngal_cols].reshape(n_draws, ngal_cols).copy()
+            xi = buf.xi_np[:n_draws * xi_cols].reshape(n_draws, xi_cols).copy()
+        return ngal, xi
+
     def predict_into_raw(self, spec, n_gauss, theta, ngal_ptr, ngal_stride, xi_ptr, xi_stride,
                          precision=_lib.TC_PRECISION_FP64):
         """Total prediction of the draws ``theta`` (CUDA ``[B, n_theta]``) with the outputs given
@@ -410,11 +440,16 @@ class _SmallBatchBuffers:
     parameters as one contiguous column per parameter (``theta_ld = capacity``), results for
     ``capacity`` draws, workspace on the device."""
 
-    def __init__(self, group, capacity):
+    def __init__(self, group, capacity, occupation=False):
         torch = _torch()
         f64 = torch.float64
         self.capacity = int(capacity)
-        self.theta = torch.zeros((len(THETA_KEYS), self.capacity), dtype=f64, pin_memory=True)
+        # occupation=True: the buffers of predict_small_occupation (any family's parameter vector,
+        # occupations of the batch on the device)
+        n_theta = 32 if occupation else len(THETA_KEYS)   # 32 >= TC_N_THETA_MAX
+        self.theta = torch.zeros((n_theta, self.capacity), dtype=f64, pin_memory=True)
+        if occupation:
+            self.occ = torch.zeros((self.capacity, group.n_rows), dtype=f64, device=group.device)
         self.one = torch.zeros(len(THETA_KEYS), dtype=f64)   # plain host memory: read at call time
         self.one_np = self.one.numpy()
         self.ngal = torch.zeros(self.capacity * 2 * group.n_tables, dtype=f64, pin_memory=True)
@@ -753,22 +788,29 @@ class TabCorr:
         fused kernel implements; None when the batch does not qualify."""
         if isinstance(params, dict):
             spec = resolve_model(model) if model is not None else spec_from_params(params)
-            if not spec.latency_paths:
+            if not spec.latency_paths and precision != _lib.TC_PRECISION_FP64:
                 return None
             columns = theta_columns(params, spec)
         else:
             spec = resolve_model(model) if model is not None else ModelSpec()
             array = np.asarray(params, dtype=np.float64)
-            if not spec.latency_paths or array.ndim != 2 or array.shape[1] not in (5, 7):
-                return None   # the general path reports shape errors
+            if not spec.latency_paths:
+                if (precision != _lib.TC_PRECISION_FP64 or array.ndim != 2 or
+                        array.shape[1] not in (spec.n_base, spec.n_theta)):
+                    return None   # the general path reports shape errors
+            elif array.ndim != 2 or array.shape[1] not in (5, 7):
+                return None
             columns = [array[:, j] for j in range(array.shape[1])]
-            columns += [np.float64(0.0)] * (7 - len(columns))
+            columns += [np.float64(0.0)] * (spec.n_theta - len(columns))
         n_draws = batch_size(columns)
         if (n_draws == 0 or n_draws > SMALL_BATCH or
                 any(np.ndim(c) > 0 and c.shape[0] != n_draws for c in columns)):
             return None
         group = self._ensure_device()
-        ngal, xi = group.predict_small(spec, n_gauss, columns, n_draws, separate, precision)
+        if spec.latency_paths:
+            ngal, xi = group.predict_small(spec, n_gauss, columns, n_draws, separate, precision)
+        else:
+            ngal, xi = group.predict_small_occupation(spec, n_gauss, columns, n_draws, separate)
         return self._format_batch(ngal, xi.reshape(n_draws, group.n_r, group.n_comp(separate)),
                                   separate, False)
 

@@ -440,3 +440,39 @@ def test_not_finite_parameters_give_nan(tb, orc):
     assert np.all(np.isnan(occ[5])) and np.all(np.isnan(occ[17]))
     rest = np.setdiff1d(np.arange(40), [5, 17])
     assert np.array_equal(occ[rest], clean[rest])
+
+
+def test_small_batch_and_one_draw_paths_equal_the_general_path(tb, orc):
+    """Host batches of at most 4096 draws and ``predict(model)`` of this family go through
+    persistent pinned buffers (occupation kernel -> contraction, no allocations or copy launches):
+    bit for bit the results of the general path."""
+    halotab, _ = table_pair(tb, orc, 'syn240')
+    model = tb.PrebuiltHodModelFactory('hearin15', threshold=10.5)
+    draws = tb.synthetic.make_draws_leauthaud11(100, seed=9, decorated=True)
+    for separate in (False, True):
+        small = halotab.predict_batch(draws, model=model, separate_gal_type=separate)
+        general = halotab.predict_batch(draws, model=model, separate_gal_type=separate,
+                                        as_numpy=False)
+        if separate:
+            for s, g in zip(small, general):
+                assert set(s) == set(g)
+                for key in s:
+                    assert np.array_equal(s[key], g[key].cpu().numpy())
+        else:
+            assert np.array_equal(small[0], general[0].cpu().numpy())
+            assert np.array_equal(small[1], general[1].cpu().numpy())
+    # [B, 18] array input and a second call that reuses the buffers with fewer draws
+    theta = tb.models.theta_from_params(draws, None, tb.models.resolve_model(model))
+    again = halotab.predict_batch(theta[:37], model=model)
+    assert np.array_equal(again[0], small_total(halotab, draws, model)[0][:37])
+    # one draw: predict(model) against the same draw in a batch
+    row = cases.draws_row(draws, 5)
+    model.param_dict.update(row)
+    ngal1, xi1 = halotab.predict(model)
+    batch = halotab.predict_batch(draws, model=model)
+    np.testing.assert_allclose(ngal1, batch[0][5], rtol=1e-13)
+    np.testing.assert_allclose(xi1, batch[1][5], rtol=1e-12, atol=1e-14 * np.abs(batch[1][5]).max())
+
+
+def small_total(halotab, draws, model):
+    return halotab.predict_batch(draws, model=model)
