@@ -227,7 +227,8 @@ class Interpolator:
                 cap = self._small_capacity()
                 self._one = {
                     'cap': cap,
-                    'theta': torch.zeros((7, cap), dtype=f64, pin_memory=True),
+                    'theta': torch.zeros((32, cap), dtype=f64, pin_memory=True),   # >= TC_N_THETA_MAX
+                    'occ': [None] * len(self._groups),   # occupation-kernel families, on demand
                     'one': torch.zeros(7, dtype=f64),
                     'x': torch.zeros((cap, n_axes), dtype=f64, pin_memory=True),
                     'flag': torch.zeros(1, dtype=torch.int32, pin_memory=True),
@@ -254,12 +255,28 @@ class Interpolator:
             stream = torch.cuda.current_stream(device)
             model = DeviceTableGroup._model_struct(spec)
             slot = 0
-            for (group, members), workspace in zip(self._groups, buf['workspace']):
+            for index, ((group, members), workspace) in enumerate(zip(self._groups,
+                                                                      buf['workspace'])):
                 group.plan(n_gauss)
                 ngal_ptr = buf['ngal_t'].data_ptr() + 8 * slot * n_ng
                 xi_ptr = buf['xi_t'].data_ptr() + 8 * slot * n_cols
-                if n_draws == 1:
-                    buf['one'].numpy()[:] = theta_np[:, 0]
+                if not spec.latency_paths:
+                    # occupation kernel -> contraction on its output (leauthaud11 / hearin15,
+                    # mass-dependent decoration), the occupations in a persistent device buffer
+                    if buf['occ'][index] is None:
+                        buf['occ'][index] = torch.zeros((cap, group.n_rows), dtype=torch.float64,
+                                                        device=device)
+                    occ = buf['occ'][index]
+                    _lib.check(self._lib.tc_occupation_batch(
+                        group.handle, ctypes.byref(model), int(n_gauss), buf['theta'].data_ptr(),
+                        cap, int(n_draws), occ.data_ptr(), stream.cuda_stream))
+                    _lib.check(self._lib.tc_predict_batch(
+                        group.handle, ctypes.byref(model), int(n_gauss), None, 0, occ.data_ptr(),
+                        int(n_draws), int(separate), _lib.TC_PRECISION_FP64, ngal_ptr,
+                        n_tables * n_ng, xi_ptr, n_tables * n_cols, workspace.data_ptr(),
+                        workspace.numel(), stream.cuda_stream))
+                elif n_draws == 1:
+                    buf['one'].numpy()[:] = theta_np[:7, 0]
                     _lib.check(self._lib.tc_predict_one(
                         group.handle, ctypes.byref(model), int(n_gauss), buf['one'].data_ptr(),
                         int(separate), int(precision), ngal_ptr, n_tables * n_ng, xi_ptr,
@@ -310,7 +327,9 @@ class Interpolator:
                 raise ValueError('The key {} is not present in the parameter dictionary of the '
                                  'model.'.format(key))
         spec = resolve_model(model) if model is not None else spec_from_params(params)
-        if as_numpy and not defer_range_check and spec.latency_paths:
+        if as_numpy and not defer_range_check and (
+                spec.latency_paths or _lib.precision_code(precision) == _lib.TC_PRECISION_FP64
+                or self._groups[0][0].mode != 'auto'):
             from .models import theta_columns
             columns = theta_columns(params, spec)
             x_columns = [np.asarray(params[key], dtype=np.float64) for key in self._keys]
@@ -404,15 +423,6 @@ class Interpolator:
             for i in self.unique_gal_type_index:
                 self.tabcorr_list[i]._check_consistency(model)
         spec = resolve_model(model)
-        if not spec.latency_paths:
-            # families outside the fused kernel: the batch path with one draw
-            params = {k: np.atleast_1d(np.float64(v)) for k, v in model.param_dict.items()
-                      if np.ndim(v) == 0}
-            ngal, xi = self.predict_batch(params, separate_gal_type, n_gauss_prim, extrapolate,
-                                          model=spec)
-            if separate_gal_type:
-                return ({k: v[0] for k, v in ngal.items()}, {k: v[0] for k, v in xi.items()})
-            return ngal[0], xi[0]
         from .models import theta_from_params
         values = theta_from_params(model.param_dict, 1, spec)[0]
         x_values = [np.float64(model.param_dict[key]) for key in self._keys]

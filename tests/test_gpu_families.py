@@ -476,3 +476,28 @@ def test_small_batch_and_one_draw_paths_equal_the_general_path(tb, orc):
 
 def small_total(halotab, draws, model):
     return halotab.predict_batch(draws, model=model)
+
+
+def test_interpolator_latency_paths_equal_the_general_path(tb, orc):
+    """``Interpolator.predict(model)`` and small host batches of this family (persistent buffers,
+    occupation kernel -> contraction per table group) against the general batch path."""
+    axes = {'alpha_s': np.linspace(0.8, 1.2, 4)}
+    tables, param_table = tb.synthetic.make_grid_tables(axes, n_mass=12, n_sec=2, n_r=5, kind='wp',
+                                                        seed=3)
+    halotabs = [tb.TabCorr.from_arrays(t['gal_type'], t['tpcf_matrix'], t['tpcf_shape'],
+                                       t['attrs']) for t in tables]
+    interp = tb.Interpolator(halotabs, param_table)
+    model = tb.PrebuiltHodModelFactory('hearin15', threshold=10.5)
+    draws = tb.synthetic.make_draws_leauthaud11(50, seed=4, decorated=True)
+    draws['alpha_s'] = np.random.default_rng(5).uniform(0.85, 1.15, 50)
+    small = interp.predict_batch(draws, model=model)
+    general = interp.predict_batch(draws, model=model, as_numpy=False)
+    assert np.array_equal(small[0], general[0].cpu().numpy())
+    assert np.array_equal(small[1], general[1].cpu().numpy())
+    model.param_dict.update(cases.draws_row(draws, 7))
+    model.param_dict['alpha_s'] = float(draws['alpha_s'][7])
+    ngal1, xi1 = interp.predict(model)
+    np.testing.assert_allclose(ngal1, small[0][7], rtol=1e-13)
+    np.testing.assert_allclose(xi1, small[1][7], rtol=1e-12, atol=1e-14 * np.abs(small[1][7]).max())
+    ngal_sep, xi_sep = interp.predict(model, separate_gal_type=True)
+    np.testing.assert_allclose(sum(ngal_sep.values()), ngal1, rtol=1e-12)
