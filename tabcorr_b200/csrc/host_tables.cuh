@@ -197,7 +197,11 @@ int build_layout(tc_table* t, int separate) {
     } else {
       segs.push_back({0, ks_total});
     }
-    const int want = std::max(1, (4 * kWarps + n_rt - 1) / n_rt / (int)segs.size());
+    // six chunks per radial tile: every chunk writes 16 scratch rows per draw tile, the DMMAs of a
+    // cross table are few, and with four chunks per warp (48) the scratch traffic cost 3-6 %
+    // (per 1e5 draws, 48 / 12 / 6 / 3 / 1 chunks: N = 1104 2.04 / 1.97 / 1.93 / 1.93 / 2.24 ms,
+    // N = 240 0.578 / 0.549 / 0.542 / 0.546 / 0.564 ms, N = 60 unchanged; TC_TUNE_CROSS_CHUNKS)
+    const int want = std::max(1, (tune("CROSS_CHUNKS", 6) + n_rt - 1) / n_rt / (int)segs.size());
     for (int rt = 0; rt < n_rt; rt++) {
       for (size_t sg = 0; sg < segs.size(); sg++) {
         const int lo = segs[sg].first, hi = segs[sg].second;
