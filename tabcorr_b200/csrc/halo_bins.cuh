@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(256) halo_bins_kernel(const HaloBinArgs args) 
   const double inv_step_s = args.n_sec / (s_se[args.n_sec] - s_se[0]);
   const long long per_block = (args.n_halos + gridDim.x - 1) / gridDim.x;
   const long long lo = blockIdx.x * per_block, hi = min(lo + per_block, args.n_halos);
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const double lp = args.log_prim[i], sp = args.sec_pct[i];
+  // One halo: its three doubles are loaded up front (the mean's operand too, although only members
+  // of a cell need it: a second, dependent trip to HBM per halo costs more than the bytes), and
+  // two haloes per thread are in flight.
+  auto bin_one = [&](double lp, double sp, double pr) {
     // np.histogramdd: searchsorted(side='right'), values on the last edge belong to the last bin
     const int ip = edges_at_or_below(s_pe, args.n_prim + 1, lp, inv_step_p);
     const int is = edges_at_or_below(s_se, args.n_sec + 1, sp, inv_step_s);
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(256) halo_bins_kernel(const HaloBinArgs args) 
     // np.digitize(right=False) of sort_into_bins: the last edge is outside
     if (ip >= 1 && ip <= args.n_prim && is >= 1 && is <= args.n_sec) {
       const int cell = (is - 1) * args.n_prim + ip - 1;
-      double v = (args.prim[i] - args.cell_min[cell]) * args.cell_inv_width[cell];
+      double v = (pr - args.cell_min[cell]) * args.cell_inv_width[cell];
       v = fmin(fmax(v, 0.0), 1.0);     // log10 rounding can leave a member a hair outside
       const unsigned long long q = (unsigned long long)(v * 4503599627370496.0);   // 2^52
       atomicAdd(&s_open[cell], 1u);
@@ -102,7 +104,16 @@ __global__ void __launch_bounds__(256) halo_bins_kernel(const HaloBinArgs args) 
       atomicAdd(&s_q[2 * n_cells + cell], (unsigned)((q >> 26) & 0x1fffu));
       atomicAdd(&s_q[3 * n_cells + cell], (unsigned)(q >> 39));   // 14 bits: v = 1 gives 2^13
     }
+  };
+  long long i = lo + threadIdx.x;
+  for (; i + blockDim.x < hi; i += 2 * blockDim.x) {
+    const long long j = i + blockDim.x;
+    const double lp0 = args.log_prim[i], sp0 = args.sec_pct[i], pr0 = args.prim[i];
+    const double lp1 = args.log_prim[j], sp1 = args.sec_pct[j], pr1 = args.prim[j];
+    bin_one(lp0, sp0, pr0);
+    bin_one(lp1, sp1, pr1);
   }
+  if (i < hi) bin_one(args.log_prim[i], args.sec_pct[i], args.prim[i]);
   __syncthreads();
   for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
     if (s_count[c]) atomicAdd(&args.counts[c], (unsigned long long)s_count[c]);
